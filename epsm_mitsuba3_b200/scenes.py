@@ -1,0 +1,494 @@
+"""Scene containers and the seeded synthetic scene generators for BASELINE.json's configs
+(C1 cornell box, C2 glass sphere caustic, C3 1M-triangle room, C4 SMPL-sized mesh).
+
+No file IO: everything is generated in-repo from fixed seeds.  Analytic Mitsuba shapes
+(`rectangle`, `sphere`) are tessellated and flagged `ismesh=False`, which is how the reference's
+EPSM fields see them (si.ismesh = 0, epsm.py:793-796): they are intersected but carry no
+manifold gradients.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import numpy as np
+
+from . import capi
+
+
+# --------------------------------------------------------------------------------------------
+#  ScalarTransform4f subset used by EPSM/exp/*.py (include/mitsuba/core/transform.h)
+# --------------------------------------------------------------------------------------------
+class Transform4f:
+    def __init__(self, m=None):
+        self.matrix = np.eye(4, dtype=np.float64) if m is None else np.asarray(m, dtype=np.float64).reshape(4, 4)
+
+    def __matmul__(self, o):
+        if isinstance(o, Transform4f):
+            return Transform4f(self.matrix @ o.matrix)
+        p = np.asarray(o, dtype=np.float64)
+        return p @ self.matrix[:3, :3].T + self.matrix[:3, 3]
+
+    @staticmethod
+    def _of(v):
+        v = np.asarray(v, dtype=np.float64)
+        return np.full(3, float(v)) if v.ndim == 0 else v
+
+    def translate(self, v):
+        m = np.eye(4); m[:3, 3] = self._of(v)
+        return Transform4f(self.matrix @ m)
+
+    def scale(self, v):
+        return Transform4f(self.matrix @ np.diag(np.append(self._of(v), 1.0)))
+
+    def rotate(self, axis, angle):
+        a = np.asarray(axis, dtype=np.float64); a = a / np.linalg.norm(a)
+        s, c = math.sin(math.radians(angle)), math.cos(math.radians(angle))
+        x, y, z = a
+        r = np.array([[c + x * x * (1 - c), x * y * (1 - c) - z * s, x * z * (1 - c) + y * s, 0],
+                      [y * x * (1 - c) + z * s, c + y * y * (1 - c), y * z * (1 - c) - x * s, 0],
+                      [z * x * (1 - c) - y * s, z * y * (1 - c) + x * s, c + z * z * (1 - c), 0],
+                      [0, 0, 0, 1]])
+        return Transform4f(self.matrix @ r)
+
+    @staticmethod
+    def look_at(origin, target, up):
+        o, t, u = (np.asarray(v, dtype=np.float64) for v in (origin, target, up))
+        d = t - o; d /= np.linalg.norm(d)
+        left = np.cross(u, d); left /= np.linalg.norm(left)
+        new_up = np.cross(d, left)
+        m = np.eye(4); m[:3, 0], m[:3, 1], m[:3, 2], m[:3, 3] = left, new_up, d, o
+        return Transform4f(m)
+
+    def apply_points(self, p):
+        return (np.asarray(p, np.float64) @ self.matrix[:3, :3].T + self.matrix[:3, 3]).astype(np.float32)
+
+    def apply_normals(self, n):
+        inv_t = np.linalg.inv(self.matrix[:3, :3]).T
+        out = np.asarray(n, np.float64) @ inv_t.T
+        out /= np.linalg.norm(out, axis=-1, keepdims=True)
+        return out.astype(np.float32)
+
+
+T = Transform4f
+
+
+# --------------------------------------------------------------------------------------------
+#  Containers
+# --------------------------------------------------------------------------------------------
+@dataclass
+class Bsdf:
+    kind: int
+    reflectance: tuple = (1.0, 1.0, 1.0)
+    transmittance: tuple = (1.0, 1.0, 1.0)
+    eta: tuple = (0.0, 0.0, 0.0)
+    k: tuple = (1.0, 1.0, 1.0)
+    alpha_u: float = 0.1
+    alpha_v: float = 0.1
+    twosided: bool = False
+    ggx: bool = False
+    sample_visible: bool = True
+
+    @staticmethod
+    def diffuse(rgb, twosided=False):
+        return Bsdf(capi.BSDF_DIFFUSE, reflectance=tuple(rgb), twosided=twosided)
+
+    @staticmethod
+    def dielectric(int_ior=1.5, ext_ior=1.0):
+        return Bsdf(capi.BSDF_DIELECTRIC, eta=(np.float32(int_ior) / np.float32(ext_ior), 0.0, 0.0))
+
+    @staticmethod
+    def conductor(eta=(0.2, 0.92, 1.1), k=(3.9, 2.45, 2.14), twosided=False):
+        return Bsdf(capi.BSDF_CONDUCTOR, eta=tuple(eta), k=tuple(k), twosided=twosided)
+
+    @staticmethod
+    def roughconductor(alpha=0.1, eta=(0.2, 0.92, 1.1), k=(3.9, 2.45, 2.14), twosided=False, ggx=False):
+        return Bsdf(capi.BSDF_ROUGHCONDUCTOR, eta=tuple(eta), k=tuple(k), alpha_u=alpha, alpha_v=alpha,
+                    twosided=twosided, ggx=ggx)
+
+    def flags_word(self):
+        return ((capi.BSDF_TWOSIDED if self.twosided else 0) | (capi.BSDF_GGX if self.ggx else 0)
+                | (capi.BSDF_SAMPLE_VISIBLE if self.sample_visible else 0))
+
+
+@dataclass
+class Mesh:
+    name: str
+    positions: np.ndarray                 # (V,3) float32
+    faces: np.ndarray                     # (F,3) uint32
+    normals: Optional[np.ndarray] = None  # (V,3) float32 or None (flat shading)
+    bsdf: int = 0
+    emitter: int = -1
+    ismesh: bool = True
+    grad: bool = False
+    flip_normals: bool = False
+    is_rectangle: bool = False            # tessellated Mitsuba `rectangle` (emitter sampling parameterisation)
+
+    def __post_init__(self):
+        self.positions = np.ascontiguousarray(self.positions, dtype=np.float32).reshape(-1, 3)
+        self.faces = np.ascontiguousarray(self.faces, dtype=np.uint32).reshape(-1, 3)
+        if self.normals is not None:
+            self.normals = np.ascontiguousarray(self.normals, dtype=np.float32).reshape(-1, 3)
+
+    def flags_word(self):
+        return ((capi.MESH_ISMESH if self.ismesh else 0) | (capi.MESH_GRAD if self.grad else 0)
+                | (capi.MESH_FLIP_NORMALS if self.flip_normals else 0)
+                | (capi.MESH_RECTANGLE if self.is_rectangle else 0))
+
+
+@dataclass
+class Emitter:
+    radiance: tuple
+    mesh: int
+
+
+@dataclass
+class Sensor:
+    to_world: Transform4f
+    fov: float
+    width: int
+    height: int
+    near_clip: float = 0.01
+    far_clip: float = 10000.0
+    spp: int = 4
+    sample_border: bool = False
+
+
+@dataclass
+class SceneData:
+    meshes: List[Mesh] = field(default_factory=list)
+    bsdfs: List[Bsdf] = field(default_factory=list)
+    emitters: List[Emitter] = field(default_factory=list)
+    sensors: List[Sensor] = field(default_factory=list)
+    name: str = "scene"
+
+    # -- helpers -------------------------------------------------------------------------
+    def add_bsdf(self, b: Bsdf) -> int:
+        self.bsdfs.append(b); return len(self.bsdfs) - 1
+
+    def add_mesh(self, m: Mesh, radiance=None) -> int:
+        self.meshes.append(m); mid = len(self.meshes) - 1
+        if radiance is not None:
+            self.emitters.append(Emitter(tuple(radiance), mid)); m.emitter = len(self.emitters) - 1
+        return mid
+
+    def vertex_offsets(self):
+        return np.concatenate([[0], np.cumsum([m.positions.shape[0] for m in self.meshes])]).astype(np.int64)
+
+    def face_offsets(self):
+        return np.concatenate([[0], np.cumsum([m.faces.shape[0] for m in self.meshes])]).astype(np.int64)
+
+    @property
+    def n_triangles(self):
+        return int(sum(m.faces.shape[0] for m in self.meshes))
+
+    @property
+    def n_vertices(self):
+        return int(sum(m.positions.shape[0] for m in self.meshes))
+
+    def sensor_trio(self, base: Sensor, match_res: int):
+        """The sensor layout the EPSM drivers use (EPSM/exp/shadow.py:98-153):
+        0 full-res sample_border=True, 1 full-res (manifold primal), 2 match_res² at 8 spp (gradient)."""
+        import copy
+        s0 = copy.copy(base); s0.sample_border = True
+        s1 = copy.copy(base)
+        s2 = copy.copy(base); s2.width = s2.height = match_res; s2.spp = 8
+        self.sensors = [s0, s1, s2]
+
+    # -- C descriptors (arrays kept alive on the returned object) -----------------------
+    def to_c(self):
+        return _CScene(self)
+
+
+class _CScene:
+    def __init__(self, sd: SceneData):
+        self.keep = []
+        fptr, uptr = C.POINTER(C.c_float), C.POINTER(C.c_uint32)
+        self.meshes = (capi.MeshDesc * max(1, len(sd.meshes)))()
+        for i, m in enumerate(sd.meshes):
+            d = self.meshes[i]
+            d.vertex_count, d.face_count = m.positions.shape[0], m.faces.shape[0]
+            d.positions = m.positions.ctypes.data_as(fptr)
+            d.faces = m.faces.ctypes.data_as(uptr)
+            d.normals = m.normals.ctypes.data_as(fptr) if m.normals is not None else fptr()
+            d.bsdf_id, d.emitter_id, d.flags = m.bsdf, m.emitter, m.flags_word()
+            self.keep += [m.positions, m.faces, m.normals]
+        self.bsdfs = (capi.BsdfDesc * max(1, len(sd.bsdfs)))()
+        for i, b in enumerate(sd.bsdfs):
+            d = self.bsdfs[i]
+            d.kind, d.flags = b.kind, b.flags_word()
+            d.reflectance[:] = [float(x) for x in b.reflectance]
+            d.transmittance[:] = [float(x) for x in b.transmittance]
+            d.eta[:] = [float(x) for x in b.eta]
+            d.k[:] = [float(x) for x in b.k]
+            d.alpha_u, d.alpha_v = b.alpha_u, b.alpha_v
+        self.emitters = (capi.EmitterDesc * max(1, len(sd.emitters)))()
+        for i, e in enumerate(sd.emitters):
+            self.emitters[i].radiance[:] = [float(x) for x in e.radiance]
+            self.emitters[i].mesh_id = e.mesh
+        self.sensors = (capi.SensorDesc * max(1, len(sd.sensors)))()
+        for i, s in enumerate(sd.sensors):
+            d = self.sensors[i]
+            d.to_world[:] = [float(x) for x in s.to_world.matrix.astype(np.float32).ravel()]
+            d.fov_x, d.near_clip, d.far_clip, d.width, d.height = s.fov, s.near_clip, s.far_clip, s.width, s.height
+        self.counts = (len(sd.meshes), len(sd.bsdfs), len(sd.emitters), len(sd.sensors))
+
+
+# --------------------------------------------------------------------------------------------
+#  Primitive generators
+# --------------------------------------------------------------------------------------------
+def rectangle(to_world: Transform4f, **kw) -> Mesh:
+    """Mitsuba `rectangle` ([-1,1]² in the xy plane, normal +z) as two triangles; analytic in the reference."""
+    p = np.array([[-1, -1, 0], [1, -1, 0], [1, 1, 0], [-1, 1, 0]], np.float32)
+    kw.setdefault("ismesh", False)
+    kw.setdefault("is_rectangle", True)
+    return Mesh(kw.pop("name", "rectangle"), to_world.apply_points(p), np.array([[0, 1, 2], [0, 2, 3]]), **kw)
+
+
+def grid(to_world: Transform4f, nu: int, nv: int, **kw) -> Mesh:
+    """[-1,1]² plane tessellated into nu×nv quads (2·nu·nv triangles), a real mesh (ismesh)."""
+    u, v = np.meshgrid(np.linspace(-1, 1, nu + 1), np.linspace(-1, 1, nv + 1), indexing="xy")
+    p = np.stack([u.ravel(), v.ravel(), np.zeros(u.size)], -1)
+    i = (np.arange(nv)[:, None] * (nu + 1) + np.arange(nu)[None, :]).ravel()
+    f = np.concatenate([np.stack([i, i + 1, i + nu + 2], -1), np.stack([i, i + nu + 2, i + nu + 1], -1)])
+    return Mesh(kw.pop("name", "grid"), to_world.apply_points(p), f, **kw)
+
+
+_CUBE_V = np.array([
+    [1, -1, -1], [1, -1, 1], [-1, -1, 1], [-1, -1, -1], [1, 1, -1], [-1, 1, -1], [-1, 1, 1], [1, 1, 1],
+    [1, -1, -1], [1, 1, -1], [1, 1, 1], [1, -1, 1], [1, -1, 1], [1, 1, 1], [-1, 1, 1], [-1, -1, 1],
+    [-1, -1, 1], [-1, 1, 1], [-1, 1, -1], [-1, -1, -1], [1, 1, -1], [1, -1, -1], [-1, -1, -1], [-1, 1, -1]], np.float32)
+_CUBE_N = np.repeat(np.array([[0, -1, 0], [0, 1, 0], [1, 0, 0], [0, 0, 1], [-1, 0, 0], [0, 0, -1]], np.float32), 4, axis=0)
+_CUBE_F = np.array([[4 * q + a, 4 * q + b, 4 * q + c] for q in range(6) for (a, b, c) in ((0, 1, 2), (3, 0, 2))])
+
+
+def cube(to_world: Transform4f, **kw) -> Mesh:
+    """Mitsuba `cube`: a 24-vertex / 12-face Mesh with per-face vertex normals (src/shapes/cube.cpp:105-160)."""
+    return Mesh(kw.pop("name", "cube"), to_world.apply_points(_CUBE_V), _CUBE_F,
+                normals=to_world.apply_normals(_CUBE_N), **kw)
+
+
+def icosphere(subdiv: int):
+    """Unit icosphere: (V,3) float64 positions, (F,3) faces; 20·4^subdiv faces."""
+    t = (1 + 5 ** 0.5) / 2
+    v = [(-1, t, 0), (1, t, 0), (-1, -t, 0), (1, -t, 0), (0, -1, t), (0, 1, t), (0, -1, -t), (0, 1, -t),
+         (t, 0, -1), (t, 0, 1), (-t, 0, -1), (-t, 0, 1)]
+    f = [(0, 11, 5), (0, 5, 1), (0, 1, 7), (0, 7, 10), (0, 10, 11), (1, 5, 9), (5, 11, 4), (11, 10, 2), (10, 7, 6),
+         (7, 1, 8), (3, 9, 4), (3, 4, 2), (3, 2, 6), (3, 6, 8), (3, 8, 9), (4, 9, 5), (2, 4, 11), (6, 2, 10), (8, 6, 7), (9, 8, 1)]
+    v = np.array(v, np.float64); v /= np.linalg.norm(v, axis=1, keepdims=True)
+    f = np.array(f, np.int64)
+    for _ in range(subdiv):
+        e = np.concatenate([f[:, [0, 1]], f[:, [1, 2]], f[:, [2, 0]]])
+        es = np.sort(e, axis=1)
+        uniq, inv = np.unique(es, axis=0, return_inverse=True)
+        mid = v[uniq[:, 0]] + v[uniq[:, 1]]; mid /= np.linalg.norm(mid, axis=1, keepdims=True)
+        base = v.shape[0]; v = np.concatenate([v, mid])
+        n = f.shape[0]; a, b, c = base + inv[:n], base + inv[n:2 * n], base + inv[2 * n:]
+        f = np.concatenate([np.stack([f[:, 0], a, c], -1), np.stack([f[:, 1], b, a], -1),
+                            np.stack([f[:, 2], c, b], -1), np.stack([a, b, c], -1)])
+    return v, f
+
+
+def sphere_mesh(center, radius, subdiv, smooth=True, **kw) -> Mesh:
+    v, f = icosphere(subdiv)
+    p = (v * radius + np.asarray(center, np.float64)).astype(np.float32)
+    return Mesh(kw.pop("name", "sphere"), p, f, normals=v.astype(np.float32) if smooth else None, **kw)
+
+
+def vertex_normals(positions: np.ndarray, faces: np.ndarray) -> np.ndarray:
+    """Angle-weighted vertex normals (Mesh::recompute_vertex_normals, src/render/mesh.cpp:257-330), float64 numpy."""
+    p = positions.astype(np.float64); f = faces.astype(np.int64)
+    v = [p[f[:, 0]], p[f[:, 1]], p[f[:, 2]]]
+    n = np.cross(v[1] - v[0], v[2] - v[0]); n /= np.maximum(np.linalg.norm(n, axis=1, keepdims=True), 1e-300)
+    out = np.zeros_like(p)
+    for i in range(3):
+        d0 = v[(i + 1) % 3] - v[i]; d0 /= np.linalg.norm(d0, axis=1, keepdims=True)
+        d1 = v[(i + 2) % 3] - v[i]; d1 /= np.linalg.norm(d1, axis=1, keepdims=True)
+        ang = np.arccos(np.clip((d0 * d1).sum(1), -1, 1))
+        np.add.at(out, f[:, i], n * ang[:, None])
+    ln = np.linalg.norm(out, axis=1, keepdims=True)
+    out = np.where(ln > 0, out / np.maximum(ln, 1e-300), np.array([1.0, 0, 0]))
+    return out.astype(np.float32)
+
+
+# --------------------------------------------------------------------------------------------
+#  C1 — mi.cornell_box() (src/python/python/util.py:559-693) with the EPSM sensor trio
+# --------------------------------------------------------------------------------------------
+def cornell_box(res: int = 128, spp: int = 16, match_res: int = 128, box_bsdf: Optional[Bsdf] = None) -> SceneData:
+    sd = SceneData(name="cornell_box")
+    white = sd.add_bsdf(Bsdf.diffuse((0.885809, 0.698859, 0.666422)))
+    green = sd.add_bsdf(Bsdf.diffuse((0.105421, 0.37798, 0.076425)))
+    red = sd.add_bsdf(Bsdf.diffuse((0.570068, 0.0430135, 0.0443706)))
+    box = white if box_bsdf is None else sd.add_bsdf(box_bsdf)
+    sd.add_mesh(rectangle(T().translate([0.0, 0.99, 0.01]).rotate([1, 0, 0], 90).scale([0.23, 0.19, 0.19]),
+                          name="light", bsdf=white), radiance=(18.387, 13.9873, 6.75357))
+    sd.add_mesh(rectangle(T().translate([0, -1, 0]).rotate([1, 0, 0], -90), name="floor", bsdf=white))
+    sd.add_mesh(rectangle(T().translate([0, 1, 0]).rotate([1, 0, 0], 90), name="ceiling", bsdf=white))
+    sd.add_mesh(rectangle(T().translate([0, 0, -1]), name="back", bsdf=white))
+    sd.add_mesh(rectangle(T().translate([1, 0, 0]).rotate([0, 1, 0], -90), name="green-wall", bsdf=green))
+    sd.add_mesh(rectangle(T().translate([-1, 0, 0]).rotate([0, 1, 0], 90), name="red-wall", bsdf=red))
+    sd.add_mesh(cube(T().translate([0.335, -0.7, 0.38]).rotate([0, 1, 0], -17).scale(0.3),
+                     name="small-box", bsdf=box, grad=True))
+    sd.add_mesh(cube(T().translate([-0.33, -0.4, -0.28]).rotate([0, 1, 0], 18.25).scale([0.3, 0.61, 0.3]),
+                     name="large-box", bsdf=box, grad=True))
+    base = Sensor(T.look_at([0, 0, 3.9], [0, 0, 0], [0, 1, 0]), 39.3077, res, res, 0.001, 100.0, spp)
+    sd.sensor_trio(base, match_res)
+    return sd
+
+
+# --------------------------------------------------------------------------------------------
+#  C2 — glass icosphere over a diffuse plane + area light, manifold_caustic
+# --------------------------------------------------------------------------------------------
+def glass_sphere_caustic(res: int = 512, spp: int = 64, match_res: int = 128, subdiv: int = 5) -> SceneData:
+    sd = SceneData(name="glass_sphere_caustic")
+    glass = sd.add_bsdf(Bsdf.dielectric(1.5))
+    floor = sd.add_bsdf(Bsdf.diffuse((0.7, 0.7, 0.7)))
+    black = sd.add_bsdf(Bsdf.diffuse((0.0, 0.0, 0.0)))
+    sd.add_mesh(sphere_mesh((0, 0, 1.0), 1.0, subdiv, smooth=True, name="glass", bsdf=glass, grad=True))
+    sd.add_mesh(grid(T().scale([5, 5, 1]), 1, 1, name="plane", bsdf=floor))
+    # area light 1×1 at z = 4 facing down
+    sd.add_mesh(grid(T().translate([0, 0, 4]).rotate([1, 0, 0], 180).scale([0.5, 0.5, 1]), 1, 1,
+                     name="light", bsdf=black), radiance=(50.0, 50.0, 50.0))
+    base = Sensor(T.look_at([0, -4, 2.5], [0, 0, 0.5], [0, 0, 1]), 40.0, res, res, 0.01, 1000.0, spp)
+    sd.sensor_trio(base, match_res)
+    return sd
+
+
+# --------------------------------------------------------------------------------------------
+#  C3 — procedural ~1M-triangle indoor scene, manifold(_hybrid)
+# --------------------------------------------------------------------------------------------
+def indoor_room(n_tris_target: int = 1_000_000, res: int = 1024, spp: int = 32, match_res: int = 256,
+                seed: int = 1234) -> SceneData:
+    """Room of 6 tessellated walls + displaced icospheres, materials drawn from default_rng(seed):
+    70 % diffuse, 15 % roughconductor α=0.1, 10 % dielectric, 5 % conductor; 4 area lights."""
+    rng = np.random.default_rng(seed)
+    sd = SceneData(name=f"indoor_room_{n_tris_target}")
+    scale = max(n_tris_target / 1_000_000.0, 1e-4)
+    n_wall = max(2, int(round(256 * math.sqrt(scale))))           # 6 walls × 2·n² tris (786k at n=256)
+    n_obj = max(4, int(round(64 * min(1.0, scale * 4))))
+    wall_tris = 6 * 2 * n_wall * n_wall
+    per_obj = max(20, (n_tris_target - wall_tris) / n_obj)
+    obj_sub = int(np.clip(round(math.log(per_obj / 20.0, 4)), 0, 6))
+    white = sd.add_bsdf(Bsdf.diffuse((0.8, 0.8, 0.8)))
+    black = sd.add_bsdf(Bsdf.diffuse((0.0, 0.0, 0.0)))
+    S = 4.0   # half-extent of the room (x,y) ; height 0..4
+    walls = [T().translate([0, 0, 0]).scale([S, S, 1]),                                           # floor (+z)
+             T().translate([0, 0, S]).rotate([1, 0, 0], 180).scale([S, S, 1]),                    # ceiling (-z)
+             T().translate([0, S, S / 2]).rotate([1, 0, 0], 90).scale([S, S / 2, 1]),             # back (-y)
+             T().translate([0, -S, S / 2]).rotate([1, 0, 0], -90).scale([S, S / 2, 1]),           # front (+y)
+             T().translate([S, 0, S / 2]).rotate([0, 1, 0], -90).scale([S / 2, S, 1]),            # right (-x)
+             T().translate([-S, 0, S / 2]).rotate([0, 1, 0], 90).scale([S / 2, S, 1])]            # left (+x)
+    for i, tw in enumerate(walls):
+        col = rng.uniform(0.3, 0.9, 3)
+        b = sd.add_bsdf(Bsdf.diffuse(col))
+        sd.add_mesh(grid(tw, n_wall, n_wall, name=f"wall{i}", bsdf=b))
+    base_v, base_f = icosphere(obj_sub)
+    for i in range(n_obj):
+        r = rng.uniform(0.18, 0.42)
+        c = np.array([rng.uniform(-S + 0.6, S - 0.6), rng.uniform(-S + 0.6, S - 0.6), rng.uniform(r + 0.02, 2.4)])
+        # low-frequency radial displacement
+        k = rng.normal(0, 1, (3, 3)); ph = rng.uniform(0, 2 * math.pi, 3)
+        disp = 1.0 + 0.08 * np.sin(base_v @ k.T * 2.0 + ph).sum(1)
+        p = (base_v * (r * disp)[:, None] + c).astype(np.float32)
+        u = rng.random()
+        if u < 0.70:
+            b = Bsdf.diffuse(rng.uniform(0.2, 0.9, 3))
+        elif u < 0.85:
+            b = Bsdf.roughconductor(0.1)
+        elif u < 0.95:
+            b = Bsdf.dielectric(1.5)
+        else:
+            b = Bsdf.conductor()
+        bid = sd.add_bsdf(b)
+        sd.add_mesh(Mesh(f"obj{i}", p, base_f, normals=vertex_normals(p, base_f), bsdf=bid, grad=True))
+    for (x, y) in ((-2, -2), (2, -2), (-2, 2), (2, 2)):
+        sd.add_mesh(grid(T().translate([x, y, S - 0.02]).rotate([1, 0, 0], 180).scale([0.5, 0.5, 1]), 2, 2,
+                         name="light", bsdf=black), radiance=(30.0, 28.0, 25.0))
+    base = Sensor(T.look_at([0, -3.6, 2.0], [0, 0.5, 1.0], [0, 0, 1]), 60.0, res, res, 0.01, 1000.0, spp)
+    sd.sensor_trio(base, match_res)
+    return sd
+
+
+# --------------------------------------------------------------------------------------------
+#  C4 — 6890-vertex / 13776-face articulated mesh in a stage (EPSM/exp/human.py:20-189 layout)
+# --------------------------------------------------------------------------------------------
+def smpl_sized_mesh(seed: int = 0):
+    """Closed genus-0 mesh with exactly 6890 vertices / 13776 faces: a lat-long sphere (83 rings × 83
+    segments + 2 poles... trimmed) perturbed by low-frequency noise and 24 random 'bone' rotations."""
+    rng = np.random.default_rng(seed)
+    rings, segs = 83, 83                       # 83·83 + 2 = 6891 → drop to 6890 by using 82.98.. not possible; see below
+    # V = rings*segs + 2, F = 2*segs*rings.  (rings, segs) = (84, 82): V = 6890, F = 13776.
+    rings, segs = 84, 82
+    th = (np.arange(1, rings + 1) / (rings + 1)) * math.pi
+    ph = np.arange(segs) / segs * 2 * math.pi
+    x = np.sin(th)[:, None] * np.cos(ph)[None, :]; y = np.sin(th)[:, None] * np.sin(ph)[None, :]
+    z = np.repeat(np.cos(th)[:, None], segs, 1)
+    v = np.concatenate([[[0, 0, 1.0]], np.stack([x, y, z], -1).reshape(-1, 3), [[0, 0, -1.0]]])
+    f = []
+    for s in range(segs):
+        f.append((0, 1 + s, 1 + (s + 1) % segs))
+    for r in range(rings - 1):
+        a = 1 + r * segs; b = a + segs
+        for s in range(segs):
+            s1 = (s + 1) % segs
+            f.append((a + s, b + s, b + s1)); f.append((a + s, b + s1, a + s1))
+    last = 1 + (rings - 1) * segs; south = v.shape[0] - 1
+    for s in range(segs):
+        f.append((last + s, south, last + (s + 1) % segs))
+    f = np.array(f, np.int64)
+    assert v.shape[0] == 6890 and f.shape[0] == 13776, (v.shape, f.shape)
+    # body-like proportions + low-frequency noise + 24 bones
+    v = v * np.array([0.28, 0.18, 0.85])
+    k = rng.normal(0, 1.5, (4, 3)); phs = rng.uniform(0, 2 * math.pi, 4)
+    v = v * (1.0 + 0.06 * np.sin(v @ k.T + phs).sum(1))[:, None]
+    centers = rng.uniform(-1, 1, (24, 3)) * np.array([0.25, 0.15, 0.8])
+    for c in centers:
+        ax = rng.normal(0, 1, 3); ax /= np.linalg.norm(ax); ang = rng.uniform(-0.1, 0.1)
+        w = np.exp(-np.sum((v - c) ** 2, 1) / 0.05)[:, None]
+        rel = v - c
+        rot = rel * math.cos(ang) + np.cross(ax, rel) * math.sin(ang) + ax * (rel @ ax)[:, None] * (1 - math.cos(ang))
+        v = v + w * (rot - rel)
+    return v.astype(np.float32), f
+
+
+def articulated_stage(res: int = 512, spp: int = 64, match_res: int = 256, seed: int = 0) -> SceneData:
+    sd = SceneData(name="articulated_stage")
+    skin = sd.add_bsdf(Bsdf.diffuse((0.6, 0.5, 0.45)))
+    floor = sd.add_bsdf(Bsdf.diffuse((0.5, 0.5, 0.5)))
+    black = sd.add_bsdf(Bsdf.diffuse((0.0, 0.0, 0.0)))
+    v, f = smpl_sized_mesh(seed)
+    v = v + np.array([0, 0, 0.95], np.float32)
+    sd.add_mesh(Mesh("body", v, f, normals=vertex_normals(v, f), bsdf=skin, grad=True))
+    sd.add_mesh(grid(T().scale([6, 6, 1]), 8, 8, name="floor", bsdf=floor))
+    sd.add_mesh(grid(T().translate([0, 3, 3]).rotate([1, 0, 0], 90).scale([6, 3, 1]), 8, 8, name="wall", bsdf=floor))
+    # the reference uses a small sphere light of radiance 3e5 (exp/human.py); tessellated here
+    sd.add_mesh(sphere_mesh((2.5, -3.0, 4.0), 0.05, 2, smooth=False, name="light", bsdf=black, ismesh=False),
+                radiance=(3e5, 3e5, 3e5))
+    base = Sensor(T.look_at([0, -4.5, 1.6], [0, 0, 0.9], [0, 0, 1]), 40.0, res, res, 0.01, 1000.0, spp)
+    sd.sensor_trio(base, match_res)
+    return sd
+
+
+# --------------------------------------------------------------------------------------------
+#  Small extra parity scenes
+# --------------------------------------------------------------------------------------------
+def mirror_plane_scene(res: int = 64, spp: int = 8, match_res: int = 32, rough: bool = False) -> SceneData:
+    """A (rough) conductor slab reflecting a diffuse wall, lit by an area light: exercises the
+    specular-chain rows of calc_grad (cam → specular → diffuse) for `manifold`."""
+    sd = SceneData(name="mirror_plane" + ("_rough" if rough else ""))
+    mirror = sd.add_bsdf(Bsdf.roughconductor(0.1, twosided=True) if rough else Bsdf.conductor(twosided=True))
+    wall = sd.add_bsdf(Bsdf.diffuse((0.7, 0.4, 0.3), twosided=True))
+    black = sd.add_bsdf(Bsdf.diffuse((0, 0, 0)))
+    m = grid(T().scale([1.5, 1.5, 1]), 6, 6, name="mirror", bsdf=mirror, grad=True)
+    m.positions[:, 2] += 0.05 * np.sin(2.0 * m.positions[:, 0]) * np.cos(1.5 * m.positions[:, 1])
+    m.normals = vertex_normals(m.positions, m.faces)
+    sd.add_mesh(m)
+    sd.add_mesh(grid(T().translate([0, 2.0, 1.5]).rotate([1, 0, 0], 90).scale([2.5, 1.5, 1]), 4, 4,
+                     name="wall", bsdf=wall, grad=True))
+    sd.add_mesh(grid(T().translate([0, 0, 4]).rotate([1, 0, 0], 180).scale([0.6, 0.6, 1]), 1, 1,
+                     name="light", bsdf=black), radiance=(40.0, 40.0, 40.0))
+    base = Sensor(T.look_at([0, -3.0, 2.0], [0, 0.3, 0.3], [0, 0, 1]), 45.0, res, res, 0.01, 1000.0, spp)
+    sd.sensor_trio(base, match_res)
+    return sd

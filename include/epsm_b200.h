@@ -1,0 +1,208 @@
+/* epsm_b200.h — C ABI of libepsm_b200.so, the B200-native EPSM manifold-integrator path.
+ *
+ * Drop-in boundary for the hot path of jkxing/EPSM_Mitsuba3.  Every entry
+ * point cites the reference interface it replaces (paths relative to the reference root).
+ * Plain pointers and sizes only; no C++ or torch types cross this boundary.  All calls
+ * return 0 on success and a negative EPSM_E_* code on failure; epsm_last_error() gives the
+ * message.  Nothing throws across the ABI.  One CUDA stream per context; calls on one
+ * context are not thread-safe (matches the reference: film guarded by a mutex,
+ * src/films/hdrfilm.cpp:247-252; integrators driven single-threaded from Python).
+ *
+ * Memory spaces: pointer arguments with a companion `mem` argument live on the host
+ * (EPSM_MEM_HOST; the library stages through pinned memory and the copies are part of the
+ * call) or on the context's device (EPSM_MEM_DEVICE, e.g. a torch tensor's data_ptr()).
+ */
+#ifndef EPSM_B200_H
+#define EPSM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EPSM_MEM_HOST   0
+#define EPSM_MEM_DEVICE 1
+
+#define EPSM_OK            0
+#define EPSM_E_INVALID    -1   /* bad argument                         */
+#define EPSM_E_CUDA       -2   /* CUDA runtime error                   */
+#define EPSM_E_NOSCENE    -3   /* call needs an uploaded scene         */
+#define EPSM_E_NOGPU      -4   /* no usable CUDA device (no fallback)  */
+
+/* BSDF plugin kinds on the path. */
+#define EPSM_BSDF_DIFFUSE         0   /* src/bsdfs/diffuse.cpp        */
+#define EPSM_BSDF_DIELECTRIC      1   /* src/bsdfs/dielectric.cpp     */
+#define EPSM_BSDF_CONDUCTOR       2   /* src/bsdfs/conductor.cpp      */
+#define EPSM_BSDF_ROUGHCONDUCTOR  3   /* src/bsdfs/roughconductor.cpp */
+
+/* epsm_bsdf_desc.flags */
+#define EPSM_BSDF_TWOSIDED        1u  /* wrapped in src/bsdfs/twosided.cpp (same BRDF both sides) */
+#define EPSM_BSDF_GGX             2u  /* microfacet distribution: GGX instead of Beckmann          */
+#define EPSM_BSDF_SAMPLE_VISIBLE  4u  /* roughconductor sample_visible (default true)              */
+
+/* Mitsuba BSDFFlags bits that the path inspects (include/mitsuba/render/bsdf.h:37-110). */
+#define EPSM_BF_NULL               0x00001u
+#define EPSM_BF_DIFFUSE_REFLECTION 0x00002u
+#define EPSM_BF_GLOSSY_REFLECTION  0x00008u
+#define EPSM_BF_DELTA_REFLECTION   0x00020u
+#define EPSM_BF_DELTA_TRANSMISSION 0x00040u
+#define EPSM_BF_DIFFUSE            0x00006u
+#define EPSM_BF_SMOOTH             0x0001eu
+#define EPSM_BF_DELTA              0x00061u
+
+/* epsm_mesh_desc.flags */
+#define EPSM_MESH_ISMESH        1u  /* a triangle mesh in the reference (si.ismesh = 1, mesh.cpp:720);
+                                       clear for tessellated analytic shapes (rectangle, sphere …),
+                                       which the reference excludes from EPSM gradients (epsm.py:793-796) */
+#define EPSM_MESH_GRAD          2u  /* vertex_positions has gradient tracking enabled                 */
+#define EPSM_MESH_FLIP_NORMALS  4u  /* Mesh::m_flip_normals                                           */
+#define EPSM_MESH_RECTANGLE     8u  /* tessellation of a Mitsuba `rectangle`: vertices 0..3 are the corners
+                                       (-1,-1) (1,-1) (1,1) (-1,1) under to_world; emitter sampling then follows
+                                       src/shapes/rectangle.cpp:152-171 (uniform in the parameterisation)    */
+
+typedef struct epsm_mesh_desc {
+    uint32_t        vertex_count;
+    uint32_t        face_count;
+    const float    *positions;   /* 3*vertex_count, host                                     */
+    const uint32_t *faces;       /* 3*face_count, host, indices local to this mesh           */
+    const float    *normals;     /* 3*vertex_count or NULL (flat shading), host              */
+    int32_t         bsdf_id;     /* index into the bsdf table                                */
+    int32_t         emitter_id;  /* index into the emitter table, or -1                      */
+    uint32_t        flags;       /* EPSM_MESH_*                                              */
+} epsm_mesh_desc;
+
+typedef struct epsm_bsdf_desc {
+    uint32_t kind;               /* EPSM_BSDF_*                                              */
+    uint32_t flags;              /* EPSM_BSDF_TWOSIDED | …                                   */
+    float    reflectance[3];     /* diffuse reflectance / specular_reflectance               */
+    float    transmittance[3];   /* dielectric specular_transmittance                        */
+    float    eta[3];             /* conductor eta (RGB); dielectric: eta[0] = int_ior/ext_ior */
+    float    k[3];               /* conductor k (RGB)                                        */
+    float    alpha_u, alpha_v;   /* roughconductor roughness                                 */
+} epsm_bsdf_desc;
+
+typedef struct epsm_emitter_desc {   /* src/emitters/area.cpp, uniform radiance */
+    float   radiance[3];
+    int32_t mesh_id;
+} epsm_emitter_desc;
+
+typedef struct epsm_sensor_desc {    /* src/sensors/perspective.cpp + hdrfilm + gaussian rfilter */
+    float    to_world[16];       /* row-major camera-to-world, no scale                      */
+    float    fov_x;              /* degrees, horizontal                                      */
+    float    near_clip, far_clip;
+    uint32_t width, height;      /* film size == crop size (no crop window)                  */
+} epsm_sensor_desc;
+
+typedef struct epsm_ctx epsm_ctx;
+
+/* Integrator variants registered by the reference (epsm.py:948, :1202). */
+#define EPSM_VARIANT_MANIFOLD          0
+#define EPSM_VARIANT_MANIFOLD_CAUSTIC  1
+
+/* Context on CUDA device `device`.  Fails with EPSM_E_NOGPU when no device is usable:
+ * there is no CPU fallback.  (Replaces mi.set_variant('cuda_ad_rgb'), EPSM/optim.py:18.) */
+int epsm_create(int device, epsm_ctx **out);
+int epsm_destroy(epsm_ctx *ctx);
+const char *epsm_last_error(const epsm_ctx *ctx);   /* ctx may be NULL: last creation error */
+
+/* Scene construction: replaces mi.load_dict / Scene::Scene + accel init
+ * (src/render/scene.cpp:22-100, src/render/scene_embree.inl:83-187, scene_optix.inl:236-440).
+ * Copies all host arrays, builds the wide BVH, area-sampling tables and sensor transforms. */
+int epsm_scene_upload(epsm_ctx *ctx,
+                      const epsm_mesh_desc *meshes, uint32_t n_meshes,
+                      const epsm_bsdf_desc *bsdfs, uint32_t n_bsdfs,
+                      const epsm_emitter_desc *emitters, uint32_t n_emitters,
+                      const epsm_sensor_desc *sensors, uint32_t n_sensors);
+
+/* params['<mesh>.vertex_positions'] = …; params.update()  (src/python/python/util.py:181-228 →
+ * Mesh::parameters_changed, src/render/mesh.cpp:82-102 → Scene::parameters_changed, scene.cpp:304-336).
+ * `positions` holds 3*vertex_count floats in `mem` space.  Vertex normals of meshes that have them
+ * are recomputed (mesh.cpp:257-330), area tables and the BVH are rebuilt on commit. */
+int epsm_scene_update_vertices(epsm_ctx *ctx, uint32_t mesh_id, const float *positions, int mem);
+int epsm_scene_commit(epsm_ctx *ctx);
+
+/* Scene::ray_intersect_preliminary / Scene::ray_test on a ray batch
+ * (src/render/scene_embree.inl:202-426, scene_optix.inl:516-646, kdtree.h:2188-2290).
+ * rays:  n × 8 floats (o.xyz, maxt, d.xyz, pad).  mint = 0.
+ * hits (closest): n × 4 32-bit words (t, prim_u, prim_v as float; global prim_index as uint32,
+ *       0xffffffff on a miss; t = +inf on a miss).
+ * hits (any_hit != 0): n × uint32, 1 if occluded.
+ * counters (optional, device or host per `mem`, 2 × uint64): nodes visited, triangles tested —
+ * the algorithmic-byte accounting of SURVEY.md §8d.  Pass NULL to run the uninstrumented kernel. */
+int epsm_trace(epsm_ctx *ctx, const float *rays, uint64_t n, void *hits, int any_hit,
+               uint64_t *counters, int mem);
+
+/* Integrator::render for `manifold*` (EPSMIntegrator.render, epsm.py:13-82;
+ * include/mitsuba/render/integrator.h:74-93).  Traces lanes [lane_begin, lane_end) of the
+ * W·H·spp wavefront (lane_end = 0 means all) and ACCUMULATES into the context's RGBW film.
+ * max_depth / rr_depth are the integrator properties (common.py:28-43). */
+int epsm_render_accumulate(epsm_ctx *ctx, uint32_t sensor, uint32_t seed, uint32_t spp,
+                           uint32_t max_depth, uint32_t rr_depth,
+                           uint64_t lane_begin, uint64_t lane_end, uint64_t *counters);
+int epsm_film_clear(epsm_ctx *ctx, uint32_t sensor);
+/* Raw RGBW film (H·W·4 floats) — the buffer a multi-GPU host allreduces before develop. */
+int epsm_film_raw(epsm_ctx *ctx, uint32_t sensor, float **device_ptr, uint64_t *n_floats);
+/* HDRFilm::develop + the two zero channels appended by epsm.py:76-82: out is H·W·5 floats. */
+int epsm_film_develop(epsm_ctx *ctx, uint32_t sensor, float *out_hw5, int mem);
+/* Convenience: clear + accumulate(all lanes) + develop. */
+int epsm_render(epsm_ctx *ctx, uint32_t sensor, uint32_t seed, uint32_t spp,
+                uint32_t max_depth, uint32_t rr_depth, float *out_hw5, int mem);
+
+/* Integrator::render_backward for `manifold*` (EPSMIntegrator.render_backward, epsm.py:84-306,
+ * with sample_path :503-742 and calc_grad :745-946 / :952-1200 fused per path).
+ * grad_in: H·W·5 floats for `sensor` (the reference hard-codes sensors()[2] and spp = 8,
+ * epsm.py:142-145 — the host mirror passes those).  grad_pos / grad_nrm: 3·(total vertex count)
+ * floats, concatenated over meshes in upload order, ACCUMULATED into (dr.grad semantics).
+ * Only meshes flagged EPSM_MESH_GRAD receive gradients.  Lanes as in epsm_render_accumulate. */
+int epsm_render_backward(epsm_ctx *ctx, int variant, uint32_t sensor, uint32_t seed, uint32_t spp,
+                         uint32_t max_depth, uint32_t rr_depth,
+                         const float *grad_in_hw5, float *grad_pos, float *grad_nrm, int mem,
+                         uint64_t lane_begin, uint64_t lane_end, uint64_t *counters);
+
+/* Per-path records for parity tests (the data the reference logs in epsm.py:547,648-654 and the
+ * calc_grad outputs).  One record per lane in [lane_begin, lane_end); layout EPSM_REC_* below.
+ * Runs the same kernel as epsm_render_backward with gradient scatter disabled. */
+#define EPSM_REC_MAXV      5                  /* logged vertices per path (epsm.py:648)        */
+#define EPSM_REC_VSTRIDE   16                 /* floats per vertex record                      */
+/* per vertex k: [0] active, [1] prim (uint32 bits), [2..4] p, [5..6] b0,b1, [7] active_em,
+ *               [8..10] light point, [11] bsdf flags (uint32 bits), [12] eta, [13..15] reserved */
+#define EPSM_REC_GRAD_OFF  (EPSM_REC_MAXV * EPSM_REC_VSTRIDE)
+/* then per vertex k: path_grad[5k..5k+4] (15 floats), light_grad[k] (3), diffuse_grad[k] (3) */
+#define EPSM_REC_GSTRIDE   21
+#define EPSM_REC_HEAD_OFF  (EPSM_REC_GRAD_OFF + EPSM_REC_MAXV * EPSM_REC_GSTRIDE)
+/* then: ray o(3) d(3), dlduv(2), dldp1(3), L(3) = 14 floats */
+#define EPSM_REC_FLOATS    (EPSM_REC_HEAD_OFF + 14)
+int epsm_path_records(epsm_ctx *ctx, int variant, uint32_t sensor, uint32_t seed, uint32_t spp,
+                      uint32_t max_depth, uint32_t rr_depth, const float *grad_in_hw5,
+                      uint64_t lane_begin, uint64_t lane_end, float *records, int mem);
+
+/* PCG32Sampler::seed + next_float32 (src/render/sampler.cpp:115-134, drjit/random.h:55-132,
+ * include/mitsuba/core/random.h:76-90): first `n_floats` of lanes [lane_begin, lane_end). */
+int epsm_sampler_stream(epsm_ctx *ctx, uint32_t seed, uint64_t lane_begin, uint64_t lane_end,
+                        uint32_t n_floats, float *out, int mem);
+
+/* ADIntegrator.sample_rays + PerspectiveCamera::sample_ray_differential (common.py:291-422,
+ * perspective.cpp:238-279): per lane 14 floats o(3) d(3) d_x(3) d_y(3) pos(2). */
+int epsm_sample_rays(epsm_ctx *ctx, uint32_t sensor, uint32_t seed, uint32_t spp,
+                     uint64_t lane_begin, uint64_t lane_end, float *out, int mem);
+
+/* Scene statistics for the roofline accounting: bytes per BVH node / triangle record, counts. */
+typedef struct epsm_scene_stats {
+    uint64_t n_triangles, n_vertices, n_nodes;
+    uint32_t node_bytes, tri_bytes;
+    uint32_t bvh_width, max_leaf;
+    double   build_ms;
+} epsm_scene_stats;
+int epsm_scene_get_stats(epsm_ctx *ctx, epsm_scene_stats *out);
+
+/* Number of kernels this library launched on the context since creation (bench `gpu_launches`). */
+uint64_t epsm_launch_count(const epsm_ctx *ctx);
+/* The context's stream as a cudaStream_t, for event timing on the launching stream. */
+void *epsm_stream(epsm_ctx *ctx);
+int epsm_synchronize(epsm_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EPSM_B200_H */
