@@ -1,0 +1,403 @@
+// epsm_api.cu — the C ABI of include/epsm_b200.h over the kernels in epsm_kernels.cu.
+// No torch types, no exceptions across the boundary, no CPU fallback.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "../../include/epsm_b200.h"
+#include "epsm_types.h"
+#include "epsm_host_scene.h"
+#include "epsm_launch.h"
+
+namespace {
+
+std::string g_create_error;
+
+template <typename T> struct DevBuf {
+    T *p = nullptr; size_t n = 0;
+    cudaError_t alloc(size_t count) {
+        if (count <= n && p) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; n = 0;
+        cudaError_t e = cudaMalloc((void **) &p, std::max<size_t>(count, 1) * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+    cudaError_t upload(const std::vector<T> &h, cudaStream_t s) {
+        cudaError_t e = alloc(h.size());
+        if (e != cudaSuccess || h.empty()) return e;
+        return cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s);
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+} // namespace
+
+struct epsm_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string error;
+    uint64_t launches = 0;
+    bool have_scene = false, dirty = false;
+    HostScene hs;                                   // host mirror (positions are needed for BVH rebuilds)
+    std::vector<uint8_t> mesh_dirty;
+    // device
+    DevBuf<f4> d_nodes, d_tris; DevBuf<float> d_pos, d_nrm, d_cdf, d_pmf; DevBuf<uint32_t> d_faces, d_face_mesh;
+    DevBuf<DMesh> d_meshes; DevBuf<DBsdf> d_bsdfs; DevBuf<DEmitter> d_emitters;
+    std::vector<DevBuf<float>> d_films;
+    DevBuf<float> stage_a, stage_b, stage_c;        // device staging for host-memory calls
+    DevBuf<unsigned long long> d_counters;
+    DScene sc;
+};
+
+namespace {
+
+int fail(epsm_ctx *c, int code, const std::string &msg) { if (c) c->error = msg; else g_create_error = msg; return code; }
+int cuda_fail(epsm_ctx *c, cudaError_t e, const char *what) {
+    return fail(c, EPSM_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CK(call, what) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return cuda_fail(ctx, e__, what); } while (0)
+
+int upload_accel(epsm_ctx *ctx) {
+    CK(ctx->d_nodes.upload(ctx->hs.bvh.nodes, ctx->stream), "upload nodes");
+    CK(ctx->d_tris.upload(ctx->hs.bvh.tris, ctx->stream), "upload tris");
+    CK(ctx->d_cdf.upload(ctx->hs.cdf, ctx->stream), "upload cdf");
+    CK(ctx->d_pmf.upload(ctx->hs.pmf, ctx->stream), "upload pmf");
+    CK(ctx->d_meshes.upload(ctx->hs.meshes, ctx->stream), "upload meshes");
+    DScene &sc = ctx->sc;
+    sc.nodes = ctx->d_nodes.p; sc.tris = ctx->d_tris.p; sc.pos = ctx->d_pos.p; sc.nrm = ctx->d_nrm.p;
+    sc.faces = ctx->d_faces.p; sc.face_mesh = ctx->d_face_mesh.p; sc.meshes = ctx->d_meshes.p; sc.bsdfs = ctx->d_bsdfs.p;
+    sc.emitters = ctx->d_emitters.p; sc.cdf = ctx->d_cdf.p; sc.pmf = ctx->d_pmf.p;
+    sc.n_emitters = (uint32_t) ctx->hs.emitters.size(); sc.n_meshes = (uint32_t) ctx->hs.meshes.size();
+    sc.n_tris = (uint32_t) (ctx->hs.faces.size() / 3); sc.n_nodes = (uint32_t) (ctx->hs.bvh.nodes.size() / EPSM_NODE_F4);
+    memcpy(sc.filter, ctx->hs.filter, sizeof(sc.filter));
+    CK(cudaStreamSynchronize(ctx->stream), "scene sync");
+    return EPSM_OK;
+}
+
+// Resolve a user pointer to a device pointer, staging host memory through `stage`.
+template <typename T>
+int to_device(epsm_ctx *ctx, const T *user, size_t count, int mem, DevBuf<T> &stage, const T **out) {
+    if (mem == EPSM_MEM_DEVICE) { *out = user; return EPSM_OK; }
+    CK(stage.alloc(count), "stage alloc");
+    CK(cudaMemcpyAsync(stage.p, user, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream), "H2D");
+    *out = stage.p; return EPSM_OK;
+}
+
+int fetch_counters(epsm_ctx *ctx, uint64_t *counters) {
+    unsigned long long h[4];
+    CK(cudaMemcpyAsync(h, ctx->d_counters.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream), "counters D2H");
+    CK(cudaStreamSynchronize(ctx->stream), "counters sync");
+    for (int i = 0; i < 4; ++i) counters[i] += h[i];
+    return EPSM_OK;
+}
+int zero_counters(epsm_ctx *ctx) {
+    CK(ctx->d_counters.alloc(4), "counters alloc");
+    CK(cudaMemsetAsync(ctx->d_counters.p, 0, 4 * sizeof(unsigned long long), ctx->stream), "counters memset");
+    return EPSM_OK;
+}
+
+int make_launch(epsm_ctx *ctx, uint32_t sensor, uint32_t seed, uint32_t spp, uint32_t max_depth, uint32_t rr_depth,
+                uint64_t lane_begin, uint64_t lane_end, int variant, DLaunch &ln) {
+    if (!ctx->have_scene) return fail(ctx, EPSM_E_NOSCENE, "no scene uploaded");
+    if (ctx->dirty) return fail(ctx, EPSM_E_INVALID, "vertex updates pending: call epsm_scene_commit first");
+    if (sensor >= ctx->hs.sensors.size()) return fail(ctx, EPSM_E_INVALID, "sensor index out of range");
+    if (spp == 0) return fail(ctx, EPSM_E_INVALID, "spp must be > 0");
+    if (rr_depth == 0) return fail(ctx, EPSM_E_INVALID, "\"rr_depth\" must be set to a value greater than zero!");   // common.py:40-41
+    ln.sensor = ctx->hs.sensors[sensor];
+    const uint64_t total = (uint64_t) ln.sensor.w * ln.sensor.h * spp;
+    if (total > (1ull << 32)) return fail(ctx, EPSM_E_INVALID, "wavefront exceeds 2^32 samples");                       // common.py:468-475
+    if (lane_end == 0 || lane_end > total) lane_end = total;
+    if (lane_begin > lane_end) return fail(ctx, EPSM_E_INVALID, "lane_begin > lane_end");
+    ln.seed = seed; ln.spp = spp; ln.max_depth = max_depth; ln.rr_depth = rr_depth;
+    ln.lane_begin = lane_begin; ln.lane_end = lane_end; ln.variant = variant; ln.tile_y0 = ln.tile_y1 = 0;
+    return EPSM_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int epsm_create(int device, epsm_ctx **out) {
+    if (!out) return fail(nullptr, EPSM_E_INVALID, "out is NULL");
+    *out = nullptr;
+    int n = 0; cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(nullptr, EPSM_E_NOGPU, std::string("no usable CUDA device (") + cudaGetErrorString(e) + "); libepsm_b200 has no CPU fallback");
+    if (device < 0 || device >= n) return fail(nullptr, EPSM_E_INVALID, "device index out of range");
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(nullptr, EPSM_E_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    epsm_ctx *c = new epsm_ctx(); c->device = device;
+    e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete c; return fail(nullptr, EPSM_E_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e)); }
+    memset(&c->sc, 0, sizeof(c->sc));
+    *out = c; return EPSM_OK;
+}
+
+int epsm_destroy(epsm_ctx *ctx) {
+    if (!ctx) return EPSM_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->d_nodes.release(); ctx->d_tris.release(); ctx->d_pos.release(); ctx->d_nrm.release(); ctx->d_cdf.release(); ctx->d_pmf.release();
+    ctx->d_faces.release(); ctx->d_face_mesh.release(); ctx->d_meshes.release(); ctx->d_bsdfs.release(); ctx->d_emitters.release();
+    for (auto &f : ctx->d_films) f.release();
+    ctx->stage_a.release(); ctx->stage_b.release(); ctx->stage_c.release(); ctx->d_counters.release();
+    cudaStreamDestroy(ctx->stream);
+    delete ctx; return EPSM_OK;
+}
+
+const char *epsm_last_error(const epsm_ctx *ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
+
+int epsm_scene_upload(epsm_ctx *ctx, const epsm_mesh_desc *meshes, uint32_t n_meshes, const epsm_bsdf_desc *bsdfs, uint32_t n_bsdfs,
+                      const epsm_emitter_desc *emitters, uint32_t n_emitters, const epsm_sensor_desc *sensors, uint32_t n_sensors) {
+    if (!ctx) return EPSM_E_INVALID;
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    std::string err = host_scene_build(ctx->hs, meshes, n_meshes, bsdfs, n_bsdfs, emitters, n_emitters, sensors, n_sensors);
+    if (!err.empty()) return fail(ctx, EPSM_E_INVALID, err);
+    for (auto &f : ctx->d_films) f.release();
+    ctx->d_films.assign(n_sensors, DevBuf<float>());
+    for (uint32_t i = 0; i < n_sensors; ++i) {
+        const DSensor &s = ctx->hs.sensors[i];
+        const size_t nf = (size_t) s.w * s.h * 4;
+        CK(ctx->d_films[i].alloc(nf), "film alloc");
+        CK(cudaMemsetAsync(ctx->d_films[i].p, 0, nf * sizeof(float), ctx->stream), "film memset");
+    }
+    CK(ctx->d_pos.upload(ctx->hs.pos, ctx->stream), "upload pos");
+    CK(ctx->d_nrm.upload(ctx->hs.nrm, ctx->stream), "upload nrm");
+    CK(ctx->d_faces.upload(ctx->hs.faces, ctx->stream), "upload faces");
+    CK(ctx->d_face_mesh.upload(ctx->hs.face_mesh, ctx->stream), "upload face_mesh");
+    CK(ctx->d_bsdfs.upload(ctx->hs.bsdfs, ctx->stream), "upload bsdfs");
+    CK(ctx->d_emitters.upload(ctx->hs.emitters, ctx->stream), "upload emitters");
+    ctx->mesh_dirty.assign(n_meshes, 0);
+    int rc = upload_accel(ctx);
+    if (rc != EPSM_OK) return rc;
+    ctx->have_scene = true; ctx->dirty = false;
+    return EPSM_OK;
+}
+
+int epsm_scene_update_vertices(epsm_ctx *ctx, uint32_t mesh_id, const float *positions, int mem) {
+    if (!ctx) return EPSM_E_INVALID;
+    if (!ctx->have_scene) return fail(ctx, EPSM_E_NOSCENE, "no scene uploaded");
+    if (mesh_id >= ctx->hs.meshes.size() || !positions) return fail(ctx, EPSM_E_INVALID, "bad mesh id / positions");
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    const DMesh &m = ctx->hs.meshes[mesh_id];
+    const size_t nb = 3 * (size_t) m.v_cnt * sizeof(float);
+    float *dst = ctx->d_pos.p + 3 * (size_t) m.v_off, *hdst = ctx->hs.pos.data() + 3 * (size_t) m.v_off;
+    if (mem == EPSM_MEM_DEVICE) {
+        CK(cudaMemcpyAsync(dst, positions, nb, cudaMemcpyDeviceToDevice, ctx->stream), "D2D positions");
+        CK(cudaMemcpyAsync(hdst, positions, nb, cudaMemcpyDeviceToHost, ctx->stream), "D2H positions");
+    } else {
+        memcpy(hdst, positions, nb);
+        CK(cudaMemcpyAsync(dst, hdst, nb, cudaMemcpyHostToDevice, ctx->stream), "H2D positions");
+    }
+    ctx->mesh_dirty[mesh_id] = 1; ctx->dirty = true;
+    return EPSM_OK;
+}
+
+int epsm_scene_commit(epsm_ctx *ctx) {
+    if (!ctx) return EPSM_E_INVALID;
+    if (!ctx->have_scene) return fail(ctx, EPSM_E_NOSCENE, "no scene uploaded");
+    if (!ctx->dirty) return EPSM_OK;
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    for (size_t i = 0; i < ctx->hs.meshes.size(); ++i) {
+        const DMesh &m = ctx->hs.meshes[i];
+        if (!ctx->mesh_dirty[i] || !m.has_normals) continue;
+        CK(epsm_launch_vertex_normals(ctx->d_pos.p, ctx->d_faces.p, m.f_off, m.f_cnt, m.v_off, m.v_cnt, ctx->d_nrm.p, ctx->stream), "vertex normals");
+        ctx->launches += 3;
+    }
+    CK(cudaStreamSynchronize(ctx->stream), "commit sync");          // host mirror of the positions is complete
+    std::fill(ctx->mesh_dirty.begin(), ctx->mesh_dirty.end(), 0);
+    host_scene_rebuild_accel(ctx->hs);
+    int rc = upload_accel(ctx);
+    if (rc != EPSM_OK) return rc;
+    ctx->dirty = false;
+    return EPSM_OK;
+}
+
+int epsm_trace(epsm_ctx *ctx, const float *rays, uint64_t n, void *hits, int any_hit, uint64_t *counters, int mem) {
+    if (!ctx) return EPSM_E_INVALID;
+    if (!ctx->have_scene) return fail(ctx, EPSM_E_NOSCENE, "no scene uploaded");
+    if (ctx->dirty) return fail(ctx, EPSM_E_INVALID, "vertex updates pending: call epsm_scene_commit first");
+    if (n == 0) return EPSM_OK;
+    if (!rays || !hits) return fail(ctx, EPSM_E_INVALID, "rays/hits is NULL");
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    const float *d_rays; int rc = to_device(ctx, rays, (size_t) n * 8, mem, ctx->stage_a, &d_rays);
+    if (rc) return rc;
+    const size_t hit_words = any_hit ? (size_t) n : (size_t) n * 4;
+    void *d_hits = hits;
+    if (mem == EPSM_MEM_HOST) { CK(ctx->stage_b.alloc(hit_words), "stage alloc"); d_hits = ctx->stage_b.p; }
+    if (counters) { rc = zero_counters(ctx); if (rc) return rc; }
+    CK(epsm_launch_trace(ctx->sc, d_rays, n, d_hits, any_hit, counters ? ctx->d_counters.p : nullptr, ctx->stream), "k_trace");
+    ctx->launches += 1;
+    if (mem == EPSM_MEM_HOST) {
+        CK(cudaMemcpyAsync(hits, d_hits, hit_words * 4, cudaMemcpyDeviceToHost, ctx->stream), "D2H hits");
+        CK(cudaStreamSynchronize(ctx->stream), "trace sync");
+    }
+    if (counters) return fetch_counters(ctx, counters);
+    return EPSM_OK;
+}
+
+int epsm_film_clear(epsm_ctx *ctx, uint32_t sensor) {
+    if (!ctx) return EPSM_E_INVALID;
+    if (!ctx->have_scene) return fail(ctx, EPSM_E_NOSCENE, "no scene uploaded");
+    if (sensor >= ctx->hs.sensors.size()) return fail(ctx, EPSM_E_INVALID, "sensor index out of range");
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    const DSensor &s = ctx->hs.sensors[sensor];
+    CK(cudaMemsetAsync(ctx->d_films[sensor].p, 0, (size_t) s.w * s.h * 4 * sizeof(float), ctx->stream), "film memset");
+    return EPSM_OK;
+}
+
+int epsm_film_raw(epsm_ctx *ctx, uint32_t sensor, float **device_ptr, uint64_t *n_floats) {
+    if (!ctx) return EPSM_E_INVALID;
+    if (!ctx->have_scene) return fail(ctx, EPSM_E_NOSCENE, "no scene uploaded");
+    if (sensor >= ctx->hs.sensors.size() || !device_ptr || !n_floats) return fail(ctx, EPSM_E_INVALID, "bad arguments");
+    const DSensor &s = ctx->hs.sensors[sensor];
+    *device_ptr = ctx->d_films[sensor].p; *n_floats = (uint64_t) s.w * s.h * 4;
+    return EPSM_OK;
+}
+
+int epsm_render_accumulate(epsm_ctx *ctx, uint32_t sensor, uint32_t seed, uint32_t spp, uint32_t max_depth, uint32_t rr_depth,
+                           uint64_t lane_begin, uint64_t lane_end, uint64_t *counters) {
+    if (!ctx) return EPSM_E_INVALID;
+    DLaunch ln; int rc = make_launch(ctx, sensor, seed, spp, max_depth, rr_depth, lane_begin, lane_end, 0, ln);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    if (counters) { rc = zero_counters(ctx); if (rc) return rc; }
+    CK(epsm_launch_render(ctx->sc, ln, ctx->d_films[sensor].p, counters ? ctx->d_counters.p : nullptr, ctx->stream), "k_render");
+    ctx->launches += 1;
+    if (counters) return fetch_counters(ctx, counters);
+    return EPSM_OK;
+}
+
+int epsm_film_develop(epsm_ctx *ctx, uint32_t sensor, float *out_hw5, int mem) {
+    if (!ctx) return EPSM_E_INVALID;
+    if (!ctx->have_scene) return fail(ctx, EPSM_E_NOSCENE, "no scene uploaded");
+    if (sensor >= ctx->hs.sensors.size() || !out_hw5) return fail(ctx, EPSM_E_INVALID, "bad arguments");
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    const DSensor &s = ctx->hs.sensors[sensor]; const uint64_t np = (uint64_t) s.w * s.h;
+    float *d_out = out_hw5;
+    if (mem == EPSM_MEM_HOST) { CK(ctx->stage_b.alloc(np * 5), "stage alloc"); d_out = ctx->stage_b.p; }
+    CK(epsm_launch_develop(ctx->d_films[sensor].p, np, d_out, ctx->stream), "k_film_develop");
+    ctx->launches += 1;
+    if (mem == EPSM_MEM_HOST) {
+        CK(cudaMemcpyAsync(out_hw5, d_out, np * 5 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream), "D2H image");
+        CK(cudaStreamSynchronize(ctx->stream), "develop sync");
+    }
+    return EPSM_OK;
+}
+
+int epsm_render(epsm_ctx *ctx, uint32_t sensor, uint32_t seed, uint32_t spp, uint32_t max_depth, uint32_t rr_depth, float *out_hw5, int mem) {
+    int rc = epsm_film_clear(ctx, sensor); if (rc) return rc;
+    rc = epsm_render_accumulate(ctx, sensor, seed, spp, max_depth, rr_depth, 0, 0, nullptr); if (rc) return rc;
+    return epsm_film_develop(ctx, sensor, out_hw5, mem);
+}
+
+int epsm_render_backward(epsm_ctx *ctx, int variant, uint32_t sensor, uint32_t seed, uint32_t spp, uint32_t max_depth, uint32_t rr_depth,
+                         const float *grad_in_hw5, float *grad_pos, float *grad_nrm, int mem,
+                         uint64_t lane_begin, uint64_t lane_end, uint64_t *counters) {
+    if (!ctx) return EPSM_E_INVALID;
+    if (variant != EPSM_VARIANT_MANIFOLD && variant != EPSM_VARIANT_MANIFOLD_CAUSTIC) return fail(ctx, EPSM_E_INVALID, "unknown integrator variant");
+    if (!grad_in_hw5 || !grad_pos || !grad_nrm) return fail(ctx, EPSM_E_INVALID, "grad_in / grad_pos / grad_nrm is NULL");
+    DLaunch ln; int rc = make_launch(ctx, sensor, seed, spp, max_depth, rr_depth, lane_begin, lane_end, variant, ln);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    const size_t n_img = (size_t) ln.sensor.w * ln.sensor.h * 5, n_v = ctx->hs.pos.size();
+    const float *d_gin; rc = to_device(ctx, grad_in_hw5, n_img, mem, ctx->stage_a, &d_gin); if (rc) return rc;
+    float *d_gp = grad_pos, *d_gn = grad_nrm;
+    if (mem == EPSM_MEM_HOST) {
+        CK(ctx->stage_b.alloc(n_v), "stage alloc"); CK(ctx->stage_c.alloc(n_v), "stage alloc");
+        d_gp = ctx->stage_b.p; d_gn = ctx->stage_c.p;
+        CK(cudaMemcpyAsync(d_gp, grad_pos, n_v * sizeof(float), cudaMemcpyHostToDevice, ctx->stream), "H2D grad_pos");
+        CK(cudaMemcpyAsync(d_gn, grad_nrm, n_v * sizeof(float), cudaMemcpyHostToDevice, ctx->stream), "H2D grad_nrm");
+    }
+    if (counters) { rc = zero_counters(ctx); if (rc) return rc; }
+    CK(epsm_launch_backward(ctx->sc, ln, d_gin, d_gp, d_gn, nullptr, counters ? ctx->d_counters.p : nullptr, ctx->stream), "k_backward");
+    ctx->launches += 1;
+    if (mem == EPSM_MEM_HOST) {
+        CK(cudaMemcpyAsync(grad_pos, d_gp, n_v * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream), "D2H grad_pos");
+        CK(cudaMemcpyAsync(grad_nrm, d_gn, n_v * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream), "D2H grad_nrm");
+        CK(cudaStreamSynchronize(ctx->stream), "backward sync");
+    }
+    if (counters) return fetch_counters(ctx, counters);
+    return EPSM_OK;
+}
+
+int epsm_path_records(epsm_ctx *ctx, int variant, uint32_t sensor, uint32_t seed, uint32_t spp, uint32_t max_depth, uint32_t rr_depth,
+                      const float *grad_in_hw5, uint64_t lane_begin, uint64_t lane_end, float *records, int mem) {
+    if (!ctx) return EPSM_E_INVALID;
+    if (variant != EPSM_VARIANT_MANIFOLD && variant != EPSM_VARIANT_MANIFOLD_CAUSTIC) return fail(ctx, EPSM_E_INVALID, "unknown integrator variant");
+    if (!grad_in_hw5 || !records) return fail(ctx, EPSM_E_INVALID, "grad_in / records is NULL");
+    DLaunch ln; int rc = make_launch(ctx, sensor, seed, spp, max_depth, rr_depth, lane_begin, lane_end, variant, ln);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    const size_t n_img = (size_t) ln.sensor.w * ln.sensor.h * 5, n_rec = (size_t) (ln.lane_end - ln.lane_begin) * EPSM_REC_FLOATS;
+    const float *d_gin; rc = to_device(ctx, grad_in_hw5, n_img, mem, ctx->stage_a, &d_gin); if (rc) return rc;
+    float *d_rec = records;
+    if (mem == EPSM_MEM_HOST) { CK(ctx->stage_b.alloc(n_rec), "stage alloc"); d_rec = ctx->stage_b.p; }
+    CK(cudaMemsetAsync(d_rec, 0, n_rec * sizeof(float), ctx->stream), "records memset");
+    CK(epsm_launch_backward(ctx->sc, ln, d_gin, nullptr, nullptr, d_rec, nullptr, ctx->stream), "k_backward(records)");
+    ctx->launches += 1;
+    if (mem == EPSM_MEM_HOST) {
+        CK(cudaMemcpyAsync(records, d_rec, n_rec * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream), "D2H records");
+        CK(cudaStreamSynchronize(ctx->stream), "records sync");
+    }
+    return EPSM_OK;
+}
+
+int epsm_sampler_stream(epsm_ctx *ctx, uint32_t seed, uint64_t lane_begin, uint64_t lane_end, uint32_t n_floats, float *out, int mem) {
+    if (!ctx) return EPSM_E_INVALID;
+    if (lane_end < lane_begin || !out) return fail(ctx, EPSM_E_INVALID, "bad arguments");
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    const uint64_t n = lane_end - lane_begin; const size_t cnt = (size_t) n * n_floats;
+    if (cnt == 0) return EPSM_OK;
+    float *d = out;
+    if (mem == EPSM_MEM_HOST) { CK(ctx->stage_b.alloc(cnt), "stage alloc"); d = ctx->stage_b.p; }
+    CK(epsm_launch_sampler_stream(seed, lane_begin, n, n_floats, d, ctx->stream), "k_sampler_stream");
+    ctx->launches += 1;
+    if (mem == EPSM_MEM_HOST) {
+        CK(cudaMemcpyAsync(out, d, cnt * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream), "D2H");
+        CK(cudaStreamSynchronize(ctx->stream), "sync");
+    }
+    return EPSM_OK;
+}
+
+int epsm_sample_rays(epsm_ctx *ctx, uint32_t sensor, uint32_t seed, uint32_t spp, uint64_t lane_begin, uint64_t lane_end, float *out, int mem) {
+    if (!ctx) return EPSM_E_INVALID;
+    if (!ctx->have_scene) return fail(ctx, EPSM_E_NOSCENE, "no scene uploaded");
+    if (sensor >= ctx->hs.sensors.size() || spp == 0 || lane_end < lane_begin || !out) return fail(ctx, EPSM_E_INVALID, "bad arguments");
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    const uint64_t n = lane_end - lane_begin; const size_t cnt = (size_t) n * 14;
+    if (cnt == 0) return EPSM_OK;
+    float *d = out;
+    if (mem == EPSM_MEM_HOST) { CK(ctx->stage_b.alloc(cnt), "stage alloc"); d = ctx->stage_b.p; }
+    CK(epsm_launch_sample_rays(ctx->hs.sensors[sensor], seed, spp, lane_begin, n, d, ctx->stream), "k_sample_rays");
+    ctx->launches += 1;
+    if (mem == EPSM_MEM_HOST) {
+        CK(cudaMemcpyAsync(out, d, cnt * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream), "D2H");
+        CK(cudaStreamSynchronize(ctx->stream), "sync");
+    }
+    return EPSM_OK;
+}
+
+int epsm_scene_get_stats(epsm_ctx *ctx, epsm_scene_stats *out) {
+    if (!ctx || !out) return EPSM_E_INVALID;
+    if (!ctx->have_scene) return fail(ctx, EPSM_E_NOSCENE, "no scene uploaded");
+    out->n_triangles = ctx->hs.faces.size() / 3; out->n_vertices = ctx->hs.pos.size() / 3;
+    out->n_nodes = ctx->hs.bvh.nodes.size() / EPSM_NODE_F4;
+    out->node_bytes = EPSM_NODE_F4 * 16; out->tri_bytes = EPSM_TRI_F4 * 16; out->bvh_width = 4; out->max_leaf = EPSM_MAX_LEAF;
+    out->build_ms = ctx->hs.bvh.build_ms;
+    return EPSM_OK;
+}
+
+uint64_t epsm_launch_count(const epsm_ctx *ctx) { return ctx ? ctx->launches : 0; }
+void *epsm_stream(epsm_ctx *ctx) { return ctx ? (void *) ctx->stream : nullptr; }
+int epsm_synchronize(epsm_ctx *ctx) {
+    if (!ctx) return EPSM_E_INVALID;
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    CK(cudaStreamSynchronize(ctx->stream), "sync");
+    return EPSM_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,375 @@
+// epsm_kernels.cu — sm_100a kernels of the EPSM manifold path and their launchers.
+//
+//   k_trace            Scene::ray_intersect_preliminary / ray_test on a ray batch (BVH4, one thread per ray)
+//   k_render           EPSMIntegrator.render: ray gen + primal path loop + tile-local film accumulation
+//   k_film_develop     HDRFilm::develop + the two zero channels of epsm.py:76-82
+//   k_backward         EPSMIntegrator.render_backward fused per path: ray gen, sample_path replay with the
+//                      path log in thread-local memory, pixel-motion seeds, manifold solve in registers,
+//                      warp-aggregated scatter into the vertex gradient buffers
+//   k_sampler_stream / k_sample_rays   parity probes for the RNG and ray-generation contracts
+//   k_normals_*        Mesh::recompute_vertex_normals (mesh.cpp:257-330)
+//
+// Work decomposition: a CTA of 128 threads owns an 8×4 pixel tile; thread i handles pixel (i & 31)
+// of the tile and the samples s = (i >> 5) + 4k of that pixel, so a warp is always 32 neighbouring
+// pixels at the same sample index (coherent primary rays) and the lane id — which alone determines
+// the random stream (sampler.cpp:122-130) — is (pixel · spp + s) exactly as in the reference
+// wavefront (common.py:326-343).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "epsm_device.cuh"
+#include "epsm_launch.h"
+
+#define TILE_W 8
+#define TILE_H 4
+#define CTA 128
+
+// ------------------------------------------------------------------------------------------------
+//  Shared-memory traversal stack for a CTA
+// ------------------------------------------------------------------------------------------------
+struct SharedStack { uint32_t ref[EPSM_SSTACK][CTA]; float t[EPSM_SSTACK][CTA]; };
+
+__device__ __forceinline__ void bind_stack(TStack &st, SharedStack &ss) {
+    st.s_ref = &ss.ref[0][threadIdx.x]; st.s_t = &ss.t[0][threadIdx.x]; st.stride = CTA; st.sp = 0;
+}
+
+__device__ __forceinline__ void flush_counters(const Tracer &tr, uint32_t lanes, unsigned long long *counters) {
+    unsigned long long a = tr.n_nodes, b = tr.n_tris, c = tr.n_rays, d = lanes;
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_down_sync(0xffffffffu, a, o); b += __shfl_down_sync(0xffffffffu, b, o);
+        c += __shfl_down_sync(0xffffffffu, c, o); d += __shfl_down_sync(0xffffffffu, d, o);
+    }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(counters, a); atomicAdd(counters + 1, b); atomicAdd(counters + 2, c); atomicAdd(counters + 3, d); }
+}
+
+// ------------------------------------------------------------------------------------------------
+//  Ray batches
+// ------------------------------------------------------------------------------------------------
+template <bool ANY, bool COUNT>
+__global__ void __launch_bounds__(CTA) k_trace(DScene sc, const f4 *__restrict__ rays, uint64_t n, uint32_t *__restrict__ hits,
+                                               unsigned long long *counters) {
+    __shared__ SharedStack ss;
+    TStack st; bind_stack(st, ss);
+    Tracer tr(sc, st);
+    uint64_t i = (uint64_t) blockIdx.x * CTA + threadIdx.x;
+    if (i < n) {
+        f4 a = ldg4(rays + 2 * i), b = ldg4(rays + 2 * i + 1);
+        Ray r{mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), a.w};
+        if (ANY) {
+            hits[i] = trace_any<COUNT>(tr, r) ? 1u : 0u;
+        } else {
+            Hit h = trace_closest<COUNT>(tr, r);
+            uint4 o = make_uint4(f2u(h.t), f2u(h.u), f2u(h.v), h.prim);
+            reinterpret_cast<uint4 *>(hits)[i] = o;
+        }
+    }
+    if (COUNT) flush_counters(tr, i < n ? 1u : 0u, counters);
+}
+
+// ------------------------------------------------------------------------------------------------
+//  Primal render
+// ------------------------------------------------------------------------------------------------
+#define FT_W (TILE_W + 4)
+#define FT_H (TILE_H + 4)
+
+template <bool COUNT>
+__global__ void __launch_bounds__(CTA) k_render(DScene sc, DLaunch ln, float *__restrict__ film, unsigned long long *counters) {
+    __shared__ SharedStack ss;
+    __shared__ float ftile[FT_H][FT_W][4];
+    TStack st; bind_stack(st, ss);
+    Tracer tr(sc, st);
+    for (int i = threadIdx.x; i < FT_H * FT_W * 4; i += CTA) (&ftile[0][0][0])[i] = 0.f;
+    __syncthreads();
+    const uint32_t W = ln.sensor.w, H = ln.sensor.h;
+    const uint32_t tiles_x = (W + TILE_W - 1) / TILE_W;
+    const uint32_t tx = blockIdx.x % tiles_x, ty = ln.tile_y0 + blockIdx.x / tiles_x;
+    const uint32_t pin = threadIdx.x & 31, slot = threadIdx.x >> 5;
+    const uint32_t px = tx * TILE_W + (pin & (TILE_W - 1)), py = ty * TILE_H + pin / TILE_W;
+    uint32_t lanes = 0;
+    if (px < W && py < H) {
+        const uint64_t pixel = (uint64_t) py * W + px;
+        for (uint32_t s = slot; s < ln.spp; s += CTA / 32) {
+            const uint64_t lane = pixel * ln.spp + s;
+            if (lane < ln.lane_begin || lane >= ln.lane_end) continue;
+            Pcg rng = pcg_for_lane(ln.seed, (uint32_t) lane);
+            CamRay c; camera_ray(ln.sensor, px, py, rng, c);
+            bool valid;
+            f3 L = path_primal<COUNT>(sc, tr, c.ray, rng, ln.max_depth, ln.rr_depth, valid);
+            ++lanes;
+            // ImageBlock::put, coalesced branch (imageblock.cpp:414-494): 5×5 footprint, separable weights
+            const int pix = (int) floorf(c.pos_x) - 2, piy = (int) floorf(c.pos_y) - 2;
+            float rel_x = (float) pix + .5f - c.pos_x, rel_y = (float) piy + .5f - c.pos_y;
+            float wx[5], wy[5];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) { wx[k] = filter_eval(sc.filter, rel_x); wy[k] = filter_eval(sc.filter, rel_y); rel_x += 1; rel_y += 1; }
+            const int lx = pix - (int) (tx * TILE_W) + 2, ly = piy - (int) (ty * TILE_H) + 2;   // tile-local, 2-px apron
+#pragma unroll
+            for (int ys = 0; ys < 5; ++ys)
+#pragma unroll
+                for (int xs = 0; xs < 5; ++xs) {
+                    const float w = wy[ys] * wx[xs];
+                    float *d = ftile[ly + ys][lx + xs];
+                    atomicAdd(d + 0, L.x * w); atomicAdd(d + 1, L.y * w); atomicAdd(d + 2, L.z * w); atomicAdd(d + 3, 1.0f * w);
+                }
+        }
+    }
+    __syncthreads();
+    // flush the tile (with apron) into the RGBW film; pixels outside the film are the cropped border
+    for (int i = threadIdx.x; i < FT_H * FT_W; i += CTA) {
+        const int fy = (int) (ty * TILE_H) + i / FT_W - 2, fx = (int) (tx * TILE_W) + i % FT_W - 2;
+        if (fx < 0 || fy < 0 || fx >= (int) W || fy >= (int) H) continue;
+        const float *s = ftile[i / FT_W][i % FT_W];
+        if (s[3] == 0.f && s[0] == 0.f && s[1] == 0.f && s[2] == 0.f) continue;
+        float *d = film + ((size_t) fy * W + fx) * 4;
+        atomicAdd(d + 0, s[0]); atomicAdd(d + 1, s[1]); atomicAdd(d + 2, s[2]); atomicAdd(d + 3, s[3]);
+    }
+    if (COUNT) flush_counters(tr, lanes, counters);
+}
+
+__global__ void k_film_develop(const float *__restrict__ film, uint64_t n_pixels, float *__restrict__ out) {
+    uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pixels) return;
+    float4 v = reinterpret_cast<const float4 *>(film)[i];
+    float d = v.w == 0.f ? 1.f : v.w;                                             // hdrfilm.cpp:372
+    out[5 * i + 0] = v.x / d; out[5 * i + 1] = v.y / d; out[5 * i + 2] = v.z / d; out[5 * i + 3] = 0.f; out[5 * i + 4] = 0.f;
+}
+
+// ------------------------------------------------------------------------------------------------
+//  Warp-aggregated gradient scatter (the adjoint of the vertex gathers; cf. the reference's scatter_reduce
+//  codegen, ext/drjit/ext/drjit-core/src/cuda_eval.cpp:808-905)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void scatter3(float *__restrict__ buf, uint32_t idx, f3 v, bool pred) {
+    pred = pred && (v.x != 0.f || v.y != 0.f || v.z != 0.f);
+    if (!pred) return;
+    const unsigned act = __activemask();
+    const unsigned peers = __match_any_sync(act, idx);
+    const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+    if (peers != (1u << lane)) {
+        f3 sum = mk3(0, 0, 0);
+        for (unsigned rem = peers; rem; rem &= rem - 1) {
+            const int src = __ffs(rem) - 1;
+            sum.x += __shfl_sync(peers, v.x, src); sum.y += __shfl_sync(peers, v.y, src); sum.z += __shfl_sync(peers, v.z, src);
+        }
+        v = sum;
+    }
+    if (lane == leader) {
+        float *d = buf + 3 * (size_t) idx;
+        atomicAdd(d, v.x); atomicAdd(d + 1, v.y); atomicAdd(d + 2, v.z);          // red.global.add.f32
+    }
+}
+
+// The Backward-mode replay seeds of sample_path (epsm.py:559-562, 609-627, 644-645)
+__device__ void scatter_path(const PathLog &P, const PathGrads &G, int variant, int n_logged, uint32_t max_depth_prop,
+                             float *__restrict__ grad_pos, float *__restrict__ grad_nrm) {
+    // len(path_grad) = 5·n_logged (manifold) or 5·(n_logged−1)+3 (caustic: n, m of the last vertex are never added)
+    const int n_pg = variant == EPSM_VARIANT_MANIFOLD ? 5 * n_logged : 5 * (n_logged - 1) + 3;
+    const bool shadow_term = (max_depth_prop < EPSM_MAX_ITER ? max_depth_prop : EPSM_MAX_ITER) <= 3;
+    for (int k = 0; k < n_logged; ++k) {
+        const VLog &v = P.v[k];
+        const bool sel = v.active && (v.mesh_flags & EPSM_MESH_GRAD);
+        if (5 * k + 4 < n_pg) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) scatter3(grad_pos, v.fi[c], G.pg[k][c], sel);                   // (i)
+            const f3 g3 = G.pg[k][3];                                                                     // (iv)
+            const bool any_g3 = sel && (g3.x != 0.f || g3.y != 0.f || g3.z != 0.f);
+            const float flip = (v.mesh_flags & EPSM_MESH_FLIP_NORMALS) ? -1.f : 1.f;
+            if (any_g3 && v.has_normals) {
+                // si_follow.sh_frame.n = normalize(Σ b_k n_k) with uv detached (mesh.cpp:788-791)
+                const f3 nt = v.n0 * v.bw[0] + v.n1 * v.bw[1] + v.n2 * v.bw[2];
+                const float il = 1.0f / len3(nt); const f3 nh = nt * il;
+                const f3 gt = (g3 - nh * dot3(nh, g3)) * (il * flip);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) scatter3(grad_nrm, v.fi[c], gt * v.bw[c], true);
+            } else if (any_g3 && v.ismesh) {
+                // flat-shaded mesh: sh_frame.n = normalize(cross(p1−p0, p2−p0)) → vertex positions (mesh.cpp:729,811)
+                const f3 e1 = v.p1 - v.p0, e2 = v.p2 - v.p0, cr = cross3(e1, e2);
+                const float il = 1.0f / len3(cr); const f3 nh = cr * il;
+                const f3 gc = (g3 - nh * dot3(nh, g3)) * (il * flip);
+                const f3 ge1 = cross3(e2, gc), ge2 = cross3(gc, e1);
+                scatter3(grad_pos, v.fi[1], ge1, true); scatter3(grad_pos, v.fi[2], ge2, true); scatter3(grad_pos, v.fi[0], -(ge1 + ge2), true);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) scatter3(grad_pos, v.fi[c], G.dg[k] * v.bw[c], sel);                 // (ii)
+        if (k == 0 && shadow_term) {                                                                      // epsm.py:609-620
+            const f3 g = G.dg[0] * v.dis;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) scatter3(grad_pos, v.dfi[c], g * v.dbw[c], v.direct_any && v.direct_grad);
+        }
+        const f3 gl = G.lg[k] * v.lr_sum;                                                                 // (iii) epsm.py:622-627
+#pragma unroll
+        for (int c = 0; c < 3; ++c) scatter3(grad_pos, v.dfi[c], gl * v.dbw[c], v.direct_valid && v.direct_grad);
+    }
+}
+
+__device__ void write_record(const PathLog &P, const PathGrads &G, int n_logged, float *__restrict__ r) {
+    for (int i = 0; i < EPSM_REC_FLOATS; ++i) r[i] = 0.f;
+    for (int k = 0; k < n_logged; ++k) {
+        const VLog &v = P.v[k]; float *o = r + k * EPSM_REC_VSTRIDE;
+        o[0] = v.active ? 1.f : 0.f; o[1] = u2f(v.prim); o[2] = v.p.x; o[3] = v.p.y; o[4] = v.p.z; o[5] = v.b0; o[6] = v.b1;
+        o[7] = v.active_em ? 1.f : 0.f; o[8] = v.light.x; o[9] = v.light.y; o[10] = v.light.z; o[11] = u2f(v.flags); o[12] = v.eta;
+        o[13] = v.lr_sum; o[14] = v.dis; o[15] = u2f((v.direct_any ? 1u : 0u) | (v.direct_valid ? 2u : 0u) | (v.direct_grad ? 4u : 0u));
+        float *g = r + EPSM_REC_GRAD_OFF + k * EPSM_REC_GSTRIDE;
+        for (int c = 0; c < 5; ++c) { g[3 * c] = G.pg[k][c].x; g[3 * c + 1] = G.pg[k][c].y; g[3 * c + 2] = G.pg[k][c].z; }
+        g[15] = G.lg[k].x; g[16] = G.lg[k].y; g[17] = G.lg[k].z; g[18] = G.dg[k].x; g[19] = G.dg[k].y; g[20] = G.dg[k].z;
+    }
+    float *h = r + EPSM_REC_HEAD_OFF;
+    h[0] = P.cam.x; h[1] = P.cam.y; h[2] = P.cam.z; h[3] = P.d.x; h[4] = P.d.y; h[5] = P.d.z;
+    h[6] = P.dlduv0; h[7] = P.dlduv1; h[8] = P.dldp1.x; h[9] = P.dldp1.y; h[10] = P.dldp1.z; h[11] = P.L.x; h[12] = P.L.y; h[13] = P.L.z;
+}
+
+// ------------------------------------------------------------------------------------------------
+//  Gradient pass
+// ------------------------------------------------------------------------------------------------
+template <bool COUNT, bool RECORD>
+__global__ void __launch_bounds__(CTA) k_backward(DScene sc, DLaunch ln, const float *__restrict__ grad_in,
+                                                  float *__restrict__ grad_pos, float *__restrict__ grad_nrm,
+                                                  float *__restrict__ records, unsigned long long *counters) {
+    __shared__ SharedStack ss;
+    TStack st; bind_stack(st, ss);
+    Tracer tr(sc, st);
+    const uint32_t W = ln.sensor.w, H = ln.sensor.h;
+    const uint32_t tiles_x = (W + TILE_W - 1) / TILE_W;
+    const uint32_t tx = blockIdx.x % tiles_x, ty = ln.tile_y0 + blockIdx.x / tiles_x;
+    const uint32_t pin = threadIdx.x & 31, slot = threadIdx.x >> 5;
+    const uint32_t px = tx * TILE_W + (pin & (TILE_W - 1)), py = ty * TILE_H + pin / TILE_W;
+    const uint32_t max_iter = ln.max_depth < EPSM_MAX_ITER ? ln.max_depth : EPSM_MAX_ITER;
+    const int n_logged = (int) (max_iter < EPSM_MAXV ? max_iter : EPSM_MAXV);      // len(path_info) − 1
+    uint32_t lanes = 0;
+    if (px < W && py < H) {
+        const uint64_t pixel = (uint64_t) py * W + px;
+        const float gx = grad_in[pixel * 5 + 3], gy = grad_in[pixel * 5 + 4];
+        for (uint32_t s = slot; s < ln.spp; s += CTA / 32) {
+            const uint64_t lane = pixel * ln.spp + s;
+            if (lane < ln.lane_begin || lane >= ln.lane_end) continue;
+            Pcg rng = pcg_for_lane(ln.seed, (uint32_t) lane);
+            CamRay c; camera_ray(ln.sensor, px, py, rng, c);
+            // pixel motion → tangent of the ray direction (epsm.py:250-257)
+            const f3 grad_d = (c.d_x - c.ray.d) * gx + (c.d_y - c.ray.d) * gy;
+            PathLog P;
+            path_log<COUNT>(sc, tr, c, grad_d, rng, ln.max_depth, ln.rr_depth, P);
+            PathGrads G;
+            calc_grad(P, ln.variant, n_logged, G);
+            ++lanes;
+            if (RECORD) write_record(P, G, n_logged, records + (lane - ln.lane_begin) * EPSM_REC_FLOATS);
+            else scatter_path(P, G, ln.variant, n_logged, ln.max_depth, grad_pos, grad_nrm);
+        }
+    }
+    if (COUNT) flush_counters(tr, lanes, counters);
+}
+
+// ------------------------------------------------------------------------------------------------
+//  Parity probes
+// ------------------------------------------------------------------------------------------------
+__global__ void k_sampler_stream(uint32_t seed, uint64_t lane_begin, uint64_t n_lanes, uint32_t n_floats, float *__restrict__ out) {
+    uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_lanes) return;
+    Pcg r = pcg_for_lane(seed, (uint32_t) (lane_begin + i));
+    for (uint32_t k = 0; k < n_floats; ++k) out[i * n_floats + k] = pcg_f32(r);
+}
+__global__ void k_sample_rays(DSensor s, uint32_t seed, uint32_t spp, uint64_t lane_begin, uint64_t n_lanes, float *__restrict__ out) {
+    uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_lanes) return;
+    uint64_t lane = lane_begin + i; uint32_t pixel = (uint32_t) (lane / spp);
+    Pcg r = pcg_for_lane(seed, (uint32_t) lane);
+    CamRay c; camera_ray(s, pixel % s.w, pixel / s.w, r, c);
+    float *o = out + 14 * i;
+    o[0] = c.ray.o.x; o[1] = c.ray.o.y; o[2] = c.ray.o.z; o[3] = c.ray.d.x; o[4] = c.ray.d.y; o[5] = c.ray.d.z;
+    o[6] = c.d_x.x; o[7] = c.d_x.y; o[8] = c.d_x.z; o[9] = c.d_y.x; o[10] = c.d_y.y; o[11] = c.d_y.z; o[12] = c.pos_x; o[13] = c.pos_y;
+}
+
+// ------------------------------------------------------------------------------------------------
+//  Mesh::recompute_vertex_normals (mesh.cpp:296-330, JIT branch): angle-weighted face normals scattered to
+//  vertices, then normalised.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_normals_accumulate(const float *__restrict__ pos, const uint32_t *__restrict__ faces, uint32_t f_off, uint32_t f_cnt,
+                                     float *__restrict__ nrm) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= f_cnt) return;
+    const uint32_t *f = faces + 3 * (size_t) (f_off + i);
+    const uint32_t fi[3] = {f[0], f[1], f[2]};
+    const f3 v[3] = {ld3(pos, fi[0]), ld3(pos, fi[1]), ld3(pos, fi[2])};
+    const f3 n = norm3(cross3(v[1] - v[0], v[2] - v[0]));
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const f3 d0 = norm3(v[(k + 1) % 3] - v[k]), d1 = norm3(v[(k + 2) % 3] - v[k]);
+        const float c = fminf(fmaxf(dot3(d0, d1), -1.f), 1.f);
+        const f3 nn = n * acosf(c);
+        if (nn.x == nn.x && nn.y == nn.y && nn.z == nn.z) {
+            float *d = nrm + 3 * (size_t) fi[k];
+            atomicAdd(d, nn.x); atomicAdd(d + 1, nn.y); atomicAdd(d + 2, nn.z);
+        }
+    }
+}
+__global__ void k_normals_finish(float *__restrict__ nrm, uint32_t v_off, uint32_t v_cnt) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= v_cnt) return;
+    float *d = nrm + 3 * (size_t) (v_off + i);
+    f3 n = mk3(d[0], d[1], d[2]); float l = len3(n);
+    n = l != 0.f ? n * (1.0f / l) : mk3(1, 0, 0);
+    d[0] = n.x; d[1] = n.y; d[2] = n.z;
+}
+__global__ void k_zero_range(float *__restrict__ p, uint64_t off, uint64_t n) {
+    uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[off + i] = 0.f;
+}
+
+// ------------------------------------------------------------------------------------------------
+//  Launchers
+// ------------------------------------------------------------------------------------------------
+static inline void tile_rows(DLaunch &ln) {
+    const uint64_t row_lanes = (uint64_t) ln.sensor.w * ln.spp;
+    uint64_t y0 = ln.lane_begin / row_lanes, y1 = (ln.lane_end + row_lanes - 1) / row_lanes;
+    if (y1 > ln.sensor.h) y1 = ln.sensor.h;
+    ln.tile_y0 = (uint32_t) (y0 / TILE_H); ln.tile_y1 = (uint32_t) ((y1 + TILE_H - 1) / TILE_H);
+}
+static inline uint32_t tile_grid(const DLaunch &ln) {
+    const uint32_t tiles_x = (ln.sensor.w + TILE_W - 1) / TILE_W;
+    return tiles_x * (ln.tile_y1 > ln.tile_y0 ? ln.tile_y1 - ln.tile_y0 : 0);
+}
+
+cudaError_t epsm_launch_trace(const DScene &sc, const float *rays, uint64_t n, void *hits, int any_hit, unsigned long long *counters, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    const uint32_t grid = (uint32_t) ((n + CTA - 1) / CTA);
+    const f4 *r = reinterpret_cast<const f4 *>(rays); uint32_t *h = reinterpret_cast<uint32_t *>(hits);
+    if (any_hit) { if (counters) k_trace<true, true><<<grid, CTA, 0, s>>>(sc, r, n, h, counters); else k_trace<true, false><<<grid, CTA, 0, s>>>(sc, r, n, h, nullptr); }
+    else { if (counters) k_trace<false, true><<<grid, CTA, 0, s>>>(sc, r, n, h, counters); else k_trace<false, false><<<grid, CTA, 0, s>>>(sc, r, n, h, nullptr); }
+    return cudaGetLastError();
+}
+cudaError_t epsm_launch_render(const DScene &sc, DLaunch ln, float *film, unsigned long long *counters, cudaStream_t s) {
+    tile_rows(ln); const uint32_t grid = tile_grid(ln);
+    if (grid == 0) return cudaSuccess;
+    if (counters) k_render<true><<<grid, CTA, 0, s>>>(sc, ln, film, counters); else k_render<false><<<grid, CTA, 0, s>>>(sc, ln, film, nullptr);
+    return cudaGetLastError();
+}
+cudaError_t epsm_launch_develop(const float *film, uint64_t n_pixels, float *out, cudaStream_t s) {
+    if (n_pixels == 0) return cudaSuccess;
+    k_film_develop<<<(uint32_t) ((n_pixels + 255) / 256), 256, 0, s>>>(film, n_pixels, out);
+    return cudaGetLastError();
+}
+cudaError_t epsm_launch_backward(const DScene &sc, DLaunch ln, const float *grad_in, float *grad_pos, float *grad_nrm, float *records,
+                                 unsigned long long *counters, cudaStream_t s) {
+    tile_rows(ln); const uint32_t grid = tile_grid(ln);
+    if (grid == 0) return cudaSuccess;
+    if (records) k_backward<false, true><<<grid, CTA, 0, s>>>(sc, ln, grad_in, nullptr, nullptr, records, nullptr);
+    else if (counters) k_backward<true, false><<<grid, CTA, 0, s>>>(sc, ln, grad_in, grad_pos, grad_nrm, nullptr, counters);
+    else k_backward<false, false><<<grid, CTA, 0, s>>>(sc, ln, grad_in, grad_pos, grad_nrm, nullptr, nullptr);
+    return cudaGetLastError();
+}
+cudaError_t epsm_launch_sampler_stream(uint32_t seed, uint64_t lane_begin, uint64_t n_lanes, uint32_t n_floats, float *out, cudaStream_t s) {
+    if (n_lanes == 0) return cudaSuccess;
+    k_sampler_stream<<<(uint32_t) ((n_lanes + 127) / 128), 128, 0, s>>>(seed, lane_begin, n_lanes, n_floats, out);
+    return cudaGetLastError();
+}
+cudaError_t epsm_launch_sample_rays(const DSensor &se, uint32_t seed, uint32_t spp, uint64_t lane_begin, uint64_t n_lanes, float *out, cudaStream_t s) {
+    if (n_lanes == 0) return cudaSuccess;
+    k_sample_rays<<<(uint32_t) ((n_lanes + 127) / 128), 128, 0, s>>>(se, seed, spp, lane_begin, n_lanes, out);
+    return cudaGetLastError();
+}
+cudaError_t epsm_launch_vertex_normals(const float *pos, const uint32_t *faces, uint32_t f_off, uint32_t f_cnt, uint32_t v_off, uint32_t v_cnt,
+                                       float *nrm, cudaStream_t s) {
+    if (v_cnt == 0 || f_cnt == 0) return cudaSuccess;
+    k_zero_range<<<(3 * v_cnt + 255) / 256, 256, 0, s>>>(nrm, 3 * (uint64_t) v_off, 3 * (uint64_t) v_cnt);
+    k_normals_accumulate<<<(f_cnt + 255) / 256, 256, 0, s>>>(pos, faces, f_off, f_cnt, nrm);
+    k_normals_finish<<<(v_cnt + 255) / 256, 256, 0, s>>>(nrm, v_off, v_cnt);
+    return cudaGetLastError();
+}

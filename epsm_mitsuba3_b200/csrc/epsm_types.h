@@ -1,0 +1,78 @@
+// epsm_types.h — device-resident scene layout shared by the host builder, the kernels and the C ABI.
+//
+// HBM layout:
+//   nodes      BVH4, 128 B per node, SoA inside the node: 8 × float4
+//                [0] lo.x[4] [1] lo.y[4] [2] lo.z[4] [3] hi.x[4] [4] hi.y[4] [5] hi.z[4] [6] child[4] [7] pad
+//              child >= 0: inner node index; child < 0: leaf, ~child = (first_tri << 2) | (count-1);
+//              empty slots have child == 0x7fffffff and are skipped.  One node = one 128-byte line, fetched
+//              as eight 128-bit loads.
+//   tris       48 B per triangle in BVH leaf order: 3 × float4
+//                [0] p0.xyz, prim_index (bits)  [1] e1.xyz, e2.x  [2] e2.yz, 0, 0
+//              e1 = p1 - p0 and e2 = p2 - p0 are the fp32 differences the reference's Möller–Trumbore
+//              computes per query (include/mitsuba/render/mesh.h:347), so results are bit-identical.
+//   pos/nrm    float[3·V] concatenated over meshes (vertex gathers on a hit: 84 B with faces)
+//   faces      uint32[3·F] GLOBAL vertex ids;  face_mesh uint32[F]
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define EPSM_HD __host__ __device__ __forceinline__
+#define EPSM_HDN __host__ __device__
+#else
+#define EPSM_HD inline
+#define EPSM_HDN
+#endif
+
+struct f3 { float x, y, z; };
+struct f4 { float x, y, z, w; };
+
+#define EPSM_NODE_F4   8      // float4 per BVH node
+#define EPSM_TRI_F4    3      // float4 per triangle record
+#define EPSM_MAX_LEAF  4
+#define EPSM_MAXV      5      // logged vertices per path (epsm.py:648)
+#define EPSM_MAX_ITER  6      // sample_path iteration cap (epsm.py:549)
+
+struct DMesh {
+    uint32_t v_off, f_off, v_cnt, f_cnt;
+    int32_t  bsdf, emitter;
+    uint32_t flags, has_normals;
+    uint32_t cdf_off;            // into DScene::cdf / pmf (only meaningful for emitter meshes)
+    uint32_t valid_lo, valid_hi;
+    float    area_sum, area_norm;
+    float    _pad[3];
+};
+
+struct DBsdf {
+    uint32_t kind, flags, bflags, _pad;   // bflags = Mitsuba BSDFFlags word
+    float reflectance[3], transmittance[3], eta[3], k[3];
+    float alpha_u, alpha_v;
+    float _pad2[2];
+};
+
+struct DEmitter { float radiance[3]; int32_t mesh; };
+
+struct DSensor {
+    float s2c[16], to_world[16];
+    f3 dx, dy;
+    float near_clip, far_clip;
+    uint32_t w, h;
+};
+
+struct DScene {
+    const f4 *nodes; const f4 *tris;
+    const float *pos; const float *nrm;
+    const uint32_t *faces; const uint32_t *face_mesh;
+    const DMesh *meshes; const DBsdf *bsdfs; const DEmitter *emitters;
+    const float *cdf; const float *pmf;
+    uint32_t n_emitters, n_meshes, n_tris, n_nodes;
+    float filter[10];            // scaled Remez coefficients of the Gaussian rfilter (gaussian.cpp:57-89)
+};
+
+// Work description of one render / backward launch.
+struct DLaunch {
+    DSensor sensor;
+    uint32_t seed, spp, max_depth, rr_depth;
+    uint64_t lane_begin, lane_end;
+    uint32_t tile_y0, tile_y1;   // tile rows covered by this launch
+    int variant;
+};

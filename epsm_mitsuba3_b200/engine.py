@@ -1,0 +1,408 @@
+"""Host side of the B200 EPSM path: a thin Python mirror of the reference's integrator-plugin interface
+over the C ABI of libepsm_b200.so.
+
+Reference surface mirrored here (paths relative to the reference root):
+  * `mi.load_dict({'type': 'manifold' | 'manifold_caustic', 'max_depth': …, 'rr_depth': …})`
+    (EPSM/optim.py:97-100; properties src/python/python/ad/integrators/common.py:28-43)
+  * `mi.register_integrator(name, factory)` (epsm.py:948,1202)
+  * `Integrator.render(scene, sensor, seed, spp)` → (H,W,5) tensor (epsm.py:13-82)
+  * `Integrator.render_backward(scene, params, grad_in, sensor, seed, spp)` (epsm.py:84-306)
+  * `mi.traverse(scene)` / `params[key] = …; params.update()` (src/python/python/util.py:181-228)
+  * `mi.render(scene, params, sensor, integrator, seed, spp)` as a differentiable op (util.py:352-519)
+
+PyTorch is used for device memory, streams and torch.distributed only; all arithmetic of the path runs
+in the hand-written CUDA kernels.  There is no CPU fallback: constructing a Scene without a CUDA device
+or without the built library raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, Dict, Optional
+
+import numpy as np
+import torch
+
+from . import capi
+from .scenes import SceneData
+
+TILE_H = 4   # pixel-tile height of the kernels; multi-GPU bands are aligned to it
+
+
+def sample_tea_32(v0: int, v1: int, rounds: int = 4):
+    """include/mitsuba/core/random.h:76-90 (host integer restatement; used for seed_grad, util.py:510-515)."""
+    m = 0xFFFFFFFF
+    s = 0
+    for _ in range(rounds):
+        s = (s + 0x9e3779b9) & m
+        v0 = (v0 + ((((v1 << 4) & m) + 0xa341316c) ^ ((v1 + s) & m) ^ ((v1 >> 5) + 0xc8013ea4))) & m
+        v1 = (v1 + ((((v0 << 4) & m) + 0xad90777d) ^ ((v0 + s) & m) ^ ((v0 >> 5) + 0x7e95761e))) & m
+    return v0, v1
+
+
+class EpsmError(RuntimeError):
+    pass
+
+
+def _dist():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist
+    return None
+
+
+def band_lanes(height: int, width: int, spp: int, rank: int, world: int):
+    """Scanline band of `rank`: whole tile rows, so that band g owns rows [y0, y1).
+    Each lane's random stream depends only on (seed, global lane index), so sharding is exact."""
+    tiles = (height + TILE_H - 1) // TILE_H
+    t0, t1 = (tiles * rank) // world, (tiles * (rank + 1)) // world
+    y0, y1 = min(height, t0 * TILE_H), min(height, t1 * TILE_H)
+    return y0 * width * spp, y1 * width * spp
+
+
+class Scene:
+    """Device-resident scene (replaces mi.load_dict(scene) + accel init)."""
+
+    def __init__(self, data: SceneData, device: int = 0):
+        if not torch.cuda.is_available():
+            raise EpsmError("epsm_mitsuba3_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = capi.load_library()
+        self.data = data
+        self.device = torch.device("cuda", device)
+        ctx = C.c_void_p()
+        rc = self.lib.epsm_create(device, C.byref(ctx))
+        if rc != 0:
+            raise EpsmError(self.lib.epsm_last_error(None).decode())
+        self.ctx = ctx
+        c = data.to_c()
+        nm, nb, ne, ns = c.counts
+        self._check(self.lib.epsm_scene_upload(ctx, c.meshes, nm, c.bsdfs, nb, c.emitters, ne, c.sensors, ns))
+        self.voff = data.vertex_offsets()
+        self.n_vertices = int(self.voff[-1])
+
+    # ---- plumbing --------------------------------------------------------------------------
+    def _check(self, rc):
+        if rc != 0:
+            raise EpsmError(self.lib.epsm_last_error(self.ctx).decode())
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.epsm_destroy(self.ctx); self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ptr(self, t):
+        """(address, mem) of a contiguous float32/uint32 torch tensor or numpy array."""
+        if isinstance(t, np.ndarray):
+            assert t.flags["C_CONTIGUOUS"]
+            return t.ctypes.data, capi.MEM_HOST
+        assert t.is_contiguous()
+        return t.data_ptr(), (capi.MEM_DEVICE if t.is_cuda else capi.MEM_HOST)
+
+    def synchronize(self):
+        self._check(self.lib.epsm_synchronize(self.ctx))
+
+    def stream(self) -> torch.cuda.ExternalStream:
+        return torch.cuda.ExternalStream(self.lib.epsm_stream(self.ctx), device=self.device)
+
+    def launch_count(self) -> int:
+        return int(self.lib.epsm_launch_count(self.ctx))
+
+    def stats(self) -> dict:
+        s = capi.SceneStats(); self._check(self.lib.epsm_scene_get_stats(self.ctx, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in s._fields_}
+
+    def sensors(self):
+        return self.data.sensors
+
+    # ---- scene updates ---------------------------------------------------------------------
+    def update_vertices(self, mesh_id: int, positions, commit: bool = True):
+        """params['<mesh>.vertex_positions'] = positions; params.update()"""
+        if isinstance(positions, torch.Tensor):
+            positions = positions.detach().to(torch.float32).contiguous()
+            if positions.is_cuda:
+                torch.cuda.current_stream(self.device).synchronize()
+        else:
+            positions = np.ascontiguousarray(positions, np.float32)
+        assert positions.size if isinstance(positions, np.ndarray) else positions.numel() == 3 * self.data.meshes[mesh_id].positions.shape[0]
+        addr, mem = self._ptr(positions)
+        self._check(self.lib.epsm_scene_update_vertices(self.ctx, mesh_id, addr, mem))
+        if commit:
+            self.commit()
+
+    def commit(self):
+        self._check(self.lib.epsm_scene_commit(self.ctx))
+
+    # ---- low-level entry points (numpy or torch in, same kind out) --------------------------
+    def trace(self, rays, any_hit: bool = False, counters: Optional[np.ndarray] = None):
+        n = rays.shape[0]
+        addr, mem = self._ptr(rays)
+        if isinstance(rays, np.ndarray):
+            hits = np.zeros(n if any_hit else (n, 4), np.uint32)
+        else:
+            hits = torch.zeros(n if any_hit else (n, 4), dtype=torch.int32, device=rays.device)
+        cp = counters.ctypes.data if counters is not None else None
+        self._check(self.lib.epsm_trace(self.ctx, addr, n, self._ptr(hits)[0], 1 if any_hit else 0, cp, mem))
+        return hits
+
+    def sampler_stream(self, seed, lane_begin, lane_end, n_floats):
+        out = np.zeros((lane_end - lane_begin, n_floats), np.float32)
+        self._check(self.lib.epsm_sampler_stream(self.ctx, seed, lane_begin, lane_end, n_floats, out.ctypes.data, capi.MEM_HOST))
+        return out
+
+    def sample_rays(self, sensor, seed, spp, lane_begin, lane_end):
+        out = np.zeros((lane_end - lane_begin, 14), np.float32)
+        self._check(self.lib.epsm_sample_rays(self.ctx, sensor, seed, spp, lane_begin, lane_end, out.ctypes.data, capi.MEM_HOST))
+        return out
+
+    def film_clear(self, sensor):
+        self._check(self.lib.epsm_film_clear(self.ctx, sensor))
+
+    def film_raw(self, sensor) -> torch.Tensor:
+        """The context's RGBW accumulation buffer as a (H,W,4) torch view (no copy)."""
+        p, n = C.c_void_p(), C.c_uint64()
+        self._check(self.lib.epsm_film_raw(self.ctx, sensor, C.byref(p), C.byref(n)))
+        s = self.data.sensors[sensor]
+        return _wrap_device(p.value, (s.height, s.width, 4), self.device)
+
+    def render_accumulate(self, sensor, seed, spp, max_depth, rr_depth, lane_begin=0, lane_end=0, counters=None):
+        cp = counters.ctypes.data if counters is not None else None
+        self._check(self.lib.epsm_render_accumulate(self.ctx, sensor, seed, spp, max_depth, rr_depth, lane_begin, lane_end, cp))
+
+    def film_develop(self, sensor, out=None):
+        s = self.data.sensors[sensor]
+        if out is None:
+            out = torch.empty((s.height, s.width, 5), dtype=torch.float32, device=self.device)
+        addr, mem = self._ptr(out)
+        self._check(self.lib.epsm_film_develop(self.ctx, sensor, addr, mem))
+        return out
+
+    def render_backward_raw(self, variant, sensor, seed, spp, max_depth, rr_depth, grad_in,
+                            grad_pos=None, grad_nrm=None, lane_begin=0, lane_end=0, counters=None):
+        """epsm_render_backward: accumulates into (and returns) grad_pos / grad_nrm, (V,3) each.
+        Buffers follow the memory space of grad_in (host numpy / pinned tensor ↔ device tensor)."""
+        vid = _variant_id(variant)
+        s = self.data.sensors[sensor]
+        host = isinstance(grad_in, np.ndarray) or not grad_in.is_cuda
+        if isinstance(grad_in, np.ndarray):
+            grad_in = np.ascontiguousarray(grad_in, np.float32)
+        else:
+            grad_in = grad_in.detach().to(torch.float32).contiguous()
+        assert tuple(grad_in.shape) == (s.height, s.width, 5), "grad_in must be (H,W,5) for the gradient sensor"
+        if grad_pos is None:
+            if isinstance(grad_in, np.ndarray):
+                grad_pos = np.zeros((self.n_vertices, 3), np.float32); grad_nrm = np.zeros((self.n_vertices, 3), np.float32)
+            else:
+                kw = dict(dtype=torch.float32, device=grad_in.device, pin_memory=host)
+                grad_pos = torch.zeros((self.n_vertices, 3), **kw); grad_nrm = torch.zeros((self.n_vertices, 3), **kw)
+        a_in, mem = self._ptr(grad_in)
+        cp = counters.ctypes.data if counters is not None else None
+        self._check(self.lib.epsm_render_backward(self.ctx, vid, sensor, seed, spp, max_depth, rr_depth, a_in,
+                                                  self._ptr(grad_pos)[0], self._ptr(grad_nrm)[0], mem, lane_begin, lane_end, cp))
+        return grad_pos, grad_nrm
+
+    def path_records(self, variant, sensor, seed, spp, max_depth, rr_depth, grad_in, lane_begin, lane_end):
+        grad_in = np.ascontiguousarray(grad_in, np.float32)
+        out = np.zeros((lane_end - lane_begin, capi.REC_FLOATS), np.float32)
+        self._check(self.lib.epsm_path_records(self.ctx, _variant_id(variant), sensor, seed, spp, max_depth, rr_depth,
+                                               grad_in.ctypes.data, lane_begin, lane_end, out.ctypes.data, capi.MEM_HOST))
+        return out
+
+
+def _variant_id(v):
+    if v in (capi.VARIANT_MANIFOLD, "manifold"):
+        return capi.VARIANT_MANIFOLD
+    if v in (capi.VARIANT_MANIFOLD_CAUSTIC, "manifold_caustic"):
+        return capi.VARIANT_MANIFOLD_CAUSTIC
+    raise EpsmError(f"unknown integrator variant {v!r}")
+
+
+def _wrap_device(ptr: int, shape, device) -> torch.Tensor:
+    """Zero-copy torch view of library-owned device memory (via __cuda_array_interface__)."""
+    class _Holder:
+        pass
+    h = _Holder()
+    h.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (ptr, False), "version": 3, "strides": None}
+    return torch.as_tensor(h, device=device)
+
+
+# ------------------------------------------------------------------------------------------------
+#  Integrator plugins
+# ------------------------------------------------------------------------------------------------
+class EPSMIntegrator:
+    """EPSMIntegrator (epsm.py:12) with the property handling of ADIntegrator (common.py:28-43)."""
+    variant: str = None
+
+    def __init__(self, props: dict):
+        max_depth = int(props.get("max_depth", 6))
+        if max_depth < 0 and max_depth != -1:
+            raise Exception("\"max_depth\" must be set to -1 (infinite) or a value >= 0")
+        self.max_depth = max_depth if max_depth != -1 else 0xffffffff
+        self.rr_depth = int(props.get("rr_depth", 5))
+        if self.rr_depth <= 0:
+            raise Exception("\"rr_depth\" must be set to a value greater than zero!")
+
+    # epsm.py:13-82
+    def render(self, scene: Scene, sensor: int = 0, seed: int = 0, spp: int = 0, develop: bool = True, evaluate: bool = True) -> torch.Tensor:
+        if not develop:
+            raise Exception("develop=True must be specified when invoking AD integrators")
+        s = scene.sensors()[sensor]
+        spp = spp if spp != 0 else s.spp
+        scene.film_clear(sensor)
+        dist = _dist()
+        if dist is None:
+            scene.render_accumulate(sensor, seed, spp, self.max_depth, self.rr_depth)
+        else:
+            lb, le = band_lanes(s.height, s.width, spp, dist.get_rank(), dist.get_world_size())
+            if le > lb:
+                scene.render_accumulate(sensor, seed, spp, self.max_depth, self.rr_depth, lb, le)
+            film = scene.film_raw(sensor)
+            scene.synchronize()
+            dist.all_reduce(film)                     # bands overlap by the filter radius: sum the RGBW film
+            torch.cuda.current_stream(scene.device).synchronize()
+        self.primal_image = scene.film_develop(sensor)
+        scene.synchronize()
+        return self.primal_image
+
+    # epsm.py:84-306
+    def render_backward(self, scene: Scene, params, grad_in: torch.Tensor, sensor: int = 0, seed: int = 0, spp: int = 0) -> None:
+        """Accumulates into `.grad` of every `<mesh>.vertex_positions` / `<mesh>.vertex_normals` entry of `params`
+        that requires grad.  As in the reference, the sensor and spp arguments are ignored: the gradient pass
+        always uses sensors()[2] at 8 spp (epsm.py:142-145)."""
+        sensor, spp = 2, 8
+        s = scene.sensors()[sensor]
+        if grad_in.shape[-1] == 3:
+            # colour-only gradients reach no scene parameter in the reference (δL is never consumed, epsm.py:728-732)
+            return
+        res = s.width                                   # epsm.py:238-240: crop to the gradient sensor's resolution
+        g = grad_in[:res, :res, :].to(device=scene.device, dtype=torch.float32).contiguous()
+        torch.cuda.current_stream(scene.device).synchronize()
+        gp, gn = self.backward_buffers(scene, g, sensor, seed, spp)
+        params.accumulate_gradients(gp, gn)
+
+    def backward_buffers(self, scene: Scene, g: torch.Tensor, sensor: int, seed: int, spp: int):
+        s = scene.sensors()[sensor]
+        dist = _dist()
+        lb, le = (0, 0) if dist is None else band_lanes(s.height, s.width, spp, dist.get_rank(), dist.get_world_size())
+        buf = torch.zeros((2, scene.n_vertices, 3), dtype=torch.float32, device=scene.device)
+        torch.cuda.current_stream(scene.device).synchronize()
+        if dist is None or le > lb:
+            scene.render_backward_raw(self.variant, sensor, seed, spp, self.max_depth, self.rr_depth, g, buf[0], buf[1], lb, le)
+        scene.synchronize()
+        if dist is not None:
+            dist.all_reduce(buf)                        # one NCCL allreduce of the mesh-gradient buffer per step
+            torch.cuda.current_stream(scene.device).synchronize()
+        return buf[0], buf[1]
+
+
+class ManifoldIntegrator(EPSMIntegrator):              # epsm.py:744
+    variant = "manifold"
+
+
+class ManifoldCausticIntegrator(EPSMIntegrator):       # epsm.py:951
+    variant = "manifold_caustic"
+
+
+_REGISTRY: Dict[str, Callable[[dict], EPSMIntegrator]] = {}
+
+
+def register_integrator(name: str, factory: Callable[[dict], EPSMIntegrator]) -> None:
+    """mi.register_integrator (include/mitsuba/python/python.h:57-90)."""
+    _REGISTRY[name] = factory
+
+
+register_integrator("manifold", lambda props: ManifoldIntegrator(props))                 # epsm.py:948
+register_integrator("manifold_caustic", lambda props: ManifoldCausticIntegrator(props))  # epsm.py:1202
+
+
+def load_dict(d: dict):
+    """mi.load_dict for the integrator plugins of this path."""
+    t = d.get("type")
+    if t not in _REGISTRY:
+        raise EpsmError(f'Plugin "{t}" not found')           # PluginManager::create_object, src/core/plugin.cpp:174-211
+    return _REGISTRY[t]({k: v for k, v in d.items() if k != "type"})
+
+
+# ------------------------------------------------------------------------------------------------
+#  SceneParameters / mi.render
+# ------------------------------------------------------------------------------------------------
+class SceneParameters(dict):
+    """mi.traverse(scene) restricted to mesh vertex data (util.py:24-228)."""
+
+    def __init__(self, scene: Scene):
+        super().__init__()
+        self.scene = scene
+        self._dirty = set()
+        for i, m in enumerate(scene.data.meshes):
+            key = f"{m.name}.vertex_positions"
+            if key in self:
+                key = f"{m.name}_{i}.vertex_positions"
+            super().__setitem__(key, torch.from_numpy(m.positions.copy()).to(scene.device))
+            self._mesh_of = getattr(self, "_mesh_of", {})
+            self._mesh_of[key] = i
+
+    def __setitem__(self, key, value):
+        if key not in self:
+            raise KeyError(key)
+        super().__setitem__(key, value)
+        self._dirty.add(key)
+
+    def update(self, values: Optional[dict] = None):
+        if values:
+            for k, v in values.items():
+                self[k] = v
+        for key in sorted(self._dirty):
+            self.scene.update_vertices(self._mesh_of[key], self[key].reshape(-1, 3), commit=False)
+        if self._dirty:
+            self.scene.commit()
+        self._dirty.clear()
+
+    def accumulate_gradients(self, grad_pos: torch.Tensor, grad_nrm: torch.Tensor):
+        voff = self.scene.voff
+        for key, i in self._mesh_of.items():
+            t = self[key]
+            if not (isinstance(t, torch.Tensor) and t.requires_grad):
+                continue
+            g = grad_pos[int(voff[i]):int(voff[i + 1])].reshape(t.shape)
+            t.grad = g.clone() if t.grad is None else t.grad + g
+
+
+def traverse(scene: Scene) -> SceneParameters:
+    return SceneParameters(scene)
+
+
+class _RenderOp(torch.autograd.Function):
+    """mi.render's custom op (util.py:352-403): forward = integrator.render, backward = render_backward with
+    seed_grad = sample_tea_32(seed, 1)[0] (util.py:510-515)."""
+
+    @staticmethod
+    def forward(ctx, scene, integrator, sensor, seed, spp, keys, *tensors):
+        ctx.scene, ctx.integrator, ctx.sensor, ctx.seed, ctx.spp, ctx.keys = scene, integrator, sensor, seed, spp, keys
+        ctx.shapes = [t.shape for t in tensors]
+        return integrator.render(scene, sensor=sensor, seed=seed, spp=spp).clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        scene, integ = ctx.scene, ctx.integrator
+        seed_grad = sample_tea_32(ctx.seed, 1)[0]
+        s2 = scene.sensors()[2]
+        g = grad_out[:s2.width, :s2.width, :].to(torch.float32).contiguous()
+        gp, gn = integ.backward_buffers(scene, g, 2, seed_grad, 8)
+        voff = scene.voff
+        outs = []
+        for mesh_id, shape in zip(ctx.keys, ctx.shapes):
+            outs.append(gp[int(voff[mesh_id]):int(voff[mesh_id + 1])].reshape(shape).clone())
+        return (None, None, None, None, None, None, *outs)
+
+
+def render(scene: Scene, params: SceneParameters, sensor: int = 0, integrator: EPSMIntegrator = None, seed: int = 0, spp: int = 0) -> torch.Tensor:
+    """mi.render(scene, params, sensor, integrator, seed, spp): differentiable w.r.t. the vertex_positions in `params`."""
+    keys, tensors = [], []
+    for key, mesh_id in params._mesh_of.items():
+        t = params[key]
+        if isinstance(t, torch.Tensor) and t.requires_grad:
+            keys.append(mesh_id); tensors.append(t)
+    return _RenderOp.apply(scene, integrator, sensor, seed, spp, keys, *tensors)

@@ -128,8 +128,9 @@ int epsm_scene_commit(epsm_ctx *ctx);
  * hits (closest): n × 4 32-bit words (t, prim_u, prim_v as float; global prim_index as uint32,
  *       0xffffffff on a miss; t = +inf on a miss).
  * hits (any_hit != 0): n × uint32, 1 if occluded.
- * counters (optional, device or host per `mem`, 2 × uint64): nodes visited, triangles tested —
- * the algorithmic-byte accounting of SURVEY.md §8d.  Pass NULL to run the uninstrumented kernel. */
+ * counters (optional, HOST pointer, 4 × uint64, accumulated into): BVH nodes fetched, triangles
+ * tested, rays traced, lanes processed — the algorithmic-byte accounting of SURVEY.md §8d.  Pass NULL
+ * to run the uninstrumented kernel (the instrumented one has identical control flow). */
 int epsm_trace(epsm_ctx *ctx, const float *rays, uint64_t n, void *hits, int any_hit,
                uint64_t *counters, int mem);
 

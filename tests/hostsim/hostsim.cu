@@ -1,0 +1,178 @@
+// hostsim.cu — TEST-ONLY harness.  Compiles the product's per-lane device code (epsm_device.cuh) for the
+// HOST so that the exact lane logic (traversal, path loops, manifold solve, scatter seeds) can be checked
+// against the oracle on a machine without a GPU.  It is not a fallback: nothing in epsm_mitsuba3_b200
+// loads this library; the product path is libepsm_b200.so on a CUDA device only.
+#include <stdint.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "../../epsm_mitsuba3_b200/csrc/epsm_device.cuh"
+#include "../../epsm_mitsuba3_b200/csrc/epsm_host_scene.h"
+
+struct sim_scene { HostScene hs; DScene sc; std::string err; };
+
+namespace {
+struct LocalStack { uint32_t ref[EPSM_SSTACK]; float t[EPSM_SSTACK]; };
+inline void bind(TStack &st, LocalStack &ls) { st.s_ref = ls.ref; st.s_t = ls.t; st.stride = 1; st.sp = 0; }
+
+DLaunch make_launch(const sim_scene *s, uint32_t sensor, uint32_t seed, uint32_t spp, uint32_t max_depth, uint32_t rr_depth, int variant) {
+    DLaunch ln; memset(&ln, 0, sizeof(ln));
+    ln.sensor = s->hs.sensors[sensor]; ln.seed = seed; ln.spp = spp; ln.max_depth = max_depth; ln.rr_depth = rr_depth; ln.variant = variant;
+    return ln;
+}
+void add3(float *buf, uint32_t idx, f3 v, bool pred) { if (!pred) return; buf[3 * idx] += v.x; buf[3 * idx + 1] += v.y; buf[3 * idx + 2] += v.z; }
+}
+
+extern "C" {
+
+sim_scene *sim_scene_create(const epsm_mesh_desc *meshes, uint32_t n_meshes, const epsm_bsdf_desc *bsdfs, uint32_t n_bsdfs,
+                            const epsm_emitter_desc *emitters, uint32_t n_emitters, const epsm_sensor_desc *sensors, uint32_t n_sensors) {
+    sim_scene *s = new sim_scene();
+    s->err = host_scene_build(s->hs, meshes, n_meshes, bsdfs, n_bsdfs, emitters, n_emitters, sensors, n_sensors);
+    memset(&s->sc, 0, sizeof(s->sc));
+    if (s->err.empty()) host_scene_view(s->hs, s->sc);
+    return s;
+}
+const char *sim_scene_error(sim_scene *s) { return s->err.c_str(); }
+void sim_scene_destroy(sim_scene *s) { delete s; }
+void sim_scene_update_vertices(sim_scene *s, uint32_t mesh_id, const float *positions) {
+    const DMesh &m = s->hs.meshes[mesh_id];
+    memcpy(s->hs.pos.data() + 3 * (size_t) m.v_off, positions, 3 * (size_t) m.v_cnt * sizeof(float));
+    host_scene_rebuild_accel(s->hs); host_scene_view(s->hs, s->sc);
+}
+void sim_scene_stats(sim_scene *s, uint64_t *out) {
+    out[0] = s->hs.faces.size() / 3; out[1] = s->hs.bvh.nodes.size() / EPSM_NODE_F4; out[2] = s->hs.bvh.depth;
+}
+
+void sim_trace(sim_scene *s, const float *rays, uint64_t n, void *hits, int any_hit, uint64_t *counters) {
+    uint64_t cn = 0, ct = 0;
+    #pragma omp parallel for schedule(dynamic, 256) reduction(+ : cn, ct)
+    for (int64_t i = 0; i < (int64_t) n; ++i) {
+        LocalStack ls; TStack st; bind(st, ls); Tracer tr(s->sc, st);
+        const float *r = rays + 8 * i;
+        Ray ray{mk3(r[0], r[1], r[2]), mk3(r[4], r[5], r[6]), r[3]};
+        if (any_hit) ((uint32_t *) hits)[i] = trace_any<true>(tr, ray) ? 1u : 0u;
+        else {
+            Hit h = trace_closest<true>(tr, ray);
+            uint32_t *o = (uint32_t *) hits + 4 * i; o[0] = f2u(h.t); o[1] = f2u(h.u); o[2] = f2u(h.v); o[3] = h.prim;
+        }
+        cn += tr.n_nodes; ct += tr.n_tris;
+    }
+    if (counters) { counters[0] += cn; counters[1] += ct; counters[2] += n; counters[3] += n; }
+}
+
+void sim_sampler_stream(uint32_t seed, uint64_t lane_begin, uint64_t lane_end, uint32_t n, float *out) {
+    for (uint64_t l = lane_begin; l < lane_end; ++l) { Pcg r = pcg_for_lane(seed, (uint32_t) l); for (uint32_t k = 0; k < n; ++k) out[(l - lane_begin) * n + k] = pcg_f32(r); }
+}
+void sim_sample_rays(sim_scene *s, uint32_t sensor, uint32_t seed, uint32_t spp, uint64_t lane_begin, uint64_t lane_end, float *out) {
+    const DSensor &se = s->hs.sensors[sensor];
+    for (uint64_t lane = lane_begin; lane < lane_end; ++lane) {
+        uint32_t pixel = (uint32_t) (lane / spp); Pcg r = pcg_for_lane(seed, (uint32_t) lane);
+        CamRay c; camera_ray(se, pixel % se.w, pixel / se.w, r, c);
+        float *o = out + 14 * (lane - lane_begin);
+        o[0] = c.ray.o.x; o[1] = c.ray.o.y; o[2] = c.ray.o.z; o[3] = c.ray.d.x; o[4] = c.ray.d.y; o[5] = c.ray.d.z;
+        o[6] = c.d_x.x; o[7] = c.d_x.y; o[8] = c.d_x.z; o[9] = c.d_y.x; o[10] = c.d_y.y; o[11] = c.d_y.z; o[12] = c.pos_x; o[13] = c.pos_y;
+    }
+}
+
+// k_render on the host: film is H·W·4, accumulated into.
+void sim_render_accumulate(sim_scene *s, uint32_t sensor, uint32_t seed, uint32_t spp, uint32_t max_depth, uint32_t rr_depth,
+                           uint64_t lane_begin, uint64_t lane_end, float *film) {
+    DLaunch ln = make_launch(s, sensor, seed, spp, max_depth, rr_depth, 0);
+    const uint32_t W = ln.sensor.w, H = ln.sensor.h;
+    const int64_t n = (int64_t) (lane_end - lane_begin);
+    std::vector<float> tmp((size_t) n * 5);
+    #pragma omp parallel for schedule(dynamic, 64)
+    for (int64_t i = 0; i < n; ++i) {
+        uint64_t lane = lane_begin + i; uint32_t pixel = (uint32_t) (lane / spp);
+        LocalStack ls; TStack st; bind(st, ls); Tracer tr(s->sc, st);
+        Pcg rng = pcg_for_lane(seed, (uint32_t) lane);
+        CamRay c; camera_ray(ln.sensor, pixel % W, pixel / W, rng, c);
+        bool valid; f3 L = path_primal<false>(s->sc, tr, c.ray, rng, max_depth, rr_depth, valid);
+        tmp[5 * i] = L.x; tmp[5 * i + 1] = L.y; tmp[5 * i + 2] = L.z; tmp[5 * i + 3] = c.pos_x; tmp[5 * i + 4] = c.pos_y;
+    }
+    for (int64_t i = 0; i < n; ++i) {
+        const float pos_x = tmp[5 * i + 3], pos_y = tmp[5 * i + 4];
+        const int pix = (int) floorf(pos_x) - 2, piy = (int) floorf(pos_y) - 2;
+        float rel_x = (float) pix + .5f - pos_x, rel_y = (float) piy + .5f - pos_y, wx[5], wy[5];
+        for (int k = 0; k < 5; ++k) { wx[k] = filter_eval(s->sc.filter, rel_x); wy[k] = filter_eval(s->sc.filter, rel_y); rel_x += 1; rel_y += 1; }
+        for (int ys = 0; ys < 5; ++ys) for (int xs = 0; xs < 5; ++xs) {
+            int x = pix + xs, y = piy + ys; if (x < 0 || y < 0 || x >= (int) W || y >= (int) H) continue;
+            float w = wy[ys] * wx[xs]; float *d = film + ((size_t) y * W + x) * 4;
+            d[0] += tmp[5 * i] * w; d[1] += tmp[5 * i + 1] * w; d[2] += tmp[5 * i + 2] * w; d[3] += 1.0f * w;
+        }
+    }
+}
+
+// k_backward on the host.  records != NULL: per-lane records (EPSM_REC_FLOATS each); else scatter into grad_pos / grad_nrm.
+void sim_backward(sim_scene *s, int variant, uint32_t sensor, uint32_t seed, uint32_t spp, uint32_t max_depth, uint32_t rr_depth,
+                  const float *grad_in, uint64_t lane_begin, uint64_t lane_end, float *grad_pos, float *grad_nrm, float *records) {
+    DLaunch ln = make_launch(s, sensor, seed, spp, max_depth, rr_depth, variant);
+    const uint32_t W = ln.sensor.w;
+    const uint32_t max_iter = max_depth < EPSM_MAX_ITER ? max_depth : EPSM_MAX_ITER;
+    const int n_logged = (int) (max_iter < EPSM_MAXV ? max_iter : EPSM_MAXV);
+    const int64_t n = (int64_t) (lane_end - lane_begin);
+    std::vector<PathLog> logs(records ? 0 : n); std::vector<PathGrads> grads(records ? 0 : n);
+    #pragma omp parallel for schedule(dynamic, 64)
+    for (int64_t i = 0; i < n; ++i) {
+        uint64_t lane = lane_begin + i; uint32_t pixel = (uint32_t) (lane / spp);
+        LocalStack ls; TStack st; bind(st, ls); Tracer tr(s->sc, st);
+        Pcg rng = pcg_for_lane(seed, (uint32_t) lane);
+        CamRay c; camera_ray(ln.sensor, pixel % W, pixel / W, rng, c);
+        const float gx = grad_in[(size_t) pixel * 5 + 3], gy = grad_in[(size_t) pixel * 5 + 4];
+        const f3 grad_d = (c.d_x - c.ray.d) * gx + (c.d_y - c.ray.d) * gy;
+        PathLog P; path_log<false>(s->sc, tr, c, grad_d, rng, max_depth, rr_depth, P);
+        PathGrads G; calc_grad(P, variant, n_logged, G);
+        if (records) {
+            float *r = records + (size_t) i * EPSM_REC_FLOATS;
+            for (int q = 0; q < EPSM_REC_FLOATS; ++q) r[q] = 0.f;
+            for (int k = 0; k < n_logged; ++k) {
+                const VLog &v = P.v[k]; float *o = r + k * EPSM_REC_VSTRIDE;
+                o[0] = v.active ? 1.f : 0.f; o[1] = u2f(v.prim); o[2] = v.p.x; o[3] = v.p.y; o[4] = v.p.z; o[5] = v.b0; o[6] = v.b1;
+                o[7] = v.active_em ? 1.f : 0.f; o[8] = v.light.x; o[9] = v.light.y; o[10] = v.light.z; o[11] = u2f(v.flags); o[12] = v.eta;
+                o[13] = v.lr_sum; o[14] = v.dis; o[15] = u2f((v.direct_any ? 1u : 0u) | (v.direct_valid ? 2u : 0u) | (v.direct_grad ? 4u : 0u));
+                float *g = r + EPSM_REC_GRAD_OFF + k * EPSM_REC_GSTRIDE;
+                for (int cc = 0; cc < 5; ++cc) { g[3 * cc] = G.pg[k][cc].x; g[3 * cc + 1] = G.pg[k][cc].y; g[3 * cc + 2] = G.pg[k][cc].z; }
+                g[15] = G.lg[k].x; g[16] = G.lg[k].y; g[17] = G.lg[k].z; g[18] = G.dg[k].x; g[19] = G.dg[k].y; g[20] = G.dg[k].z;
+            }
+            float *h = r + EPSM_REC_HEAD_OFF;
+            h[0] = P.cam.x; h[1] = P.cam.y; h[2] = P.cam.z; h[3] = P.d.x; h[4] = P.d.y; h[5] = P.d.z;
+            h[6] = P.dlduv0; h[7] = P.dlduv1; h[8] = P.dldp1.x; h[9] = P.dldp1.y; h[10] = P.dldp1.z; h[11] = P.L.x; h[12] = P.L.y; h[13] = P.L.z;
+        } else { logs[i] = P; grads[i] = G; }
+    }
+    if (records) return;
+    // scatter_path of epsm_kernels.cu with plain adds (same seeds, same masks)
+    const int n_pg = variant == EPSM_VARIANT_MANIFOLD ? 5 * n_logged : 5 * (n_logged - 1) + 3;
+    const bool shadow_term = max_iter <= 3;
+    for (int64_t i = 0; i < n; ++i) {
+        const PathLog &P = logs[i]; const PathGrads &G = grads[i];
+        for (int k = 0; k < n_logged; ++k) {
+            const VLog &v = P.v[k];
+            const bool sel = v.active && (v.mesh_flags & EPSM_MESH_GRAD);
+            if (5 * k + 4 < n_pg) {
+                for (int c = 0; c < 3; ++c) add3(grad_pos, v.fi[c], G.pg[k][c], sel);
+                const f3 g3 = G.pg[k][3];
+                const bool any_g3 = sel && (g3.x != 0.f || g3.y != 0.f || g3.z != 0.f);
+                const float flip = (v.mesh_flags & EPSM_MESH_FLIP_NORMALS) ? -1.f : 1.f;
+                if (any_g3 && v.has_normals) {
+                    const f3 nt = v.n0 * v.bw[0] + v.n1 * v.bw[1] + v.n2 * v.bw[2];
+                    const float il = 1.0f / len3(nt); const f3 nh = nt * il;
+                    const f3 gt = (g3 - nh * dot3(nh, g3)) * (il * flip);
+                    for (int c = 0; c < 3; ++c) add3(grad_nrm, v.fi[c], gt * v.bw[c], true);
+                } else if (any_g3 && v.ismesh) {
+                    const f3 e1 = v.p1 - v.p0, e2 = v.p2 - v.p0, cr = cross3(e1, e2);
+                    const float il = 1.0f / len3(cr); const f3 nh = cr * il;
+                    const f3 gc = (g3 - nh * dot3(nh, g3)) * (il * flip);
+                    const f3 ge1 = cross3(e2, gc), ge2 = cross3(gc, e1);
+                    add3(grad_pos, v.fi[1], ge1, true); add3(grad_pos, v.fi[2], ge2, true); add3(grad_pos, v.fi[0], -(ge1 + ge2), true);
+                }
+            }
+            for (int c = 0; c < 3; ++c) add3(grad_pos, v.fi[c], G.dg[k] * v.bw[c], sel);
+            if (k == 0 && shadow_term) { const f3 g = G.dg[0] * v.dis; for (int c = 0; c < 3; ++c) add3(grad_pos, v.dfi[c], g * v.dbw[c], v.direct_any && v.direct_grad); }
+            const f3 gl = G.lg[k] * v.lr_sum;
+            for (int c = 0; c < 3; ++c) add3(grad_pos, v.dfi[c], gl * v.dbw[c], v.direct_valid && v.direct_grad);
+        }
+    }
+}
+
+} // extern "C"

@@ -1,0 +1,92 @@
+"""ctypes front-end of the TEST-ONLY host harness (libepsm_hostsim.so): the product's per-lane device code
+compiled for the CPU.  Presents the same low-level calls as epsm_mitsuba3_b200.engine.Scene so that the
+parity tests can run on the harness here (no GPU) and on the real library on the B200 (`-m gpu`)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from epsm_mitsuba3_b200 import capi
+from epsm_mitsuba3_b200.scenes import SceneData
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        import __graft_entry__ as ge
+        L = C.CDLL(ge.build_hostsim())
+        vp, u32, u64, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int
+        L.sim_scene_create.restype = vp
+        L.sim_scene_create.argtypes = [C.POINTER(capi.MeshDesc), u32, C.POINTER(capi.BsdfDesc), u32,
+                                       C.POINTER(capi.EmitterDesc), u32, C.POINTER(capi.SensorDesc), u32]
+        L.sim_scene_error.restype = C.c_char_p; L.sim_scene_error.argtypes = [vp]
+        L.sim_scene_destroy.argtypes = [vp]
+        L.sim_scene_update_vertices.argtypes = [vp, u32, vp]
+        L.sim_scene_stats.argtypes = [vp, vp]
+        L.sim_trace.argtypes = [vp, vp, u64, vp, i32, vp]
+        L.sim_sampler_stream.argtypes = [u32, u64, u64, u32, vp]
+        L.sim_sample_rays.argtypes = [vp, u32, u32, u32, u64, u64, vp]
+        L.sim_render_accumulate.argtypes = [vp, u32, u32, u32, u32, u32, u64, u64, vp]
+        L.sim_backward.argtypes = [vp, i32, u32, u32, u32, u32, u32, vp, u64, u64, vp, vp, vp]
+        _LIB = L
+    return _LIB
+
+
+def _vid(v):
+    return {"manifold": 0, "manifold_caustic": 1}.get(v, v)
+
+
+class SimScene:
+    def __init__(self, sd: SceneData):
+        self.data = sd; self._c = sd.to_c(); nm, nb, ne, ns = self._c.counts
+        self.h = lib().sim_scene_create(self._c.meshes, nm, self._c.bsdfs, nb, self._c.emitters, ne, self._c.sensors, ns)
+        err = lib().sim_scene_error(self.h).decode()
+        if err:
+            raise RuntimeError(err)
+        self.n_vertices = sd.n_vertices
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().sim_scene_destroy(self.h); self.h = None
+
+    def stats(self):
+        out = np.zeros(3, np.uint64); lib().sim_scene_stats(self.h, out.ctypes.data)
+        return dict(n_triangles=int(out[0]), n_nodes=int(out[1]), depth=int(out[2]))
+
+    def update_vertices(self, mesh_id, positions):
+        p = np.ascontiguousarray(positions, np.float32); lib().sim_scene_update_vertices(self.h, mesh_id, p.ctypes.data)
+
+    def trace(self, rays, any_hit=False, counters=None):
+        rays = np.ascontiguousarray(rays, np.float32); n = rays.shape[0]
+        hits = np.zeros(n if any_hit else (n, 4), np.uint32)
+        lib().sim_trace(self.h, rays.ctypes.data, n, hits.ctypes.data, 1 if any_hit else 0,
+                        counters.ctypes.data if counters is not None else None)
+        return hits
+
+    def sampler_stream(self, seed, lb, le, n):
+        out = np.zeros((le - lb, n), np.float32); lib().sim_sampler_stream(seed, lb, le, n, out.ctypes.data); return out
+
+    def sample_rays(self, sensor, seed, spp, lb, le):
+        out = np.zeros((le - lb, 14), np.float32); lib().sim_sample_rays(self.h, sensor, seed, spp, lb, le, out.ctypes.data); return out
+
+    def render_raw(self, sensor, seed, spp, max_depth=6, rr_depth=5, lb=0, le=None):
+        s = self.data.sensors[sensor]; le = s.width * s.height * spp if le is None else le
+        film = np.zeros((s.height, s.width, 4), np.float32)
+        lib().sim_render_accumulate(self.h, sensor, seed, spp, max_depth, rr_depth, lb, le, film.ctypes.data)
+        return film
+
+    def path_records(self, variant, sensor, seed, spp, max_depth, rr_depth, grad_in, lb, le):
+        g = np.ascontiguousarray(grad_in, np.float32); out = np.zeros((le - lb, capi.REC_FLOATS), np.float32)
+        lib().sim_backward(self.h, _vid(variant), sensor, seed, spp, max_depth, rr_depth, g.ctypes.data, lb, le, None, None, out.ctypes.data)
+        return out
+
+    def backward(self, variant, sensor, seed, spp, max_depth, rr_depth, grad_in, lb=0, le=None):
+        s = self.data.sensors[sensor]; le = s.width * s.height * spp if le is None else le
+        g = np.ascontiguousarray(grad_in, np.float32)
+        gp = np.zeros((self.n_vertices, 3), np.float32); gn = np.zeros((self.n_vertices, 3), np.float32)
+        lib().sim_backward(self.h, _vid(variant), sensor, seed, spp, max_depth, rr_depth, g.ctypes.data, lb, le,
+                           gp.ctypes.data, gn.ctypes.data, None)
+        return gp, gn

@@ -1,0 +1,135 @@
+"""Shared parity checks: a backend (the GPU library through the C ABI, or the test-only host harness of the
+same device code) against the CPU oracle on identical seeded inputs.
+
+Bars (BASELINE.json north_star): hit/miss and primitive indices bit-exact; per-path vertex positions and
+gradients within 1e-4 relative; images / accumulated gradients within a stated RMSE."""
+import numpy as np
+
+from epsm_mitsuba3_b200 import capi
+from oracle.calc_grad_ref import calc_grad, scatter_gradients
+
+REL_TOL = 1e-4            # north_star: per-path positions and gradients within 1e-4 relative
+
+
+def random_rays(sd, n, seed=3, finite_fraction=0.5):
+    rng = np.random.default_rng(seed)
+    P = np.concatenate([m.positions for m in sd.meshes]); lo, hi = P.min(0), P.max(0)
+    org = rng.uniform(lo - 0.2 * (hi - lo), hi + 0.2 * (hi - lo), (n, 3)).astype(np.float32)
+    tgt = rng.uniform(lo, hi, (n, 3)); d = tgt - org; d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.zeros((n, 8), np.float32); rays[:, :3] = org; rays[:, 3] = 3.4e38; rays[:, 4:7] = d
+    k = int(n * (1 - finite_fraction))
+    rays[k:, 3] = rng.uniform(0.1, float(np.linalg.norm(hi - lo)), n - k)       # finite maxt (shadow-ray style)
+    return rays
+
+
+def camera_rays(oracle_scene, sensor, seed, spp, n):
+    r = oracle_scene.sample_rays(sensor, seed, spp, 0, n)
+    rays = np.zeros((n, 8), np.float32); rays[:, :3] = r[:, 0:3]; rays[:, 3] = 3.4e38; rays[:, 4:7] = r[:, 3:6]
+    return rays
+
+
+def synthetic_grad_in(res, seed=7):
+    """The matcher stand-in of SURVEY.md §8d: rgb ~ N(0, 0.1), (dx, dy) ~ N(0, 0.02)."""
+    rng = np.random.default_rng(seed)
+    g = np.zeros((res, res, 5), np.float32)
+    g[..., :3] = rng.normal(0, 0.1, (res, res, 3)); g[..., 3:] = rng.normal(0, 0.02, (res, res, 2))
+    return g
+
+
+def n_logged(max_depth):
+    return min(min(max_depth, 6), 5)
+
+
+def check_trace(backend, oracle_scene, rays):
+    """Closest hit (t,u,v,prim) and occlusion must be bit-identical to the brute-force loop over all triangles."""
+    ref = oracle_scene.trace(rays).view(np.uint32)
+    got = np.asarray(backend.trace(rays)).view(np.uint32).reshape(-1, 4)
+    assert np.array_equal(ref[:, 3], got[:, 3]), f"prim index mismatch on {(ref[:, 3] != got[:, 3]).sum()} rays"
+    assert np.array_equal(ref, got), "t/u/v not bit-exact"
+    ref_any = oracle_scene.trace(rays, any_hit=True)
+    got_any = np.asarray(backend.trace(rays, any_hit=True)).view(np.uint32).reshape(-1)
+    assert np.array_equal(ref_any, got_any), "occlusion mismatch"
+    return float((ref[:, 3] != 0xffffffff).mean())
+
+
+def split_records(rec, nl):
+    n = rec.shape[0]
+    v = rec[:, :capi.REC_GRAD_OFF].reshape(n, capi.REC_MAXV, capi.REC_VSTRIDE)[:, :nl]
+    g = rec[:, capi.REC_GRAD_OFF:capi.REC_HEAD_OFF].reshape(n, capi.REC_MAXV, capi.REC_GSTRIDE)[:, :nl]
+    h = rec[:, capi.REC_HEAD_OFF:]
+    return v, g, h
+
+
+def check_path_records(rec, paths, variant, max_depth, min_same=0.999):
+    """Per-path records of the backend vs the oracle's path log + torch calc_grad.
+    Returns statistics; asserts the north_star tolerances on the paths whose prim sequences agree."""
+    nl = n_logged(max_depth)
+    n = rec.shape[0]
+    v, g, h = split_records(rec, nl)
+    pv = paths["v"][:, :nl]
+    act_o, act_s = pv["active"] > 0, v[:, :, 0] > 0
+    prim_o, prim_s = pv["prim"], v[:, :, 1].view(np.uint32)
+    same = (act_o == act_s).all(1) & ((prim_o == prim_s) | ~act_o).all(1)
+    frac_same = float(same.mean())
+    assert frac_same >= min_same, f"only {frac_same:.5f} of the paths follow the oracle's primitive sequence"
+    # vertex positions, barycentrics, flags, NEE state on agreeing paths
+    m = same[:, None] & act_o
+    scale = max(1.0, float(np.abs(pv["p"]).max()))
+    assert np.abs(v[:, :, 2:5] - pv["p"])[m].max(initial=0) <= REL_TOL * scale
+    assert np.abs(v[:, :, 5] - pv["b0"])[m].max(initial=0) <= REL_TOL and np.abs(v[:, :, 6] - pv["b1"])[m].max(initial=0) <= REL_TOL
+    assert np.array_equal(v[:, :, 11].view(np.uint32)[m], pv["bsdf_flags"][m])
+    assert np.array_equal((v[:, :, 7] > 0)[m], (pv["active_em"] > 0)[m])
+    em = m & (pv["active_em"] > 0)
+    assert np.abs(v[:, :, 8:11] - pv["light"])[em].max(initial=0) <= REL_TOL * scale
+    assert np.abs(h[:, 0:3] - paths["cam"]).max() <= REL_TOL * scale and np.abs(h[:, 3:6] - paths["d"]).max() <= REL_TOL
+    assert np.abs(h[:, 6:8] - paths["dlduv"])[same].max(initial=0) <= REL_TOL * max(1e-3, float(np.abs(paths["dlduv"]).max()))
+    assert np.abs(h[:, 11:14] - paths["L"])[same].max(initial=0) <= REL_TOL * max(1.0, float(np.abs(paths["L"]).max()))
+    # gradients: the three lists calc_grad returns
+    pg, lg, dg = calc_grad(paths, variant, nl)
+    stats = dict(frac_same=frac_same, n=n, nonzero=0, max_rel=0.0, flipped=0)
+
+    def cmp(ref, got, name):
+        ref, got = ref[same], got[same]
+        # The ±0.1 outlier filter is a hard threshold (epsm.py:933-944): values within float rounding of it may
+        # fall on either side.  Such components are counted, not compared.
+        edge = (np.abs(np.abs(ref) - 0.1) < 1e-5) | (np.abs(np.abs(got) - 0.1) < 1e-5)
+        flipped = ((ref == 0) != (got == 0)) & edge
+        stats["flipped"] += int(flipped.sum())
+        err = np.abs(ref - got); err[flipped] = 0
+        tol = REL_TOL * np.maximum(np.abs(ref).max(axis=1, keepdims=True), 1e-3)
+        bad = err > tol
+        assert not bad.any(), f"{name}: {int(bad.sum())} components beyond 1e-4 relative (max err {err.max():.3g})"
+        stats["nonzero"] += int((ref != 0).any(1).sum())
+        nz = np.abs(ref).max(axis=1) > 1e-6
+        if nz.any():
+            stats["max_rel"] = max(stats["max_rel"], float((err.max(1)[nz] / np.abs(ref).max(1)[nz]).max()))
+
+    for k in range(nl):
+        for c in range(5):
+            if 5 * k + c < len(pg):
+                cmp(pg[5 * k + c], g[:, k, 3 * c:3 * c + 3], f"path_grad[{5 * k + c}]")
+        cmp(lg[k], g[:, k, 15:18], f"light_grad[{k}]")
+        cmp(dg[k], g[:, k, 18:21], f"diffuse_grad[{k}]")
+    assert stats["flipped"] <= max(2, n // 5000)
+    return stats, (pg, lg, dg)
+
+
+def oracle_gradients(oracle_scene, sd, variant, sensor, seed, spp, max_depth, rr_depth, grad_in):
+    paths = oracle_scene.path_log(sensor, seed, spp, max_depth, rr_depth, grad_in)
+    nl = n_logged(max_depth)
+    pg, lg, dg = calc_grad(paths, variant, nl)
+    return scatter_gradients(paths, variant, nl, pg, lg, dg, sd.n_vertices, max_depth)
+
+
+def check_accumulated(gp, gn, ref_p, ref_n, rmse_rel=1e-4):
+    """Accumulated vertex gradients: float atomics make the order arbitrary ⇒ RMSE relative to the RMS of the reference."""
+    for got, ref, name in ((gp, ref_p, "grad_pos"), (gn, ref_n, "grad_nrm")):
+        got = np.asarray(got, np.float64); rms = float(np.sqrt(np.mean(ref ** 2)))
+        rmse = float(np.sqrt(np.mean((got - ref) ** 2)))
+        assert rmse <= rmse_rel * max(rms, 1e-12) + 1e-9, f"{name}: RMSE {rmse:.3g} vs RMS {rms:.3g}"
+
+
+def check_film(film, ref, rmse_rel=1e-5):
+    film = np.asarray(film, np.float64); ref = ref.astype(np.float64)
+    rms = float(np.sqrt(np.mean(ref ** 2))); rmse = float(np.sqrt(np.mean((film - ref) ** 2)))
+    assert rmse <= rmse_rel * rms, f"film RMSE {rmse:.3g} vs RMS {rms:.3g}"
