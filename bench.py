@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py — gradient-carrying path samples/sec of the EPSM manifold path on N B200s (BASELINE.json metric).
+
+A "step" is one gradient pass (render_backward-equivalent: ray generation, sample_path replay, manifold solve,
+gradient scatter; epsm.py:84-306) over the W·H·spp wavefront of the workload, followed — for N > 1 — by the one
+NCCL allreduce of the mesh-gradient buffer.  Work is sharded across ranks by sample index (strong scaling: the
+total wavefront is fixed, every rank traces spp/N samples of every pixel).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload room|glass|cbox|smpl]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N … bench.py --gpus N …
+
+Prints ONE JSON line (rank 0).  `value` = device-resident inputs, CUDA-event time on the library's stream, max over
+ranks; `e2e` = the same pass through the C ABI with HOST buffers (pinned grad_in H2D, gradient buffers D2H inside
+the timed region); `roofline` = algorithmic traversal bytes of the gradient kernel ÷ its measured duration ÷ the
+measured HBM copy bandwidth; `cpu_baseline` = the CPU oracle (a port of the reference's path; the reference itself
+needs cmake + a CUDA-only torch path and cannot be built from a few files) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (builder kwargs, variant, max_depth, description)
+    "room": dict(variant="manifold", max_depth=8, res=1024, spp=32,
+                 desc="procedural 1M-triangle indoor scene, manifold(_hybrid phase 1), 1024x1024, 32 spp (BASELINE configs[2])"),
+    "glass": dict(variant="manifold_caustic", max_depth=6, res=512, spp=64,
+                  desc="glass icosphere (20480 tris) over diffuse plane + area light, manifold_caustic, 512x512, 64 spp (configs[1])"),
+    "cbox": dict(variant="manifold", max_depth=6, res=128, spp=16, desc="mi.cornell_box() 128x128, 16 spp, manifold (configs[0])"),
+    "smpl": dict(variant="manifold_caustic", max_depth=3, res=512, spp=64,
+                 desc="6890-vertex articulated mesh stage, manifold_caustic, 512x512, 64 spp (configs[3])"),
+}
+
+
+def build_scene(name, res, spp, tris):
+    from epsm_mitsuba3_b200 import scenes as S
+    if name == "room":
+        sd = S.indoor_room(tris, res, spp, res)
+    elif name == "glass":
+        sd = S.glass_sphere_caustic(res, spp, res)
+    elif name == "cbox":
+        sd = S.cornell_box(res, spp, res, box_bsdf=S.Bsdf.conductor())
+    elif name == "smpl":
+        sd = S.articulated_stage(res, spp, res)
+    else:
+        raise SystemExit(f"unknown workload {name}")
+    return sd
+
+
+def synthetic_grad_in(res, seed=7):
+    rng = np.random.default_rng(seed)                      # matcher stand-in of SURVEY.md §8d
+    g = np.zeros((res, res, 5), np.float32)
+    g[..., :3] = rng.normal(0, 0.1, (res, res, 3)); g[..., 3:] = rng.normal(0, 0.02, (res, res, 2))
+    return g
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            v = d.get("hbm_gbs") or d.get("hbm_gb_s")
+            if v:
+                return float(v), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu=0):
+        super().__init__(daemon=True); self.gpu = gpu; self.rows = []; self.stop_evt = threading.Event(); self.proc = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+                if self.stop_evt.is_set():
+                    break
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_evt.set()
+        if self.proc:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(np.max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_port_throughput(sd, wl, grad_in, target_seconds=12.0):
+    """The CPU oracle (port of the reference's path) on a bounded sample of the workload, all host threads."""
+    import torch
+    from oracle import oracle
+    from oracle.calc_grad_ref import calc_grad, scatter_gradients
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    o = oracle.OracleScene(sd, accel=True)
+    sensor, spp, md = 1, wl["spp"], wl["max_depth"]
+    total = sd.sensors[sensor].width * sd.sensors[sensor].height * spp
+    nl = min(min(md, 6), 5)
+
+    def run(n):
+        t0 = time.perf_counter()
+        # a contiguous block of whole pixels from the middle of the image
+        lb = (total // 2 // spp) * spp; le = min(total, lb + n)
+        paths = o.path_log(sensor, 1, spp, md, 5, grad_in, lb, le)
+        pg, lg, dg = calc_grad(paths, wl["variant"], nl)
+        scatter_gradients(paths, wl["variant"], nl, pg, lg, dg, sd.n_vertices, md)
+        return le - lb, time.perf_counter() - t0
+
+    n, dt = run(4096)
+    rate = n / dt
+    n2 = int(min(total // 4, max(4096, rate * target_seconds)))
+    n, dt = run(n2)
+    return {"value": n / dt, "unit": "gradient path samples/s", "cores": cores, "kind": "port",
+            "sample": f"{n} consecutive lanes (whole pixels, image centre) of the same wavefront: oracle path_log (OpenMP, median-split BVH) "
+                      f"+ torch calc_grad + NumPy scatter; {dt:.1f} s"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="room", choices=sorted(WORKLOADS))
+    ap.add_argument("--res", type=int, default=0)
+    ap.add_argument("--spp", type=int, default=0)
+    ap.add_argument("--tris", type=int, default=1_000_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    wl = dict(WORKLOADS[args.workload])
+    if args.res: wl["res"] = args.res
+    if args.spp: wl["spp"] = args.spp
+    res, spp = wl["res"], wl["spp"]
+    config = {"workload": wl["desc"], "scene": args.workload, "integrator": wl["variant"], "max_depth": wl["max_depth"],
+              "resolution": [res, res], "spp": spp, "paths_per_step": res * res * spp,
+              "sharding": f"sample-index shards over {world} rank(s) + 1 NCCL allreduce of the vertex-gradient buffer" if world > 1 else "single GPU",
+              "l2": "256 MiB buffer written between timed steps (L2 flush); BVH+triangles of the 1M-tri scene are ~80 MB"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        sd = build_scene(args.workload, res, spp, args.tris)
+        g = synthetic_grad_in(res)
+        vals = []
+        for i in range(args.warmup + args.steps):
+            r = cpu_port_throughput(sd, wl, g, target_seconds=8.0)
+            if i >= args.warmup:
+                vals.append(r)
+        v = float(np.mean([r["value"] for r in vals])) if vals else 0.0
+        r = vals[-1] if vals else {"cores": os.cpu_count(), "kind": "port", "sample": "none"}
+        out = {"impl": "reference", "metric": "gradient path samples/sec", "value": v, "unit": "samples/s", "n_gpus": args.gpus,
+               "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "strong",
+               "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+               "cpu_baseline": {"value": v, "unit": "samples/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+               "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+               "note": "the reference's own path is Python + CUDA-only torch on top of a cmake build (SURVEY F4, §8c) and cannot be compiled from "
+                       "a few source files; this arm times the CPU oracle, a line-by-line port of the same path, on all host cores"}
+        print(json.dumps(out)); return
+
+    import torch
+    import torch.distributed as dist
+    import epsm_mitsuba3_b200 as ep
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    sd = build_scene(args.workload, res, spp, args.tris)
+    scene = ep.Scene(sd, device=local)
+    stats = scene.stats()
+    integ = ep.load_dict({"type": wl["variant"], "max_depth": wl["max_depth"]})
+    sensor = 1                                                # full-resolution sensor; benchmark semantics N_g = W·H·spp
+    g_host = torch.from_numpy(synthetic_grad_in(res)).pin_memory()
+    g_dev = g_host.cuda()
+    s0, s1 = ep.sample_shard(spp, rank, world)
+    my_paths = res * res * (s1 - s0)
+    buf = torch.zeros((2, scene.n_vertices, 3), dtype=torch.float32, device=scene.device)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=scene.device)
+    torch.cuda.synchronize()
+    import ctypes as C
+    cu_stream = scene.stream()
+
+    def step(k, timed):
+        """One gradient pass over this rank's shard (+ allreduce).  Returns device ms of the pass."""
+        buf.zero_(); flush.fill_(k & 0xff)                   # L2 flush, outside the event pair
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(cu_stream)
+        scene.set_sample_range(s0, s1)
+        scene.render_backward_raw(wl["variant"], sensor, 100 + k, spp, integ.max_depth, integ.rr_depth, g_dev, buf[0], buf[1])
+        ev1.record(cu_stream)
+        scene.synchronize()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e2.record(); dist.all_reduce(buf); e3.record(); torch.cuda.synchronize()
+            ms += e2.elapsed_time(e3)
+        return ms
+
+    for k in range(args.warmup):
+        step(k, False)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clk = ClockSampler(local); clk.start()
+    launches0 = scene.launch_count()
+    t_wall0 = time.perf_counter()
+    ms_steps = [step(args.warmup + k, True) for k in range(args.steps)]
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = scene.launch_count() - launches0
+    clocks = clk.finish()
+    ms_total = float(np.sum(ms_steps))
+    if world > 1:
+        t = torch.tensor([ms_total], device=scene.device); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms_total = float(t.item())
+        l = torch.tensor([launches], device=scene.device); dist.all_reduce(l); launches = int(l.item())
+    ms_per_step = ms_total / args.steps
+    total_paths = res * res * spp
+    value = total_paths / (ms_per_step * 1e-3)
+
+    # ---- e2e: the same pass through the C ABI with host buffers (pinned H2D of grad_in, D2H of the gradient buffers)
+    e2e = None
+    if not args.no_e2e:
+        gp_h = torch.zeros((scene.n_vertices, 3), dtype=torch.float32).pin_memory(); gn_h = torch.zeros_like(gp_h).pin_memory()
+        scene.set_sample_range(s0, s1)
+        ts = []
+        for k in range(2 + args.steps):
+            gp_h.zero_(); gn_h.zero_(); flush.fill_(k & 0xff); torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            scene.render_backward_raw(wl["variant"], sensor, 200 + k, spp, integ.max_depth, integ.rr_depth, g_host, gp_h, gn_h)   # returns after D2H
+            if world > 1:
+                b2 = torch.stack([gp_h, gn_h]).cuda(non_blocking=True); dist.all_reduce(b2); gp_h.copy_(b2[0]); torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if k >= 2:
+                ts.append(dt)
+        te = float(np.mean(ts))
+        if world > 1:
+            t = torch.tensor([te], device=scene.device); dist.all_reduce(t, op=dist.ReduceOp.MAX); te = float(t.item())
+        h2d = g_host.numel() * 4 + 2 * gp_h.numel() * 4; d2h = 2 * gp_h.numel() * 4
+        e2e = {"value": total_paths / te, "unit": "samples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": te * 1e3}
+    scene.set_sample_range(s0, s1)
+
+    # ---- roofline of the dominant kernel (k_backward): algorithmic traversal bytes from the instrumented kernel
+    cnt = np.zeros(4, np.uint64)
+    buf.zero_(); torch.cuda.synchronize()
+    scene.render_backward_raw(wl["variant"], sensor, 100 + args.warmup, spp, integ.max_depth, integ.rr_depth, g_dev, buf[0], buf[1], counters=cnt)
+    scene.synchronize()
+    nodes, tris, rays, lanes = (int(x) for x in cnt)
+    alg_bytes = nodes * stats["node_bytes"] + tris * stats["tri_bytes"] + rays * 48
+    kern_ms = float(np.mean(ms_steps)) if world == 1 else None
+    peak, peak_src = peaks()
+    roof = None
+    if rank == 0:
+        k_ms = float(np.mean(ms_steps))                       # this rank's kernel time (allreduce excluded when world == 1)
+        ach = alg_bytes / (k_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get(args.workload)
+            except Exception:
+                traffic = None
+        roof = {"bound": "hbm", "kernel": "k_backward", "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                "frac": ach / peak, "traffic": traffic,
+                "algorithmic_bytes_per_launch": alg_bytes, "per_path": {"rays": rays / max(lanes, 1), "nodes": nodes / max(lanes, 1),
+                                                                         "tris": tris / max(lanes, 1), "bytes": alg_bytes / max(lanes, 1)},
+                "definition": "nodes_fetched*128 + tris_tested*48 + rays*(32+16) bytes per launch (SURVEY §8d), counted by the instrumented "
+                              "kernel on the same seed; cache hits are not subtracted"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            cpu = cpu_port_throughput(sd, wl, synthetic_grad_in(res))
+        except Exception as e:                                # the baseline leg must not take the bench line down
+            cpu = {"value": None, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
+
+    if rank == 0:
+        out = {"metric": "gradient path samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+               "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+               "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
+               "roofline": roof, "cpu_baseline": cpu,
+               "scene": {"triangles": int(stats["n_triangles"]), "vertices": int(stats["n_vertices"]), "bvh_nodes": int(stats["n_nodes"]),
+                         "bvh_build_ms": stats["build_ms"]},
+               "wall_s_timed_region": t_wall}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

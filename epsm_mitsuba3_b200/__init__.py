@@ -8,8 +8,8 @@ generators (`scenes`) and the hybrid schedule helper (`schedule`).
 from . import capi, scenes  # noqa: F401
 from .engine import (EpsmError, Scene, SceneParameters, EPSMIntegrator, ManifoldIntegrator,  # noqa: F401
                      ManifoldCausticIntegrator, load_dict, register_integrator, traverse, render,
-                     sample_tea_32, band_lanes)
+                     sample_tea_32, band_lanes, sample_shard)
 
 __all__ = ["capi", "scenes", "EpsmError", "Scene", "SceneParameters", "EPSMIntegrator", "ManifoldIntegrator",
            "ManifoldCausticIntegrator", "load_dict", "register_integrator", "traverse", "render", "sample_tea_32",
-           "band_lanes"]
+           "band_lanes", "sample_shard"]

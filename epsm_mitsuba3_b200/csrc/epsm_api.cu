@@ -41,6 +41,7 @@ struct epsm_ctx {
     std::string error;
     uint64_t launches = 0;
     bool have_scene = false, dirty = false;
+    uint32_t s_begin = 0, s_end = 0;                // sample-range shard (0,0 = all)
     HostScene hs;                                   // host mirror (positions are needed for BVH rebuilds)
     std::vector<uint8_t> mesh_dirty;
     // device
@@ -113,6 +114,11 @@ int make_launch(epsm_ctx *ctx, uint32_t sensor, uint32_t seed, uint32_t spp, uin
     if (lane_begin > lane_end) return fail(ctx, EPSM_E_INVALID, "lane_begin > lane_end");
     ln.seed = seed; ln.spp = spp; ln.max_depth = max_depth; ln.rr_depth = rr_depth;
     ln.lane_begin = lane_begin; ln.lane_end = lane_end; ln.variant = variant; ln.tile_y0 = ln.tile_y1 = 0;
+    ln.s_begin = 0; ln.s_end = spp;
+    if (ctx->s_end != 0) {
+        if (ctx->s_begin > ctx->s_end || ctx->s_end > spp) return fail(ctx, EPSM_E_INVALID, "sample range exceeds spp");
+        ln.s_begin = ctx->s_begin; ln.s_end = ctx->s_end;
+    }
     return EPSM_OK;
 }
 
@@ -388,6 +394,13 @@ int epsm_scene_get_stats(epsm_ctx *ctx, epsm_scene_stats *out) {
     out->n_nodes = ctx->hs.bvh.nodes.size() / EPSM_NODE_F4;
     out->node_bytes = EPSM_NODE_F4 * 16; out->tri_bytes = EPSM_TRI_F4 * 16; out->bvh_width = 4; out->max_leaf = EPSM_MAX_LEAF;
     out->build_ms = ctx->hs.bvh.build_ms;
+    return EPSM_OK;
+}
+
+int epsm_set_sample_range(epsm_ctx *ctx, uint32_t s_begin, uint32_t s_end) {
+    if (!ctx) return EPSM_E_INVALID;
+    if (s_begin > s_end) return fail(ctx, EPSM_E_INVALID, "s_begin > s_end");
+    ctx->s_begin = s_begin; ctx->s_end = s_end;
     return EPSM_OK;
 }
 

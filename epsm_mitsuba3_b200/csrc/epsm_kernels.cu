@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(CTA) k_render(DScene sc, DLaunch ln, float *__
     uint32_t lanes = 0;
     if (px < W && py < H) {
         const uint64_t pixel = (uint64_t) py * W + px;
-        for (uint32_t s = slot; s < ln.spp; s += CTA / 32) {
+        for (uint32_t s = ln.s_begin + slot; s < ln.s_end; s += CTA / 32) {
             const uint64_t lane = pixel * ln.spp + s;
             if (lane < ln.lane_begin || lane >= ln.lane_end) continue;
             Pcg rng = pcg_for_lane(ln.seed, (uint32_t) lane);
@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(CTA) k_backward(DScene sc, DLaunch ln, const f
     if (px < W && py < H) {
         const uint64_t pixel = (uint64_t) py * W + px;
         const float gx = grad_in[pixel * 5 + 3], gy = grad_in[pixel * 5 + 4];
-        for (uint32_t s = slot; s < ln.spp; s += CTA / 32) {
+        for (uint32_t s = ln.s_begin + slot; s < ln.s_end; s += CTA / 32) {
             const uint64_t lane = pixel * ln.spp + s;
             if (lane < ln.lane_begin || lane >= ln.lane_end) continue;
             Pcg rng = pcg_for_lane(ln.seed, (uint32_t) lane);

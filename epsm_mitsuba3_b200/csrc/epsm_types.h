@@ -74,5 +74,6 @@ struct DLaunch {
     uint32_t seed, spp, max_depth, rr_depth;
     uint64_t lane_begin, lane_end;
     uint32_t tile_y0, tile_y1;   // tile rows covered by this launch
+    uint32_t s_begin, s_end;     // sample slots of each pixel handled by this launch (multi-GPU sharding)
     int variant;
 };

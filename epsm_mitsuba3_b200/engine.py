@@ -50,6 +50,12 @@ def _dist():
     return None
 
 
+def sample_shard(spp: int, rank: int, world: int):
+    """Sample-index shard of `rank`: samples [s0, s1) of every pixel (epsm_set_sample_range).  Balanced by
+    construction (every rank sees every pixel) and exact: the union over ranks is the single-GPU wavefront."""
+    return (spp * rank) // world, (spp * (rank + 1)) // world
+
+
 def band_lanes(height: int, width: int, spp: int, rank: int, world: int):
     """Scanline band of `rank`: whole tile rows, so that band g owns rows [y0, y1).
     Each lane's random stream depends only on (seed, global lane index), so sharding is exact."""
@@ -117,6 +123,9 @@ class Scene:
 
     def sensors(self):
         return self.data.sensors
+
+    def set_sample_range(self, s_begin: int = 0, s_end: int = 0):
+        self._check(self.lib.epsm_set_sample_range(self.ctx, s_begin, s_end))
 
     # ---- scene updates ---------------------------------------------------------------------
     def update_vertices(self, mesh_id: int, positions, commit: bool = True):
@@ -256,12 +265,14 @@ class EPSMIntegrator:
         if dist is None:
             scene.render_accumulate(sensor, seed, spp, self.max_depth, self.rr_depth)
         else:
-            lb, le = band_lanes(s.height, s.width, spp, dist.get_rank(), dist.get_world_size())
-            if le > lb:
-                scene.render_accumulate(sensor, seed, spp, self.max_depth, self.rr_depth, lb, le)
+            s0, s1 = sample_shard(spp, dist.get_rank(), dist.get_world_size())
+            if s1 > s0:
+                scene.set_sample_range(s0, s1)
+                scene.render_accumulate(sensor, seed, spp, self.max_depth, self.rr_depth)
+                scene.set_sample_range(0, 0)
             film = scene.film_raw(sensor)
             scene.synchronize()
-            dist.all_reduce(film)                     # bands overlap by the filter radius: sum the RGBW film
+            dist.all_reduce(film)                     # every rank splatted its samples of every pixel: sum the RGBW film
             torch.cuda.current_stream(scene.device).synchronize()
         self.primal_image = scene.film_develop(sensor)
         scene.synchronize()
@@ -286,11 +297,13 @@ class EPSMIntegrator:
     def backward_buffers(self, scene: Scene, g: torch.Tensor, sensor: int, seed: int, spp: int):
         s = scene.sensors()[sensor]
         dist = _dist()
-        lb, le = (0, 0) if dist is None else band_lanes(s.height, s.width, spp, dist.get_rank(), dist.get_world_size())
+        s0, s1 = (0, spp) if dist is None else sample_shard(spp, dist.get_rank(), dist.get_world_size())
         buf = torch.zeros((2, scene.n_vertices, 3), dtype=torch.float32, device=scene.device)
         torch.cuda.current_stream(scene.device).synchronize()
-        if dist is None or le > lb:
-            scene.render_backward_raw(self.variant, sensor, seed, spp, self.max_depth, self.rr_depth, g, buf[0], buf[1], lb, le)
+        if s1 > s0:
+            scene.set_sample_range(s0, s1)
+            scene.render_backward_raw(self.variant, sensor, seed, spp, self.max_depth, self.rr_depth, g, buf[0], buf[1])
+            scene.set_sample_range(0, 0)
         scene.synchronize()
         if dist is not None:
             dist.all_reduce(buf)                        # one NCCL allreduce of the mesh-gradient buffer per step

@@ -366,11 +366,11 @@ def indoor_room(n_tris_target: int = 1_000_000, res: int = 1024, spp: int = 32, 
     rng = np.random.default_rng(seed)
     sd = SceneData(name=f"indoor_room_{n_tris_target}")
     scale = max(n_tris_target / 1_000_000.0, 1e-4)
-    n_wall = max(2, int(round(256 * math.sqrt(scale))))           # 6 walls × 2·n² tris (786k at n=256)
-    n_obj = max(4, int(round(64 * min(1.0, scale * 4))))
+    n_wall = max(2, int(round(256 * math.sqrt(scale))))           # 6 walls × 2·n² tris (786 432 at n = 256)
     wall_tris = 6 * 2 * n_wall * n_wall
-    per_obj = max(20, (n_tris_target - wall_tris) / n_obj)
-    obj_sub = int(np.clip(round(math.log(per_obj / 20.0, 4)), 0, 6))
+    remaining = max(80, n_tris_target - wall_tris - 32)           # 4 lights × 8 tris
+    obj_sub = int(np.clip(math.floor(math.log(max(remaining / 4 / 20.0, 1.0), 4)), 0, 3))
+    n_obj = max(4, int(round(remaining / (20 * 4 ** obj_sub))))   # 167 level-3 icospheres for the 1M target
     white = sd.add_bsdf(Bsdf.diffuse((0.8, 0.8, 0.8)))
     black = sd.add_bsdf(Bsdf.diffuse((0.0, 0.0, 0.0)))
     S = 4.0   # half-extent of the room (x,y) ; height 0..4

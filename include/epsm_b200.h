@@ -188,6 +188,12 @@ int epsm_sampler_stream(epsm_ctx *ctx, uint32_t seed, uint64_t lane_begin, uint6
 int epsm_sample_rays(epsm_ctx *ctx, uint32_t sensor, uint32_t seed, uint32_t spp,
                      uint64_t lane_begin, uint64_t lane_end, float *out, int mem);
 
+/* Multi-GPU sharding by sample index: restrict render / backward launches of this context to the samples
+ * s ∈ [s_begin, s_end) of every pixel (lane = pixel·spp + s, common.py:326-343).  Every rank then sees every
+ * pixel, so the load is balanced, and the union over ranks is exactly the single-GPU wavefront because a
+ * lane's random stream depends only on (seed, lane) (sampler.cpp:122-130).  (0, 0) = all samples (default). */
+int epsm_set_sample_range(epsm_ctx *ctx, uint32_t s_begin, uint32_t s_end);
+
 /* Scene statistics for the roofline accounting: bytes per BVH node / triangle record, counts. */
 typedef struct epsm_scene_stats {
     uint64_t n_triangles, n_vertices, n_nodes;

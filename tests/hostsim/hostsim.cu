@@ -17,7 +17,7 @@ inline void bind(TStack &st, LocalStack &ls) { st.s_ref = ls.ref; st.s_t = ls.t;
 
 DLaunch make_launch(const sim_scene *s, uint32_t sensor, uint32_t seed, uint32_t spp, uint32_t max_depth, uint32_t rr_depth, int variant) {
     DLaunch ln; memset(&ln, 0, sizeof(ln));
-    ln.sensor = s->hs.sensors[sensor]; ln.seed = seed; ln.spp = spp; ln.max_depth = max_depth; ln.rr_depth = rr_depth; ln.variant = variant;
+    ln.sensor = s->hs.sensors[sensor]; ln.seed = seed; ln.spp = spp; ln.max_depth = max_depth; ln.rr_depth = rr_depth; ln.variant = variant; ln.s_begin = 0; ln.s_end = spp;
     return ln;
 }
 void add3(float *buf, uint32_t idx, f3 v, bool pred) { if (!pred) return; buf[3 * idx] += v.x; buf[3 * idx + 1] += v.y; buf[3 * idx + 2] += v.z; }
