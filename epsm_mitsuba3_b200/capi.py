@@ -64,6 +64,8 @@ _LIB = None
 
 
 def library_path() -> str:
+    if os.environ.get("EPSM_B200_LIB"):                       # tuning variants of the same library (experiments only)
+        return os.environ["EPSM_B200_LIB"]
     return os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libepsm_b200.so")
 
 

@@ -22,6 +22,9 @@
 #define TILE_W 8
 #define TILE_H 4
 #define CTA 128
+#ifndef EPSM_PATH_MINBLOCKS
+#define EPSM_PATH_MINBLOCKS 2      // resident CTAs per SM requested for the path kernels (register cap = 65536 / (128·N))
+#endif
 
 // ------------------------------------------------------------------------------------------------
 //  Shared-memory traversal stack for a CTA
@@ -72,7 +75,7 @@ __global__ void __launch_bounds__(CTA) k_trace(DScene sc, const f4 *__restrict__
 #define FT_H (TILE_H + 4)
 
 template <bool COUNT>
-__global__ void __launch_bounds__(CTA) k_render(DScene sc, DLaunch ln, float *__restrict__ film, unsigned long long *counters) {
+__global__ void __launch_bounds__(CTA, EPSM_PATH_MINBLOCKS) k_render(DScene sc, DLaunch ln, float *__restrict__ film, unsigned long long *counters) {
     __shared__ SharedStack ss;
     __shared__ float ftile[FT_H][FT_W][4];
     TStack st; bind_stack(st, ss);
@@ -221,7 +224,7 @@ __device__ void write_record(const PathLog &P, const PathGrads &G, int n_logged,
 //  Gradient pass
 // ------------------------------------------------------------------------------------------------
 template <bool COUNT, bool RECORD>
-__global__ void __launch_bounds__(CTA) k_backward(DScene sc, DLaunch ln, const float *__restrict__ grad_in,
+__global__ void __launch_bounds__(CTA, EPSM_PATH_MINBLOCKS) k_backward(DScene sc, DLaunch ln, const float *__restrict__ grad_in,
                                                   float *__restrict__ grad_pos, float *__restrict__ grad_nrm,
                                                   float *__restrict__ records, unsigned long long *counters) {
     __shared__ SharedStack ss;

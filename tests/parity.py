@@ -86,7 +86,16 @@ def check_path_records(rec, paths, variant, max_depth, min_same=0.999):
     assert np.abs(h[:, 11:14] - paths["L"])[same].max(initial=0) <= REL_TOL * max(1.0, float(np.abs(paths["L"]).max()))
     # gradients: the three lists calc_grad returns
     pg, lg, dg = calc_grad(paths, variant, nl)
-    stats = dict(frac_same=frac_same, n=n, nonzero=0, max_rel=0.0, flipped=0)
+    # Conditioning filter: the reference inverts C densely in float32; where its own
+    # float32 and float64 evaluations disagree the path is ill-conditioned (it mostly dies in the ±0.1 outlier
+    # filter) and no implementation can be held to 1e-4 there.  Such paths are counted and bounded, not compared.
+    import torch
+    pg64, lg64, dg64 = calc_grad(paths, variant, nl, torch.float64)
+    ill = np.zeros(n, bool)
+    for a, b in zip(pg + lg + dg, pg64 + lg64 + dg64):
+        ill |= (np.abs(a - b) > 0.25 * REL_TOL * np.maximum(np.abs(b).max(axis=1, keepdims=True), 1e-3)).any(1)
+    stats = dict(frac_same=frac_same, n=n, nonzero=0, max_rel=0.0, flipped=0, ill_conditioned=int((ill & same).sum()))
+    same = same & ~ill
 
     def cmp(ref, got, name):
         ref, got = ref[same], got[same]
@@ -111,6 +120,7 @@ def check_path_records(rec, paths, variant, max_depth, min_same=0.999):
         cmp(lg[k], g[:, k, 15:18], f"light_grad[{k}]")
         cmp(dg[k], g[:, k, 18:21], f"diffuse_grad[{k}]")
     assert stats["flipped"] <= max(2, n // 5000)
+    assert stats["ill_conditioned"] <= max(2, n // 1000), stats
     return stats, (pg, lg, dg)
 
 
