@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
@@ -50,6 +51,7 @@ struct epsm_ctx {
     std::vector<DevBuf<float>> d_films;
     DevBuf<float> stage_a, stage_b, stage_c;        // device staging for host-memory calls
     DevBuf<unsigned long long> d_counters;
+    DevBuf<unsigned char> d_workspace; uint32_t wf_capacity = 0, trace_grid = 0;   // wavefront workspace (one chunk of lanes)
     DScene sc;
 };
 
@@ -100,6 +102,19 @@ int zero_counters(epsm_ctx *ctx) {
     return EPSM_OK;
 }
 
+// Workspace for one chunk of the wavefront: at most EPSM_WF_CHUNK lanes (default 2^22 ≈ 6 GB of the 180 GB HBM).
+int ensure_workspace(epsm_ctx *ctx, uint64_t lanes) {
+    uint64_t cap = 1ull << 22;
+    if (const char *e = getenv("EPSM_WF_CHUNK")) { uint64_t v = strtoull(e, nullptr, 10); if (v >= 1024) cap = v; }
+    if (lanes < cap) cap = (lanes + 1023) & ~1023ull;
+    if (cap < 1024) cap = 1024;
+    if (ctx->wf_capacity >= cap && ctx->d_workspace.p) return EPSM_OK;
+    CK(cudaStreamSynchronize(ctx->stream), "workspace sync");
+    CK(ctx->d_workspace.alloc(epsm_wf_workspace_bytes((uint32_t) cap)), "workspace alloc");
+    ctx->wf_capacity = (uint32_t) cap;
+    return EPSM_OK;
+}
+
 int make_launch(epsm_ctx *ctx, uint32_t sensor, uint32_t seed, uint32_t spp, uint32_t max_depth, uint32_t rr_depth,
                 uint64_t lane_begin, uint64_t lane_end, int variant, DLaunch &ln) {
     if (!ctx->have_scene) return fail(ctx, EPSM_E_NOSCENE, "no scene uploaded");
@@ -139,6 +154,8 @@ int epsm_create(int device, epsm_ctx **out) {
     e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete c; return fail(nullptr, EPSM_E_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e)); }
     memset(&c->sc, 0, sizeof(c->sc));
+    cudaDeviceProp prop; cudaGetDeviceProperties(&prop, device);
+    c->trace_grid = (uint32_t) prop.multiProcessorCount * 8u;        // persistent traversal CTAs: 148 SMs × 8 resident CTAs of 128 threads (≤ 64 regs)
     *out = c; return EPSM_OK;
 }
 
@@ -149,7 +166,7 @@ int epsm_destroy(epsm_ctx *ctx) {
     ctx->d_nodes.release(); ctx->d_tris.release(); ctx->d_pos.release(); ctx->d_nrm.release(); ctx->d_cdf.release(); ctx->d_pmf.release();
     ctx->d_faces.release(); ctx->d_face_mesh.release(); ctx->d_meshes.release(); ctx->d_bsdfs.release(); ctx->d_emitters.release();
     for (auto &f : ctx->d_films) f.release();
-    ctx->stage_a.release(); ctx->stage_b.release(); ctx->stage_c.release(); ctx->d_counters.release();
+    ctx->stage_a.release(); ctx->stage_b.release(); ctx->stage_c.release(); ctx->d_counters.release(); ctx->d_workspace.release();
     cudaStreamDestroy(ctx->stream);
     delete ctx; return EPSM_OK;
 }
@@ -319,8 +336,12 @@ int epsm_render_backward(epsm_ctx *ctx, int variant, uint32_t sensor, uint32_t s
         CK(cudaMemcpyAsync(d_gn, grad_nrm, n_v * sizeof(float), cudaMemcpyHostToDevice, ctx->stream), "H2D grad_nrm");
     }
     if (counters) { rc = zero_counters(ctx); if (rc) return rc; }
-    CK(epsm_launch_backward(ctx->sc, ln, d_gin, d_gp, d_gn, nullptr, counters ? ctx->d_counters.p : nullptr, ctx->stream), "k_backward");
-    ctx->launches += 1;
+    {
+        const uint64_t S = (uint64_t) (ln.s_end - ln.s_begin);
+        rc = ensure_workspace(ctx, (uint64_t) ((ln.sensor.w + 7) / 8) * ((ln.sensor.h + 3) / 4) * 32ull * S); if (rc) return rc;
+    }
+    CK(epsm_launch_backward(ctx->sc, ln, d_gin, d_gp, d_gn, nullptr, counters ? ctx->d_counters.p : nullptr, ctx->d_workspace.p, ctx->wf_capacity,
+                            ctx->trace_grid, &ctx->launches, ctx->stream), "wavefront backward");
     if (mem == EPSM_MEM_HOST) {
         CK(cudaMemcpyAsync(grad_pos, d_gp, n_v * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream), "D2H grad_pos");
         CK(cudaMemcpyAsync(grad_nrm, d_gn, n_v * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream), "D2H grad_nrm");
@@ -343,8 +364,12 @@ int epsm_path_records(epsm_ctx *ctx, int variant, uint32_t sensor, uint32_t seed
     float *d_rec = records;
     if (mem == EPSM_MEM_HOST) { CK(ctx->stage_b.alloc(n_rec), "stage alloc"); d_rec = ctx->stage_b.p; }
     CK(cudaMemsetAsync(d_rec, 0, n_rec * sizeof(float), ctx->stream), "records memset");
-    CK(epsm_launch_backward(ctx->sc, ln, d_gin, nullptr, nullptr, d_rec, nullptr, ctx->stream), "k_backward(records)");
-    ctx->launches += 1;
+    {
+        const uint64_t S = (uint64_t) (ln.s_end - ln.s_begin);
+        rc = ensure_workspace(ctx, (uint64_t) ((ln.sensor.w + 7) / 8) * ((ln.sensor.h + 3) / 4) * 32ull * S); if (rc) return rc;
+    }
+    CK(epsm_launch_backward(ctx->sc, ln, d_gin, nullptr, nullptr, d_rec, nullptr, ctx->d_workspace.p, ctx->wf_capacity, ctx->trace_grid,
+                            &ctx->launches, ctx->stream), "wavefront backward (records)");
     if (mem == EPSM_MEM_HOST) {
         CK(cudaMemcpyAsync(records, d_rec, n_rec * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream), "D2H records");
         CK(cudaStreamSynchronize(ctx->stream), "records sync");

@@ -663,7 +663,7 @@ EPSM_HDN f3 path_primal(const DScene &sc, Tracer &tr, Ray ray, Pcg &rng, uint32_
 //  memory, then the manifold solve, then the scatter seeds.
 // ------------------------------------------------------------------------------------------------
 struct VLog {
-    bool active, active_em, direct_valid, direct_any, direct_grad;
+    bool active, active_em, direct_valid, direct_any, direct_grad, direct_traced;
     uint32_t flags, ismesh, mesh_flags, has_normals, prim;
     uint32_t fi[3], dfi[3];
     float bw[3], dbw[3];
@@ -675,99 +675,154 @@ struct PathLog {
     VLog v[EPSM_MAXV];
 };
 
+// Per-lane path state that persists between the wavefront stages (k_wf_* in epsm_kernels.cu).  The stages are
+// cut exactly where sample_path queries the scene, so the trace kernels run between them on compacted queues:
+//
+//   wf_begin → [closest: path ray] → wf_stage_a → [any-hit: shadow ray] → wf_stage_b → [closest: direct ray ∥ next path ray] → …
+//
+// The random-number draw order is that of epsm.py:503-742 (2 emitter + 3 discarded + 3 kept + 1 RR per bounce).
+struct WfState {
+    Pcg rng;
+    Ray ray;                      // current path ray
+    f3 beta, L, prev_p, grad_d;
+    float eta, prev_pdf;
+    uint32_t depth;
+    bool active, prev_delta;
+    // stage A → stage B
+    bool active_next, smooth, need_shadow;
+    DSamp ds; f3 em_weight;
+    Ray shadow_ray;
+};
+
+EPSM_HDN void wf_begin(const DSensor &sensor, uint32_t px, uint32_t py, uint32_t seed, uint32_t lane, float gx, float gy, WfState &S, PathLog &P) {
+    S.rng = pcg_for_lane(seed, lane);
+    CamRay c; camera_ray(sensor, px, py, S.rng, c);
+    S.ray = c.ray;
+    S.grad_d = (c.d_x - c.ray.d) * gx + (c.d_y - c.ray.d) * gy;                    // pixel motion → tangent of ray.d (epsm.py:250-257)
+    S.beta = mk3(1, 1, 1); S.L = mk3(0, 0, 0); S.prev_p = mk3(0, 0, 0); S.eta = 1.f; S.prev_pdf = 1.f; S.depth = 0;
+    S.active = true; S.prev_delta = true; S.active_next = S.smooth = S.need_shadow = false;
+    P.cam = c.ray.o; P.d = c.ray.d; P.dlduv0 = P.dlduv1 = 0.f; P.dldp1 = mk3(0, 0, 0); P.L = mk3(0, 0, 0);
+}
+
+// After the closest hit `h` of S.ray: surface interaction, first-hit tangents, emission, emitter sampling up to
+// (not including) its visibility test.  Returns true when S.shadow_ray must be tested.
+EPSM_HDN bool wf_stage_a(const DScene &sc, WfState &S, PathLog &P, const Hit &h_in, uint32_t it, uint32_t max_depth_prop) {
+    Hit h = h_in;
+    if (!S.active) { h.t = INFINITY; h.u = h.v = 0.f; h.prim = 0xffffffffu; }
+    SI si; compute_si(sc, S.ray, h, si);
+    if (it == 0 && si.valid) {
+        // forward-mode derivative of the first hit w.r.t. ray.d with the triangle detached (epsm.py:263-270)
+        f3 p0 = ld3(sc.pos, si.fi[0]), e1 = ld3(sc.pos, si.fi[1]) - p0, e2 = ld3(sc.pos, si.fi[2]) - p0;
+        f3 pvec = cross3(S.ray.d, e2), tvec = S.ray.o - p0, qvec = cross3(tvec, e1);
+        float det = dot3(e1, pvec), inv_det = 1.f / det;
+        f3 dpvec = cross3(S.grad_d, e2);
+        float ddet = dot3(e1, dpvec), dinv = -ddet * inv_det * inv_det;
+        float du = dot3(tvec, dpvec) * inv_det + dot3(tvec, pvec) * dinv;
+        float dv = dot3(S.grad_d, qvec) * inv_det + dot3(S.ray.d, qvec) * dinv;
+        if (si.ismesh) { P.dlduv0 = -(du + dv); P.dlduv1 = du; }                   // b0 = 1-u-v, b1 = u
+        P.dldp1 = e1 * du + e2 * dv;
+    }
+    float em_pdf = pdf_emitter_direction(sc, si, S.prev_p, !S.prev_delta);
+    float mis = mis_weight(S.prev_pdf, em_pdf);
+    f3 Le = S.beta * mis * emitter_eval(sc, si);
+    S.L = S.L + Le;
+    S.active_next = (S.depth + 1 < max_depth_prop) && si.valid;
+    uint32_t flags = si.valid ? sc.bsdfs[si.bsdf].bflags : 0u;
+    S.smooth = S.active_next && (flags & EPSM_BF_SMOOTH);
+    float e1r = pcg_f32(S.rng), e2r = pcg_f32(S.rng);
+    S.need_shadow = false;
+    // the visibility query is deferred: record the shadow ray, assume visible, fix up in stage B (scene.cpp:259-263)
+    sample_emitter_direction(sc, si, e1r, e2r, S.smooth, S.ds, S.em_weight, [&](const Ray &r) { S.shadow_ray = r; S.need_shadow = true; return false; });
+    return S.need_shadow;
+}
+
+// After the visibility test: NEE contribution, the two BSDF samples, the vertex log, the ray towards the light
+// sample (returned in `direct`, traced later as a closest-hit query) and the next path ray.
+EPSM_HDN void wf_stage_b(const DScene &sc, WfState &S, PathLog &P, const Hit &h_in, bool occluded, uint32_t it, uint32_t rr_depth,
+                         Ray &direct, bool &direct_valid) {
+    Hit h = h_in;
+    if (!S.active) { h.t = INFINITY; h.u = h.v = 0.f; h.prim = 0xffffffffu; }
+    SI si; compute_si(sc, S.ray, h, si);
+    DBsdf b; uint32_t flags = 0;
+    if (si.valid) { b = sc.bsdfs[si.bsdf]; flags = b.bflags; }
+    if (S.need_shadow && occluded) { S.em_weight = mk3(0, 0, 0); S.ds.pdf = 0.f; }
+    bool active_em = S.smooth && S.ds.pdf != 0.f;
+    f3 Lr_dir = mk3(0, 0, 0), dir_to_light = mk3(0, 0, 0);
+    if (S.smooth) dir_to_light = norm3(S.ds.p - si.p);                             // epsm.py:596
+    if (active_em) {
+        // Backward mode re-evaluates the emitter for the recomputed direction (epsm.py:596-598)
+        f3 em_val = dot3(dir_to_light, S.ds.n) < 0.f ? a3(sc.emitters[S.ds.emitter].radiance) : mk3(0, 0, 0);
+        f3 emw = em_val * (1.0f / S.ds.pdf);
+        f3 wo = to_local(si, dir_to_light); f3 val; float bpdf;
+        bsdf_eval_pdf(b, si.wi, wo, val, bpdf);
+        Lr_dir = S.beta * mis_weight(S.ds.pdf, bpdf) * val * emw;
+    }
+    pcg_f32(S.rng); pcg_f32(S.rng); pcg_f32(S.rng);                                // discarded detached sample (epsm.py:633-636)
+    float s1 = pcg_f32(S.rng), s2x = pcg_f32(S.rng), s2y = pcg_f32(S.rng);
+    BSample bs; bs.wo = bs.hf = bs.weight = mk3(0, 0, 0); bs.pdf = 0.f; bs.eta = 0.f; bs.type = 0;
+    if (si.valid) bsdf_sample(b, si.wi, s1, s2x, s2y, S.active_next, bs);
+    direct_valid = false;
+    if (it < EPSM_MAXV) {                                                          // epsm.py:648-654
+        VLog &v = P.v[it];
+        v.active = S.active && si.valid; v.flags = flags; v.ismesh = si.ismesh; v.light = S.ds.p; v.active_em = active_em;
+        v.p0 = si.p0; v.p1 = si.p1; v.p2 = si.p2; v.p = si.p; v.b0 = si.b0; v.b1 = si.b1;
+        v.n0 = si.n0; v.n1 = si.n1; v.n2 = si.n2; v.eta = bs.eta; v.hf = bs.hf;
+        v.prim = si.prim; v.mesh_flags = si.mesh_flags; v.has_normals = si.has_normals;
+        for (int k = 0; k < 3; ++k) { v.fi[k] = si.fi[k]; v.bw[k] = si.bw[k]; v.dfi[k] = 0; v.dbw[k] = 0.f; }
+        v.lr_sum = Lr_dir.x + Lr_dir.y + Lr_dir.z;
+        v.direct_valid = v.direct_any = v.direct_grad = false; v.dis = 0.f;
+        v.direct_traced = S.smooth;
+        if (S.smooth) { direct = spawn_ray(si, dir_to_light); direct_valid = true; }    // si_direct, epsm.py:609-625
+    }
+    S.L = S.L + Lr_dir;
+    if (si.valid) S.ray = spawn_ray(si, to_world(si, bs.wo));
+    S.eta *= bs.eta; S.beta = S.beta * bs.weight;
+    S.prev_p = si.p; S.prev_pdf = bs.pdf; S.prev_delta = (bs.type & EPSM_BF_DELTA) != 0;
+    float bmax = max3(S.beta);
+    bool active_next = S.active_next && bmax != 0.f;
+    float rr_prob = fminf(bmax * S.eta * S.eta, .95f);
+    bool rr_active = S.depth >= rr_depth;
+    if (rr_active) S.beta = S.beta * rcp_e(rr_prob);
+    bool rr_continue = pcg_f32(S.rng) < rr_prob;
+    active_next = active_next && (!rr_active || rr_continue);
+    if (si.valid) S.depth += 1;
+    S.active = active_next;
+}
+
+// Closest hit of the ray towards the light sample (FollowShape): barycentric weights on the hit triangle, the
+// shadow-term distance ratio of epsm.py:614-615.
+EPSM_HDN void wf_direct_hit(const DScene &sc, VLog &v, const Hit &hd) {
+    if (hd.prim == 0xffffffffu) return;
+    const uint32_t g0 = sc.faces[3 * hd.prim], g1 = sc.faces[3 * hd.prim + 1], g2 = sc.faces[3 * hd.prim + 2];
+    const float w1 = hd.u, w2 = hd.v, w0 = 1.f - w1 - w2;
+    f3 q = fma3(ld3(sc.pos, g0), w0, fma3(ld3(sc.pos, g1), w1, ld3(sc.pos, g2) * w2));
+    v.direct_any = true; v.direct_valid = v.active_em;
+    v.direct_grad = (sc.meshes[sc.face_mesh[hd.prim]].flags & EPSM_MESH_GRAD) != 0;
+    v.dfi[0] = g0; v.dfi[1] = g1; v.dfi[2] = g2; v.dbw[0] = w0; v.dbw[1] = w1; v.dbw[2] = w2;
+    float dis = len3(v.light - q) / len3(v.light - v.p);
+    v.dis = dis < 0.01f ? 0.f : dis;
+}
+
+EPSM_HD uint32_t wf_iterations(uint32_t max_depth_prop) { return max_depth_prop < EPSM_MAX_ITER ? max_depth_prop : EPSM_MAX_ITER; }   // epsm.py:549
+
+// The whole replay for one lane with immediate scene queries (the test-only host harness and the record probe use
+// this; the production kernels run the same stages as a wavefront).
 template <bool COUNT>
-EPSM_HDN void path_log(const DScene &sc, Tracer &tr, const CamRay &c, f3 grad_d, Pcg &rng, uint32_t max_depth_prop, uint32_t rr_depth, PathLog &P) {
-    const uint32_t max_iter = max_depth_prop < EPSM_MAX_ITER ? max_depth_prop : EPSM_MAX_ITER;   // epsm.py:549
-    Ray ray = c.ray;
-    P.cam = ray.o; P.d = ray.d; P.dlduv0 = P.dlduv1 = 0.f; P.dldp1 = mk3(0, 0, 0);
-    uint32_t depth = 0; f3 L = mk3(0, 0, 0), beta = mk3(1, 1, 1); float eta = 1.f; bool active = true;
-    f3 prev_p = mk3(0, 0, 0); float prev_pdf = 1.f; bool prev_delta = true;
-    SI si;
+EPSM_HDN void path_log(const DScene &sc, Tracer &tr, const DSensor &sensor, uint32_t px, uint32_t py, uint32_t seed, uint32_t lane,
+                       float gx, float gy, uint32_t max_depth_prop, uint32_t rr_depth, PathLog &P) {
+    WfState S; wf_begin(sensor, px, py, seed, lane, gx, gy, S, P);
+    const uint32_t max_iter = wf_iterations(max_depth_prop);
     for (uint32_t it = 0; it < max_iter; ++it) {
         Hit h; h.t = INFINITY; h.u = h.v = 0.f; h.prim = 0xffffffffu;
-        if (active) h = trace_closest<COUNT>(tr, ray);
-        compute_si(sc, ray, h, si);
-        if (it == 0 && si.valid) {
-            // forward-mode derivative of the first hit w.r.t. ray.d with the triangle detached (epsm.py:263-270)
-            f3 p0 = ld3(sc.pos, si.fi[0]), e1 = ld3(sc.pos, si.fi[1]) - p0, e2 = ld3(sc.pos, si.fi[2]) - p0;
-            f3 pvec = cross3(ray.d, e2), tvec = ray.o - p0, qvec = cross3(tvec, e1);
-            float det = dot3(e1, pvec), inv_det = 1.f / det;
-            f3 dpvec = cross3(grad_d, e2);
-            float ddet = dot3(e1, dpvec), dinv = -ddet * inv_det * inv_det;
-            float du = dot3(tvec, dpvec) * inv_det + dot3(tvec, pvec) * dinv;
-            float dv = dot3(grad_d, qvec) * inv_det + dot3(ray.d, qvec) * dinv;
-            if (si.ismesh) { P.dlduv0 = -(du + dv); P.dlduv1 = du; }               // b0 = 1-u-v, b1 = u
-            P.dldp1 = e1 * du + e2 * dv;
-        }
-        float em_pdf = pdf_emitter_direction(sc, si, prev_p, !prev_delta);
-        float mis = mis_weight(prev_pdf, em_pdf);
-        f3 Le = beta * mis * emitter_eval(sc, si);
-        bool active_next = (depth + 1 < max_depth_prop) && si.valid;
-        DBsdf b; uint32_t flags = 0;
-        if (si.valid) { b = sc.bsdfs[si.bsdf]; flags = b.bflags; }
-        bool smooth = active_next && (flags & EPSM_BF_SMOOTH);
-        bool active_em = smooth;
-        float e1r = pcg_f32(rng), e2r = pcg_f32(rng);
-        DSamp ds; f3 em_weight;
-        sample_emitter_direction(sc, si, e1r, e2r, active_em, ds, em_weight, [&](const Ray &r) { return trace_any<COUNT>(tr, r); });
-        active_em &= ds.pdf != 0.f;
-        f3 Lr_dir = mk3(0, 0, 0), dir_to_light = mk3(0, 0, 0);
-        if (smooth) dir_to_light = norm3(ds.p - si.p);                             // epsm.py:596
-        if (active_em) {
-            // Backward mode re-evaluates the emitter for the recomputed direction (epsm.py:596-598)
-            f3 em_val = dot3(dir_to_light, ds.n) < 0.f ? a3(sc.emitters[ds.emitter].radiance) : mk3(0, 0, 0);
-            f3 emw = em_val * (1.0f / ds.pdf);
-            f3 wo = to_local(si, dir_to_light); f3 val; float bpdf;
-            bsdf_eval_pdf(b, si.wi, wo, val, bpdf);
-            Lr_dir = beta * mis_weight(ds.pdf, bpdf) * val * emw;
-        }
-        pcg_f32(rng); pcg_f32(rng); pcg_f32(rng);                                  // discarded detached sample (epsm.py:633-636)
-        float s1 = pcg_f32(rng), s2x = pcg_f32(rng), s2y = pcg_f32(rng);
-        BSample bs; bs.wo = bs.hf = bs.weight = mk3(0, 0, 0); bs.pdf = 0.f; bs.eta = 0.f; bs.type = 0;
-        if (si.valid) bsdf_sample(b, si.wi, s1, s2x, s2y, active_next, bs);
-        if (it < EPSM_MAXV) {
-            VLog &v = P.v[it];
-            v.active = active && si.valid; v.flags = flags; v.ismesh = si.ismesh; v.light = ds.p; v.active_em = active_em;
-            v.p0 = si.p0; v.p1 = si.p1; v.p2 = si.p2; v.p = si.p; v.b0 = si.b0; v.b1 = si.b1;
-            v.n0 = si.n0; v.n1 = si.n1; v.n2 = si.n2; v.eta = bs.eta; v.hf = bs.hf;
-            v.prim = si.prim; v.mesh_flags = si.mesh_flags; v.has_normals = si.has_normals;
-            for (int k = 0; k < 3; ++k) { v.fi[k] = si.fi[k]; v.bw[k] = si.bw[k]; v.dfi[k] = 0; v.dbw[k] = 0.f; }
-            v.lr_sum = Lr_dir.x + Lr_dir.y + Lr_dir.z;
-            v.direct_valid = v.direct_any = v.direct_grad = false; v.dis = 0.f;
-            if (smooth) {
-                // si_direct: closest hit towards the light sample, FollowShape (epsm.py:609-625)
-                Ray rd = spawn_ray(si, dir_to_light);
-                Hit hd = trace_closest<COUNT>(tr, rd);
-                if (hd.prim != 0xffffffffu) {
-                    const uint32_t g0 = sc.faces[3 * hd.prim], g1 = sc.faces[3 * hd.prim + 1], g2 = sc.faces[3 * hd.prim + 2];
-                    const float w1 = hd.u, w2 = hd.v, w0 = 1.f - w1 - w2;
-                    f3 q = fma3(ld3(sc.pos, g0), w0, fma3(ld3(sc.pos, g1), w1, ld3(sc.pos, g2) * w2));
-                    v.direct_any = true; v.direct_valid = active_em;
-                    v.direct_grad = (sc.meshes[sc.face_mesh[hd.prim]].flags & EPSM_MESH_GRAD) != 0;
-                    v.dfi[0] = g0; v.dfi[1] = g1; v.dfi[2] = g2; v.dbw[0] = w0; v.dbw[1] = w1; v.dbw[2] = w2;
-                    float dis = len3(ds.p - q) / len3(ds.p - si.p);
-                    v.dis = dis < 0.01f ? 0.f : dis;
-                }
-            }
-        }
-        L = L + Le + Lr_dir;
-        if (si.valid) ray = spawn_ray(si, to_world(si, bs.wo));
-        eta *= bs.eta; beta = beta * bs.weight;
-        prev_p = si.p; prev_pdf = bs.pdf; prev_delta = (bs.type & EPSM_BF_DELTA) != 0;
-        float bmax = max3(beta);
-        active_next &= bmax != 0.f;
-        float rr_prob = fminf(bmax * eta * eta, .95f);
-        bool rr_active = depth >= rr_depth;
-        if (rr_active) beta = beta * rcp_e(rr_prob);
-        bool rr_continue = pcg_f32(rng) < rr_prob;
-        active_next &= !rr_active || rr_continue;
-        if (si.valid) depth += 1;
-        active = active_next;
+        if (S.active) h = trace_closest<COUNT>(tr, S.ray);
+        bool occluded = false;
+        if (wf_stage_a(sc, S, P, h, it, max_depth_prop)) occluded = trace_any<COUNT>(tr, S.shadow_ray);
+        Ray direct; bool dv;
+        wf_stage_b(sc, S, P, h, occluded, it, rr_depth, direct, dv);
+        if (dv) wf_direct_hit(sc, P.v[it], trace_closest<COUNT>(tr, direct));
     }
-    for (uint32_t it = max_iter; it < EPSM_MAXV; ++it) {
-        VLog &v = P.v[it]; memset(&v, 0, sizeof(VLog));
-    }
-    P.L = L;
+    for (uint32_t it = max_iter; it < EPSM_MAXV; ++it) memset(&P.v[it], 0, sizeof(VLog));
+    P.L = S.L;
 }
 
 // ---- the manifold constraint and its Jacobian (epsm.py:805-821, 868-883) ---------------------------

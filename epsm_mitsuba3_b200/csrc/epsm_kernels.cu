@@ -221,43 +221,173 @@ __device__ void write_record(const PathLog &P, const PathGrads &G, int n_logged,
 }
 
 // ------------------------------------------------------------------------------------------------
-//  Gradient pass
+//  Gradient pass — wavefront
+//
+//  The replay of sample_path is cut at every scene query (epsm_device.cuh: wf_begin / wf_stage_a / wf_stage_b /
+//  wf_direct_hit).  Between the stages a lean persistent traversal kernel drains a compacted ray queue, so the
+//  traversal runs with full warps, ~56 registers and a few KB of code instead of sitting inside a divergent
+//  > 64 KB megakernel (profiles/r01_a_*).  Per-lane state, the path log and the queues live in an HBM workspace
+//  sized for one chunk of the wavefront; chunks are processed back to back.
 // ------------------------------------------------------------------------------------------------
-template <bool COUNT, bool RECORD>
-__global__ void __launch_bounds__(CTA, EPSM_PATH_MINBLOCKS) k_backward(DScene sc, DLaunch ln, const float *__restrict__ grad_in,
-                                                  float *__restrict__ grad_pos, float *__restrict__ grad_nrm,
-                                                  float *__restrict__ records, unsigned long long *counters) {
+struct QRay { float ox, oy, oz, maxt, dx, dy, dz; uint32_t out; };      // 32 B, out = index into the result arena
+
+struct WfBuffers {
+    WfState *states; PathLog *logs; Hit *hits /* [C] path hits, then [MAXV·C] direct hits */; uint32_t *occl;
+    QRay *q_closest /* 2C */, *q_any /* C */;
+    uint32_t *counters;        // [0..15] closest-queue sizes, [16..31] closest heads, [32..47] any sizes, [48..63] any heads
+    uint32_t capacity;
+};
+
+size_t epsm_wf_workspace_bytes(uint32_t capacity) {
+    size_t c = capacity;
+    return c * (sizeof(WfState) + sizeof(PathLog) + sizeof(Hit) * (1 + EPSM_MAXV) + sizeof(uint32_t) + sizeof(QRay) * 3) + 64 * sizeof(uint32_t) + 4096;
+}
+static WfBuffers wf_carve(void *base, uint32_t capacity) {
+    WfBuffers w; char *p = (char *) base; size_t c = capacity;
+    auto take = [&](size_t bytes) { char *r = p; p += (bytes + 255) & ~(size_t) 255; return r; };
+    w.counters = (uint32_t *) take(64 * sizeof(uint32_t));
+    w.states = (WfState *) take(c * sizeof(WfState)); w.logs = (PathLog *) take(c * sizeof(PathLog));
+    w.hits = (Hit *) take(c * sizeof(Hit) * (1 + EPSM_MAXV)); w.occl = (uint32_t *) take(c * sizeof(uint32_t));
+    w.q_closest = (QRay *) take(2 * c * sizeof(QRay)); w.q_any = (QRay *) take(c * sizeof(QRay));
+    w.capacity = capacity; return w;
+}
+
+// Work index → lane.  Work items are enumerated tile by tile (8×4 pixels), then by sample, then by pixel in the
+// tile, so 32 consecutive items are neighbouring pixels at the same sample index (coherent primary rays), and the
+// lane id — which alone fixes the random stream — is pixel·spp + s as in the reference wavefront.
+struct WorkItem { uint32_t px, py, s; uint64_t lane; bool valid; };
+__device__ __forceinline__ WorkItem wf_work_item(const DLaunch &ln, uint64_t w) {
+    const uint32_t W = ln.sensor.w, H = ln.sensor.h, S = ln.s_end - ln.s_begin;
+    const uint32_t tiles_x = (W + TILE_W - 1) / TILE_W;
+    const uint64_t per_tile = 32ull * S;
+    const uint64_t tile = w / per_tile; const uint32_t r = (uint32_t) (w % per_tile);
+    const uint32_t tx = (uint32_t) (tile % tiles_x), ty = ln.tile_y0 + (uint32_t) (tile / tiles_x);
+    WorkItem wi; wi.s = ln.s_begin + r / 32; const uint32_t pin = r & 31;
+    wi.px = tx * TILE_W + (pin & (TILE_W - 1)); wi.py = ty * TILE_H + pin / TILE_W;
+    wi.lane = ((uint64_t) wi.py * W + wi.px) * ln.spp + wi.s;
+    wi.valid = wi.px < W && wi.py < H && ty < ln.tile_y1 && wi.lane >= ln.lane_begin && wi.lane < ln.lane_end;
+    return wi;
+}
+
+// Warp-aggregated queue append; returns the entry index (undefined when !pred).
+__device__ __forceinline__ uint32_t queue_push(uint32_t *count, bool pred) {
+    const unsigned m = __ballot_sync(__activemask(), pred);
+    if (!pred) return 0;
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(count, __popc(m));
+    base = __shfl_sync(m, base, leader);
+    return base + __popc(m & ((1u << lane) - 1));
+}
+__device__ __forceinline__ void queue_write(QRay *q, uint32_t idx, const Ray &r, uint32_t out) {
+    float4 *d = reinterpret_cast<float4 *>(q + idx);
+    d[0] = make_float4(r.o.x, r.o.y, r.o.z, r.maxt); d[1] = make_float4(r.d.x, r.d.y, r.d.z, __uint_as_float(out));
+}
+
+__global__ void __launch_bounds__(128) k_wf_init(DLaunch ln, uint64_t work_base, uint32_t n, const float *__restrict__ grad_in, WfBuffers wb) {
+    const uint32_t i = blockIdx.x * 128 + threadIdx.x;
+    bool push = false; WfState S;
+    if (i < n) {
+        const WorkItem wi = wf_work_item(ln, work_base + i);
+        if (wi.valid) {
+            const uint64_t pixel = (uint64_t) wi.py * ln.sensor.w + wi.px;
+            wf_begin(ln.sensor, wi.px, wi.py, ln.seed, (uint32_t) wi.lane, grad_in[pixel * 5 + 3], grad_in[pixel * 5 + 4], S, wb.logs[i]);
+            push = true;
+        } else { S.active = false; S.depth = 0xffffffffu; }      // depth = ~0 marks a slot without a lane
+        wb.states[i] = S;
+    }
+    const uint32_t q = queue_push(wb.counters + 0, push);
+    if (push) queue_write(wb.q_closest, q, S.ray, i);
+}
+
+// Persistent traversal kernel: each warp repeatedly claims 32 queue entries until the queue is drained.
+template <bool ANY, bool COUNT>
+__global__ void __launch_bounds__(CTA) k_wf_trace(DScene sc, const QRay *__restrict__ queue, const uint32_t *__restrict__ count, uint32_t *head,
+                                                  Hit *__restrict__ hits, uint32_t *__restrict__ occl, unsigned long long *counters) {
     __shared__ SharedStack ss;
     TStack st; bind_stack(st, ss);
     Tracer tr(sc, st);
-    const uint32_t W = ln.sensor.w, H = ln.sensor.h;
-    const uint32_t tiles_x = (W + TILE_W - 1) / TILE_W;
-    const uint32_t tx = blockIdx.x % tiles_x, ty = ln.tile_y0 + blockIdx.x / tiles_x;
-    const uint32_t pin = threadIdx.x & 31, slot = threadIdx.x >> 5;
-    const uint32_t px = tx * TILE_W + (pin & (TILE_W - 1)), py = ty * TILE_H + pin / TILE_W;
-    const uint32_t max_iter = ln.max_depth < EPSM_MAX_ITER ? ln.max_depth : EPSM_MAX_ITER;
-    const int n_logged = (int) (max_iter < EPSM_MAXV ? max_iter : EPSM_MAXV);      // len(path_info) − 1
-    uint32_t lanes = 0;
-    if (px < W && py < H) {
-        const uint64_t pixel = (uint64_t) py * W + px;
-        const float gx = grad_in[pixel * 5 + 3], gy = grad_in[pixel * 5 + 4];
-        for (uint32_t s = ln.s_begin + slot; s < ln.s_end; s += CTA / 32) {
-            const uint64_t lane = pixel * ln.spp + s;
-            if (lane < ln.lane_begin || lane >= ln.lane_end) continue;
-            Pcg rng = pcg_for_lane(ln.seed, (uint32_t) lane);
-            CamRay c; camera_ray(ln.sensor, px, py, rng, c);
-            // pixel motion → tangent of the ray direction (epsm.py:250-257)
-            const f3 grad_d = (c.d_x - c.ray.d) * gx + (c.d_y - c.ray.d) * gy;
-            PathLog P;
-            path_log<COUNT>(sc, tr, c, grad_d, rng, ln.max_depth, ln.rr_depth, P);
-            PathGrads G;
-            calc_grad(P, ln.variant, n_logged, G);
-            ++lanes;
-            if (RECORD) write_record(P, G, n_logged, records + (lane - ln.lane_begin) * EPSM_REC_FLOATS);
-            else scatter_path(P, G, ln.variant, n_logged, ln.max_depth, grad_pos, grad_nrm);
+    const uint32_t n = *count; const int lane = threadIdx.x & 31;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(head, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        const uint32_t i = base + lane;
+        if (i < n) {
+            const float4 a = __ldg(reinterpret_cast<const float4 *>(queue + i)), b = __ldg(reinterpret_cast<const float4 *>(queue + i) + 1);
+            const Ray r{mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), a.w}; const uint32_t out = __float_as_uint(b.w);
+            if (ANY) occl[out] = trace_any<COUNT>(tr, r) ? 1u : 0u;
+            else { const Hit h = trace_closest<COUNT>(tr, r); reinterpret_cast<uint4 *>(hits)[out] = make_uint4(f2u(h.t), f2u(h.u), f2u(h.v), h.prim); }
         }
     }
-    if (COUNT) flush_counters(tr, lanes, counters);
+    if (COUNT) flush_counters(tr, 0u, counters);
+}
+
+__global__ void __launch_bounds__(128) k_wf_stage_a(DScene sc, DLaunch ln, uint32_t it, uint32_t n, WfBuffers wb) {
+    const uint32_t i = blockIdx.x * 128 + threadIdx.x;
+    bool push = false; Ray sr;
+    if (i < n) {
+        WfState S = wb.states[i];
+        if (S.depth != 0xffffffffu && S.active) {
+            const Hit h = wb.hits[i];
+            push = wf_stage_a(sc, S, wb.logs[i], h, it, ln.max_depth);
+            sr = S.shadow_ray;
+            wb.states[i] = S;
+        }
+    }
+    const uint32_t q = queue_push(wb.counters + 32 + it, push);
+    if (push) queue_write(wb.q_any, q, sr, i);
+}
+
+__global__ void __launch_bounds__(128) k_wf_stage_b(DScene sc, DLaunch ln, uint32_t it, uint32_t max_iter, uint32_t n, WfBuffers wb) {
+    const uint32_t i = blockIdx.x * 128 + threadIdx.x;
+    bool push_direct = false, push_next = false; Ray direct, next;
+    if (i < n) {
+        WfState S = wb.states[i];
+        if (S.depth != 0xffffffffu) {
+            if (S.active) {
+                const Hit h = wb.hits[i];
+                const bool occluded = S.need_shadow && wb.occl[i] != 0u;
+                wf_stage_b(sc, S, wb.logs[i], h, occluded, it, ln.rr_depth, direct, push_direct);
+                push_next = S.active && it + 1 < max_iter; next = S.ray;
+                wb.states[i] = S;
+            } else if (it < EPSM_MAXV) {
+                // a lane that has left the path: its logged vertex is inactive (every use is masked by `active`)
+                VLog &v = wb.logs[i].v[it];
+                memset(&v, 0, sizeof(VLog)); v.prim = 0xffffffffu;
+            }
+        }
+    }
+    const uint32_t qd = queue_push(wb.counters + (it + 1), push_direct);
+    if (push_direct) queue_write(wb.q_closest, qd, direct, wb.capacity + it * wb.capacity + i);
+    const uint32_t qn = queue_push(wb.counters + (it + 1), push_next);
+    if (push_next) queue_write(wb.q_closest, qn, next, i);
+}
+
+__global__ void k_count_lanes(uint32_t n, WfBuffers wb, unsigned long long *counters) {
+    const uint32_t i = blockIdx.x * 128 + threadIdx.x;
+    const bool live = i < n && wb.states[i].depth != 0xffffffffu;
+    const unsigned m = __ballot_sync(0xffffffffu, live);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(counters + 3, (unsigned long long) __popc(m));
+}
+
+template <bool RECORD>
+__global__ void __launch_bounds__(128) k_wf_finish(DScene sc, DLaunch ln, uint64_t work_base, uint32_t n, WfBuffers wb,
+                                                   float *__restrict__ grad_pos, float *__restrict__ grad_nrm, float *__restrict__ records) {
+    const uint32_t i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= n) return;
+    if (wb.states[i].depth == 0xffffffffu) return;
+    PathLog &P = wb.logs[i];
+    const uint32_t max_iter = wf_iterations(ln.max_depth);
+    const int n_logged = (int) (max_iter < EPSM_MAXV ? max_iter : EPSM_MAXV);      // len(path_info) − 1
+    for (int k = 0; k < n_logged; ++k)
+        if (P.v[k].active && P.v[k].direct_traced) wf_direct_hit(sc, P.v[k], wb.hits[wb.capacity + (size_t) k * wb.capacity + i]);
+    P.L = wb.states[i].L;
+    PathGrads G;
+    calc_grad(P, ln.variant, n_logged, G);
+    if (RECORD) { const WorkItem wi = wf_work_item(ln, work_base + i); write_record(P, G, n_logged, records + (wi.lane - ln.lane_begin) * EPSM_REC_FLOATS); }
+    else scatter_path(P, G, ln.variant, n_logged, ln.max_depth, grad_pos, grad_nrm);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -350,12 +480,38 @@ cudaError_t epsm_launch_develop(const float *film, uint64_t n_pixels, float *out
     return cudaGetLastError();
 }
 cudaError_t epsm_launch_backward(const DScene &sc, DLaunch ln, const float *grad_in, float *grad_pos, float *grad_nrm, float *records,
-                                 unsigned long long *counters, cudaStream_t s) {
-    tile_rows(ln); const uint32_t grid = tile_grid(ln);
-    if (grid == 0) return cudaSuccess;
-    if (records) k_backward<false, true><<<grid, CTA, 0, s>>>(sc, ln, grad_in, nullptr, nullptr, records, nullptr);
-    else if (counters) k_backward<true, false><<<grid, CTA, 0, s>>>(sc, ln, grad_in, grad_pos, grad_nrm, nullptr, counters);
-    else k_backward<false, false><<<grid, CTA, 0, s>>>(sc, ln, grad_in, grad_pos, grad_nrm, nullptr, nullptr);
+                                 unsigned long long *counters, void *workspace, uint32_t capacity, uint32_t trace_grid, uint64_t *n_launches,
+                                 cudaStream_t s) {
+    tile_rows(ln);
+    const uint32_t tiles = tile_grid(ln);
+    if (tiles == 0 || ln.s_end <= ln.s_begin) return cudaSuccess;
+    const uint64_t total = (uint64_t) tiles * 32ull * (ln.s_end - ln.s_begin);
+    const uint32_t max_iter = ln.max_depth < EPSM_MAX_ITER ? ln.max_depth : EPSM_MAX_ITER;
+    WfBuffers wb = wf_carve(workspace, capacity);
+    uint64_t launches = 0;
+    for (uint64_t base = 0; base < total; base += capacity) {
+        const uint32_t n = (uint32_t) ((total - base) < capacity ? (total - base) : capacity);
+        const uint32_t grid = (n + 127) / 128;
+        cudaMemsetAsync(wb.counters, 0, 64 * sizeof(uint32_t), s);
+        k_wf_init<<<grid, 128, 0, s>>>(ln, base, n, grad_in, wb); ++launches;
+        for (uint32_t it = 0; it <= max_iter; ++it) {
+            // closest-hit queue `it`: path rays of iteration `it` and the direct rays of iteration `it − 1`
+            if (counters) k_wf_trace<false, true><<<trace_grid, CTA, 0, s>>>(sc, wb.q_closest, wb.counters + it, wb.counters + 16 + it, wb.hits, nullptr, counters);
+            else k_wf_trace<false, false><<<trace_grid, CTA, 0, s>>>(sc, wb.q_closest, wb.counters + it, wb.counters + 16 + it, wb.hits, nullptr, nullptr);
+            ++launches;
+            if (it == max_iter) break;
+            k_wf_stage_a<<<grid, 128, 0, s>>>(sc, ln, it, n, wb); ++launches;
+            if (counters) k_wf_trace<true, true><<<trace_grid, CTA, 0, s>>>(sc, wb.q_any, wb.counters + 32 + it, wb.counters + 48 + it, nullptr, wb.occl, counters);
+            else k_wf_trace<true, false><<<trace_grid, CTA, 0, s>>>(sc, wb.q_any, wb.counters + 32 + it, wb.counters + 48 + it, nullptr, wb.occl, nullptr);
+            ++launches;
+            k_wf_stage_b<<<grid, 128, 0, s>>>(sc, ln, it, max_iter, n, wb); ++launches;
+        }
+        if (records) k_wf_finish<true><<<grid, 128, 0, s>>>(sc, ln, base, n, wb, nullptr, nullptr, records);
+        else k_wf_finish<false><<<grid, 128, 0, s>>>(sc, ln, base, n, wb, grad_pos, grad_nrm, nullptr);
+        ++launches;
+        if (counters) { k_count_lanes<<<grid, 128, 0, s>>>(n, wb, counters); ++launches; }
+    }
+    if (n_launches) *n_launches += launches;
     return cudaGetLastError();
 }
 cudaError_t epsm_launch_sampler_stream(uint32_t seed, uint64_t lane_begin, uint64_t n_lanes, uint32_t n_floats, float *out, cudaStream_t s) {

@@ -117,11 +117,8 @@ void sim_backward(sim_scene *s, int variant, uint32_t sensor, uint32_t seed, uin
     for (int64_t i = 0; i < n; ++i) {
         uint64_t lane = lane_begin + i; uint32_t pixel = (uint32_t) (lane / spp);
         LocalStack ls; TStack st; bind(st, ls); Tracer tr(s->sc, st);
-        Pcg rng = pcg_for_lane(seed, (uint32_t) lane);
-        CamRay c; camera_ray(ln.sensor, pixel % W, pixel / W, rng, c);
         const float gx = grad_in[(size_t) pixel * 5 + 3], gy = grad_in[(size_t) pixel * 5 + 4];
-        const f3 grad_d = (c.d_x - c.ray.d) * gx + (c.d_y - c.ray.d) * gy;
-        PathLog P; path_log<false>(s->sc, tr, c, grad_d, rng, max_depth, rr_depth, P);
+        PathLog P; path_log<false>(s->sc, tr, ln.sensor, pixel % W, pixel / W, seed, (uint32_t) lane, gx, gy, max_depth, rr_depth, P);
         PathGrads G; calc_grad(P, variant, n_logged, G);
         if (records) {
             float *r = records + (size_t) i * EPSM_REC_FLOATS;
