@@ -141,8 +141,11 @@ class OracleScene:
             lib().orc_scene_set_accel(self.h, 1)
 
     def __del__(self):
-        if getattr(self, "h", None):
-            lib().orc_scene_destroy(self.h); self.h = None
+        try:
+            if getattr(self, "h", None):
+                lib().orc_scene_destroy(self.h); self.h = None
+        except Exception:       # interpreter shutdown
+            pass
 
     def set_accel(self, on: bool):
         lib().orc_scene_set_accel(self.h, 1 if on else 0)

@@ -91,10 +91,13 @@ def check_path_records(rec, paths, variant, max_depth, min_same=0.999):
     # filter) and no implementation can be held to 1e-4 there.  Such paths are counted and bounded, not compared.
     import torch
     pg64, lg64, dg64 = calc_grad(paths, variant, nl, torch.float64)
-    ill = np.zeros(n, bool)
+    ill = np.zeros(n, bool); nz_path = np.zeros(n, bool)
     for a, b in zip(pg + lg + dg, pg64 + lg64 + dg64):
         ill |= (np.abs(a - b) > 0.25 * REL_TOL * np.maximum(np.abs(b).max(axis=1, keepdims=True), 1e-3)).any(1)
-    stats = dict(frac_same=frac_same, n=n, nonzero=0, max_rel=0.0, flipped=0, ill_conditioned=int((ill & same).sum()))
+        nz_path |= (b != 0).any(1)
+    stats = dict(frac_same=frac_same, n=n, nonzero=0, max_rel=0.0, flipped=0, ill_conditioned=int((ill & same).sum()),
+                 paths_with_gradient=int((nz_path & same).sum()))
+    ill_sel = same & ill
     same = same & ~ill
 
     def cmp(ref, got, name):
@@ -113,14 +116,24 @@ def check_path_records(rec, paths, variant, max_depth, min_same=0.999):
         if nz.any():
             stats["max_rel"] = max(stats["max_rel"], float((err.max(1)[nz] / np.abs(ref).max(1)[nz]).max()))
 
+    def cmp_ill(ref32, ref64, got, name):
+        # ill-conditioned paths: hold the result to the float64 evaluation, within the reference's own float32 error
+        r32, r64, gg = ref32[ill_sel], ref64[ill_sel], got[ill_sel]
+        if r32.size == 0:
+            return
+        dead = (np.abs(r32) == 0) | (gg == 0) | (np.abs(np.abs(r64) - 0.1) < 1e-3)     # one side fell to the outlier filter
+        err = np.abs(gg - r64); bound = 4 * np.abs(r32 - r64) + REL_TOL * np.maximum(np.abs(r64).max(axis=1, keepdims=True), 1e-3)
+        assert not ((err > bound) & ~dead).any(), f"{name}: ill-conditioned path further from float64 than the reference's float32"
+
     for k in range(nl):
         for c in range(5):
             if 5 * k + c < len(pg):
                 cmp(pg[5 * k + c], g[:, k, 3 * c:3 * c + 3], f"path_grad[{5 * k + c}]")
+                cmp_ill(pg[5 * k + c], pg64[5 * k + c], g[:, k, 3 * c:3 * c + 3], f"path_grad[{5 * k + c}]")
         cmp(lg[k], g[:, k, 15:18], f"light_grad[{k}]")
         cmp(dg[k], g[:, k, 18:21], f"diffuse_grad[{k}]")
     assert stats["flipped"] <= max(2, n // 5000)
-    assert stats["ill_conditioned"] <= max(2, n // 1000), stats
+    assert stats["ill_conditioned"] <= max(4, n // 100), stats                                # ≤ 1 % of the paths
     return stats, (pg, lg, dg)
 
 
