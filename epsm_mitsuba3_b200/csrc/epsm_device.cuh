@@ -670,8 +670,8 @@ struct VLog {
     float eta, b0, b1, lr_sum, dis;
     f3 light, p0, p1, p2, n0, n1, n2, hf, p;
 };
-struct PathLog {
-    f3 cam, d, dldp1, L; float dlduv0, dlduv1;
+struct PathHead { f3 cam, d, dldp1, L; float dlduv0, dlduv1; };
+struct PathLog : PathHead {
     VLog v[EPSM_MAXV];
 };
 
@@ -694,7 +694,7 @@ struct WfState {
     Ray shadow_ray;
 };
 
-EPSM_HDN void wf_begin(const DSensor &sensor, uint32_t px, uint32_t py, uint32_t seed, uint32_t lane, float gx, float gy, WfState &S, PathLog &P) {
+EPSM_HDN void wf_begin(const DSensor &sensor, uint32_t px, uint32_t py, uint32_t seed, uint32_t lane, float gx, float gy, WfState &S, PathHead &P) {
     S.rng = pcg_for_lane(seed, lane);
     CamRay c; camera_ray(sensor, px, py, S.rng, c);
     S.ray = c.ray;
@@ -706,7 +706,7 @@ EPSM_HDN void wf_begin(const DSensor &sensor, uint32_t px, uint32_t py, uint32_t
 
 // After the closest hit `h` of S.ray: surface interaction, first-hit tangents, emission, emitter sampling up to
 // (not including) its visibility test.  Returns true when S.shadow_ray must be tested.
-EPSM_HDN bool wf_stage_a(const DScene &sc, WfState &S, PathLog &P, const Hit &h_in, uint32_t it, uint32_t max_depth_prop) {
+EPSM_HDN bool wf_stage_a(const DScene &sc, WfState &S, PathHead &P, const Hit &h_in, uint32_t it, uint32_t max_depth_prop) {
     Hit h = h_in;
     if (!S.active) { h.t = INFINITY; h.u = h.v = 0.f; h.prim = 0xffffffffu; }
     SI si; compute_si(sc, S.ray, h, si);
@@ -738,7 +738,8 @@ EPSM_HDN bool wf_stage_a(const DScene &sc, WfState &S, PathLog &P, const Hit &h_
 
 // After the visibility test: NEE contribution, the two BSDF samples, the vertex log, the ray towards the light
 // sample (returned in `direct`, traced later as a closest-hit query) and the next path ray.
-EPSM_HDN void wf_stage_b(const DScene &sc, WfState &S, PathLog &P, const Hit &h_in, bool occluded, uint32_t it, uint32_t rr_depth,
+// `v` receives the logged vertex when it < EPSM_MAXV (epsm.py:648).
+EPSM_HDN void wf_stage_b(const DScene &sc, WfState &S, VLog &v, const Hit &h_in, bool occluded, uint32_t it, uint32_t rr_depth,
                          Ray &direct, bool &direct_valid) {
     Hit h = h_in;
     if (!S.active) { h.t = INFINITY; h.u = h.v = 0.f; h.prim = 0xffffffffu; }
@@ -763,7 +764,6 @@ EPSM_HDN void wf_stage_b(const DScene &sc, WfState &S, PathLog &P, const Hit &h_
     if (si.valid) bsdf_sample(b, si.wi, s1, s2x, s2y, S.active_next, bs);
     direct_valid = false;
     if (it < EPSM_MAXV) {                                                          // epsm.py:648-654
-        VLog &v = P.v[it];
         v.active = S.active && si.valid; v.flags = flags; v.ismesh = si.ismesh; v.light = S.ds.p; v.active_em = active_em;
         v.p0 = si.p0; v.p1 = si.p1; v.p2 = si.p2; v.p = si.p; v.b0 = si.b0; v.b1 = si.b1;
         v.n0 = si.n0; v.n1 = si.n1; v.n2 = si.n2; v.eta = bs.eta; v.hf = bs.hf;
@@ -817,9 +817,10 @@ EPSM_HDN void path_log(const DScene &sc, Tracer &tr, const DSensor &sensor, uint
         if (S.active) h = trace_closest<COUNT>(tr, S.ray);
         bool occluded = false;
         if (wf_stage_a(sc, S, P, h, it, max_depth_prop)) occluded = trace_any<COUNT>(tr, S.shadow_ray);
-        Ray direct; bool dv;
-        wf_stage_b(sc, S, P, h, occluded, it, rr_depth, direct, dv);
-        if (dv) wf_direct_hit(sc, P.v[it], trace_closest<COUNT>(tr, direct));
+        Ray direct; bool dv; VLog scratch;
+        VLog &v = it < EPSM_MAXV ? P.v[it] : scratch;
+        wf_stage_b(sc, S, v, h, occluded, it, rr_depth, direct, dv);
+        if (dv) wf_direct_hit(sc, v, trace_closest<COUNT>(tr, direct));
     }
     for (uint32_t it = max_iter; it < EPSM_MAXV; ++it) memset(&P.v[it], 0, sizeof(VLog));
     P.L = S.L;

@@ -231,8 +231,36 @@ __device__ void write_record(const PathLog &P, const PathGrads &G, int n_logged,
 // ------------------------------------------------------------------------------------------------
 struct QRay { float ox, oy, oz, maxt, dx, dy, dz; uint32_t out; };      // 32 B, out = index into the result arena
 
+// Per-lane records live in HBM word-major ("SoA by 32-bit word"): word w of lane i sits at base[w·capacity + i], so
+// a warp moving its 32 lanes' records issues fully coalesced 128-byte transactions (the AoS first version wrote one
+// 32-byte sector per thread per store: profiles/r01_b_*).
+#define WORDS_OF(T) ((sizeof(T) + 3) / 4)
+template <typename T> __device__ __forceinline__ void soa_load(T &dst, const uint32_t *__restrict__ base, uint32_t stride, uint32_t i) {
+    uint32_t w[WORDS_OF(T)];
+#pragma unroll
+    for (uint32_t k = 0; k < WORDS_OF(T); ++k) w[k] = base[(size_t) k * stride + i];
+    memcpy(&dst, w, sizeof(T));
+}
+template <typename T> __device__ __forceinline__ void soa_store(const T &src, uint32_t *__restrict__ base, uint32_t stride, uint32_t i) {
+    uint32_t w[WORDS_OF(T)];
+    w[WORDS_OF(T) - 1] = 0u;
+    memcpy(w, &src, sizeof(T));
+#pragma unroll
+    for (uint32_t k = 0; k < WORDS_OF(T); ++k) base[(size_t) k * stride + i] = w[k];
+}
+
+#define WF_NONE 0u      // slot without a lane
+#define WF_LIVE 1u      // path still being traced
+#define WF_DONE 2u      // path has terminated (its remaining logged vertices are inactive)
+
 struct WfBuffers {
-    WfState *states; PathLog *logs; Hit *hits /* [C] path hits, then [MAXV·C] direct hits */; uint32_t *occl;
+    uint32_t *status;          // [C]
+    uint32_t *states;          // WfState, word-major
+    uint32_t *heads;           // PathHead, word-major
+    uint32_t *vlogs;           // EPSM_MAXV × VLog, word-major per vertex: base + it·WORDS_OF(VLog)·C
+    uint8_t *vmask;            // [MAXV·C] 1 where a vertex record was written
+    Hit *hits;                 // [C] path hits, then [MAXV·C] direct hits
+    uint32_t *occl;            // [C]
     QRay *q_closest /* 2C */, *q_any /* C */;
     uint32_t *counters;        // [0..15] closest-queue sizes, [16..31] closest heads, [32..47] any sizes, [48..63] any heads
     uint32_t capacity;
@@ -240,13 +268,16 @@ struct WfBuffers {
 
 size_t epsm_wf_workspace_bytes(uint32_t capacity) {
     size_t c = capacity;
-    return c * (sizeof(WfState) + sizeof(PathLog) + sizeof(Hit) * (1 + EPSM_MAXV) + sizeof(uint32_t) + sizeof(QRay) * 3) + 64 * sizeof(uint32_t) + 4096;
+    return c * (4 * (1 + WORDS_OF(WfState) + WORDS_OF(PathHead) + EPSM_MAXV * WORDS_OF(VLog)) + EPSM_MAXV + sizeof(Hit) * (1 + EPSM_MAXV)
+                + sizeof(uint32_t) + sizeof(QRay) * 3) + 64 * sizeof(uint32_t) + 16 * 256;
 }
 static WfBuffers wf_carve(void *base, uint32_t capacity) {
     WfBuffers w; char *p = (char *) base; size_t c = capacity;
     auto take = [&](size_t bytes) { char *r = p; p += (bytes + 255) & ~(size_t) 255; return r; };
     w.counters = (uint32_t *) take(64 * sizeof(uint32_t));
-    w.states = (WfState *) take(c * sizeof(WfState)); w.logs = (PathLog *) take(c * sizeof(PathLog));
+    w.status = (uint32_t *) take(c * 4);
+    w.states = (uint32_t *) take(c * 4 * WORDS_OF(WfState)); w.heads = (uint32_t *) take(c * 4 * WORDS_OF(PathHead));
+    w.vlogs = (uint32_t *) take(c * 4 * EPSM_MAXV * WORDS_OF(VLog)); w.vmask = (uint8_t *) take(c * EPSM_MAXV);
     w.hits = (Hit *) take(c * sizeof(Hit) * (1 + EPSM_MAXV)); w.occl = (uint32_t *) take(c * sizeof(uint32_t));
     w.q_closest = (QRay *) take(2 * c * sizeof(QRay)); w.q_any = (QRay *) take(c * sizeof(QRay));
     w.capacity = capacity; return w;
@@ -291,50 +322,163 @@ __global__ void __launch_bounds__(128) k_wf_init(DLaunch ln, uint64_t work_base,
         const WorkItem wi = wf_work_item(ln, work_base + i);
         if (wi.valid) {
             const uint64_t pixel = (uint64_t) wi.py * ln.sensor.w + wi.px;
-            wf_begin(ln.sensor, wi.px, wi.py, ln.seed, (uint32_t) wi.lane, grad_in[pixel * 5 + 3], grad_in[pixel * 5 + 4], S, wb.logs[i]);
+            PathHead H;
+            wf_begin(ln.sensor, wi.px, wi.py, ln.seed, (uint32_t) wi.lane, grad_in[pixel * 5 + 3], grad_in[pixel * 5 + 4], S, H);
+            soa_store(S, wb.states, wb.capacity, i); soa_store(H, wb.heads, wb.capacity, i);
             push = true;
-        } else { S.active = false; S.depth = 0xffffffffu; }      // depth = ~0 marks a slot without a lane
-        wb.states[i] = S;
+        }
+        wb.status[i] = wi.valid ? WF_LIVE : WF_NONE;
+#pragma unroll
+        for (int k = 0; k < EPSM_MAXV; ++k) wb.vmask[(size_t) k * wb.capacity + i] = 0;
     }
     const uint32_t q = queue_push(wb.counters + 0, push);
     if (push) queue_write(wb.q_closest, q, S.ray, i);
 }
 
-// Persistent traversal kernel: each warp repeatedly claims 32 queue entries until the queue is drained.
+// Persistent traversal kernel.  Every lane owns one ray at a time and, when its ray finishes, claims the next queue
+// entry (warp-aggregated atomic) while the other lanes keep traversing — a warp never idles on its slowest ray
+// (the first version claimed 32 rays per warp and ran at 9.6/32 active lanes: profiles/r01_b_*).  One loop iteration =
+// one traversal step per lane: an inner node (one 128-byte line as 7 × 128-bit loads, 4 slab tests, nearest child kept
+// in a register, the others pushed far → near) or a leaf (≤ 4 Möller–Trumbore tests).  Stack entries are 64-bit
+// (ref, entry distance) words in shared memory, [entry][thread] ⇒ conflict-free.  The arithmetic is that of bvh_trace
+// (epsm_device.cuh), so hits stay bit-identical to the oracle.
+#define WF_STACK 16
+#define WF_LSTACK 80
+#define WF_REF_NONE 0x7fffffffu
 template <bool ANY, bool COUNT>
 __global__ void __launch_bounds__(CTA) k_wf_trace(DScene sc, const QRay *__restrict__ queue, const uint32_t *__restrict__ count, uint32_t *head,
                                                   Hit *__restrict__ hits, uint32_t *__restrict__ occl, unsigned long long *counters) {
-    __shared__ SharedStack ss;
-    TStack st; bind_stack(st, ss);
-    Tracer tr(sc, st);
+    __shared__ uint2 sstack[WF_STACK][CTA];
+    uint2 lstack[WF_LSTACK];
     const uint32_t n = *count; const int lane = threadIdx.x & 31;
+    uint32_t c_nodes = 0, c_tris = 0, c_rays = 0;
+    bool has_ray = false, exhausted = false;
+    Ray ray; float ix = 0, iy = 0, iz = 0, ox = 0, oy = 0, oz = 0;
+    float best_t = 0, best_u = 0, best_v = 0; uint32_t best_prim = 0xffffffffu, out = 0, cur = WF_REF_NONE; bool found = false; int sp = 0;
+    ray.o = ray.d = mk3(0, 0, 0); ray.maxt = 0;
     for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(head, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        const uint32_t i = base + lane;
-        if (i < n) {
-            const float4 a = __ldg(reinterpret_cast<const float4 *>(queue + i)), b = __ldg(reinterpret_cast<const float4 *>(queue + i) + 1);
-            const Ray r{mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), a.w}; const uint32_t out = __float_as_uint(b.w);
-            if (ANY) occl[out] = trace_any<COUNT>(tr, r) ? 1u : 0u;
-            else { const Hit h = trace_closest<COUNT>(tr, r); reinterpret_cast<uint4 *>(hits)[out] = make_uint4(f2u(h.t), f2u(h.u), f2u(h.v), h.prim); }
+        const unsigned idle = __ballot_sync(0xffffffffu, !has_ray);
+        if (idle) {
+            if (!exhausted) {
+                // claim queue entries for the idle lanes
+                uint32_t base = 0;
+                if (lane == __ffs(idle) - 1) base = atomicAdd(head, (uint32_t) __popc(idle));
+                base = __shfl_sync(0xffffffffu, base, __ffs(idle) - 1);
+                if (!has_ray) {
+                    const uint32_t i = base + __popc(idle & ((1u << lane) - 1));
+                    if (i < n) {
+                        const float4 a = __ldg(reinterpret_cast<const float4 *>(queue + i)), b = __ldg(reinterpret_cast<const float4 *>(queue + i) + 1);
+                        ray.o = mk3(a.x, a.y, a.z); ray.d = mk3(b.x, b.y, b.z); ray.maxt = a.w; out = __float_as_uint(b.w);
+                        const float dx = fabsf(ray.d.x) < 1e-20f ? mulsign(1e-20f, ray.d.x) : ray.d.x;
+                        const float dy = fabsf(ray.d.y) < 1e-20f ? mulsign(1e-20f, ray.d.y) : ray.d.y;
+                        const float dz = fabsf(ray.d.z) < 1e-20f ? mulsign(1e-20f, ray.d.z) : ray.d.z;
+                        ix = 1.0f / dx; iy = 1.0f / dy; iz = 1.0f / dz; ox = ray.o.x * ix; oy = ray.o.y * iy; oz = ray.o.z * iz;
+                        best_t = ray.maxt; best_u = best_v = 0.f; best_prim = 0xffffffffu; found = false; sp = 0;
+                        cur = sc.n_nodes ? 0u : WF_REF_NONE; has_ray = true;
+                        if (COUNT) ++c_rays;
+                    }
+                }
+                if (base + __popc(idle) >= n) exhausted = true;
+            }
+            if (__ballot_sync(0xffffffffu, has_ray) == 0u) break;
         }
+        if (!has_ray) continue;
+        if (cur == WF_REF_NONE) {
+            // pop the next subtree that can still contain a closer (or equally close) hit
+            bool got = false;
+            while (sp > 0) {
+                --sp;
+                const uint2 e = sp < WF_STACK ? sstack[sp][threadIdx.x] : lstack[sp - WF_STACK];
+                if (__uint_as_float(e.y) <= best_t) { cur = e.x; got = true; break; }
+            }
+            if (!got) {
+                // ray finished
+                if (ANY) occl[out] = 0u;
+                else reinterpret_cast<uint4 *>(hits)[out] = make_uint4(f2u(found ? best_t : INFINITY), f2u(best_u), f2u(best_v), best_prim);
+                has_ray = false;
+                continue;
+            }
+        }
+        if ((int32_t) cur < 0) {
+            // ---- leaf ----
+            const uint32_t code = ~cur, first = code >> 2, cnt = (code & 3u) + 1u;
+            bool done = false;
+            for (uint32_t k = 0; k < cnt; ++k) {
+                const f4 *tp = sc.tris + (size_t) (first + k) * EPSM_TRI_F4;
+                const f4 a = ldg4(tp), b = ldg4(tp + 1), c = ldg4(tp + 2);
+                if (COUNT) ++c_tris;
+                float t, u, v;
+                if (tri_test(ray, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(b.w, c.x, c.y), best_t, t, u, v)) {
+                    if (ANY) { done = true; break; }
+                    const uint32_t prim = f2u(a.w);
+                    if (!found || t < best_t || prim > best_prim) { best_t = t; best_u = u; best_v = v; best_prim = prim; found = true; }
+                }
+            }
+            cur = WF_REF_NONE;
+            if (ANY && done) { occl[out] = 1u; has_ray = false; }
+            continue;
+        }
+        // ---- inner node ----
+        const f4 *np = sc.nodes + (size_t) cur * EPSM_NODE_F4;
+        const f4 lx = ldg4(np), ly = ldg4(np + 1), lz = ldg4(np + 2), hx = ldg4(np + 3), hy = ldg4(np + 4), hz = ldg4(np + 5), ch = ldg4(np + 6);
+        if (COUNT) ++c_nodes;
+        uint32_t key[4]; float tmn[4];
+        const uint32_t cref[4] = {f2u(ch.x), f2u(ch.y), f2u(ch.z), f2u(ch.w)};
+#define WF_SLAB(k, LX, LY, LZ, HX, HY, HZ)                                                          \
+        {                                                                                           \
+            const float ax = fmaf(LX, ix, -ox), bx = fmaf(HX, ix, -ox);                             \
+            const float ay = fmaf(LY, iy, -oy), by = fmaf(HY, iy, -oy);                             \
+            const float az = fmaf(LZ, iz, -oz), bz = fmaf(HZ, iz, -oz);                             \
+            const float t0 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f)); \
+            const float t1 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), best_t)); \
+            tmn[k] = t0;                                                                            \
+            key[k] = (t0 <= t1 * 1.0000004f && cref[k] != 0x7fffffffu) ? ((f2u(t0) & ~3u) | (uint32_t) k) : 0xffffffffu; \
+        }
+        WF_SLAB(0, lx.x, ly.x, lz.x, hx.x, hy.x, hz.x)
+        WF_SLAB(1, lx.y, ly.y, lz.y, hx.y, hy.y, hz.y)
+        WF_SLAB(2, lx.z, ly.z, lz.z, hx.z, hy.z, hz.z)
+        WF_SLAB(3, lx.w, ly.w, lz.w, hx.w, hy.w, hz.w)
+#undef WF_SLAB
+        cswap(key[0], key[1]); cswap(key[2], key[3]); cswap(key[0], key[2]); cswap(key[1], key[3]); cswap(key[1], key[2]);
+#pragma unroll
+        for (int i = 3; i >= 1; --i) {
+            if (key[i] != 0xffffffffu) {
+                const uint32_t k = key[i] & 3u;
+                const uint32_t r = k == 0 ? cref[0] : k == 1 ? cref[1] : k == 2 ? cref[2] : cref[3];
+                const float t = k == 0 ? tmn[0] : k == 1 ? tmn[1] : k == 2 ? tmn[2] : tmn[3];
+                const uint2 e = make_uint2(r, __float_as_uint(t));
+                if (sp < WF_STACK) sstack[sp][threadIdx.x] = e; else if (sp < WF_STACK + WF_LSTACK) lstack[sp - WF_STACK] = e;
+                if (sp < WF_STACK + WF_LSTACK) ++sp;
+            }
+        }
+        if (key[0] != 0xffffffffu) {
+            const uint32_t k = key[0] & 3u;
+            cur = k == 0 ? cref[0] : k == 1 ? cref[1] : k == 2 ? cref[2] : cref[3];
+        } else cur = WF_REF_NONE;
     }
-    if (COUNT) flush_counters(tr, 0u, counters);
+    if (COUNT) {
+        unsigned long long a = c_nodes, b = c_tris, c = c_rays;
+        for (int o = 16; o > 0; o >>= 1) { a += __shfl_down_sync(0xffffffffu, a, o); b += __shfl_down_sync(0xffffffffu, b, o); c += __shfl_down_sync(0xffffffffu, c, o); }
+        if (lane == 0) { atomicAdd(counters, a); atomicAdd(counters + 1, b); atomicAdd(counters + 2, c); }
+    }
 }
 
 __global__ void __launch_bounds__(128) k_wf_stage_a(DScene sc, DLaunch ln, uint32_t it, uint32_t n, WfBuffers wb) {
     const uint32_t i = blockIdx.x * 128 + threadIdx.x;
     bool push = false; Ray sr;
-    if (i < n) {
-        WfState S = wb.states[i];
-        if (S.depth != 0xffffffffu && S.active) {
-            const Hit h = wb.hits[i];
-            push = wf_stage_a(sc, S, wb.logs[i], h, it, ln.max_depth);
-            sr = S.shadow_ray;
-            wb.states[i] = S;
+    if (i < n && wb.status[i] == WF_LIVE) {
+        WfState S; soa_load(S, wb.states, wb.capacity, i);
+        const Hit h = wb.hits[i];
+        if (it == 0) {
+            PathHead H; soa_load(H, wb.heads, wb.capacity, i);
+            push = wf_stage_a(sc, S, H, h, it, ln.max_depth);
+            soa_store(H, wb.heads, wb.capacity, i);
+        } else {
+            PathHead H;                                   // only written at the first hit
+            push = wf_stage_a(sc, S, H, h, it, ln.max_depth);
         }
+        sr = S.shadow_ray;
+        soa_store(S, wb.states, wb.capacity, i);
     }
     const uint32_t q = queue_push(wb.counters + 32 + it, push);
     if (push) queue_write(wb.q_any, q, sr, i);
@@ -343,21 +487,19 @@ __global__ void __launch_bounds__(128) k_wf_stage_a(DScene sc, DLaunch ln, uint3
 __global__ void __launch_bounds__(128) k_wf_stage_b(DScene sc, DLaunch ln, uint32_t it, uint32_t max_iter, uint32_t n, WfBuffers wb) {
     const uint32_t i = blockIdx.x * 128 + threadIdx.x;
     bool push_direct = false, push_next = false; Ray direct, next;
-    if (i < n) {
-        WfState S = wb.states[i];
-        if (S.depth != 0xffffffffu) {
-            if (S.active) {
-                const Hit h = wb.hits[i];
-                const bool occluded = S.need_shadow && wb.occl[i] != 0u;
-                wf_stage_b(sc, S, wb.logs[i], h, occluded, it, ln.rr_depth, direct, push_direct);
-                push_next = S.active && it + 1 < max_iter; next = S.ray;
-                wb.states[i] = S;
-            } else if (it < EPSM_MAXV) {
-                // a lane that has left the path: its logged vertex is inactive (every use is masked by `active`)
-                VLog &v = wb.logs[i].v[it];
-                memset(&v, 0, sizeof(VLog)); v.prim = 0xffffffffu;
-            }
+    if (i < n && wb.status[i] == WF_LIVE) {
+        WfState S; soa_load(S, wb.states, wb.capacity, i);
+        const Hit h = wb.hits[i];
+        const bool occluded = S.need_shadow && wb.occl[i] != 0u;
+        VLog v;
+        wf_stage_b(sc, S, v, h, occluded, it, ln.rr_depth, direct, push_direct);
+        if (it < EPSM_MAXV) {
+            soa_store(v, wb.vlogs + (size_t) it * WORDS_OF(VLog) * wb.capacity, wb.capacity, i);
+            wb.vmask[(size_t) it * wb.capacity + i] = 1;
         }
+        push_next = S.active && it + 1 < max_iter; next = S.ray;
+        soa_store(S, wb.states, wb.capacity, i);
+        if (!S.active) wb.status[i] = WF_DONE;
     }
     const uint32_t qd = queue_push(wb.counters + (it + 1), push_direct);
     if (push_direct) queue_write(wb.q_closest, qd, direct, wb.capacity + it * wb.capacity + i);
@@ -367,7 +509,7 @@ __global__ void __launch_bounds__(128) k_wf_stage_b(DScene sc, DLaunch ln, uint3
 
 __global__ void k_count_lanes(uint32_t n, WfBuffers wb, unsigned long long *counters) {
     const uint32_t i = blockIdx.x * 128 + threadIdx.x;
-    const bool live = i < n && wb.states[i].depth != 0xffffffffu;
+    const bool live = i < n && wb.status[i] != WF_NONE;
     const unsigned m = __ballot_sync(0xffffffffu, live);
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(counters + 3, (unsigned long long) __popc(m));
 }
@@ -377,13 +519,21 @@ __global__ void __launch_bounds__(128) k_wf_finish(DScene sc, DLaunch ln, uint64
                                                    float *__restrict__ grad_pos, float *__restrict__ grad_nrm, float *__restrict__ records) {
     const uint32_t i = blockIdx.x * 128 + threadIdx.x;
     if (i >= n) return;
-    if (wb.states[i].depth == 0xffffffffu) return;
-    PathLog &P = wb.logs[i];
+    if (wb.status[i] == WF_NONE) return;
+    PathLog P;
+    soa_load(static_cast<PathHead &>(P), wb.heads, wb.capacity, i);
     const uint32_t max_iter = wf_iterations(ln.max_depth);
     const int n_logged = (int) (max_iter < EPSM_MAXV ? max_iter : EPSM_MAXV);      // len(path_info) − 1
-    for (int k = 0; k < n_logged; ++k)
-        if (P.v[k].active && P.v[k].direct_traced) wf_direct_hit(sc, P.v[k], wb.hits[wb.capacity + (size_t) k * wb.capacity + i]);
-    P.L = wb.states[i].L;
+    for (int k = 0; k < EPSM_MAXV; ++k) {
+        if (k < n_logged && wb.vmask[(size_t) k * wb.capacity + i]) {
+            soa_load(P.v[k], wb.vlogs + (size_t) k * WORDS_OF(VLog) * wb.capacity, wb.capacity, i);
+            if (P.v[k].active && P.v[k].direct_traced) wf_direct_hit(sc, P.v[k], wb.hits[wb.capacity + (size_t) k * wb.capacity + i]);
+        } else {
+            // a lane that has left the path: its logged vertex is inactive (every use is masked by `active`)
+            memset(&P.v[k], 0, sizeof(VLog)); P.v[k].prim = 0xffffffffu;
+        }
+    }
+    { WfState S; soa_load(S, wb.states, wb.capacity, i); P.L = S.L; }
     PathGrads G;
     calc_grad(P, ln.variant, n_logged, G);
     if (RECORD) { const WorkItem wi = wf_work_item(ln, work_base + i); write_record(P, G, n_logged, records + (wi.lane - ln.lane_begin) * EPSM_REC_FLOATS); }
