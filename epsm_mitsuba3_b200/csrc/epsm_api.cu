@@ -53,6 +53,7 @@ struct epsm_ctx {
     DevBuf<unsigned long long> d_counters;
     DevBuf<unsigned char> d_workspace; uint32_t wf_capacity = 0, trace_grid = 0;   // wavefront workspace (one chunk of lanes)
     DScene sc;
+    bool trace_profiling = false; EpsmEventList trace_events;
 };
 
 namespace {
@@ -341,7 +342,7 @@ int epsm_render_backward(epsm_ctx *ctx, int variant, uint32_t sensor, uint32_t s
         rc = ensure_workspace(ctx, (uint64_t) ((ln.sensor.w + 7) / 8) * ((ln.sensor.h + 3) / 4) * 32ull * S); if (rc) return rc;
     }
     CK(epsm_launch_backward(ctx->sc, ln, d_gin, d_gp, d_gn, nullptr, counters ? ctx->d_counters.p : nullptr, ctx->d_workspace.p, ctx->wf_capacity,
-                            ctx->trace_grid, &ctx->launches, ctx->stream), "wavefront backward");
+                            ctx->trace_grid, &ctx->launches, ctx->trace_profiling ? &ctx->trace_events : nullptr, ctx->stream), "wavefront backward");
     if (mem == EPSM_MEM_HOST) {
         CK(cudaMemcpyAsync(grad_pos, d_gp, n_v * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream), "D2H grad_pos");
         CK(cudaMemcpyAsync(grad_nrm, d_gn, n_v * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream), "D2H grad_nrm");
@@ -369,7 +370,7 @@ int epsm_path_records(epsm_ctx *ctx, int variant, uint32_t sensor, uint32_t seed
         rc = ensure_workspace(ctx, (uint64_t) ((ln.sensor.w + 7) / 8) * ((ln.sensor.h + 3) / 4) * 32ull * S); if (rc) return rc;
     }
     CK(epsm_launch_backward(ctx->sc, ln, d_gin, nullptr, nullptr, d_rec, nullptr, ctx->d_workspace.p, ctx->wf_capacity, ctx->trace_grid,
-                            &ctx->launches, ctx->stream), "wavefront backward (records)");
+                            &ctx->launches, nullptr, ctx->stream), "wavefront backward (records)");
     if (mem == EPSM_MEM_HOST) {
         CK(cudaMemcpyAsync(records, d_rec, n_rec * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream), "D2H records");
         CK(cudaStreamSynchronize(ctx->stream), "records sync");
@@ -426,6 +427,26 @@ int epsm_set_sample_range(epsm_ctx *ctx, uint32_t s_begin, uint32_t s_end) {
     if (!ctx) return EPSM_E_INVALID;
     if (s_begin > s_end) return fail(ctx, EPSM_E_INVALID, "s_begin > s_end");
     ctx->s_begin = s_begin; ctx->s_end = s_end;
+    return EPSM_OK;
+}
+
+int epsm_set_trace_profiling(epsm_ctx *ctx, int enable) {
+    if (!ctx) return EPSM_E_INVALID;
+    ctx->trace_profiling = enable != 0;
+    return EPSM_OK;
+}
+
+int epsm_get_trace_profile(epsm_ctx *ctx, double *ms, uint64_t *launches) {
+    if (!ctx || !ms || !launches) return EPSM_E_INVALID;
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    CK(cudaStreamSynchronize(ctx->stream), "sync");
+    double total = 0;
+    for (auto &e : ctx->trace_events) {
+        float t = 0; cudaEventElapsedTime(&t, e.first, e.second); total += t;
+        cudaEventDestroy(e.first); cudaEventDestroy(e.second);
+    }
+    *ms = total; *launches = ctx->trace_events.size();
+    ctx->trace_events.clear();
     return EPSM_OK;
 }
 

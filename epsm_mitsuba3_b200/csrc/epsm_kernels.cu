@@ -524,13 +524,24 @@ __global__ void __launch_bounds__(128) k_wf_finish(DScene sc, DLaunch ln, uint64
     soa_load(static_cast<PathHead &>(P), wb.heads, wb.capacity, i);
     const uint32_t max_iter = wf_iterations(ln.max_depth);
     const int n_logged = (int) (max_iter < EPSM_MAXV ? max_iter : EPSM_MAXV);      // len(path_info) − 1
+    // Only the prefix of the path that can carry gradients is fetched: the chain ends at the first diffuse vertex
+    // (manifold, epsm.py:855,920) or at the second one (caustic: vertex 1 must be diffuse, epsm.py:999,1008), at a
+    // non-mesh vertex or where the path left the scene; every output beyond it is masked to zero by calc_grad.
+    bool chain = true; int n_diffuse = 0;
     for (int k = 0; k < EPSM_MAXV; ++k) {
-        if (k < n_logged && wb.vmask[(size_t) k * wb.capacity + i]) {
+        if (k < n_logged && (chain || RECORD) && wb.vmask[(size_t) k * wb.capacity + i]) {
             soa_load(P.v[k], wb.vlogs + (size_t) k * WORDS_OF(VLog) * wb.capacity, wb.capacity, i);
-            if (P.v[k].active && P.v[k].direct_traced) wf_direct_hit(sc, P.v[k], wb.hits[wb.capacity + (size_t) k * wb.capacity + i]);
+            VLog &v = P.v[k];
+            if (v.active && v.direct_traced) wf_direct_hit(sc, v, wb.hits[wb.capacity + (size_t) k * wb.capacity + i]);
+            const bool diffuse = (v.flags & EPSM_BF_DIFFUSE) != 0;
+            n_diffuse += diffuse ? 1 : 0;
+            if (!v.active || !v.ismesh) chain = false;
+            if (ln.variant == EPSM_VARIANT_MANIFOLD) { if (diffuse) chain = false; }
+            else { if ((k == 0 && !diffuse) || n_diffuse >= 2) chain = false; }
         } else {
-            // a lane that has left the path: its logged vertex is inactive (every use is masked by `active`)
+            // a lane that has left the path (or the gradient-dead tail): the logged vertex is inactive
             memset(&P.v[k], 0, sizeof(VLog)); P.v[k].prim = 0xffffffffu;
+            chain = false;
         }
     }
     { WfState S; soa_load(S, wb.states, wb.capacity, i); P.L = S.L; }
@@ -631,7 +642,9 @@ cudaError_t epsm_launch_develop(const float *film, uint64_t n_pixels, float *out
 }
 cudaError_t epsm_launch_backward(const DScene &sc, DLaunch ln, const float *grad_in, float *grad_pos, float *grad_nrm, float *records,
                                  unsigned long long *counters, void *workspace, uint32_t capacity, uint32_t trace_grid, uint64_t *n_launches,
-                                 cudaStream_t s) {
+                                 EpsmEventList *trace_events, cudaStream_t s) {
+    auto ev_begin = [&]() { if (trace_events) { cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, s); trace_events->push_back({a, b}); } };
+    auto ev_end = [&]() { if (trace_events) cudaEventRecord(trace_events->back().second, s); };
     tile_rows(ln);
     const uint32_t tiles = tile_grid(ln);
     if (tiles == 0 || ln.s_end <= ln.s_begin) return cudaSuccess;
@@ -646,13 +659,17 @@ cudaError_t epsm_launch_backward(const DScene &sc, DLaunch ln, const float *grad
         k_wf_init<<<grid, 128, 0, s>>>(ln, base, n, grad_in, wb); ++launches;
         for (uint32_t it = 0; it <= max_iter; ++it) {
             // closest-hit queue `it`: path rays of iteration `it` and the direct rays of iteration `it − 1`
+            ev_begin();
             if (counters) k_wf_trace<false, true><<<trace_grid, CTA, 0, s>>>(sc, wb.q_closest, wb.counters + it, wb.counters + 16 + it, wb.hits, nullptr, counters);
             else k_wf_trace<false, false><<<trace_grid, CTA, 0, s>>>(sc, wb.q_closest, wb.counters + it, wb.counters + 16 + it, wb.hits, nullptr, nullptr);
+            ev_end();
             ++launches;
             if (it == max_iter) break;
             k_wf_stage_a<<<grid, 128, 0, s>>>(sc, ln, it, n, wb); ++launches;
+            ev_begin();
             if (counters) k_wf_trace<true, true><<<trace_grid, CTA, 0, s>>>(sc, wb.q_any, wb.counters + 32 + it, wb.counters + 48 + it, nullptr, wb.occl, counters);
             else k_wf_trace<true, false><<<trace_grid, CTA, 0, s>>>(sc, wb.q_any, wb.counters + 32 + it, wb.counters + 48 + it, nullptr, wb.occl, nullptr);
+            ev_end();
             ++launches;
             k_wf_stage_b<<<grid, 128, 0, s>>>(sc, ln, it, max_iter, n, wb); ++launches;
         }

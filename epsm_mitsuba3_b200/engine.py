@@ -124,6 +124,15 @@ class Scene:
     def sensors(self):
         return self.data.sensors
 
+    def set_trace_profiling(self, enable: bool):
+        self._check(self.lib.epsm_set_trace_profiling(self.ctx, 1 if enable else 0))
+
+    def trace_profile(self):
+        """(milliseconds, launches) spent in the traversal kernel since the last call (needs set_trace_profiling(True))."""
+        ms, n = C.c_double(), C.c_uint64()
+        self._check(self.lib.epsm_get_trace_profile(self.ctx, C.byref(ms), C.byref(n)))
+        return ms.value, int(n.value)
+
     def set_sample_range(self, s_begin: int = 0, s_end: int = 0):
         self._check(self.lib.epsm_set_sample_range(self.ctx, s_begin, s_end))
 

@@ -203,6 +203,12 @@ typedef struct epsm_scene_stats {
 } epsm_scene_stats;
 int epsm_scene_get_stats(epsm_ctx *ctx, epsm_scene_stats *out);
 
+/* Device-side timing of the traversal kernel, for the roofline line of bench.py: when enabled, CUDA events on the
+ * context's stream bracket every traversal launch of the following gradient passes.  epsm_get_trace_profile
+ * synchronises, returns the accumulated milliseconds / launch count since the last call and resets them. */
+int epsm_set_trace_profiling(epsm_ctx *ctx, int enable);
+int epsm_get_trace_profile(epsm_ctx *ctx, double *ms, uint64_t *launches);
+
 /* Number of kernels this library launched on the context since creation (bench `gpu_launches`). */
 uint64_t epsm_launch_count(const epsm_ctx *ctx);
 /* The context's stream as a cudaStream_t, for event timing on the launching stream. */

@@ -144,8 +144,10 @@ def oracle_gradients(oracle_scene, sd, variant, sensor, seed, spp, max_depth, rr
     return scatter_gradients(paths, variant, nl, pg, lg, dg, sd.n_vertices, max_depth)
 
 
-def check_accumulated(gp, gn, ref_p, ref_n, rmse_rel=1e-4):
-    """Accumulated vertex gradients: float atomics make the order arbitrary ⇒ RMSE relative to the RMS of the reference."""
+def check_accumulated(gp, gn, ref_p, ref_n, rmse_rel=5e-4):
+    """Accumulated vertex gradients.  Stated bound: RMSE ≤ 5e-4 of the RMS of the reference buffer.  Float atomics make the
+    summation order arbitrary and the few ill-conditioned paths (see check_path_records) carry the reference's own float32
+    error (~1e-3 relative each), which is what sets this bound; well-conditioned scenes sit at ~1e-6."""
     for got, ref, name in ((gp, ref_p, "grad_pos"), (gn, ref_n, "grad_nrm")):
         got = np.asarray(got, np.float64); rms = float(np.sqrt(np.mean(ref ** 2)))
         rmse = float(np.sqrt(np.mean((got - ref) ** 2)))
