@@ -158,6 +158,8 @@ def main():
     ap.add_argument("--tris", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--full-replay", action="store_true", help="time the unpruned replay (every lane runs min(max_depth,6) iterations, as the reference does)")
+    ap.add_argument("--no-full-replay-leg", action="store_true", help="skip the extra full-replay measurement reported beside the default")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -169,7 +171,9 @@ def main():
     config = {"workload": wl["desc"], "scene": args.workload, "integrator": wl["variant"], "max_depth": wl["max_depth"],
               "resolution": [res, res], "spp": spp, "paths_per_step": res * res * spp,
               "sharding": f"sample-index shards over {world} rank(s) + 1 NCCL allreduce of the vertex-gradient buffer" if world > 1 else "single GPU",
-              "l2": "256 MiB buffer written between timed steps (L2 flush); BVH+triangles of the 1M-tri scene are ~80 MB"}
+              "l2": "256 MiB buffer written between timed steps (L2 flush); BVH+triangles of the 1M-tri scene are ~100 MB",
+              "replay": "full (every lane replays min(max_depth,6) iterations)" if args.full_replay else
+                        "gradient-live prefix (each path stops where calc_grad masks everything behind it; gradients identical to the full replay)"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -200,6 +204,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     sd = build_scene(args.workload, res, spp, args.tris)
     scene = ep.Scene(sd, device=local)
+    scene.set_full_replay(args.full_replay)
     stats = scene.stats()
     integ = ep.load_dict({"type": wl["variant"], "max_depth": wl["max_depth"]})
     sensor = 1                                                # full-resolution sensor; benchmark semantics N_g = W·H·spp
@@ -252,6 +257,19 @@ def main():
     ms_per_step = ms_total / args.steps
     total_paths = res * res * spp
     value = total_paths / (ms_per_step * 1e-3)
+
+    # ---- the unpruned replay beside the default, for transparency (same scene, same seeds)
+    full_leg = None
+    if not args.full_replay and not args.no_full_replay_leg:
+        scene.set_full_replay(True)
+        step(0, False)
+        fm = [step(args.warmup + k, True) for k in range(2)]
+        scene.set_full_replay(False)
+        fms = float(np.mean(fm))
+        if world > 1:
+            t = torch.tensor([fms], device=scene.device); dist.all_reduce(t, op=dist.ReduceOp.MAX); fms = float(t.item())
+        full_leg = {"value": total_paths / (fms * 1e-3), "unit": "samples/s", "ms_per_step": fms,
+                    "note": "epsm_set_full_replay(1): no gradient-liveness pruning, 1 warm-up + 2 timed steps"}
 
     # ---- e2e: the same pass through the C ABI with host buffers (pinned H2D of grad_in, D2H of the gradient buffers)
     e2e = None
@@ -327,7 +345,7 @@ def main():
         out = {"metric": "gradient path samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
-               "roofline": roof, "cpu_baseline": cpu,
+               "roofline": roof, "cpu_baseline": cpu, "full_replay": full_leg,
                "scene": {"triangles": int(stats["n_triangles"]), "vertices": int(stats["n_vertices"]), "bvh_nodes": int(stats["n_nodes"]),
                          "bvh_build_ms": stats["build_ms"]},
                "wall_s_timed_region": t_wall}

@@ -57,7 +57,7 @@ EXPORTS = [
     "epsm_scene_update_vertices", "epsm_scene_commit", "epsm_trace",
     "epsm_render_accumulate", "epsm_film_clear", "epsm_film_raw", "epsm_film_develop", "epsm_render",
     "epsm_render_backward", "epsm_path_records", "epsm_sampler_stream", "epsm_sample_rays",
-    "epsm_set_sample_range", "epsm_set_trace_profiling", "epsm_get_trace_profile", "epsm_scene_get_stats", "epsm_launch_count", "epsm_stream", "epsm_synchronize",
+    "epsm_set_sample_range", "epsm_set_full_replay", "epsm_set_trace_profiling", "epsm_get_trace_profile", "epsm_scene_get_stats", "epsm_launch_count", "epsm_stream", "epsm_synchronize",
 ]
 
 _LIB = None
@@ -101,6 +101,7 @@ def load_library() -> C.CDLL:
     lib.epsm_sampler_stream.argtypes = [vp, u32, u64, u64, u32, fp, i32]
     lib.epsm_sample_rays.argtypes = [vp, u32, u32, u32, u64, u64, fp, i32]
     lib.epsm_set_sample_range.argtypes = [vp, u32, u32]
+    lib.epsm_set_full_replay.argtypes = [vp, i32]
     lib.epsm_set_trace_profiling.argtypes = [vp, i32]
     lib.epsm_get_trace_profile.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(u64)]
     lib.epsm_scene_get_stats.argtypes = [vp, C.POINTER(SceneStats)]

@@ -43,6 +43,7 @@ struct epsm_ctx {
     uint64_t launches = 0;
     bool have_scene = false, dirty = false;
     uint32_t s_begin = 0, s_end = 0;                // sample-range shard (0,0 = all)
+    bool full_replay = false;                       // gradient pass without liveness pruning (epsm_set_full_replay)
     HostScene hs;                                   // host mirror (positions are needed for BVH rebuilds)
     std::vector<uint8_t> mesh_dirty;
     // device
@@ -130,7 +131,7 @@ int make_launch(epsm_ctx *ctx, uint32_t sensor, uint32_t seed, uint32_t spp, uin
     if (lane_begin > lane_end) return fail(ctx, EPSM_E_INVALID, "lane_begin > lane_end");
     ln.seed = seed; ln.spp = spp; ln.max_depth = max_depth; ln.rr_depth = rr_depth;
     ln.lane_begin = lane_begin; ln.lane_end = lane_end; ln.variant = variant; ln.tile_y0 = ln.tile_y1 = 0;
-    ln.s_begin = 0; ln.s_end = spp;
+    ln.s_begin = 0; ln.s_end = spp; ln.prune = ctx->full_replay ? 0u : 1u;
     if (ctx->s_end != 0) {
         if (ctx->s_begin > ctx->s_end || ctx->s_end > spp) return fail(ctx, EPSM_E_INVALID, "sample range exceeds spp");
         ln.s_begin = ctx->s_begin; ln.s_end = ctx->s_end;
@@ -155,6 +156,7 @@ int epsm_create(int device, epsm_ctx **out) {
     e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete c; return fail(nullptr, EPSM_E_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e)); }
     memset(&c->sc, 0, sizeof(c->sc));
+    if (const char *e = getenv("EPSM_FULL_REPLAY")) c->full_replay = atoi(e) != 0;
     cudaDeviceProp prop; cudaGetDeviceProperties(&prop, device);
     c->trace_grid = (uint32_t) prop.multiProcessorCount * 8u;        // persistent traversal CTAs: 148 SMs × 8 resident CTAs of 128 threads (≤ 64 regs)
     *out = c; return EPSM_OK;
@@ -359,6 +361,7 @@ int epsm_path_records(epsm_ctx *ctx, int variant, uint32_t sensor, uint32_t seed
     if (!grad_in_hw5 || !records) return fail(ctx, EPSM_E_INVALID, "grad_in / records is NULL");
     DLaunch ln; int rc = make_launch(ctx, sensor, seed, spp, max_depth, rr_depth, lane_begin, lane_end, variant, ln);
     if (rc) return rc;
+    ln.prune = 0;                                    // records are those of the full replay (every logged vertex of epsm.py:648-654)
     CK(cudaSetDevice(ctx->device), "cudaSetDevice");
     const size_t n_img = (size_t) ln.sensor.w * ln.sensor.h * 5, n_rec = (size_t) (ln.lane_end - ln.lane_begin) * EPSM_REC_FLOATS;
     const float *d_gin; rc = to_device(ctx, grad_in_hw5, n_img, mem, ctx->stage_a, &d_gin); if (rc) return rc;
@@ -418,7 +421,7 @@ int epsm_scene_get_stats(epsm_ctx *ctx, epsm_scene_stats *out) {
     if (!ctx->have_scene) return fail(ctx, EPSM_E_NOSCENE, "no scene uploaded");
     out->n_triangles = ctx->hs.faces.size() / 3; out->n_vertices = ctx->hs.pos.size() / 3;
     out->n_nodes = ctx->hs.bvh.nodes.size() / EPSM_NODE_F4;
-    out->node_bytes = EPSM_NODE_F4 * 16; out->tri_bytes = EPSM_TRI_F4 * 16; out->bvh_width = 4; out->max_leaf = EPSM_MAX_LEAF;
+    out->node_bytes = EPSM_NODE_F4 * 16; out->tri_bytes = EPSM_TRI_BYTES; out->bvh_width = 4; out->max_leaf = EPSM_MAX_LEAF;
     out->build_ms = ctx->hs.bvh.build_ms;
     return EPSM_OK;
 }
@@ -427,6 +430,12 @@ int epsm_set_sample_range(epsm_ctx *ctx, uint32_t s_begin, uint32_t s_end) {
     if (!ctx) return EPSM_E_INVALID;
     if (s_begin > s_end) return fail(ctx, EPSM_E_INVALID, "s_begin > s_end");
     ctx->s_begin = s_begin; ctx->s_end = s_end;
+    return EPSM_OK;
+}
+
+int epsm_set_full_replay(epsm_ctx *ctx, int enable) {
+    if (!ctx) return EPSM_E_INVALID;
+    ctx->full_replay = enable != 0;
     return EPSM_OK;
 }
 

@@ -129,6 +129,7 @@ struct Collapser {
             out.tris.push_back(f4{p0[0], p0[1], p0[2], pf});
             out.tris.push_back(f4{e1[0], e1[1], e1[2], e2[0]});
             out.tris.push_back(f4{e2[1], e2[2], 0.f, 0.f});
+            out.tris.push_back(f4{0.f, 0.f, 0.f, 0.f});
         }
         return first;
     }

@@ -48,6 +48,28 @@ EPSM_HD f4 ldg4(const f4 *p) {
     return *p;
 #endif
 }
+// 256-bit read-only load (sm_100a: LDG.E.256.CONSTANT — one L1 data-pipe wavefront per thread instead of two);
+// `p` must be 32-byte aligned.
+struct f8 { f4 a, b; };
+EPSM_HD f8 ldg8(const f4 *p) {
+#ifdef __CUDA_ARCH__
+    f8 r;
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w) : "l"(p));
+    return r;
+#else
+    return f8{p[0], p[1]};
+#endif
+}
+struct f2 { float x, y; };
+EPSM_HD f2 ldg2(const f4 *p) {
+#ifdef __CUDA_ARCH__
+    float2 v = __ldg(reinterpret_cast<const float2 *>(p));
+    return f2{v.x, v.y};
+#else
+    return f2{p->x, p->y};
+#endif
+}
 EPSM_HD f3 mk3(float x, float y, float z) { return f3{x, y, z}; }
 EPSM_HD f3 operator+(f3 a, f3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
 EPSM_HD f3 operator-(f3 a, f3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
@@ -222,11 +244,11 @@ EPSM_HDN Hit bvh_trace(const DScene &sc, const Ray &ray, TStack &st, uint32_t &n
         st.pop(ref, tn);
         if (tn > hit.t) continue;
         if ((int32_t) ref < 0) {
-            // ---- leaf: up to 4 triangles, 3 × 128-bit loads each ----
+            // ---- leaf: up to 4 triangles, one 256-bit + one 64-bit load each ----
             uint32_t code = ~ref, first = code >> 2, cnt = (code & 3u) + 1u;
             for (uint32_t i = 0; i < cnt; ++i) {
                 const f4 *tp = sc.tris + (size_t) (first + i) * EPSM_TRI_F4;
-                f4 a = ldg4(tp), b = ldg4(tp + 1), c = ldg4(tp + 2);
+                const f8 ab = ldg8(tp); const f2 c = ldg2(tp + 2); const f4 a = ab.a, b = ab.b;
                 if (COUNT) ++n_tris;
                 float t, u, v;
                 if (tri_test(ray, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(b.w, c.x, c.y), hit.t, t, u, v)) {
@@ -237,9 +259,10 @@ EPSM_HDN Hit bvh_trace(const DScene &sc, const Ray &ray, TStack &st, uint32_t &n
             }
             continue;
         }
-        // ---- inner node: one 128-byte line as eight 128-bit loads ----
+        // ---- inner node: one 128-byte line as three 256-bit loads + one 128-bit load ----
         const f4 *np = sc.nodes + (size_t) ref * EPSM_NODE_F4;
-        f4 lx = ldg4(np), ly = ldg4(np + 1), lz = ldg4(np + 2), hx = ldg4(np + 3), hy = ldg4(np + 4), hz = ldg4(np + 5), ch = ldg4(np + 6);
+        const f8 n0 = ldg8(np), n1 = ldg8(np + 2), n2 = ldg8(np + 4);
+        const f4 lx = n0.a, ly = n0.b, lz = n1.a, hx = n1.b, hy = n2.a, hz = n2.b, ch = ldg4(np + 6);
         if (COUNT) ++n_nodes;
         uint32_t key[4];
         float tmn[4];
@@ -688,11 +711,21 @@ struct WfState {
     float eta, prev_pdf;
     uint32_t depth;
     bool active, prev_delta;
+    bool chain;                   // every vertex so far continues the gradient chain of calc_grad (see wf_chain_vertex)
     // stage A → stage B
-    bool active_next, smooth, need_shadow;
+    bool active_next, smooth, need_shadow, chain_vertex;
     DSamp ds; f3 em_weight;
     Ray shadow_ray;
 };
+
+EPSM_HD uint32_t wf_iterations(uint32_t max_depth_prop) { return max_depth_prop < EPSM_MAX_ITER ? max_depth_prop : EPSM_MAX_ITER; }   // epsm.py:549
+
+// Iterations of the replay: min(max_depth, 6) (epsm.py:549); only the first EPSM_MAXV vertices are logged (epsm.py:648), so a
+// pruned replay never needs the sixth.
+EPSM_HD uint32_t wf_replay_iterations(uint32_t max_depth_prop, bool prune) {
+    const uint32_t m = wf_iterations(max_depth_prop);
+    return prune && m > EPSM_MAXV ? EPSM_MAXV : m;
+}
 
 EPSM_HDN void wf_begin(const DSensor &sensor, uint32_t px, uint32_t py, uint32_t seed, uint32_t lane, float gx, float gy, WfState &S, PathHead &P) {
     S.rng = pcg_for_lane(seed, lane);
@@ -700,13 +733,28 @@ EPSM_HDN void wf_begin(const DSensor &sensor, uint32_t px, uint32_t py, uint32_t
     S.ray = c.ray;
     S.grad_d = (c.d_x - c.ray.d) * gx + (c.d_y - c.ray.d) * gy;                    // pixel motion → tangent of ray.d (epsm.py:250-257)
     S.beta = mk3(1, 1, 1); S.L = mk3(0, 0, 0); S.prev_p = mk3(0, 0, 0); S.eta = 1.f; S.prev_pdf = 1.f; S.depth = 0;
-    S.active = true; S.prev_delta = true; S.active_next = S.smooth = S.need_shadow = false;
+    S.active = true; S.prev_delta = true; S.active_next = S.smooth = S.need_shadow = false; S.chain = true; S.chain_vertex = false;
     P.cam = c.ray.o; P.d = c.ray.d; P.dlduv0 = P.dlduv1 = 0.f; P.dldp1 = mk3(0, 0, 0); P.L = mk3(0, 0, 0);
+}
+
+// Gradient liveness.  calc_grad walks the logged vertices in order and stops producing outputs at the first vertex that
+// ends the specular chain: `manifold` stops at the first vertex that is diffuse, not on a mesh or inactive
+// (epsm.py:793-796,855,862,920,928 — `valid`, `hasdiffuse > 0`, `active` masks); `manifold_caustic` needs a diffuse
+// first vertex (epsm.py:999,1008) and then stops at the second diffuse / non-mesh / inactive vertex.  That terminating
+// vertex is still read as the "next vertex" of section B (position, triangle, flags), but nothing behind it and none
+// of its own emitter / BSDF data reach path_grad, light_grad or diffuse_grad, which are the only things
+// render_backward's scatter consumes.  With `prune` the replay therefore stops there (and skips emitter sampling,
+// shadow and light-direction rays wherever their results cannot reach an output); the gradients are unchanged and
+// tests hold the pruned pass to the full replay.  Every random number is still drawn in the reference order.
+EPSM_HD bool wf_chain_vertex(const WfState &S, int variant, uint32_t it, bool vact, uint32_t ismesh, uint32_t flags) {
+    const bool diffuse = (flags & EPSM_BF_DIFFUSE) != 0;
+    if (variant == EPSM_VARIANT_MANIFOLD) return S.chain && vact && ismesh && !diffuse;
+    return S.chain && vact && ismesh && (it == 0 ? diffuse : !diffuse);
 }
 
 // After the closest hit `h` of S.ray: surface interaction, first-hit tangents, emission, emitter sampling up to
 // (not including) its visibility test.  Returns true when S.shadow_ray must be tested.
-EPSM_HDN bool wf_stage_a(const DScene &sc, WfState &S, PathHead &P, const Hit &h_in, uint32_t it, uint32_t max_depth_prop) {
+EPSM_HDN bool wf_stage_a(const DScene &sc, WfState &S, PathHead &P, const Hit &h_in, uint32_t it, uint32_t max_depth_prop, int variant, bool prune) {
     Hit h = h_in;
     if (!S.active) { h.t = INFINITY; h.u = h.v = 0.f; h.prim = 0xffffffffu; }
     SI si; compute_si(sc, S.ray, h, si);
@@ -728,18 +776,27 @@ EPSM_HDN bool wf_stage_a(const DScene &sc, WfState &S, PathHead &P, const Hit &h
     S.L = S.L + Le;
     S.active_next = (S.depth + 1 < max_depth_prop) && si.valid;
     uint32_t flags = si.valid ? sc.bsdfs[si.bsdf].bflags : 0u;
-    S.smooth = S.active_next && (flags & EPSM_BF_SMOOTH);
+    const bool vact = S.active && si.valid;
+    S.chain_vertex = wf_chain_vertex(S, variant, it, vact, si.ismesh, flags);
+    bool need_nee = true, need_occl = true;
+    if (prune) {
+        // active_em is read by section A of `manifold` only (epsm.py:855-866); ds.p and si_direct of the first
+        // vertex feed the shadow seed when max_depth ≤ 3 (epsm.py:609-620)
+        need_occl = variant == EPSM_VARIANT_MANIFOLD && S.chain_vertex;
+        need_nee = need_occl || (it == 0 && vact && wf_iterations(max_depth_prop) <= 3);
+    }
+    S.smooth = S.active_next && (flags & EPSM_BF_SMOOTH) && need_nee;
     float e1r = pcg_f32(S.rng), e2r = pcg_f32(S.rng);
     S.need_shadow = false;
     // the visibility query is deferred: record the shadow ray, assume visible, fix up in stage B (scene.cpp:259-263)
-    sample_emitter_direction(sc, si, e1r, e2r, S.smooth, S.ds, S.em_weight, [&](const Ray &r) { S.shadow_ray = r; S.need_shadow = true; return false; });
+    sample_emitter_direction(sc, si, e1r, e2r, S.smooth, S.ds, S.em_weight, [&](const Ray &r) { if (need_occl) { S.shadow_ray = r; S.need_shadow = true; } return false; });
     return S.need_shadow;
 }
 
 // After the visibility test: NEE contribution, the two BSDF samples, the vertex log, the ray towards the light
 // sample (returned in `direct`, traced later as a closest-hit query) and the next path ray.
 // `v` receives the logged vertex when it < EPSM_MAXV (epsm.py:648).
-EPSM_HDN void wf_stage_b(const DScene &sc, WfState &S, VLog &v, const Hit &h_in, bool occluded, uint32_t it, uint32_t rr_depth,
+EPSM_HDN void wf_stage_b(const DScene &sc, WfState &S, VLog &v, const Hit &h_in, bool occluded, uint32_t it, uint32_t rr_depth, bool prune,
                          Ray &direct, bool &direct_valid) {
     Hit h = h_in;
     if (!S.active) { h.t = INFINITY; h.u = h.v = 0.f; h.prim = 0xffffffffu; }
@@ -786,6 +843,9 @@ EPSM_HDN void wf_stage_b(const DScene &sc, WfState &S, VLog &v, const Hit &h_in,
     bool rr_continue = pcg_f32(S.rng) < rr_prob;
     active_next = active_next && (!rr_active || rr_continue);
     if (si.valid) S.depth += 1;
+    // the gradient chain ends at this vertex: nothing behind it reaches an output of calc_grad (see wf_chain_vertex)
+    S.chain = S.chain && S.chain_vertex;
+    if (prune && !S.chain) active_next = false;
     S.active = active_next;
 }
 
@@ -803,26 +863,27 @@ EPSM_HDN void wf_direct_hit(const DScene &sc, VLog &v, const Hit &hd) {
     v.dis = dis < 0.01f ? 0.f : dis;
 }
 
-EPSM_HD uint32_t wf_iterations(uint32_t max_depth_prop) { return max_depth_prop < EPSM_MAX_ITER ? max_depth_prop : EPSM_MAX_ITER; }   // epsm.py:549
 
 // The whole replay for one lane with immediate scene queries (the test-only host harness and the record probe use
 // this; the production kernels run the same stages as a wavefront).
 template <bool COUNT>
 EPSM_HDN void path_log(const DScene &sc, Tracer &tr, const DSensor &sensor, uint32_t px, uint32_t py, uint32_t seed, uint32_t lane,
-                       float gx, float gy, uint32_t max_depth_prop, uint32_t rr_depth, PathLog &P) {
+                       float gx, float gy, uint32_t max_depth_prop, uint32_t rr_depth, int variant, bool prune, PathLog &P) {
     WfState S; wf_begin(sensor, px, py, seed, lane, gx, gy, S, P);
-    const uint32_t max_iter = wf_iterations(max_depth_prop);
-    for (uint32_t it = 0; it < max_iter; ++it) {
+    const uint32_t max_iter = wf_replay_iterations(max_depth_prop, prune);
+    uint32_t it = 0;
+    for (; it < max_iter; ++it) {
+        if (prune && !S.active) break;                 // the remaining logged vertices are inactive
         Hit h; h.t = INFINITY; h.u = h.v = 0.f; h.prim = 0xffffffffu;
         if (S.active) h = trace_closest<COUNT>(tr, S.ray);
         bool occluded = false;
-        if (wf_stage_a(sc, S, P, h, it, max_depth_prop)) occluded = trace_any<COUNT>(tr, S.shadow_ray);
+        if (wf_stage_a(sc, S, P, h, it, max_depth_prop, variant, prune)) occluded = trace_any<COUNT>(tr, S.shadow_ray);
         Ray direct; bool dv; VLog scratch;
         VLog &v = it < EPSM_MAXV ? P.v[it] : scratch;
-        wf_stage_b(sc, S, v, h, occluded, it, rr_depth, direct, dv);
+        wf_stage_b(sc, S, v, h, occluded, it, rr_depth, prune, direct, dv);
         if (dv) wf_direct_hit(sc, v, trace_closest<COUNT>(tr, direct));
     }
-    for (uint32_t it = max_iter; it < EPSM_MAXV; ++it) memset(&P.v[it], 0, sizeof(VLog));
+    for (; it < EPSM_MAXV; ++it) { memset(&P.v[it], 0, sizeof(VLog)); P.v[it].prim = 0xffffffffu; }
     P.L = S.L;
 }
 

@@ -335,16 +335,34 @@ __global__ void __launch_bounds__(128) k_wf_init(DLaunch ln, uint64_t work_base,
     if (push) queue_write(wb.q_closest, q, S.ray, i);
 }
 
-// Persistent traversal kernel.  Every lane owns one ray at a time and, when its ray finishes, claims the next queue
-// entry (warp-aggregated atomic) while the other lanes keep traversing — a warp never idles on its slowest ray
-// (the first version claimed 32 rays per warp and ran at 9.6/32 active lanes: profiles/r01_b_*).  One loop iteration =
-// one traversal step per lane: an inner node (one 128-byte line as 7 × 128-bit loads, 4 slab tests, nearest child kept
-// in a register, the others pushed far → near) or a leaf (≤ 4 Möller–Trumbore tests).  Stack entries are 64-bit
-// (ref, entry distance) words in shared memory, [entry][thread] ⇒ conflict-free.  The arithmetic is that of bvh_trace
-// (epsm_device.cuh), so hits stay bit-identical to the oracle.
+// Persistent traversal kernel.  Every lane owns one ray at a time; the warp schedules itself between three phases so
+// that each phase runs with many active lanes (the first wavefront version executed "one step of whatever each lane
+// needs" per iteration and ran its leaf code at 3.2/32 and its refill code at 1.9/32 active lanes: profiles/r01_b_*):
+//
+//   refill   when ≥ WF_REFILL_MIN lanes are idle (or none has a ray): one warp-aggregated atomic claims queue entries,
+//            each idle lane loads its 32-byte ray with one 256-bit load;
+//   inner    lanes whose `cur` is an inner node: one 128-byte node (3 × LDG.E.256 + 1 × LDG.E.128), 4 slab tests,
+//            nearest child kept in a register, the others pushed far → near.  A lane that reaches a leaf parks it in
+//            `leaf` and (WF_SPECULATE) keeps descending from its stack until it meets a second leaf;
+//   leaf     run when ≥ WF_LEAF_MIN lanes hold a parked leaf or no lane can descend: ≤ 4 Möller–Trumbore tests each
+//            (1 × LDG.E.256 + 1 × LDG.E.64 per triangle).
+//
+// Stack entries are 64-bit (ref, entry distance) words in shared memory, [entry][thread] ⇒ conflict-free, spilling to
+// a thread-local array beyond WF_STACK.  The arithmetic is that of bvh_trace (epsm_device.cuh) and the result does
+// not depend on the visiting order (closest t, ties → larger primitive index; every subtree whose padded box reaches
+// t ≤ best is visited), so hits stay bit-identical to the oracle.
 #define WF_STACK 16
 #define WF_LSTACK 80
 #define WF_REF_NONE 0x7fffffffu
+#ifndef WF_REFILL_MIN
+#define WF_REFILL_MIN 8
+#endif
+#ifndef WF_LEAF_MIN
+#define WF_LEAF_MIN 12
+#endif
+#ifndef WF_SPECULATE
+#define WF_SPECULATE 1
+#endif
 template <bool ANY, bool COUNT>
 __global__ void __launch_bounds__(CTA) k_wf_trace(DScene sc, const QRay *__restrict__ queue, const uint32_t *__restrict__ count, uint32_t *head,
                                                   Hit *__restrict__ hits, uint32_t *__restrict__ occl, unsigned long long *counters) {
@@ -354,73 +372,87 @@ __global__ void __launch_bounds__(CTA) k_wf_trace(DScene sc, const QRay *__restr
     uint32_t c_nodes = 0, c_tris = 0, c_rays = 0;
     bool has_ray = false, exhausted = false;
     Ray ray; float ix = 0, iy = 0, iz = 0, ox = 0, oy = 0, oz = 0;
-    float best_t = 0, best_u = 0, best_v = 0; uint32_t best_prim = 0xffffffffu, out = 0, cur = WF_REF_NONE; bool found = false; int sp = 0;
+    float best_t = 0, best_u = 0, best_v = 0; uint32_t best_prim = 0xffffffffu, out = 0, cur = WF_REF_NONE, leaf = WF_REF_NONE; bool found = false; int sp = 0;
     ray.o = ray.d = mk3(0, 0, 0); ray.maxt = 0;
     for (;;) {
+        // ---- refill ----
         const unsigned idle = __ballot_sync(0xffffffffu, !has_ray);
         if (idle) {
-            if (!exhausted) {
-                // claim queue entries for the idle lanes
+            const int n_idle = __popc(idle);
+            if (!exhausted && (n_idle >= WF_REFILL_MIN || idle == 0xffffffffu)) {
+                const int leader = __ffs(idle) - 1;
                 uint32_t base = 0;
-                if (lane == __ffs(idle) - 1) base = atomicAdd(head, (uint32_t) __popc(idle));
-                base = __shfl_sync(0xffffffffu, base, __ffs(idle) - 1);
+                if (lane == leader) base = atomicAdd(head, (uint32_t) n_idle);
+                base = __shfl_sync(0xffffffffu, base, leader);
                 if (!has_ray) {
                     const uint32_t i = base + __popc(idle & ((1u << lane) - 1));
                     if (i < n) {
-                        const float4 a = __ldg(reinterpret_cast<const float4 *>(queue + i)), b = __ldg(reinterpret_cast<const float4 *>(queue + i) + 1);
-                        ray.o = mk3(a.x, a.y, a.z); ray.d = mk3(b.x, b.y, b.z); ray.maxt = a.w; out = __float_as_uint(b.w);
+                        const f8 q = ldg8(reinterpret_cast<const f4 *>(queue + i));
+                        ray.o = mk3(q.a.x, q.a.y, q.a.z); ray.d = mk3(q.b.x, q.b.y, q.b.z); ray.maxt = q.a.w; out = f2u(q.b.w);
                         const float dx = fabsf(ray.d.x) < 1e-20f ? mulsign(1e-20f, ray.d.x) : ray.d.x;
                         const float dy = fabsf(ray.d.y) < 1e-20f ? mulsign(1e-20f, ray.d.y) : ray.d.y;
                         const float dz = fabsf(ray.d.z) < 1e-20f ? mulsign(1e-20f, ray.d.z) : ray.d.z;
                         ix = 1.0f / dx; iy = 1.0f / dy; iz = 1.0f / dz; ox = ray.o.x * ix; oy = ray.o.y * iy; oz = ray.o.z * iz;
                         best_t = ray.maxt; best_u = best_v = 0.f; best_prim = 0xffffffffu; found = false; sp = 0;
-                        cur = sc.n_nodes ? 0u : WF_REF_NONE; has_ray = true;
+                        cur = sc.n_nodes ? 0u : WF_REF_NONE; leaf = WF_REF_NONE; has_ray = true;
                         if (COUNT) ++c_rays;
                     }
                 }
-                if (base + __popc(idle) >= n) exhausted = true;
+                if (base + (uint32_t) n_idle >= n) exhausted = true;
             }
-            if (__ballot_sync(0xffffffffu, has_ray) == 0u) break;
+            if (__ballot_sync(0xffffffffu, has_ray) == 0u) break;      // queue drained and every lane finished
         }
-        if (!has_ray) continue;
-        if (cur == WF_REF_NONE) {
-            // pop the next subtree that can still contain a closer (or equally close) hit
-            bool got = false;
-            while (sp > 0) {
-                --sp;
-                const uint2 e = sp < WF_STACK ? sstack[sp][threadIdx.x] : lstack[sp - WF_STACK];
-                if (__uint_as_float(e.y) <= best_t) { cur = e.x; got = true; break; }
-            }
-            if (!got) {
-                // ray finished
-                if (ANY) occl[out] = 0u;
-                else reinterpret_cast<uint4 *>(hits)[out] = make_uint4(f2u(found ? best_t : INFINITY), f2u(best_u), f2u(best_v), best_prim);
-                has_ray = false;
-                continue;
-            }
-        }
-        if ((int32_t) cur < 0) {
-            // ---- leaf ----
-            const uint32_t code = ~cur, first = code >> 2, cnt = (code & 3u) + 1u;
-            bool done = false;
-            for (uint32_t k = 0; k < cnt; ++k) {
-                const f4 *tp = sc.tris + (size_t) (first + k) * EPSM_TRI_F4;
-                const f4 a = ldg4(tp), b = ldg4(tp + 1), c = ldg4(tp + 2);
-                if (COUNT) ++c_tris;
-                float t, u, v;
-                if (tri_test(ray, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(b.w, c.x, c.y), best_t, t, u, v)) {
-                    if (ANY) { done = true; break; }
-                    const uint32_t prim = f2u(a.w);
-                    if (!found || t < best_t || prim > best_prim) { best_t = t; best_u = u; best_v = v; best_prim = prim; found = true; }
+        // ---- park a reached leaf, pop the next subtree, retire finished rays ----
+        if (has_ray) {
+            if ((int32_t) cur < 0 && leaf == WF_REF_NONE) { leaf = cur; cur = WF_REF_NONE; }
+            while (cur == WF_REF_NONE && (WF_SPECULATE || leaf == WF_REF_NONE)) {
+                bool got = false;
+                while (sp > 0) {
+                    --sp;
+                    const uint2 e = sp < WF_STACK ? sstack[sp][threadIdx.x] : lstack[sp - WF_STACK];
+                    if (__uint_as_float(e.y) <= best_t) { cur = e.x; got = true; break; }
                 }
+                if (!got) {
+                    if (leaf == WF_REF_NONE) {                           // nothing left: the ray is finished
+                        if (ANY) occl[out] = 0u;
+                        else reinterpret_cast<uint4 *>(hits)[out] = make_uint4(f2u(found ? best_t : INFINITY), f2u(best_u), f2u(best_v), best_prim);
+                        has_ray = false;
+                    }
+                    break;
+                }
+                if ((int32_t) cur < 0 && leaf == WF_REF_NONE) { leaf = cur; cur = WF_REF_NONE; }
             }
-            cur = WF_REF_NONE;
-            if (ANY && done) { occl[out] = 1u; has_ray = false; }
+        }
+        // ---- choose the phase ----
+        const bool can_inner = has_ray && (int32_t) cur >= 0 && cur != WF_REF_NONE;
+        const bool has_leaf = has_ray && leaf != WF_REF_NONE;
+        const unsigned m_in = __ballot_sync(0xffffffffu, can_inner), m_leaf = __ballot_sync(0xffffffffu, has_leaf);
+        if (m_leaf != 0u && (m_in == 0u || __popc(m_leaf) >= WF_LEAF_MIN)) {
+            // ---- leaf phase ----
+            if (has_leaf) {
+                const uint32_t code = ~leaf, first = code >> 2, cnt = (code & 3u) + 1u;
+                bool done = false;
+                for (uint32_t k = 0; k < cnt; ++k) {
+                    const f4 *tp = sc.tris + (size_t) (first + k) * EPSM_TRI_F4;
+                    const f8 ab = ldg8(tp); const f2 c = ldg2(tp + 2); const f4 a = ab.a, b = ab.b;
+                    if (COUNT) ++c_tris;
+                    float t, u, v;
+                    if (tri_test(ray, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(b.w, c.x, c.y), best_t, t, u, v)) {
+                        if (ANY) { done = true; break; }
+                        const uint32_t prim = f2u(a.w);
+                        if (!found || t < best_t || prim > best_prim) { best_t = t; best_u = u; best_v = v; best_prim = prim; found = true; }
+                    }
+                }
+                leaf = WF_REF_NONE;
+                if (ANY && done) { occl[out] = 1u; has_ray = false; cur = WF_REF_NONE; sp = 0; }
+            }
             continue;
         }
-        // ---- inner node ----
+        if (!can_inner) continue;
+        // ---- inner phase ----
         const f4 *np = sc.nodes + (size_t) cur * EPSM_NODE_F4;
-        const f4 lx = ldg4(np), ly = ldg4(np + 1), lz = ldg4(np + 2), hx = ldg4(np + 3), hy = ldg4(np + 4), hz = ldg4(np + 5), ch = ldg4(np + 6);
+        const f8 n0 = ldg8(np), n1 = ldg8(np + 2), n2 = ldg8(np + 4);
+        const f4 lx = n0.a, ly = n0.b, lz = n1.a, hx = n1.b, hy = n2.a, hz = n2.b, ch = ldg4(np + 6);
         if (COUNT) ++c_nodes;
         uint32_t key[4]; float tmn[4];
         const uint32_t cref[4] = {f2u(ch.x), f2u(ch.y), f2u(ch.z), f2u(ch.w)};
@@ -471,11 +503,11 @@ __global__ void __launch_bounds__(128) k_wf_stage_a(DScene sc, DLaunch ln, uint3
         const Hit h = wb.hits[i];
         if (it == 0) {
             PathHead H; soa_load(H, wb.heads, wb.capacity, i);
-            push = wf_stage_a(sc, S, H, h, it, ln.max_depth);
+            push = wf_stage_a(sc, S, H, h, it, ln.max_depth, ln.variant, ln.prune != 0);
             soa_store(H, wb.heads, wb.capacity, i);
         } else {
             PathHead H;                                   // only written at the first hit
-            push = wf_stage_a(sc, S, H, h, it, ln.max_depth);
+            push = wf_stage_a(sc, S, H, h, it, ln.max_depth, ln.variant, ln.prune != 0);
         }
         sr = S.shadow_ray;
         soa_store(S, wb.states, wb.capacity, i);
@@ -492,7 +524,7 @@ __global__ void __launch_bounds__(128) k_wf_stage_b(DScene sc, DLaunch ln, uint3
         const Hit h = wb.hits[i];
         const bool occluded = S.need_shadow && wb.occl[i] != 0u;
         VLog v;
-        wf_stage_b(sc, S, v, h, occluded, it, ln.rr_depth, direct, push_direct);
+        wf_stage_b(sc, S, v, h, occluded, it, ln.rr_depth, ln.prune != 0, direct, push_direct);
         if (it < EPSM_MAXV) {
             soa_store(v, wb.vlogs + (size_t) it * WORDS_OF(VLog) * wb.capacity, wb.capacity, i);
             wb.vmask[(size_t) it * wb.capacity + i] = 1;
@@ -523,7 +555,7 @@ __global__ void __launch_bounds__(128) k_wf_finish(DScene sc, DLaunch ln, uint64
     PathLog P;
     soa_load(static_cast<PathHead &>(P), wb.heads, wb.capacity, i);
     const uint32_t max_iter = wf_iterations(ln.max_depth);
-    const int n_logged = (int) (max_iter < EPSM_MAXV ? max_iter : EPSM_MAXV);      // len(path_info) − 1
+    const int n_logged = (int) (max_iter < EPSM_MAXV ? max_iter : EPSM_MAXV);      // len(path_info) − 1 (independent of pruning)
     // Only the prefix of the path that can carry gradients is fetched: the chain ends at the first diffuse vertex
     // (manifold, epsm.py:855,920) or at the second one (caustic: vertex 1 must be diffuse, epsm.py:999,1008), at a
     // non-mesh vertex or where the path left the scene; every output beyond it is masked to zero by calc_grad.
@@ -544,7 +576,7 @@ __global__ void __launch_bounds__(128) k_wf_finish(DScene sc, DLaunch ln, uint64
             chain = false;
         }
     }
-    { WfState S; soa_load(S, wb.states, wb.capacity, i); P.L = S.L; }
+    if (RECORD) { WfState S; soa_load(S, wb.states, wb.capacity, i); P.L = S.L; }
     PathGrads G;
     calc_grad(P, ln.variant, n_logged, G);
     if (RECORD) { const WorkItem wi = wf_work_item(ln, work_base + i); write_record(P, G, n_logged, records + (wi.lane - ln.lane_begin) * EPSM_REC_FLOATS); }
@@ -649,7 +681,7 @@ cudaError_t epsm_launch_backward(const DScene &sc, DLaunch ln, const float *grad
     const uint32_t tiles = tile_grid(ln);
     if (tiles == 0 || ln.s_end <= ln.s_begin) return cudaSuccess;
     const uint64_t total = (uint64_t) tiles * 32ull * (ln.s_end - ln.s_begin);
-    const uint32_t max_iter = ln.max_depth < EPSM_MAX_ITER ? ln.max_depth : EPSM_MAX_ITER;
+    const uint32_t max_iter = wf_replay_iterations(ln.max_depth, ln.prune != 0);
     WfBuffers wb = wf_carve(workspace, capacity);
     uint64_t launches = 0;
     for (uint64_t base = 0; base < total; base += capacity) {

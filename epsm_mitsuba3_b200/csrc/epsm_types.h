@@ -5,9 +5,10 @@
 //                [0] lo.x[4] [1] lo.y[4] [2] lo.z[4] [3] hi.x[4] [4] hi.y[4] [5] hi.z[4] [6] child[4] [7] pad
 //              child >= 0: inner node index; child < 0: leaf, ~child = (first_tri << 2) | (count-1);
 //              empty slots have child == 0x7fffffff and are skipped.  One node = one 128-byte line, fetched
-//              as eight 128-bit loads.
-//   tris       48 B per triangle in BVH leaf order: 3 × float4
-//                [0] p0.xyz, prim_index (bits)  [1] e1.xyz, e2.x  [2] e2.yz, 0, 0
+//              as three 256-bit loads (sm_100a LDG.E.256) for the boxes + one 128-bit load for the children.
+//   tris       64-byte slots (32-byte aligned), 48 B of payload per triangle in BVH leaf order: 4 × float4
+//                [0] p0.xyz, prim_index (bits)  [1] e1.xyz, e2.x  [2] e2.yz, 0, 0  [3] alignment pad (never read)
+//              fetched as one 256-bit load (LDG.E.256: [0],[1]) + one 64-bit load (e2.yz)
 //              e1 = p1 - p0 and e2 = p2 - p0 are the fp32 differences the reference's Möller–Trumbore
 //              computes per query (include/mitsuba/render/mesh.h:347), so results are bit-identical.
 //   pos/nrm    float[3·V] concatenated over meshes (vertex gathers on a hit: 84 B with faces)
@@ -27,7 +28,8 @@ struct f3 { float x, y, z; };
 struct f4 { float x, y, z, w; };
 
 #define EPSM_NODE_F4   8      // float4 per BVH node
-#define EPSM_TRI_F4    3      // float4 per triangle record
+#define EPSM_TRI_F4    4      // float4 per triangle slot (3 used: EPSM_TRI_BYTES of payload)
+#define EPSM_TRI_BYTES 48     // algorithmic bytes per triangle test
 #define EPSM_MAX_LEAF  4
 #define EPSM_MAXV      5      // logged vertices per path (epsm.py:648)
 #define EPSM_MAX_ITER  6      // sample_path iteration cap (epsm.py:549)
@@ -76,4 +78,5 @@ struct DLaunch {
     uint32_t tile_y0, tile_y1;   // tile rows covered by this launch
     uint32_t s_begin, s_end;     // sample slots of each pixel handled by this launch (multi-GPU sharding)
     int variant;
+    uint32_t prune;              // gradient pass: stop each path where its gradient chain ends (epsm_device.cuh: wf_chain_vertex)
 };

@@ -133,6 +133,10 @@ class Scene:
         self._check(self.lib.epsm_get_trace_profile(self.ctx, C.byref(ms), C.byref(n)))
         return ms.value, int(n.value)
 
+    def set_full_replay(self, enable: bool):
+        """Gradient pass without liveness pruning (epsm_set_full_replay): every lane replays min(max_depth, 6) iterations."""
+        self._check(self.lib.epsm_set_full_replay(self.ctx, 1 if enable else 0))
+
     def set_sample_range(self, s_begin: int = 0, s_end: int = 0):
         self._check(self.lib.epsm_set_sample_range(self.ctx, s_begin, s_end))
 

@@ -194,6 +194,15 @@ int epsm_sample_rays(epsm_ctx *ctx, uint32_t sensor, uint32_t seed, uint32_t spp
  * lane's random stream depends only on (seed, lane) (sampler.cpp:122-130).  (0, 0) = all samples (default). */
 int epsm_set_sample_range(epsm_ctx *ctx, uint32_t s_begin, uint32_t s_end);
 
+/* Gradient liveness pruning.  By default epsm_render_backward stops the replay of each path at the vertex where its
+ * gradient chain ends: calc_grad masks every output behind the first diffuse / non-mesh / inactive vertex (`manifold`,
+ * epsm.py:793-796,855,862,920,928) or behind the second diffuse one (`manifold_caustic`, epsm.py:999,1008,1169-1182), and
+ * render_backward consumes nothing else of the path (its radiance δL is never propagated, epsm.py:728-732).  The
+ * accumulated gradients are those of the full replay (tests/ hold the two to each other and to the oracle).
+ * enable != 0 runs the full min(max_depth, 6)-iteration replay of sample_path (epsm.py:503-742) for every lane, as the
+ * reference does; epsm_path_records always does.  Environment override at context creation: EPSM_FULL_REPLAY=1. */
+int epsm_set_full_replay(epsm_ctx *ctx, int enable);
+
 /* Scene statistics for the roofline accounting: bytes per BVH node / triangle record, counts. */
 typedef struct epsm_scene_stats {
     uint64_t n_triangles, n_vertices, n_nodes;

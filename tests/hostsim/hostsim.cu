@@ -106,7 +106,7 @@ void sim_render_accumulate(sim_scene *s, uint32_t sensor, uint32_t seed, uint32_
 
 // k_backward on the host.  records != NULL: per-lane records (EPSM_REC_FLOATS each); else scatter into grad_pos / grad_nrm.
 void sim_backward(sim_scene *s, int variant, uint32_t sensor, uint32_t seed, uint32_t spp, uint32_t max_depth, uint32_t rr_depth,
-                  const float *grad_in, uint64_t lane_begin, uint64_t lane_end, float *grad_pos, float *grad_nrm, float *records) {
+                  const float *grad_in, uint64_t lane_begin, uint64_t lane_end, float *grad_pos, float *grad_nrm, float *records, int prune) {
     DLaunch ln = make_launch(s, sensor, seed, spp, max_depth, rr_depth, variant);
     const uint32_t W = ln.sensor.w;
     const uint32_t max_iter = max_depth < EPSM_MAX_ITER ? max_depth : EPSM_MAX_ITER;
@@ -118,7 +118,7 @@ void sim_backward(sim_scene *s, int variant, uint32_t sensor, uint32_t seed, uin
         uint64_t lane = lane_begin + i; uint32_t pixel = (uint32_t) (lane / spp);
         LocalStack ls; TStack st; bind(st, ls); Tracer tr(s->sc, st);
         const float gx = grad_in[(size_t) pixel * 5 + 3], gy = grad_in[(size_t) pixel * 5 + 4];
-        PathLog P; path_log<false>(s->sc, tr, ln.sensor, pixel % W, pixel / W, seed, (uint32_t) lane, gx, gy, max_depth, rr_depth, P);
+        PathLog P; path_log<false>(s->sc, tr, ln.sensor, pixel % W, pixel / W, seed, (uint32_t) lane, gx, gy, max_depth, rr_depth, variant, prune != 0 && !records, P);
         PathGrads G; calc_grad(P, variant, n_logged, G);
         if (records) {
             float *r = records + (size_t) i * EPSM_REC_FLOATS;

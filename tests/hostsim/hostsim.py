@@ -30,7 +30,7 @@ def lib():
         L.sim_sampler_stream.argtypes = [u32, u64, u64, u32, vp]
         L.sim_sample_rays.argtypes = [vp, u32, u32, u32, u64, u64, vp]
         L.sim_render_accumulate.argtypes = [vp, u32, u32, u32, u32, u32, u64, u64, vp]
-        L.sim_backward.argtypes = [vp, i32, u32, u32, u32, u32, u32, vp, u64, u64, vp, vp, vp]
+        L.sim_backward.argtypes = [vp, i32, u32, u32, u32, u32, u32, vp, u64, u64, vp, vp, vp, i32]
         _LIB = L
     return _LIB
 
@@ -80,13 +80,13 @@ class SimScene:
 
     def path_records(self, variant, sensor, seed, spp, max_depth, rr_depth, grad_in, lb, le):
         g = np.ascontiguousarray(grad_in, np.float32); out = np.zeros((le - lb, capi.REC_FLOATS), np.float32)
-        lib().sim_backward(self.h, _vid(variant), sensor, seed, spp, max_depth, rr_depth, g.ctypes.data, lb, le, None, None, out.ctypes.data)
+        lib().sim_backward(self.h, _vid(variant), sensor, seed, spp, max_depth, rr_depth, g.ctypes.data, lb, le, None, None, out.ctypes.data, 0)
         return out
 
-    def backward(self, variant, sensor, seed, spp, max_depth, rr_depth, grad_in, lb=0, le=None):
+    def backward(self, variant, sensor, seed, spp, max_depth, rr_depth, grad_in, lb=0, le=None, prune=True):
         s = self.data.sensors[sensor]; le = s.width * s.height * spp if le is None else le
         g = np.ascontiguousarray(grad_in, np.float32)
         gp = np.zeros((self.n_vertices, 3), np.float32); gn = np.zeros((self.n_vertices, 3), np.float32)
         lib().sim_backward(self.h, _vid(variant), sensor, seed, spp, max_depth, rr_depth, g.ctypes.data, lb, le,
-                           gp.ctypes.data, gn.ctypes.data, None)
+                           gp.ctypes.data, gn.ctypes.data, None, 1 if prune else 0)
         return gp, gn

@@ -151,6 +151,20 @@ def test_per_path_gradients_and_scatter(case):
     o.set_accel(False)
 
 
+def test_pruned_replay_equals_full_replay(case):
+    """The default (gradient-liveness pruned) pass against epsm_set_full_replay(1): same gradients up to the order of
+    the float atomics."""
+    sd, b, o, variant, max_depth = case
+    res = sd.sensors[2].width; g = parity.synthetic_grad_in(res)
+    for md in sorted({max_depth, 3, 8}):
+        b.scene.set_full_replay(True)
+        full = b.backward(variant, 2, 13, 8, md, 5, g)
+        b.scene.set_full_replay(False)
+        pruned = b.backward(variant, 2, 13, 8, md, 5, g)
+        for x, y in zip(full, pruned):
+            assert np.allclose(x, y, rtol=1e-5, atol=1e-7 * max(1.0, float(np.abs(x).max()))), f"max_depth={md}"
+
+
 def test_lane_ranges_partition_the_wavefront(case):
     sd, b, o, variant, max_depth = case
     res = sd.sensors[2].width; g = parity.synthetic_grad_in(res); n = res * res * 8

@@ -78,6 +78,18 @@ def test_lane_ranges_partition_the_wavefront(case):
     assert np.allclose(a[0] + b[0], full[0], rtol=1e-5, atol=1e-7) and np.allclose(a[1] + b[1], full[1], rtol=1e-5, atol=1e-7)
 
 
+def test_pruned_replay_equals_full_replay(case):
+    """Gradient-liveness pruning (epsm_set_full_replay) must not change the accumulated gradients: the host harness adds
+    the per-path seeds in lane order, so the two passes are required to agree bit for bit."""
+    sd, sim, o, variant, max_depth = case
+    res = sd.sensors[2].width; g = parity.synthetic_grad_in(res)
+    for md in sorted({max_depth, 3, 8}):
+        full = sim.backward(variant, 2, 13, 8, md, 5, g, prune=False)
+        pruned = sim.backward(variant, 2, 13, 8, md, 5, g, prune=True)
+        assert np.array_equal(full[0], pruned[0]) and np.array_equal(full[1], pruned[1]), f"max_depth={md}"
+    assert np.abs(full[0]).max() > 0 or variant == "manifold_caustic"
+
+
 def test_update_vertices_rebuilds(orc):
     sd = S.mirror_plane_scene(8, 2, 8)
     sim, o = SimScene(sd), orc.OracleScene(sd)
