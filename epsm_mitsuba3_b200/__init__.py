@@ -9,7 +9,8 @@ from . import capi, scenes  # noqa: F401
 from .engine import (EpsmError, Scene, SceneParameters, EPSMIntegrator, ManifoldIntegrator,  # noqa: F401
                      ManifoldCausticIntegrator, load_dict, register_integrator, traverse, render,
                      sample_tea_32, band_lanes, sample_shard)
+from .schedule import HybridSchedule, Phase  # noqa: F401
 
 __all__ = ["capi", "scenes", "EpsmError", "Scene", "SceneParameters", "EPSMIntegrator", "ManifoldIntegrator",
            "ManifoldCausticIntegrator", "load_dict", "register_integrator", "traverse", "render", "sample_tea_32",
-           "band_lanes", "sample_shard"]
+           "band_lanes", "sample_shard", "HybridSchedule", "Phase"]

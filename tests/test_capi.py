@@ -67,3 +67,19 @@ def test_seed_grad_derivation(orc, kats):
     import epsm_mitsuba3_b200 as ep
     for v0 in (0, 1, 2, 12345, 0xffffffff):
         assert ep.sample_tea_32(v0, 1) == orc.tea32(v0, 1, 4)
+
+
+def test_hybrid_schedule_follows_optim_py():
+    # EPSM/optim.py:87-119: suffix strip, sensor choice, optimiser reset exactly at it == thres, phase-2 plugin lookup
+    import epsm_mitsuba3_b200 as ep
+    s = ep.HybridSchedule("manifold_caustic_hybrid", max_depth=4, thres=3)
+    assert (s.method, s.thres, s.integrator1.variant, s.integrator1.max_depth) == ("manifold_caustic", 3, "manifold_caustic", 4)
+    p = s.phase(2)
+    assert (p.integrator_type, p.sensor, p.loss, p.reset_optimizer) == ("manifold_caustic", 1, "matcher", False)
+    with pytest.raises(ep.EpsmError, match="prb_reparam"):
+        s.phase(3)                                          # phase 2 is SURVEY §8f rank 1: not built, fails like a missing plugin
+    made = []
+    s2 = ep.HybridSchedule("manifold_hybrid", 6, thres=5, phase2_factory=lambda props: made.append(props) or "prb")
+    assert s2.phase(5).reset_optimizer and not s2.phase(6).reset_optimizer and s2.phase(6).sensor == 0 and s2.phase(6).loss == "l2"
+    assert made == [{"type": "prb_reparam", "max_depth": 6}]
+    assert ep.HybridSchedule("manifold", 6, thres=5).thres == 10000      # non-hybrid: never switches (optim.py:95)
