@@ -1133,6 +1133,35 @@ void orc_path_log(orc_scene *s, uint32_t sensor, uint32_t seed, uint32_t spp, ui
         P.L[0] = L.x; P.L[1] = L.y; P.L[2] = L.z;
     }
 }
+// The restatement behind the same switch as oracle/ref_probe.cpp (which drives the REFERENCE's header code): function
+// numbering, input and output layouts are identical, so tests compare the two call for call.
+int orc_probe(int fn, uint64_t n, const float *in_, int in_stride, float *out_, int out_stride) {
+    for (uint64_t i = 0; i < n; ++i) {
+        const float *in = in_ + i * (uint64_t) in_stride; float *out = out_ + i * (uint64_t) out_stride;
+        auto mf = [&]() { return Microfacet{in[2] != 0.f, in[0], in[1], true}; };
+        switch (fn) {
+        case 0: { uint32_t v0, v1, o0, o1; memcpy(&v0, in, 4); memcpy(&v1, in + 1, 4); tea32(v0, v1, 4, &o0, &o1); memcpy(out, &o0, 4); memcpy(out + 1, &o1, 4); } break;
+        case 2: sincos_dr(in[0], &out[0], &out[1]); break;
+        case 3: { V3 v = square_to_cosine_hemisphere(in[0], in[1]); out[0] = v.x; out[1] = v.y; out[2] = v.z; } break;
+        case 4: { V3 s, t; coordinate_system(mk(in[0], in[1], in[2]), &s, &t); out[0] = s.x; out[1] = s.y; out[2] = s.z; out[3] = t.x; out[4] = t.y; out[5] = t.z; } break;
+        case 5: fresnel(in[0], in[1], &out[0], &out[1], &out[2], &out[3]); break;
+        case 6: out[0] = fresnel_conductor(in[0], in[1], in[2]); break;
+        case 7: { V3 m; mf().sample(in[6], in[7], &m, &out[3]); out[0] = m.x; out[1] = m.y; out[2] = m.z; } break;
+        case 8: out[0] = mf().eval(mk(in[3], in[4], in[5])); break;
+        case 9: out[0] = mf().smith_g1(mk(in[3], in[4], in[5]), mk(in[6], in[7], in[8])); break;
+        case 10: { float t = safe_sqrt(1.f - in[0]); out[0] = 1.f - t; out[1] = t * in[1]; } break;       // as in sample_emitter_direction
+        case 11: { V3 r = reflect(mk(in[0], in[1], in[2]), mk(in[3], in[4], in[5])); out[0] = r.x; out[1] = r.y; out[2] = r.z; } break;
+        case 12: {
+            SI si; si.sh_n = mk(in[0], in[1], in[2]); coordinate_system(si.sh_n, &si.sh_s, &si.sh_t);     // Frame3f(n), frame.h:21-26
+            V3 v = mk(in[3], in[4], in[5]), l = to_local(si, v), w = to_world(si, v);
+            out[0] = l.x; out[1] = l.y; out[2] = l.z; out[3] = w.x; out[4] = w.y; out[5] = w.z;
+        } break;
+        default: return -1;
+        }
+    }
+    return 0;
+}
+
 uint32_t orc_sizeof_path() { return (uint32_t) sizeof(orc_path); }
 uint32_t orc_sizeof_vertex() { return (uint32_t) sizeof(orc_vertex); }
 

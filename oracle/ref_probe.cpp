@@ -21,6 +21,14 @@
 //   fn 12 Frame3f(n) + to_local / to_world     include/mitsuba/core/frame.h:21-50
 // The triangle test, Mesh::compute_surface_interaction, the BSDF plugins, the area emitter and the film live in
 // .cpp files behind libmitsuba's object model (cmake build) and are pinned by tests/golden/reference_kats.json instead.
+// Instantiation note.  Float = plain `float` evaluates every explicit dr::fmadd fused (as the LLVM backend's llvm.fma) and
+// everything else unfused (-ffp-contract=off; the LLVM backend emits plain fmul/fadd), which is the arithmetic of
+// llvm_ad_rgb — except for dr::dot / squared_norm / normalize on static arrays: with array-valued entries (the JIT
+// variants) Dr.Jit evaluates them as an fmadd chain (ext/drjit/include/drjit/array_base.h:603-631) whereas plain-float
+// entries take the SSE dp_ps route (packet_sse42.h:370).  The restatement follows the JIT form, so functions built on
+// dot() (fn 3, 11, 12) agree with this probe to the last 1–2 ulp instead of bit for bit; all others are bit-exact
+// (tests/test_ref_probe.py states the tolerance per function).  Dr.Jit's 1-wide host arrays are no way around this:
+// their generic fmadd_ is the unfused `a*b+c` (array_base.h:429-460,509).
 #include <mitsuba/core/random.h>
 #include <mitsuba/core/warp.h>
 #include <mitsuba/core/frame.h>
