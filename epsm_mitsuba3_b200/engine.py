@@ -50,6 +50,12 @@ def _dist():
     return None
 
 
+def _sync_torch(device):
+    """Order torch's stream before the library's stream (the library runs on its own CUDA stream)."""
+    if torch.device(device).type == "cuda":
+        torch.cuda.current_stream(device).synchronize()
+
+
 def sample_shard(spp: int, rank: int, world: int):
     """Sample-index shard of `rank`: samples [s0, s1) of every pixel (epsm_set_sample_range).  Balanced by
     construction (every rank sees every pixel) and exact: the union over ranks is the single-GPU wavefront."""
@@ -286,7 +292,7 @@ class EPSMIntegrator:
             film = scene.film_raw(sensor)
             scene.synchronize()
             dist.all_reduce(film)                     # every rank splatted its samples of every pixel: sum the RGBW film
-            torch.cuda.current_stream(scene.device).synchronize()
+            _sync_torch(scene.device)
         self.primal_image = scene.film_develop(sensor)
         scene.synchronize()
         return self.primal_image
@@ -303,7 +309,7 @@ class EPSMIntegrator:
             return
         res = s.width                                   # epsm.py:238-240: crop to the gradient sensor's resolution
         g = grad_in[:res, :res, :].to(device=scene.device, dtype=torch.float32).contiguous()
-        torch.cuda.current_stream(scene.device).synchronize()
+        _sync_torch(scene.device)
         gp, gn = self.backward_buffers(scene, g, sensor, seed, spp)
         params.accumulate_gradients(gp, gn)
 
@@ -312,7 +318,7 @@ class EPSMIntegrator:
         dist = _dist()
         s0, s1 = (0, spp) if dist is None else sample_shard(spp, dist.get_rank(), dist.get_world_size())
         buf = torch.zeros((2, scene.n_vertices, 3), dtype=torch.float32, device=scene.device)
-        torch.cuda.current_stream(scene.device).synchronize()
+        _sync_torch(scene.device)
         if s1 > s0:
             scene.set_sample_range(s0, s1)
             scene.render_backward_raw(self.variant, sensor, seed, spp, self.max_depth, self.rr_depth, g, buf[0], buf[1])
@@ -320,7 +326,7 @@ class EPSMIntegrator:
         scene.synchronize()
         if dist is not None:
             dist.all_reduce(buf)                        # one NCCL allreduce of the mesh-gradient buffer per step
-            torch.cuda.current_stream(scene.device).synchronize()
+            _sync_torch(scene.device)
         return buf[0], buf[1]
 
 
