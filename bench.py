@@ -3,8 +3,10 @@
 
 A "step" is one gradient pass (render_backward-equivalent: ray generation, sample_path replay, manifold solve,
 gradient scatter; epsm.py:84-306) over the W·H·spp wavefront of the workload, followed — for N > 1 — by the one
-NCCL allreduce of the mesh-gradient buffer.  Work is sharded across ranks by sample index (strong scaling: the
-total wavefront is fixed, every rank traces spp/N samples of every pixel).
+NCCL allreduce of the mesh-gradient buffer.  Work is sharded across ranks by sample index.  Default `--scaling weak`:
+every rank traces the workload's spp samples of every pixel, i.e. N ranks render an (N·spp)-sample wavefront (rank r owns
+samples [r·spp, (r+1)·spp) of each pixel — BASELINE's resolution/spp sweep); `--scaling strong` keeps the wavefront at
+spp and gives each rank spp/N samples per pixel.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload room|glass|cbox|smpl]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N … bench.py --gpus N …
@@ -156,6 +158,8 @@ def main():
     ap.add_argument("--res", type=int, default=0)
     ap.add_argument("--spp", type=int, default=0)
     ap.add_argument("--tris", type=int, default=1_000_000)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: per-GPU work fixed (N ranks trace N*spp samples per pixel); strong: the spp-sample wavefront is split over the ranks")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--full-replay", action="store_true", help="time the unpruned replay (every lane runs min(max_depth,6) iterations, as the reference does)")
@@ -168,9 +172,11 @@ def main():
     if args.res: wl["res"] = args.res
     if args.spp: wl["spp"] = args.spp
     res, spp = wl["res"], wl["spp"]
+    spp_total = spp * world if args.scaling == "weak" else spp       # samples per pixel of the whole job
     config = {"workload": wl["desc"], "scene": args.workload, "integrator": wl["variant"], "max_depth": wl["max_depth"],
-              "resolution": [res, res], "spp": spp, "paths_per_step": res * res * spp,
-              "sharding": f"sample-index shards over {world} rank(s) + 1 NCCL allreduce of the vertex-gradient buffer" if world > 1 else "single GPU",
+              "resolution": [res, res], "spp": spp_total, "spp_per_gpu": spp_total // world, "paths_per_step": res * res * spp_total,
+              "sharding": f"sample-index shards over {world} rank(s) ({args.scaling} scaling: {spp_total // world} of the {spp_total} samples of every pixel per rank) "
+                          f"+ 1 NCCL allreduce of the vertex-gradient buffer" if world > 1 else "single GPU",
               "l2": "256 MiB buffer written between timed steps (L2 flush); BVH+triangles of the 1M-tri scene are ~100 MB",
               "replay": "full (every lane replays min(max_depth,6) iterations)" if args.full_replay else
                         "gradient-live prefix (each path stops where calc_grad masks everything behind it; gradients identical to the full replay)"}
@@ -188,7 +194,7 @@ def main():
         v = float(np.mean([r["value"] for r in vals])) if vals else 0.0
         r = vals[-1] if vals else {"cores": os.cpu_count(), "kind": "port", "sample": "none"}
         out = {"impl": "reference", "metric": "gradient path samples/sec", "value": v, "unit": "samples/s", "n_gpus": args.gpus,
-               "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "strong",
+               "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": args.scaling,
                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                "cpu_baseline": {"value": v, "unit": "samples/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
                "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -210,8 +216,8 @@ def main():
     sensor = 1                                                # full-resolution sensor; benchmark semantics N_g = W·H·spp
     g_host = torch.from_numpy(synthetic_grad_in(res)).pin_memory()
     g_dev = g_host.cuda()
-    s0, s1 = ep.sample_shard(spp, rank, world)
-    my_paths = res * res * (s1 - s0)
+    spp_job = spp_total                                       # lane ids are pixel·spp_job + s for every rank
+    s0, s1 = ep.sample_shard(spp_job, rank, world)
     buf = torch.zeros((2, scene.n_vertices, 3), dtype=torch.float32, device=scene.device)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=scene.device)
     torch.cuda.synchronize()
@@ -225,7 +231,7 @@ def main():
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record(cu_stream)
         scene.set_sample_range(s0, s1)
-        scene.render_backward_raw(wl["variant"], sensor, 100 + k, spp, integ.max_depth, integ.rr_depth, g_dev, buf[0], buf[1])
+        scene.render_backward_raw(wl["variant"], sensor, 100 + k, spp_job, integ.max_depth, integ.rr_depth, g_dev, buf[0], buf[1])
         ev1.record(cu_stream)
         scene.synchronize()
         ms = ev0.elapsed_time(ev1)
@@ -255,7 +261,7 @@ def main():
         t = torch.tensor([ms_total], device=scene.device); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms_total = float(t.item())
         l = torch.tensor([launches], device=scene.device); dist.all_reduce(l); launches = int(l.item())
     ms_per_step = ms_total / args.steps
-    total_paths = res * res * spp
+    total_paths = res * res * spp_job
     value = total_paths / (ms_per_step * 1e-3)
 
     # ---- the unpruned replay beside the default, for transparency (same scene, same seeds)
@@ -282,7 +288,7 @@ def main():
             if world > 1:
                 dist.barrier()
             t0 = time.perf_counter()
-            scene.render_backward_raw(wl["variant"], sensor, 200 + k, spp, integ.max_depth, integ.rr_depth, g_host, gp_h, gn_h)   # returns after D2H
+            scene.render_backward_raw(wl["variant"], sensor, 200 + k, spp_job, integ.max_depth, integ.rr_depth, g_host, gp_h, gn_h)   # returns after D2H
             if world > 1:
                 b2 = torch.stack([gp_h, gn_h]).cuda(non_blocking=True); dist.all_reduce(b2); gp_h.copy_(b2[0]); torch.cuda.synchronize()
             dt = time.perf_counter() - t0
@@ -301,14 +307,14 @@ def main():
     #      every traversal launch of one un-instrumented pass on the library's stream.
     cnt = np.zeros(4, np.uint64)
     buf.zero_(); torch.cuda.synchronize()
-    scene.render_backward_raw(wl["variant"], sensor, 100 + args.warmup, spp, integ.max_depth, integ.rr_depth, g_dev, buf[0], buf[1], counters=cnt)
+    scene.render_backward_raw(wl["variant"], sensor, 100 + args.warmup, spp_job, integ.max_depth, integ.rr_depth, g_dev, buf[0], buf[1], counters=cnt)
     scene.synchronize()
     nodes, tris, rays, lanes = (int(x) for x in cnt)
     alg_bytes = nodes * stats["node_bytes"] + tris * stats["tri_bytes"] + rays * 48
     scene.set_trace_profiling(True)
     scene.trace_profile()
     buf.zero_(); flush.fill_(1); torch.cuda.synchronize()
-    scene.render_backward_raw(wl["variant"], sensor, 100 + args.warmup, spp, integ.max_depth, integ.rr_depth, g_dev, buf[0], buf[1])
+    scene.render_backward_raw(wl["variant"], sensor, 100 + args.warmup, spp_job, integ.max_depth, integ.rr_depth, g_dev, buf[0], buf[1])
     trace_ms, trace_launches = scene.trace_profile()
     scene.set_trace_profiling(False)
     peak, peak_src = peaks()
@@ -343,7 +349,7 @@ def main():
 
     if rank == 0:
         out = {"metric": "gradient path samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
-               "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+               "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
                "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
                "roofline": roof, "cpu_baseline": cpu, "full_replay": full_leg,
                "scene": {"triangles": int(stats["n_triangles"]), "vertices": int(stats["n_vertices"]), "bvh_nodes": int(stats["n_nodes"]),

@@ -1,6 +1,7 @@
 // epsm_api.cu — the C ABI of include/epsm_b200.h over the kernels in epsm_kernels.cu.
 // No torch types, no exceptions across the boundary, no CPU fallback.
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -44,6 +45,7 @@ struct epsm_ctx {
     bool have_scene = false, dirty = false;
     uint32_t s_begin = 0, s_end = 0;                // sample-range shard (0,0 = all)
     bool full_replay = false;                       // gradient pass without liveness pruning (epsm_set_full_replay)
+    bool primal_megakernel = false;                 // EPSM_PRIMAL_MEGAKERNEL=1: render with the single-kernel k_render instead of the wavefront
     HostScene hs;                                   // host mirror (positions are needed for BVH rebuilds)
     std::vector<uint8_t> mesh_dirty;
     // device
@@ -157,6 +159,7 @@ int epsm_create(int device, epsm_ctx **out) {
     if (e != cudaSuccess) { delete c; return fail(nullptr, EPSM_E_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e)); }
     memset(&c->sc, 0, sizeof(c->sc));
     if (const char *e = getenv("EPSM_FULL_REPLAY")) c->full_replay = atoi(e) != 0;
+    if (const char *e = getenv("EPSM_PRIMAL_MEGAKERNEL")) c->primal_megakernel = atoi(e) != 0;
     cudaDeviceProp prop; cudaGetDeviceProperties(&prop, device);
     c->trace_grid = (uint32_t) prop.multiProcessorCount * 8u;        // persistent traversal CTAs: 148 SMs × 8 resident CTAs of 128 threads (≤ 64 regs)
     *out = c; return EPSM_OK;
@@ -291,8 +294,19 @@ int epsm_render_accumulate(epsm_ctx *ctx, uint32_t sensor, uint32_t seed, uint32
     if (rc) return rc;
     CK(cudaSetDevice(ctx->device), "cudaSetDevice");
     if (counters) { rc = zero_counters(ctx); if (rc) return rc; }
-    CK(epsm_launch_render(ctx->sc, ln, ctx->d_films[sensor].p, counters ? ctx->d_counters.p : nullptr, ctx->stream), "k_render");
-    ctx->launches += 1;
+    if (ctx->primal_megakernel) {
+        CK(epsm_launch_render(ctx->sc, ln, ctx->d_films[sensor].p, counters ? ctx->d_counters.p : nullptr, ctx->stream), "k_render");
+        ctx->launches += 1;
+    } else {
+        const uint64_t S = (uint64_t) (ln.s_end - ln.s_begin);
+        // lanes of the whole-tile enumeration that cover [lane_begin, lane_end)
+        const uint64_t row_lanes = (uint64_t) ln.sensor.w * ln.spp;
+        const uint64_t y0 = ln.lane_begin / row_lanes, y1 = std::min<uint64_t>((ln.lane_end + row_lanes - 1) / row_lanes, ln.sensor.h);
+        const uint64_t tile_rows = y1 > y0 ? (y1 + 3) / 4 - y0 / 4 : 0;
+        rc = ensure_workspace(ctx, (uint64_t) ((ln.sensor.w + 7) / 8) * tile_rows * 32ull * S); if (rc) return rc;
+        CK(epsm_launch_render_wf(ctx->sc, ln, ctx->d_films[sensor].p, counters ? ctx->d_counters.p : nullptr, ctx->d_workspace.p, ctx->wf_capacity,
+                                 ctx->trace_grid, &ctx->launches, ctx->stream), "wavefront render");
+    }
     if (counters) return fetch_counters(ctx, counters);
     return EPSM_OK;
 }

@@ -682,9 +682,87 @@ EPSM_HDN f3 path_primal(const DScene &sc, Tracer &tr, Ray ray, Pcg &rng, uint32_
 }
 
 // ------------------------------------------------------------------------------------------------
+//  The same primal path as a wavefront stage (k_pr_* in epsm_kernels.cu).  One stage per bounce: the emitter sample's
+//  visibility is the only thing the rest of the bounce does not need (it gates Lr_dir alone, epsm.py:590-605 via
+//  scene.cpp:259-263), so Lr_dir is parked in `pend` together with a shadow ray and added by the next stage (or by the
+//  film kernel) once the any-hit query has answered.  Random-number order and arithmetic are those of path_primal.
+// ------------------------------------------------------------------------------------------------
+#define PR_ACTIVE 1u
+#define PR_PREV_DELTA 2u
+#define PR_PEND 4u
+struct PrState {
+    // the first PR_INIT_WORDS words are what ray generation hands over; pr_state_defaults() restores the rest
+    Pcg rng;
+    Ray ray;
+    f3 beta, L, prev_p, pend;
+    float eta, prev_pdf;
+    uint32_t depth, bits;
+};
+#define PR_INIT_WORDS 11          // rng (4) + ray (7)
+EPSM_HD void pr_state_defaults(PrState &S) {
+    S.beta = mk3(1, 1, 1); S.L = S.prev_p = S.pend = mk3(0, 0, 0); S.eta = 1.f; S.prev_pdf = 1.f; S.depth = 0; S.bits = PR_ACTIVE | PR_PREV_DELTA;
+}
+EPSM_HD void pr_resolve_pending(PrState &S, bool occluded) {
+    if (S.bits & PR_PEND) { if (!occluded) S.L = S.L + S.pend; S.bits &= ~PR_PEND; }
+}
+// One bounce after the closest hit `h` of S.ray (pending NEE of the previous bounce already resolved).  Returns true
+// when `shadow` must be traced for S.pend; (S.bits & PR_ACTIVE) tells whether S.ray is the next path ray.
+EPSM_HDN bool pr_stage(const DScene &sc, PrState &S, const Hit &h, uint32_t max_depth, uint32_t rr_depth, Ray &shadow) {
+    SI si; compute_si(sc, S.ray, h, si);
+    const bool prev_delta = (S.bits & PR_PREV_DELTA) != 0;
+    float em_pdf = pdf_emitter_direction(sc, si, S.prev_p, !prev_delta);
+    float mis = mis_weight(S.prev_pdf, em_pdf);
+    f3 Le = S.beta * mis * emitter_eval(sc, si);
+    bool active_next = (S.depth + 1 < max_depth) && si.valid;
+    DBsdf b; uint32_t flags = 0;
+    if (si.valid) { b = sc.bsdfs[si.bsdf]; flags = b.bflags; }
+    bool active_em = active_next && (flags & EPSM_BF_SMOOTH);
+    float e1 = pcg_f32(S.rng), e2 = pcg_f32(S.rng);
+    DSamp ds; f3 em_weight; bool need_shadow = false;
+    sample_emitter_direction(sc, si, e1, e2, active_em, ds, em_weight, [&](const Ray &r) { shadow = r; need_shadow = true; return false; });
+    active_em = active_em && ds.pdf != 0.f;
+    f3 Lr_dir = mk3(0, 0, 0);
+    if (active_em) {
+        f3 wo = to_local(si, ds.d); f3 val; float bpdf;
+        bsdf_eval_pdf(b, si.wi, wo, val, bpdf);
+        Lr_dir = S.beta * mis_weight(ds.pdf, bpdf) * val * em_weight;
+    }
+    float s1 = pcg_f32(S.rng), s2x = pcg_f32(S.rng), s2y = pcg_f32(S.rng);
+    BSample bs; bs.wo = bs.hf = bs.weight = mk3(0, 0, 0); bs.pdf = 0.f; bs.eta = 0.f; bs.type = 0;
+    if (si.valid) bsdf_sample(b, si.wi, s1, s2x, s2y, active_next, bs);
+    // L = L + Le + Lr_dir (epsm.py:466): Lr_dir joins when its visibility is known — same operands, same order
+    S.L = S.L + Le;
+    if (need_shadow) { S.pend = Lr_dir; S.bits |= PR_PEND; } else S.L = S.L + Lr_dir;
+    if (si.valid) S.ray = spawn_ray(si, to_world(si, bs.wo));
+    S.eta *= bs.eta; S.beta = S.beta * bs.weight;
+    S.prev_p = si.p; S.prev_pdf = bs.pdf;
+    S.bits = (bs.type & EPSM_BF_DELTA) ? (S.bits | PR_PREV_DELTA) : (S.bits & ~PR_PREV_DELTA);
+    float bmax = max3(S.beta);
+    active_next = active_next && bmax != 0.f;
+    float rr_prob = fminf(bmax * S.eta * S.eta, .95f);
+    bool rr_active = S.depth >= rr_depth;
+    if (rr_active) S.beta = S.beta * rcp_e(rr_prob);
+    bool rr_continue = pcg_f32(S.rng) < rr_prob;
+    active_next = active_next && (!rr_active || rr_continue);
+    if (si.valid) S.depth += 1;
+    S.bits = active_next ? (S.bits | PR_ACTIVE) : (S.bits & ~PR_ACTIVE);
+    return need_shadow;
+}
+
+// ------------------------------------------------------------------------------------------------
 //  Gradient pass: sample_path replay (epsm.py:503-742) with the per-path log kept in thread-local
 //  memory, then the manifold solve, then the scatter seeds.
 // ------------------------------------------------------------------------------------------------
+EPSM_HD float nan_to_num(float x) {                       // torch.nan_to_num defaults
+    if (x != x) return 0.f;
+    if (x > FLT_MAX) return FLT_MAX;
+    if (x < -FLT_MAX) return -FLT_MAX;
+    return x;
+}
+EPSM_HD f3 ntn3(f3 v) { return mk3(nan_to_num(v.x), nan_to_num(v.y), nan_to_num(v.z)); }
+EPSM_HD float outlier(float x) { return (x > 0.1f || x < -0.1f) ? 0.f : x; }   // epsm.py:933-944
+EPSM_HD f3 outlier3(f3 v) { return mk3(outlier(v.x), outlier(v.y), outlier(v.z)); }
+
 struct VLog {
     bool active, active_em, direct_valid, direct_any, direct_grad, direct_traced;
     uint32_t flags, ismesh, mesh_flags, has_normals, prim;
@@ -705,9 +783,11 @@ struct PathLog : PathHead {
 //
 // The random-number draw order is that of epsm.py:503-742 (2 emitter + 3 discarded + 3 kept + 1 RR per bounce).
 struct WfState {
+    // the first WF_INIT_WORDS words are all that wf_begin needs to hand over; wf_state_defaults() restores the rest
     Pcg rng;
     Ray ray;                      // current path ray
-    f3 beta, L, prev_p, grad_d;
+    f3 grad_d;
+    f3 beta, L, prev_p;
     float eta, prev_pdf;
     uint32_t depth;
     bool active, prev_delta;
@@ -717,6 +797,12 @@ struct WfState {
     DSamp ds; f3 em_weight;
     Ray shadow_ray;
 };
+
+#define WF_INIT_WORDS 14          // rng (4) + ray (7) + grad_d (3)
+EPSM_HD void wf_state_defaults(WfState &S) {
+    S.beta = mk3(1, 1, 1); S.L = mk3(0, 0, 0); S.prev_p = mk3(0, 0, 0); S.eta = 1.f; S.prev_pdf = 1.f; S.depth = 0;
+    S.active = true; S.prev_delta = true; S.active_next = S.smooth = S.need_shadow = false; S.chain = true; S.chain_vertex = false;
+}
 
 EPSM_HD uint32_t wf_iterations(uint32_t max_depth_prop) { return max_depth_prop < EPSM_MAX_ITER ? max_depth_prop : EPSM_MAX_ITER; }   // epsm.py:549
 
@@ -732,8 +818,7 @@ EPSM_HDN void wf_begin(const DSensor &sensor, uint32_t px, uint32_t py, uint32_t
     CamRay c; camera_ray(sensor, px, py, S.rng, c);
     S.ray = c.ray;
     S.grad_d = (c.d_x - c.ray.d) * gx + (c.d_y - c.ray.d) * gy;                    // pixel motion → tangent of ray.d (epsm.py:250-257)
-    S.beta = mk3(1, 1, 1); S.L = mk3(0, 0, 0); S.prev_p = mk3(0, 0, 0); S.eta = 1.f; S.prev_pdf = 1.f; S.depth = 0;
-    S.active = true; S.prev_delta = true; S.active_next = S.smooth = S.need_shadow = false; S.chain = true; S.chain_vertex = false;
+    wf_state_defaults(S);
     P.cam = c.ray.o; P.d = c.ray.d; P.dlduv0 = P.dlduv1 = 0.f; P.dldp1 = mk3(0, 0, 0); P.L = mk3(0, 0, 0);
 }
 
@@ -754,10 +839,11 @@ EPSM_HD bool wf_chain_vertex(const WfState &S, int variant, uint32_t it, bool va
 
 // After the closest hit `h` of S.ray: surface interaction, first-hit tangents, emission, emitter sampling up to
 // (not including) its visibility test.  Returns true when S.shadow_ray must be tested.
-EPSM_HDN bool wf_stage_a(const DScene &sc, WfState &S, PathHead &P, const Hit &h_in, uint32_t it, uint32_t max_depth_prop, int variant, bool prune) {
+// `si` returns the surface interaction of the hit (the first-vertex fast path of k_wf_stage_a scatters from it).
+EPSM_HDN bool wf_stage_a(const DScene &sc, WfState &S, PathHead &P, const Hit &h_in, uint32_t it, uint32_t max_depth_prop, int variant, bool prune, SI &si) {
     Hit h = h_in;
     if (!S.active) { h.t = INFINITY; h.u = h.v = 0.f; h.prim = 0xffffffffu; }
-    SI si; compute_si(sc, S.ray, h, si);
+    compute_si(sc, S.ray, h, si);
     if (it == 0 && si.valid) {
         // forward-mode derivative of the first hit w.r.t. ray.d with the triangle detached (epsm.py:263-270)
         f3 p0 = ld3(sc.pos, si.fi[0]), e1 = ld3(sc.pos, si.fi[1]) - p0, e2 = ld3(sc.pos, si.fi[2]) - p0;
@@ -791,6 +877,21 @@ EPSM_HDN bool wf_stage_a(const DScene &sc, WfState &S, PathHead &P, const Hit &h
     // the visibility query is deferred: record the shadow ray, assume visible, fix up in stage B (scene.cpp:259-263)
     sample_emitter_direction(sc, si, e1r, e2r, S.smooth, S.ds, S.em_weight, [&](const Ray &r) { if (need_occl) { S.shadow_ray = r; S.need_shadow = true; } return false; });
     return S.need_shadow;
+}
+
+EPSM_HDN bool wf_stage_a(const DScene &sc, WfState &S, PathHead &P, const Hit &h_in, uint32_t it, uint32_t max_depth_prop, int variant, bool prune) {
+    SI si; return wf_stage_a(sc, S, P, h_in, it, max_depth_prop, variant, prune, si);
+}
+
+// A path whose first vertex already ends the gradient chain and needs no light-direction ray (see wf_chain_vertex and
+// need_nee above) has exactly one output: diffuse_grad[0] = dldp1 on a diffuse first hit (epsm.py:789-792, :1056 in
+// the caustic variant), ±0.1 outlier filter applied (epsm.py:933-944), scattered by seed (ii) onto the hit triangle.
+EPSM_HD bool wf_first_vertex_final(const WfState &S, uint32_t it, bool prune) { return prune && it == 0 && !S.chain_vertex && !S.smooth; }
+// … its value and whether the hit mesh takes gradients (the scatter targets are si.fi[c] with weights si.bw[c]).
+EPSM_HD bool wf_first_vertex_seed(const DScene &sc, const WfState &S, const PathHead &H, const SI &si, f3 &dg) {
+    const bool diffuse = si.valid && (sc.bsdfs[si.bsdf].bflags & EPSM_BF_DIFFUSE) != 0;
+    dg = outlier3(diffuse ? H.dldp1 : mk3(0, 0, 0));
+    return S.active && si.valid && (si.mesh_flags & EPSM_MESH_GRAD);
 }
 
 // After the visibility test: NEE contribution, the two BSDF samples, the vertex log, the ray towards the light
@@ -962,15 +1063,6 @@ EPSM_HD V2 v2_add(V2 a, V2 b) { return V2{a.x + b.x, a.y + b.y}; }
 // block of ∂c/∂u: rows i ∈ {0,1}, columns (b0, b1) — position part g·(p0−p2), g·(p1−p2)
 EPSM_HD M2 uv_block(const f3 g[2], f3 a0, f3 a1) { return M2{dot3(g[0], a0), dot3(g[0], a1), dot3(g[1], a0), dot3(g[1], a1)}; }
 
-EPSM_HD float nan_to_num(float x) {                       // torch.nan_to_num defaults
-    if (x != x) return 0.f;
-    if (x > FLT_MAX) return FLT_MAX;
-    if (x < -FLT_MAX) return -FLT_MAX;
-    return x;
-}
-EPSM_HD f3 ntn3(f3 v) { return mk3(nan_to_num(v.x), nan_to_num(v.y), nan_to_num(v.z)); }
-EPSM_HD float outlier(float x) { return (x > 0.1f || x < -0.1f) ? 0.f : x; }   // epsm.py:933-944
-EPSM_HD f3 outlier3(f3 v) { return mk3(outlier(v.x), outlier(v.y), outlier(v.z)); }
 
 struct PathGrads {
     f3 pg[EPSM_MAXV][5];         // path_grad[5k + {0,1,2: p0 p1 p2, 3: n, 4: m}]
@@ -1116,9 +1208,11 @@ EPSM_HDN void calc_grad_caustic(const PathLog &P, int n_logged, PathGrads &G) {
     }
 }
 
-EPSM_HDN void calc_grad(const PathLog &P, int variant, int n_logged, PathGrads &G) {
-    for (int k = 0; k < EPSM_MAXV; ++k) { for (int c = 0; c < 5; ++c) G.pg[k][c] = mk3(0, 0, 0); G.lg[k] = G.dg[k] = mk3(0, 0, 0); }
+// `n_avail` (optional): only vertices 0 … n_avail−1 of the log are active — outputs are produced for those alone, so the
+// zero-fill and the outlier pass stop there (the gradient pass passes the loaded prefix; default: all).
+EPSM_HDN void calc_grad(const PathLog &P, int variant, int n_logged, PathGrads &G, int n_avail = EPSM_MAXV) {
+    for (int k = 0; k < EPSM_MAXV && k < n_avail; ++k) { for (int c = 0; c < 5; ++c) G.pg[k][c] = mk3(0, 0, 0); G.lg[k] = G.dg[k] = mk3(0, 0, 0); }
     if (variant == EPSM_VARIANT_MANIFOLD) calc_grad_manifold(P, n_logged, G);
     else calc_grad_caustic(P, n_logged, G);
-    for (int k = 0; k < EPSM_MAXV; ++k) { for (int c = 0; c < 5; ++c) G.pg[k][c] = outlier3(G.pg[k][c]); G.lg[k] = outlier3(G.lg[k]); G.dg[k] = outlier3(G.dg[k]); }
+    for (int k = 0; k < EPSM_MAXV && k < n_avail; ++k) { for (int c = 0; c < 5; ++c) G.pg[k][c] = outlier3(G.pg[k][c]); G.lg[k] = outlier3(G.lg[k]); G.dg[k] = outlier3(G.dg[k]); }
 }

@@ -161,12 +161,13 @@ __device__ __forceinline__ void scatter3(float *__restrict__ buf, uint32_t idx, 
 }
 
 // The Backward-mode replay seeds of sample_path (epsm.py:559-562, 609-627, 644-645)
-__device__ void scatter_path(const PathLog &P, const PathGrads &G, int variant, int n_logged, uint32_t max_depth_prop,
+// `n_avail`: vertices 0 … n_avail−1 of the log are present; the rest are inactive and contribute nothing.
+__device__ void scatter_path(const PathLog &P, const PathGrads &G, int variant, int n_logged, int n_avail, uint32_t max_depth_prop,
                              float *__restrict__ grad_pos, float *__restrict__ grad_nrm) {
     // len(path_grad) = 5·n_logged (manifold) or 5·(n_logged−1)+3 (caustic: n, m of the last vertex are never added)
     const int n_pg = variant == EPSM_VARIANT_MANIFOLD ? 5 * n_logged : 5 * (n_logged - 1) + 3;
     const bool shadow_term = (max_depth_prop < EPSM_MAX_ITER ? max_depth_prop : EPSM_MAX_ITER) <= 3;
-    for (int k = 0; k < n_logged; ++k) {
+    for (int k = 0; k < n_logged && k < n_avail; ++k) {
         const VLog &v = P.v[k];
         const bool sel = v.active && (v.mesh_flags & EPSM_MESH_GRAD);
         if (5 * k + 4 < n_pg) {
@@ -249,16 +250,39 @@ template <typename T> __device__ __forceinline__ void soa_store(const T &src, ui
     for (uint32_t k = 0; k < WORDS_OF(T); ++k) base[(size_t) k * stride + i] = w[k];
 }
 
+// the first NW words only (a record whose tail is reconstructed by the consumer)
+template <uint32_t NW, typename T> __device__ __forceinline__ void soa_load_prefix(T &dst, const uint32_t *__restrict__ base, uint32_t stride, uint32_t i) {
+    static_assert(NW * 4 <= sizeof(T), "prefix longer than the record");
+    uint32_t w[NW];
+#pragma unroll
+    for (uint32_t k = 0; k < NW; ++k) w[k] = base[(size_t) k * stride + i];
+    memcpy(&dst, w, NW * 4);
+}
+template <uint32_t NW, typename T> __device__ __forceinline__ void soa_store_prefix(const T &src, uint32_t *__restrict__ base, uint32_t stride, uint32_t i) {
+    static_assert(NW * 4 <= sizeof(T), "prefix longer than the record");
+    uint32_t w[NW];
+    memcpy(w, &src, NW * 4);
+#pragma unroll
+    for (uint32_t k = 0; k < NW; ++k) base[(size_t) k * stride + i] = w[k];
+}
+
+// Lane status word: low byte = one of the codes below, bits 8… = number of vertex records written so far.
+// Resident CTAs per SM requested for the stage / finish kernels (register cap = 65536 / (128·N)).  They are chains of
+// dependent gathers (status → state → hit → faces → vertices → BSDF), i.e. latency-bound: at the compiler's free choice
+// of 255 registers only 8 warps/SM are resident (profiles/r01_d_*).
+#ifndef EPSM_STAGE_MINBLOCKS
+#define EPSM_STAGE_MINBLOCKS 2
+#endif
 #define WF_NONE 0u      // slot without a lane
 #define WF_LIVE 1u      // path still being traced
 #define WF_DONE 2u      // path has terminated (its remaining logged vertices are inactive)
+#define WF_SCATTERED 3u // gradient chain ended at the first vertex and its only seed is already in grad_pos (k_wf_stage_a)
 
 struct WfBuffers {
     uint32_t *status;          // [C]
     uint32_t *states;          // WfState, word-major
     uint32_t *heads;           // PathHead, word-major
     uint32_t *vlogs;           // EPSM_MAXV × VLog, word-major per vertex: base + it·WORDS_OF(VLog)·C
-    uint8_t *vmask;            // [MAXV·C] 1 where a vertex record was written
     Hit *hits;                 // [C] path hits, then [MAXV·C] direct hits
     uint32_t *occl;            // [C]
     QRay *q_closest /* 2C */, *q_any /* C */;
@@ -268,7 +292,7 @@ struct WfBuffers {
 
 size_t epsm_wf_workspace_bytes(uint32_t capacity) {
     size_t c = capacity;
-    return c * (4 * (1 + WORDS_OF(WfState) + WORDS_OF(PathHead) + EPSM_MAXV * WORDS_OF(VLog)) + EPSM_MAXV + sizeof(Hit) * (1 + EPSM_MAXV)
+    return c * (4 * (1 + WORDS_OF(WfState) + WORDS_OF(PathHead) + EPSM_MAXV * WORDS_OF(VLog)) + sizeof(Hit) * (1 + EPSM_MAXV)
                 + sizeof(uint32_t) + sizeof(QRay) * 3) + 64 * sizeof(uint32_t) + 16 * 256;
 }
 static WfBuffers wf_carve(void *base, uint32_t capacity) {
@@ -277,7 +301,7 @@ static WfBuffers wf_carve(void *base, uint32_t capacity) {
     w.counters = (uint32_t *) take(64 * sizeof(uint32_t));
     w.status = (uint32_t *) take(c * 4);
     w.states = (uint32_t *) take(c * 4 * WORDS_OF(WfState)); w.heads = (uint32_t *) take(c * 4 * WORDS_OF(PathHead));
-    w.vlogs = (uint32_t *) take(c * 4 * EPSM_MAXV * WORDS_OF(VLog)); w.vmask = (uint8_t *) take(c * EPSM_MAXV);
+    w.vlogs = (uint32_t *) take(c * 4 * EPSM_MAXV * WORDS_OF(VLog));
     w.hits = (Hit *) take(c * sizeof(Hit) * (1 + EPSM_MAXV)); w.occl = (uint32_t *) take(c * sizeof(uint32_t));
     w.q_closest = (QRay *) take(2 * c * sizeof(QRay)); w.q_any = (QRay *) take(c * sizeof(QRay));
     w.capacity = capacity; return w;
@@ -324,12 +348,10 @@ __global__ void __launch_bounds__(128) k_wf_init(DLaunch ln, uint64_t work_base,
             const uint64_t pixel = (uint64_t) wi.py * ln.sensor.w + wi.px;
             PathHead H;
             wf_begin(ln.sensor, wi.px, wi.py, ln.seed, (uint32_t) wi.lane, grad_in[pixel * 5 + 3], grad_in[pixel * 5 + 4], S, H);
-            soa_store(S, wb.states, wb.capacity, i); soa_store(H, wb.heads, wb.capacity, i);
+            soa_store_prefix<WF_INIT_WORDS>(S, wb.states, wb.capacity, i); soa_store(H, wb.heads, wb.capacity, i);
             push = true;
         }
         wb.status[i] = wi.valid ? WF_LIVE : WF_NONE;
-#pragma unroll
-        for (int k = 0; k < EPSM_MAXV; ++k) wb.vmask[(size_t) k * wb.capacity + i] = 0;
     }
     const uint32_t q = queue_push(wb.counters + 0, push);
     if (push) queue_write(wb.q_closest, q, S.ray, i);
@@ -495,43 +517,50 @@ __global__ void __launch_bounds__(CTA) k_wf_trace(DScene sc, const QRay *__restr
     }
 }
 
-__global__ void __launch_bounds__(128) k_wf_stage_a(DScene sc, DLaunch ln, uint32_t it, uint32_t n, WfBuffers wb) {
+// `grad_pos` != NULL enables the first-vertex fast path (scatter passes; the record probe keeps every lane).
+__global__ void __launch_bounds__(128, EPSM_STAGE_MINBLOCKS) k_wf_stage_a(DScene sc, DLaunch ln, uint32_t it, uint32_t n, WfBuffers wb, float *__restrict__ grad_pos) {
     const uint32_t i = blockIdx.x * 128 + threadIdx.x;
     bool push = false; Ray sr;
-    if (i < n && wb.status[i] == WF_LIVE) {
-        WfState S; soa_load(S, wb.states, wb.capacity, i);
-        const Hit h = wb.hits[i];
+    if (i < n && (wb.status[i] & 0xffu) == WF_LIVE) {
+        WfState S; const Hit h = wb.hits[i];
+        bool keep = true;
         if (it == 0) {
+            soa_load_prefix<WF_INIT_WORDS>(S, wb.states, wb.capacity, i); wf_state_defaults(S);
             PathHead H; soa_load(H, wb.heads, wb.capacity, i);
-            push = wf_stage_a(sc, S, H, h, it, ln.max_depth, ln.variant, ln.prune != 0);
-            soa_store(H, wb.heads, wb.capacity, i);
+            SI si;
+            push = wf_stage_a(sc, S, H, h, it, ln.max_depth, ln.variant, ln.prune != 0, si);
+            if (grad_pos && wf_first_vertex_final(S, it, ln.prune != 0)) {
+                // the path ends here for the gradient: seed (ii) of its first vertex is its only output
+                f3 dg; const bool sel = wf_first_vertex_seed(sc, S, H, si, dg);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) scatter3(grad_pos, si.fi[c], dg * si.bw[c], sel);
+                wb.status[i] = WF_SCATTERED; keep = false; push = false;
+            } else soa_store(H, wb.heads, wb.capacity, i);
         } else {
+            soa_load(S, wb.states, wb.capacity, i);
             PathHead H;                                   // only written at the first hit
             push = wf_stage_a(sc, S, H, h, it, ln.max_depth, ln.variant, ln.prune != 0);
         }
-        sr = S.shadow_ray;
-        soa_store(S, wb.states, wb.capacity, i);
+        if (keep) { sr = S.shadow_ray; soa_store(S, wb.states, wb.capacity, i); }
     }
     const uint32_t q = queue_push(wb.counters + 32 + it, push);
     if (push) queue_write(wb.q_any, q, sr, i);
 }
 
-__global__ void __launch_bounds__(128) k_wf_stage_b(DScene sc, DLaunch ln, uint32_t it, uint32_t max_iter, uint32_t n, WfBuffers wb) {
+__global__ void __launch_bounds__(128, EPSM_STAGE_MINBLOCKS) k_wf_stage_b(DScene sc, DLaunch ln, uint32_t it, uint32_t max_iter, uint32_t n, WfBuffers wb, bool keep_state) {
     const uint32_t i = blockIdx.x * 128 + threadIdx.x;
     bool push_direct = false, push_next = false; Ray direct, next;
-    if (i < n && wb.status[i] == WF_LIVE) {
+    if (i < n && (wb.status[i] & 0xffu) == WF_LIVE) {
         WfState S; soa_load(S, wb.states, wb.capacity, i);
         const Hit h = wb.hits[i];
         const bool occluded = S.need_shadow && wb.occl[i] != 0u;
         VLog v;
         wf_stage_b(sc, S, v, h, occluded, it, ln.rr_depth, ln.prune != 0, direct, push_direct);
-        if (it < EPSM_MAXV) {
-            soa_store(v, wb.vlogs + (size_t) it * WORDS_OF(VLog) * wb.capacity, wb.capacity, i);
-            wb.vmask[(size_t) it * wb.capacity + i] = 1;
-        }
+        if (it < EPSM_MAXV) soa_store(v, wb.vlogs + (size_t) it * WORDS_OF(VLog) * wb.capacity, wb.capacity, i);
         push_next = S.active && it + 1 < max_iter; next = S.ray;
-        soa_store(S, wb.states, wb.capacity, i);
-        if (!S.active) wb.status[i] = WF_DONE;
+        if (S.active || keep_state) soa_store(S, wb.states, wb.capacity, i);       // a finished lane's state is read by the record probe only (P.L)
+        const uint32_t n_written = it + 1 < EPSM_MAXV ? it + 1 : EPSM_MAXV;
+        wb.status[i] = (S.active ? WF_LIVE : WF_DONE) | (n_written << 8);
     }
     const uint32_t qd = queue_push(wb.counters + (it + 1), push_direct);
     if (push_direct) queue_write(wb.q_closest, qd, direct, wb.capacity + it * wb.capacity + i);
@@ -541,17 +570,27 @@ __global__ void __launch_bounds__(128) k_wf_stage_b(DScene sc, DLaunch ln, uint3
 
 __global__ void k_count_lanes(uint32_t n, WfBuffers wb, unsigned long long *counters) {
     const uint32_t i = blockIdx.x * 128 + threadIdx.x;
-    const bool live = i < n && wb.status[i] != WF_NONE;
+    const bool live = i < n && (wb.status[i] & 0xffu) != WF_NONE;
     const unsigned m = __ballot_sync(0xffffffffu, live);
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(counters + 3, (unsigned long long) __popc(m));
 }
 
+// Minimal "inactive vertex" for the slot just behind the loaded prefix: calc_grad reads it as the next vertex of
+// section B (active / flags / triangle) and as the loop terminator.
+__device__ __forceinline__ void vlog_inactive(VLog &v) {
+    v.active = v.active_em = v.direct_valid = v.direct_any = v.direct_grad = v.direct_traced = false;
+    v.flags = v.ismesh = v.mesh_flags = v.has_normals = 0; v.prim = 0xffffffffu;
+    v.p0 = v.p1 = v.p2 = mk3(0, 0, 0); v.b0 = v.b1 = 0.f;
+}
+
 template <bool RECORD>
-__global__ void __launch_bounds__(128) k_wf_finish(DScene sc, DLaunch ln, uint64_t work_base, uint32_t n, WfBuffers wb,
+__global__ void __launch_bounds__(128, EPSM_STAGE_MINBLOCKS) k_wf_finish(DScene sc, DLaunch ln, uint64_t work_base, uint32_t n, WfBuffers wb,
                                                    float *__restrict__ grad_pos, float *__restrict__ grad_nrm, float *__restrict__ records) {
     const uint32_t i = blockIdx.x * 128 + threadIdx.x;
     if (i >= n) return;
-    if (wb.status[i] == WF_NONE) return;
+    const uint32_t status = wb.status[i], code = status & 0xffu;
+    if (code == WF_NONE || code == WF_SCATTERED) return;
+    const int n_written = (int) (status >> 8);
     PathLog P;
     soa_load(static_cast<PathHead &>(P), wb.heads, wb.capacity, i);
     const uint32_t max_iter = wf_iterations(ln.max_depth);
@@ -559,9 +598,9 @@ __global__ void __launch_bounds__(128) k_wf_finish(DScene sc, DLaunch ln, uint64
     // Only the prefix of the path that can carry gradients is fetched: the chain ends at the first diffuse vertex
     // (manifold, epsm.py:855,920) or at the second one (caustic: vertex 1 must be diffuse, epsm.py:999,1008), at a
     // non-mesh vertex or where the path left the scene; every output beyond it is masked to zero by calc_grad.
-    bool chain = true; int n_diffuse = 0;
+    bool chain = true; int n_diffuse = 0, n_avail = 0;
     for (int k = 0; k < EPSM_MAXV; ++k) {
-        if (k < n_logged && (chain || RECORD) && wb.vmask[(size_t) k * wb.capacity + i]) {
+        if (k < n_logged && k < n_written && (chain || RECORD)) {
             soa_load(P.v[k], wb.vlogs + (size_t) k * WORDS_OF(VLog) * wb.capacity, wb.capacity, i);
             VLog &v = P.v[k];
             if (v.active && v.direct_traced) wf_direct_hit(sc, v, wb.hits[wb.capacity + (size_t) k * wb.capacity + i]);
@@ -570,17 +609,113 @@ __global__ void __launch_bounds__(128) k_wf_finish(DScene sc, DLaunch ln, uint64
             if (!v.active || !v.ismesh) chain = false;
             if (ln.variant == EPSM_VARIANT_MANIFOLD) { if (diffuse) chain = false; }
             else { if ((k == 0 && !diffuse) || n_diffuse >= 2) chain = false; }
-        } else {
-            // a lane that has left the path (or the gradient-dead tail): the logged vertex is inactive
+            n_avail = k + 1;
+        } else if (RECORD) {
+            // a lane that has left the path: the logged vertex is inactive
             memset(&P.v[k], 0, sizeof(VLog)); P.v[k].prim = 0xffffffffu;
-            chain = false;
+        } else {
+            vlog_inactive(P.v[k]);                        // the gradient-dead tail starts here; nothing behind it is read
+            break;
         }
     }
-    if (RECORD) { WfState S; soa_load(S, wb.states, wb.capacity, i); P.L = S.L; }
+    if (RECORD) { WfState S; soa_load(S, wb.states, wb.capacity, i); P.L = S.L; n_avail = EPSM_MAXV; }
     PathGrads G;
-    calc_grad(P, ln.variant, n_logged, G);
+    calc_grad(P, ln.variant, n_logged, G, n_avail);
     if (RECORD) { const WorkItem wi = wf_work_item(ln, work_base + i); write_record(P, G, n_logged, records + (wi.lane - ln.lane_begin) * EPSM_REC_FLOATS); }
-    else scatter_path(P, G, ln.variant, n_logged, ln.max_depth, grad_pos, grad_nrm);
+    else scatter_path(P, G, ln.variant, n_logged, n_avail, ln.max_depth, grad_pos, grad_nrm);
+}
+
+// ------------------------------------------------------------------------------------------------
+//  Primal render — wavefront (EPSMIntegrator.render / sample, epsm.py:13-82, 308-501)
+//
+//  k_pr_init → [closest] → k_pr_stage(0) → [any ∥ closest] → k_pr_stage(1) → … → k_pr_film.  One stage per bounce
+//  (pr_stage, epsm_device.cuh); both queries of a bounce are drained by the persistent traversal kernel of the gradient
+//  pass.  The film kernel owns one 8×4-pixel tile per CTA — work items are enumerated tile by tile, so a tile's samples
+//  are contiguous — accumulates the 5×5 Gaussian footprints in shared memory and flushes each film pixel once.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_pr_init(DLaunch ln, uint64_t work_base, uint32_t n, WfBuffers wb) {
+    const uint32_t i = blockIdx.x * 128 + threadIdx.x;
+    bool push = false; PrState S;
+    if (i < n) {
+        const WorkItem wi = wf_work_item(ln, work_base + i);
+        if (wi.valid) {
+            S.rng = pcg_for_lane(ln.seed, (uint32_t) wi.lane);
+            CamRay c; camera_ray(ln.sensor, wi.px, wi.py, S.rng, c);
+            S.ray = c.ray;
+            soa_store_prefix<PR_INIT_WORDS>(S, wb.states, wb.capacity, i);
+            push = true;
+        }
+        wb.status[i] = wi.valid ? WF_LIVE : WF_NONE;
+    }
+    const uint32_t q = queue_push(wb.counters + 0, push);
+    if (push) queue_write(wb.q_closest, q, S.ray, i);
+}
+
+__global__ void __launch_bounds__(128, EPSM_STAGE_MINBLOCKS) k_pr_stage(DScene sc, DLaunch ln, uint32_t it, uint32_t n, WfBuffers wb) {
+    const uint32_t i = blockIdx.x * 128 + threadIdx.x;
+    bool push_shadow = false, push_next = false; Ray shadow; PrState S;
+    if (i < n && wb.status[i] == WF_LIVE) {
+        if (it == 0) { soa_load_prefix<PR_INIT_WORDS>(S, wb.states, wb.capacity, i); pr_state_defaults(S); }
+        else { soa_load(S, wb.states, wb.capacity, i); pr_resolve_pending(S, wb.occl[i] != 0u); }
+        push_shadow = pr_stage(sc, S, wb.hits[i], ln.max_depth, ln.rr_depth, shadow);
+        push_next = (S.bits & PR_ACTIVE) != 0 && it + 1 < ln.max_depth;
+        soa_store(S, wb.states, wb.capacity, i);
+        if (!push_next) wb.status[i] = WF_DONE;
+    }
+    const uint32_t slot = (it + 1) & 15u;
+    const uint32_t qa = queue_push(wb.counters + 32 + slot, push_shadow);
+    if (push_shadow) queue_write(wb.q_any, qa, shadow, i);
+    const uint32_t qn = queue_push(wb.counters + slot, push_next);
+    if (push_next) queue_write(wb.q_closest, qn, S.ray, i);
+}
+
+// ImageBlock::put, coalesced branch (imageblock.cpp:414-494) into a tile-local RGBW block with a 2-pixel apron, then
+// HDRFilm::put_block (hdrfilm.cpp:286-320): pixels outside the film are the cropped border.
+__global__ void __launch_bounds__(128) k_pr_film(DScene sc, DLaunch ln, uint64_t work_base, uint32_t n, WfBuffers wb, float *__restrict__ film) {
+    __shared__ float ftile[FT_H][FT_W][4];
+    for (int k = threadIdx.x; k < FT_H * FT_W * 4; k += 128) (&ftile[0][0][0])[k] = 0.f;
+    __syncthreads();
+    const uint32_t W = ln.sensor.w, H = ln.sensor.h, S = ln.s_end - ln.s_begin;
+    const uint32_t tiles_x = (W + TILE_W - 1) / TILE_W;
+    const uint64_t per_tile = 32ull * S;
+    const uint64_t tile = work_base / per_tile + blockIdx.x;
+    const uint64_t w0 = tile * per_tile > work_base ? tile * per_tile : work_base;
+    const uint64_t w1 = (tile + 1) * per_tile < work_base + n ? (tile + 1) * per_tile : work_base + n;
+    const uint32_t tx = (uint32_t) (tile % tiles_x), ty = ln.tile_y0 + (uint32_t) (tile / tiles_x);
+    for (uint64_t w = w0 + threadIdx.x; w < w1; w += 128) {
+        const uint32_t i = (uint32_t) (w - work_base);
+        if (wb.status[i] == WF_NONE) continue;
+        const WorkItem wi = wf_work_item(ln, w);
+        // radiance: words of PrState::L (+ the NEE term still waiting for its shadow ray)
+        PrState St; soa_load(St, wb.states, wb.capacity, i);
+        pr_resolve_pending(St, wb.occl[i] != 0u);
+        const f3 L = St.L;
+        Pcg rng = pcg_for_lane(ln.seed, (uint32_t) wi.lane);
+        const float pos_x = (float) wi.px + pcg_f32(rng), pos_y = (float) wi.py + pcg_f32(rng);     // camera_ray's jitter
+        const int pix = (int) floorf(pos_x) - 2, piy = (int) floorf(pos_y) - 2;
+        float rel_x = (float) pix + .5f - pos_x, rel_y = (float) piy + .5f - pos_y;
+        float wx[5], wy[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) { wx[k] = filter_eval(sc.filter, rel_x); wy[k] = filter_eval(sc.filter, rel_y); rel_x += 1; rel_y += 1; }
+        const int lx = pix - (int) (tx * TILE_W) + 2, ly = piy - (int) (ty * TILE_H) + 2;
+#pragma unroll
+        for (int ys = 0; ys < 5; ++ys)
+#pragma unroll
+            for (int xs = 0; xs < 5; ++xs) {
+                const float wgt = wy[ys] * wx[xs];
+                float *d = ftile[ly + ys][lx + xs];
+                atomicAdd(d + 0, L.x * wgt); atomicAdd(d + 1, L.y * wgt); atomicAdd(d + 2, L.z * wgt); atomicAdd(d + 3, 1.0f * wgt);
+            }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < FT_H * FT_W; k += 128) {
+        const int fy = (int) (ty * TILE_H) + k / FT_W - 2, fx = (int) (tx * TILE_W) + k % FT_W - 2;
+        if (fx < 0 || fy < 0 || fx >= (int) W || fy >= (int) H) continue;
+        const float *sv = ftile[k / FT_W][k % FT_W];
+        if (sv[3] == 0.f && sv[0] == 0.f && sv[1] == 0.f && sv[2] == 0.f) continue;
+        float *d = film + ((size_t) fy * W + fx) * 4;
+        atomicAdd(d + 0, sv[0]); atomicAdd(d + 1, sv[1]); atomicAdd(d + 2, sv[2]); atomicAdd(d + 3, sv[3]);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -667,6 +802,59 @@ cudaError_t epsm_launch_render(const DScene &sc, DLaunch ln, float *film, unsign
     if (counters) k_render<true><<<grid, CTA, 0, s>>>(sc, ln, film, counters); else k_render<false><<<grid, CTA, 0, s>>>(sc, ln, film, nullptr);
     return cudaGetLastError();
 }
+// Wavefront primal render.  `host_count` is a pinned (or pageable) word used to poll the queue size once the path
+// length exceeds 8 bounces (max_depth = −1 means "until every path has died", common.py:33-37).
+cudaError_t epsm_launch_render_wf(const DScene &sc, DLaunch ln, float *film, unsigned long long *counters, void *workspace, uint32_t capacity,
+                                  uint32_t trace_grid, uint64_t *n_launches, cudaStream_t s) {
+    tile_rows(ln);
+    const uint32_t tiles = tile_grid(ln);
+    if (tiles == 0 || ln.s_end <= ln.s_begin) return cudaSuccess;
+    const uint64_t per_tile = 32ull * (ln.s_end - ln.s_begin);
+    const uint64_t total = (uint64_t) tiles * per_tile;
+    WfBuffers wb = wf_carve(workspace, capacity);
+    uint64_t launches = 0;
+    for (uint64_t base = 0; base < total; base += capacity) {
+        const uint32_t n = (uint32_t) ((total - base) < capacity ? (total - base) : capacity);
+        const uint32_t grid = (n + 127) / 128;
+        cudaMemsetAsync(wb.counters, 0, 64 * sizeof(uint32_t), s);
+        k_pr_init<<<grid, 128, 0, s>>>(ln, base, n, wb); ++launches;
+        auto trace = [&](bool any, uint32_t slot) {
+            if (any) {
+                if (counters) k_wf_trace<true, true><<<trace_grid, CTA, 0, s>>>(sc, wb.q_any, wb.counters + 32 + slot, wb.counters + 48 + slot, nullptr, wb.occl, counters);
+                else k_wf_trace<true, false><<<trace_grid, CTA, 0, s>>>(sc, wb.q_any, wb.counters + 32 + slot, wb.counters + 48 + slot, nullptr, wb.occl, nullptr);
+            } else {
+                if (counters) k_wf_trace<false, true><<<trace_grid, CTA, 0, s>>>(sc, wb.q_closest, wb.counters + slot, wb.counters + 16 + slot, wb.hits, nullptr, counters);
+                else k_wf_trace<false, false><<<trace_grid, CTA, 0, s>>>(sc, wb.q_closest, wb.counters + slot, wb.counters + 16 + slot, wb.hits, nullptr, nullptr);
+            }
+            ++launches;
+        };
+        uint32_t last_slot = 0; bool shadow_left = true;
+        for (uint32_t it = 0; it < ln.max_depth; ++it) {
+            const uint32_t slot = it & 15u, next = (it + 1) & 15u;
+            trace(false, slot);
+            if (it > 0) trace(true, slot);
+            if (it + 1 >= 16) {                           // the counter slots are reused cyclically
+                cudaMemsetAsync(wb.counters + next, 0, 4, s); cudaMemsetAsync(wb.counters + 16 + next, 0, 4, s);
+                cudaMemsetAsync(wb.counters + 32 + next, 0, 4, s); cudaMemsetAsync(wb.counters + 48 + next, 0, 4, s);
+            }
+            k_pr_stage<<<grid, 128, 0, s>>>(sc, ln, it, n, wb); ++launches;
+            last_slot = next;
+            if (it + 1 >= 8 && it + 1 < ln.max_depth) {   // long paths: poll the queue sizes, stop when no path ray is left
+                uint32_t left[2] = {0, 0};
+                cudaMemcpyAsync(&left[0], wb.counters + next, 4, cudaMemcpyDeviceToHost, s);
+                cudaMemcpyAsync(&left[1], wb.counters + 32 + next, 4, cudaMemcpyDeviceToHost, s);
+                cudaError_t e = cudaStreamSynchronize(s); if (e != cudaSuccess) return e;
+                if (left[0] == 0) { shadow_left = left[1] != 0; break; }
+            }
+        }
+        if (shadow_left && ln.max_depth > 0) trace(true, last_slot);      // shadow rays pushed by the last stage
+        const uint32_t n_tiles = (uint32_t) ((base + n - 1) / per_tile - base / per_tile + 1);
+        k_pr_film<<<n_tiles, 128, 0, s>>>(sc, ln, base, n, wb, film); ++launches;
+        if (counters) { k_count_lanes<<<grid, 128, 0, s>>>(n, wb, counters); ++launches; }
+    }
+    if (n_launches) *n_launches += launches;
+    return cudaGetLastError();
+}
 cudaError_t epsm_launch_develop(const float *film, uint64_t n_pixels, float *out, cudaStream_t s) {
     if (n_pixels == 0) return cudaSuccess;
     k_film_develop<<<(uint32_t) ((n_pixels + 255) / 256), 256, 0, s>>>(film, n_pixels, out);
@@ -697,13 +885,13 @@ cudaError_t epsm_launch_backward(const DScene &sc, DLaunch ln, const float *grad
             ev_end();
             ++launches;
             if (it == max_iter) break;
-            k_wf_stage_a<<<grid, 128, 0, s>>>(sc, ln, it, n, wb); ++launches;
+            k_wf_stage_a<<<grid, 128, 0, s>>>(sc, ln, it, n, wb, records ? nullptr : grad_pos); ++launches;
             ev_begin();
             if (counters) k_wf_trace<true, true><<<trace_grid, CTA, 0, s>>>(sc, wb.q_any, wb.counters + 32 + it, wb.counters + 48 + it, nullptr, wb.occl, counters);
             else k_wf_trace<true, false><<<trace_grid, CTA, 0, s>>>(sc, wb.q_any, wb.counters + 32 + it, wb.counters + 48 + it, nullptr, wb.occl, nullptr);
             ev_end();
             ++launches;
-            k_wf_stage_b<<<grid, 128, 0, s>>>(sc, ln, it, max_iter, n, wb); ++launches;
+            k_wf_stage_b<<<grid, 128, 0, s>>>(sc, ln, it, max_iter, n, wb, records != nullptr); ++launches;
         }
         if (records) k_wf_finish<true><<<grid, 128, 0, s>>>(sc, ln, base, n, wb, nullptr, nullptr, records);
         else k_wf_finish<false><<<grid, 128, 0, s>>>(sc, ln, base, n, wb, grad_pos, grad_nrm, nullptr);

@@ -15,6 +15,9 @@ size_t epsm_wf_workspace_bytes(uint32_t capacity);
 cudaError_t epsm_launch_backward(const DScene &sc, DLaunch ln, const float *grad_in, float *grad_pos, float *grad_nrm, float *records,
                                  unsigned long long *counters, void *workspace, uint32_t capacity, uint32_t trace_grid, uint64_t *n_launches,
                                  EpsmEventList *trace_events, cudaStream_t s);
+// Wavefront primal render (same workspace); k_render (epsm_launch_render) is the single-kernel variant kept for comparison.
+cudaError_t epsm_launch_render_wf(const DScene &sc, DLaunch ln, float *film, unsigned long long *counters, void *workspace, uint32_t capacity,
+                                  uint32_t trace_grid, uint64_t *n_launches, cudaStream_t s);
 cudaError_t epsm_launch_sampler_stream(uint32_t seed, uint64_t lane_begin, uint64_t n_lanes, uint32_t n_floats, float *out, cudaStream_t s);
 cudaError_t epsm_launch_sample_rays(const DSensor &se, uint32_t seed, uint32_t spp, uint64_t lane_begin, uint64_t n_lanes, float *out, cudaStream_t s);
 cudaError_t epsm_launch_vertex_normals(const float *pos, const uint32_t *faces, uint32_t f_off, uint32_t f_cnt, uint32_t v_off, uint32_t v_cnt,

@@ -76,8 +76,10 @@ void sim_sample_rays(sim_scene *s, uint32_t sensor, uint32_t seed, uint32_t spp,
 }
 
 // k_render on the host: film is H·W·4, accumulated into.
+// `staged` != 0: the lane runs the wavefront stages of k_pr_stage (pr_stage with the NEE term parked until its shadow
+// ray has answered) instead of path_primal.
 void sim_render_accumulate(sim_scene *s, uint32_t sensor, uint32_t seed, uint32_t spp, uint32_t max_depth, uint32_t rr_depth,
-                           uint64_t lane_begin, uint64_t lane_end, float *film) {
+                           uint64_t lane_begin, uint64_t lane_end, float *film, int staged) {
     DLaunch ln = make_launch(s, sensor, seed, spp, max_depth, rr_depth, 0);
     const uint32_t W = ln.sensor.w, H = ln.sensor.h;
     const int64_t n = (int64_t) (lane_end - lane_begin);
@@ -88,7 +90,19 @@ void sim_render_accumulate(sim_scene *s, uint32_t sensor, uint32_t seed, uint32_
         LocalStack ls; TStack st; bind(st, ls); Tracer tr(s->sc, st);
         Pcg rng = pcg_for_lane(seed, (uint32_t) lane);
         CamRay c; camera_ray(ln.sensor, pixel % W, pixel / W, rng, c);
-        bool valid; f3 L = path_primal<false>(s->sc, tr, c.ray, rng, max_depth, rr_depth, valid);
+        f3 L;
+        if (staged) {
+            PrState S; S.rng = rng; S.ray = c.ray; pr_state_defaults(S);
+            bool occluded = false;
+            for (uint32_t it = 0; it < max_depth && (S.bits & PR_ACTIVE); ++it) {
+                const Hit h = trace_closest<false>(tr, S.ray);
+                pr_resolve_pending(S, occluded);
+                Ray shadow;
+                if (pr_stage(s->sc, S, h, max_depth, rr_depth, shadow)) occluded = trace_any<false>(tr, shadow);
+            }
+            pr_resolve_pending(S, occluded);
+            L = S.L;
+        } else { bool valid; L = path_primal<false>(s->sc, tr, c.ray, rng, max_depth, rr_depth, valid); }
         tmp[5 * i] = L.x; tmp[5 * i + 1] = L.y; tmp[5 * i + 2] = L.z; tmp[5 * i + 3] = c.pos_x; tmp[5 * i + 4] = c.pos_y;
     }
     for (int64_t i = 0; i < n; ++i) {
@@ -113,12 +127,58 @@ void sim_backward(sim_scene *s, int variant, uint32_t sensor, uint32_t seed, uin
     const int n_logged = (int) (max_iter < EPSM_MAXV ? max_iter : EPSM_MAXV);
     const int64_t n = (int64_t) (lane_end - lane_begin);
     std::vector<PathLog> logs(records ? 0 : n); std::vector<PathGrads> grads(records ? 0 : n);
+    std::vector<uint8_t> mode(n, 0), fast_sel(n, 0); std::vector<int> navail(n, EPSM_MAXV);
+    std::vector<f3> fast_dg(n); std::vector<uint32_t> fast_fi(3 * (size_t) n); std::vector<float> fast_bw(3 * (size_t) n);
     #pragma omp parallel for schedule(dynamic, 64)
     for (int64_t i = 0; i < n; ++i) {
         uint64_t lane = lane_begin + i; uint32_t pixel = (uint32_t) (lane / spp);
         LocalStack ls; TStack st; bind(st, ls); Tracer tr(s->sc, st);
         const float gx = grad_in[(size_t) pixel * 5 + 3], gy = grad_in[(size_t) pixel * 5 + 4];
-        PathLog P; path_log<false>(s->sc, tr, ln.sensor, pixel % W, pixel / W, seed, (uint32_t) lane, gx, gy, max_depth, rr_depth, variant, prune != 0 && !records, P);
+        PathLog P;
+        if (prune == 2 && !records) {
+            // the production schedule of the gradient pass: first-vertex fast path (k_wf_stage_a) and a log that holds
+            // only the gradient-carrying prefix (k_wf_finish)
+            WfState S; wf_begin(ln.sensor, pixel % W, pixel / W, seed, (uint32_t) lane, gx, gy, S, P);
+            const uint32_t iters = wf_replay_iterations(max_depth, true);
+            int n_written = 0; bool scattered = false;
+            for (uint32_t it = 0; it < iters && S.active; ++it) {
+                Hit h = trace_closest<false>(tr, S.ray);
+                SI si; bool occluded = false;
+                const bool need_shadow = wf_stage_a(s->sc, S, P, h, it, max_depth, variant, true, si);
+                if (wf_first_vertex_final(S, it, true)) {
+                    f3 dg; fast_sel[i] = wf_first_vertex_seed(s->sc, S, P, si, dg) ? 1 : 0; fast_dg[i] = dg;
+                    for (int c = 0; c < 3; ++c) { fast_fi[3 * i + c] = si.fi[c]; fast_bw[3 * i + c] = si.bw[c]; }
+                    scattered = true; break;
+                }
+                if (need_shadow) occluded = trace_any<false>(tr, S.shadow_ray);
+                Ray direct; bool dv; VLog scratch;
+                VLog &v = it < EPSM_MAXV ? P.v[it] : scratch;
+                wf_stage_b(s->sc, S, v, h, occluded, it, rr_depth, true, direct, dv);
+                if (dv) wf_direct_hit(s->sc, v, trace_closest<false>(tr, direct));
+                if (it < EPSM_MAXV) n_written = (int) it + 1;
+            }
+            mode[i] = scattered ? 1 : 0;
+            if (scattered) continue;
+            // k_wf_finish: keep the chain prefix, mark the vertex behind it inactive, poison the rest
+            int n_avail = 0, n_diffuse = 0; bool chain = true;
+            for (int k = 0; k < EPSM_MAXV; ++k) {
+                if (k < n_logged && k < n_written && chain) {
+                    const VLog &v = P.v[k]; const bool diffuse = (v.flags & EPSM_BF_DIFFUSE) != 0; n_diffuse += diffuse ? 1 : 0;
+                    if (!v.active || !v.ismesh) chain = false;
+                    if (variant == EPSM_VARIANT_MANIFOLD) { if (diffuse) chain = false; } else { if ((k == 0 && !diffuse) || n_diffuse >= 2) chain = false; }
+                    n_avail = k + 1;
+                } else if (k == n_avail) {
+                    VLog &v = P.v[k]; memset(&v, 0xff, sizeof(VLog));
+                    v.active = v.active_em = v.direct_valid = v.direct_any = v.direct_grad = v.direct_traced = false;
+                    v.flags = v.ismesh = v.mesh_flags = v.has_normals = 0; v.prim = 0xffffffffu; v.p0 = v.p1 = v.p2 = mk3(0, 0, 0); v.b0 = v.b1 = 0.f;
+                } else memset(&P.v[k], 0xff, sizeof(VLog));          // never read
+            }
+            navail[i] = n_avail;
+            PathGrads G; memset(&G, 0xff, sizeof(G)); calc_grad(P, variant, n_logged, G, n_avail);
+            logs[i] = P; grads[i] = G;
+            continue;
+        }
+        path_log<false>(s->sc, tr, ln.sensor, pixel % W, pixel / W, seed, (uint32_t) lane, gx, gy, max_depth, rr_depth, variant, prune != 0 && !records, P);
         PathGrads G; calc_grad(P, variant, n_logged, G);
         if (records) {
             float *r = records + (size_t) i * EPSM_REC_FLOATS;
@@ -143,7 +203,11 @@ void sim_backward(sim_scene *s, int variant, uint32_t sensor, uint32_t seed, uin
     const bool shadow_term = max_iter <= 3;
     for (int64_t i = 0; i < n; ++i) {
         const PathLog &P = logs[i]; const PathGrads &G = grads[i];
-        for (int k = 0; k < n_logged; ++k) {
+        if (mode[i] == 1) {                                   // seed (ii) of the first vertex, scattered by k_wf_stage_a
+            for (int c = 0; c < 3; ++c) add3(grad_pos, fast_fi[3 * i + c], fast_dg[i] * fast_bw[3 * i + c], fast_sel[i] != 0);
+            continue;
+        }
+        for (int k = 0; k < n_logged && k < navail[i]; ++k) {
             const VLog &v = P.v[k];
             const bool sel = v.active && (v.mesh_flags & EPSM_MESH_GRAD);
             if (5 * k + 4 < n_pg) {

@@ -29,7 +29,7 @@ def lib():
         L.sim_trace.argtypes = [vp, vp, u64, vp, i32, vp]
         L.sim_sampler_stream.argtypes = [u32, u64, u64, u32, vp]
         L.sim_sample_rays.argtypes = [vp, u32, u32, u32, u64, u64, vp]
-        L.sim_render_accumulate.argtypes = [vp, u32, u32, u32, u32, u32, u64, u64, vp]
+        L.sim_render_accumulate.argtypes = [vp, u32, u32, u32, u32, u32, u64, u64, vp, i32]
         L.sim_backward.argtypes = [vp, i32, u32, u32, u32, u32, u32, vp, u64, u64, vp, vp, vp, i32]
         _LIB = L
     return _LIB
@@ -72,10 +72,10 @@ class SimScene:
     def sample_rays(self, sensor, seed, spp, lb, le):
         out = np.zeros((le - lb, 14), np.float32); lib().sim_sample_rays(self.h, sensor, seed, spp, lb, le, out.ctypes.data); return out
 
-    def render_raw(self, sensor, seed, spp, max_depth=6, rr_depth=5, lb=0, le=None):
+    def render_raw(self, sensor, seed, spp, max_depth=6, rr_depth=5, lb=0, le=None, staged=False):
         s = self.data.sensors[sensor]; le = s.width * s.height * spp if le is None else le
         film = np.zeros((s.height, s.width, 4), np.float32)
-        lib().sim_render_accumulate(self.h, sensor, seed, spp, max_depth, rr_depth, lb, le, film.ctypes.data)
+        lib().sim_render_accumulate(self.h, sensor, seed, spp, max_depth, rr_depth, lb, le, film.ctypes.data, 1 if staged else 0)
         return film
 
     def path_records(self, variant, sensor, seed, spp, max_depth, rr_depth, grad_in, lb, le):
@@ -88,5 +88,5 @@ class SimScene:
         g = np.ascontiguousarray(grad_in, np.float32)
         gp = np.zeros((self.n_vertices, 3), np.float32); gn = np.zeros((self.n_vertices, 3), np.float32)
         lib().sim_backward(self.h, _vid(variant), sensor, seed, spp, max_depth, rr_depth, g.ctypes.data, lb, le,
-                           gp.ctypes.data, gn.ctypes.data, None, 1 if prune else 0)
+                           gp.ctypes.data, gn.ctypes.data, None, int(prune))     # 2 = production schedule (fast path + chain prefix)
         return gp, gn

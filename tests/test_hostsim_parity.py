@@ -53,6 +53,16 @@ def test_primal_film(case):
     o.set_accel(False)
 
 
+def test_staged_primal_equals_path_loop(case):
+    """The wavefront stage of the primal render (pr_stage: NEE term parked until its shadow ray answers) must give the
+    radiance of the plain path loop bit for bit — same operands, same order (epsm.py:466)."""
+    sd, sim, o, _, max_depth = case
+    for md in sorted({max_depth, 2, 12}):
+        a, b = sim.render_raw(1, 3, 4, md, 5), sim.render_raw(1, 3, 4, md, 5, staged=True)
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), f"max_depth={md}"
+    assert np.abs(a[..., :3]).max() > 0
+
+
 def test_per_path_gradients_and_scatter(case):
     sd, sim, o, variant, max_depth = case
     o.set_accel(True)
@@ -87,6 +97,9 @@ def test_pruned_replay_equals_full_replay(case):
         full = sim.backward(variant, 2, 13, 8, md, 5, g, prune=False)
         pruned = sim.backward(variant, 2, 13, 8, md, 5, g, prune=True)
         assert np.array_equal(full[0], pruned[0]) and np.array_equal(full[1], pruned[1]), f"max_depth={md}"
+        # the production schedule: first-vertex fast path of k_wf_stage_a + the chain-prefix log of k_wf_finish
+        fast = sim.backward(variant, 2, 13, 8, md, 5, g, prune=2)
+        assert np.array_equal(full[0], fast[0]) and np.array_equal(full[1], fast[1]), f"fast path, max_depth={md}"
     assert np.abs(full[0]).max() > 0 or variant == "manifold_caustic"
 
 
