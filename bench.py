@@ -79,6 +79,47 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
 
 
+def iteration_leg(ep, scene, sd, integ, wl, sensor, spp, g_dev, buf, n=5, warm=2):
+    import torch
+    params = ep.traverse(scene)
+    keys = [k for k, i in params._mesh_of.items() if sd.meshes[i].grad] or list(params._mesh_of)
+    base = {k: params[k].clone() for k in keys}
+    out = {"unit": "ms per iteration (wall, median)", "iterations": n, "meshes_updated": len(keys),
+           "vertices_updated": int(sum(base[k].shape[0] for k in keys)),
+           "what": "params.update() of every differentiable mesh (device tensors) + vertex normals + BVH refresh + primal render "
+                   "(sensor 1, same res/spp) + gradient pass + Adam-style vertex step; matcher (third-party geomloss) not included"}
+    scene.set_sample_range(0, 0)
+    for mode in ("refit", "rebuild"):
+        scene.accel_update = mode
+        ts, parts = [], []
+        for it in range(warm + n):
+            buf.zero_(); torch.cuda.synchronize(); scene.synchronize()
+            t0 = time.perf_counter()
+            for k in keys:
+                params[k] = base[k] + 1e-3 * float(np.sin(it + 1.0))
+            params.update(); scene.synchronize()
+            t1 = time.perf_counter()
+            integ.render(scene, sensor=1, seed=it, spp=spp); scene.synchronize(); torch.cuda.synchronize()
+            t2 = time.perf_counter()
+            scene.render_backward_raw(wl["variant"], sensor, ep.sample_tea_32(it, 1)[0], spp, integ.max_depth, integ.rr_depth, g_dev, buf[0], buf[1])
+            scene.synchronize()
+            t3 = time.perf_counter()
+            voff = scene.voff
+            for k in keys:
+                i = params._mesh_of[k]
+                base[k].add_(buf[0][int(voff[i]):int(voff[i + 1])].reshape(base[k].shape), alpha=0.0)   # optimiser step stand-in (lr 0: the scene stays put)
+            torch.cuda.synchronize()
+            t4 = time.perf_counter()
+            if it >= warm:
+                ts.append((t4 - t0) * 1e3); parts.append(((t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3, (t4 - t3) * 1e3))
+        pm = np.median(np.array(parts), axis=0)
+        out[mode] = {"ms": float(np.median(ts)), "update_ms": float(pm[0]), "primal_ms": float(pm[1]), "backward_ms": float(pm[2]), "step_ms": float(pm[3])}
+    for k in keys:                                            # leave the scene as it was built
+        params[k] = base[k]
+    scene.accel_update = "rebuild"; params.update(); scene.accel_update = "auto"
+    return out
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
 
@@ -162,6 +203,7 @@ def main():
                     help="weak: per-GPU work fixed (N ranks trace N*spp samples per pixel); strong: the spp-sample wavefront is split over the ranks")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-iteration-leg", action="store_true", help="skip the ms-per-optimisation-iteration measurement (BASELINE.json's second metric)")
     ap.add_argument("--full-replay", action="store_true", help="time the unpruned replay (every lane runs min(max_depth,6) iterations, as the reference does)")
     ap.add_argument("--no-full-replay-leg", action="store_true", help="skip the extra full-replay measurement reported beside the default")
     args = ap.parse_args()
@@ -340,6 +382,13 @@ def main():
                 "definition": "nodes_fetched*128 + tris_tested*48 + rays*(32+16) bytes (SURVEY 8d), counted by the instrumented kernel on the "
                               "same seed, divided by the summed CUDA-event duration of the traversal launches; cache hits are not subtracted"}
 
+    # ---- ms per optim.py iteration (BASELINE.json's second metric; EPSM/optim.py:110-157 without the third-party matcher):
+    #      vertex update of every differentiable mesh → normals + BVH refresh → primal render (sensor 1) → gradient pass →
+    #      Adam-style step on the vertex tensors.  Wall clock, median, once per BVH policy.
+    iteration = None
+    if rank == 0 and world == 1 and not args.no_iteration_leg:
+        iteration = iteration_leg(ep, scene, sd, integ, wl, sensor, spp_job, g_dev, buf)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
@@ -351,7 +400,7 @@ def main():
         out = {"metric": "gradient path samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
                "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
-               "roofline": roof, "cpu_baseline": cpu, "full_replay": full_leg,
+               "roofline": roof, "cpu_baseline": cpu, "full_replay": full_leg, "iteration": iteration,
                "scene": {"triangles": int(stats["n_triangles"]), "vertices": int(stats["n_vertices"]), "bvh_nodes": int(stats["n_nodes"]),
                          "bvh_build_ms": stats["build_ms"]},
                "wall_s_timed_region": t_wall}

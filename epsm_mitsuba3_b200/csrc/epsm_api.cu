@@ -48,6 +48,9 @@ struct epsm_ctx {
     bool primal_megakernel = false;                 // EPSM_PRIMAL_MEGAKERNEL=1: render with the single-kernel k_render instead of the wavefront
     HostScene hs;                                   // host mirror (positions are needed for BVH rebuilds)
     std::vector<uint8_t> mesh_dirty;
+    std::vector<uint8_t> host_pos_stale;            // meshes whose newest positions exist only on the device (pulled before a host rebuild)
+    DevBuf<uint32_t> d_refit;                       // refit scratch: max|coordinate|, Σ half-area, per-node arrival counters
+    uint64_t refits_since_build = 0; double refit_ms_last = 0;
     // device
     DevBuf<f4> d_nodes, d_tris; DevBuf<float> d_pos, d_nrm, d_cdf, d_pmf; DevBuf<uint32_t> d_faces, d_face_mesh;
     DevBuf<DMesh> d_meshes; DevBuf<DBsdf> d_bsdfs; DevBuf<DEmitter> d_emitters;
@@ -199,7 +202,7 @@ int epsm_scene_upload(epsm_ctx *ctx, const epsm_mesh_desc *meshes, uint32_t n_me
     CK(ctx->d_face_mesh.upload(ctx->hs.face_mesh, ctx->stream), "upload face_mesh");
     CK(ctx->d_bsdfs.upload(ctx->hs.bsdfs, ctx->stream), "upload bsdfs");
     CK(ctx->d_emitters.upload(ctx->hs.emitters, ctx->stream), "upload emitters");
-    ctx->mesh_dirty.assign(n_meshes, 0);
+    ctx->mesh_dirty.assign(n_meshes, 0); ctx->host_pos_stale.assign(n_meshes, 0); ctx->refits_since_build = 0;
     int rc = upload_accel(ctx);
     if (rc != EPSM_OK) return rc;
     ctx->have_scene = true; ctx->dirty = false;
@@ -216,32 +219,111 @@ int epsm_scene_update_vertices(epsm_ctx *ctx, uint32_t mesh_id, const float *pos
     float *dst = ctx->d_pos.p + 3 * (size_t) m.v_off, *hdst = ctx->hs.pos.data() + 3 * (size_t) m.v_off;
     if (mem == EPSM_MEM_DEVICE) {
         CK(cudaMemcpyAsync(dst, positions, nb, cudaMemcpyDeviceToDevice, ctx->stream), "D2D positions");
-        CK(cudaMemcpyAsync(hdst, positions, nb, cudaMemcpyDeviceToHost, ctx->stream), "D2H positions");
+        ctx->host_pos_stale[mesh_id] = 1;            // the host mirror is refreshed only when a host rebuild needs it
     } else {
         memcpy(hdst, positions, nb);
         CK(cudaMemcpyAsync(dst, hdst, nb, cudaMemcpyHostToDevice, ctx->stream), "H2D positions");
+        ctx->host_pos_stale[mesh_id] = 0;
     }
     ctx->mesh_dirty[mesh_id] = 1; ctx->dirty = true;
     return EPSM_OK;
 }
 
-int epsm_scene_commit(epsm_ctx *ctx) {
-    if (!ctx) return EPSM_E_INVALID;
-    if (!ctx->have_scene) return fail(ctx, EPSM_E_NOSCENE, "no scene uploaded");
-    if (!ctx->dirty) return EPSM_OK;
-    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+namespace {
+// Bring the host mirror of the positions up to date (device-pointer updates are mirrored lazily).
+int pull_stale_positions(epsm_ctx *ctx) {
+    bool any = false;
+    for (size_t i = 0; i < ctx->hs.meshes.size(); ++i) {
+        if (!ctx->host_pos_stale[i]) continue;
+        const DMesh &m = ctx->hs.meshes[i];
+        CK(cudaMemcpyAsync(ctx->hs.pos.data() + 3 * (size_t) m.v_off, ctx->d_pos.p + 3 * (size_t) m.v_off, 3 * (size_t) m.v_cnt * sizeof(float),
+                           cudaMemcpyDeviceToHost, ctx->stream), "D2H positions");
+        ctx->host_pos_stale[i] = 0; any = true;
+    }
+    if (any) CK(cudaStreamSynchronize(ctx->stream), "positions sync");
+    return EPSM_OK;
+}
+int recompute_dirty_normals(epsm_ctx *ctx) {
     for (size_t i = 0; i < ctx->hs.meshes.size(); ++i) {
         const DMesh &m = ctx->hs.meshes[i];
         if (!ctx->mesh_dirty[i] || !m.has_normals) continue;
         CK(epsm_launch_vertex_normals(ctx->d_pos.p, ctx->d_faces.p, m.f_off, m.f_cnt, m.v_off, m.v_cnt, ctx->d_nrm.p, ctx->stream), "vertex normals");
         ctx->launches += 3;
     }
+    return EPSM_OK;
+}
+} // namespace
+
+int epsm_scene_commit(epsm_ctx *ctx) {
+    if (!ctx) return EPSM_E_INVALID;
+    if (!ctx->have_scene) return fail(ctx, EPSM_E_NOSCENE, "no scene uploaded");
+    if (!ctx->dirty && ctx->refits_since_build == 0) return EPSM_OK;   // the tree is already a fresh build of these positions
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    int rc = recompute_dirty_normals(ctx);
+    if (rc != EPSM_OK) return rc;
+    rc = pull_stale_positions(ctx);
+    if (rc != EPSM_OK) return rc;
     CK(cudaStreamSynchronize(ctx->stream), "commit sync");          // host mirror of the positions is complete
     std::fill(ctx->mesh_dirty.begin(), ctx->mesh_dirty.end(), 0);
     host_scene_rebuild_accel(ctx->hs);
-    int rc = upload_accel(ctx);
+    rc = upload_accel(ctx);
     if (rc != EPSM_OK) return rc;
-    ctx->dirty = false;
+    ctx->dirty = false; ctx->refits_since_build = 0;
+    return EPSM_OK;
+}
+
+int epsm_scene_refit(epsm_ctx *ctx) {
+    if (!ctx) return EPSM_E_INVALID;
+    if (!ctx->have_scene) return fail(ctx, EPSM_E_NOSCENE, "no scene uploaded");
+    if (!ctx->dirty) return EPSM_OK;
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    int rc = recompute_dirty_normals(ctx);
+    if (rc != EPSM_OK) return rc;
+    const uint32_t n_nodes = ctx->sc.n_nodes, n_tris = ctx->sc.n_tris;
+    CK(ctx->d_refit.alloc(epsm_refit_scratch_words(n_nodes)), "refit scratch alloc");
+    CK(epsm_launch_refit(ctx->d_nodes.p, n_nodes, ctx->d_tris.p, n_tris, ctx->d_faces.p, ctx->d_pos.p, ctx->d_refit.p, ctx->stream), "k_refit");
+    ctx->launches += 2;
+    // emitter sampling tables (Mesh::build_pmf, mesh.cpp:361-393) of moved emitter meshes: small, rebuilt on the host
+    bool emitter_moved = false;
+    for (size_t i = 0; i < ctx->hs.meshes.size(); ++i) emitter_moved |= ctx->mesh_dirty[i] && ctx->hs.meshes[i].emitter >= 0;
+    if (emitter_moved) {
+        rc = pull_stale_positions(ctx);
+        if (rc != EPSM_OK) return rc;
+        host_scene_rebuild_area_tables(ctx->hs);
+        CK(ctx->d_cdf.upload(ctx->hs.cdf, ctx->stream), "upload cdf");
+        CK(ctx->d_pmf.upload(ctx->hs.pmf, ctx->stream), "upload pmf");
+        CK(ctx->d_meshes.upload(ctx->hs.meshes, ctx->stream), "upload meshes");
+        ctx->sc.cdf = ctx->d_cdf.p; ctx->sc.pmf = ctx->d_pmf.p; ctx->sc.meshes = ctx->d_meshes.p;
+        CK(cudaStreamSynchronize(ctx->stream), "refit sync");        // the uploads read host vectors
+    }
+    std::fill(ctx->mesh_dirty.begin(), ctx->mesh_dirty.end(), 0);
+    ctx->dirty = false; ctx->refits_since_build += 1;
+    return EPSM_OK;
+}
+
+int epsm_scene_accel_cost(epsm_ctx *ctx, double *cost_built, double *cost_now, uint64_t *refits_since_build) {
+    if (!ctx) return EPSM_E_INVALID;
+    if (!ctx->have_scene) return fail(ctx, EPSM_E_NOSCENE, "no scene uploaded");
+    if (cost_built) *cost_built = ctx->hs.bvh.cost;
+    if (refits_since_build) *refits_since_build = ctx->refits_since_build;
+    if (cost_now) {
+        *cost_now = ctx->hs.bvh.cost;
+        if (ctx->refits_since_build > 0 && ctx->d_refit.p) {
+            CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+            CK(cudaMemcpyAsync(cost_now, ctx->d_refit.p + 2, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream), "cost D2H");
+            CK(cudaStreamSynchronize(ctx->stream), "cost sync");
+        }
+    }
+    return EPSM_OK;
+}
+
+int epsm_scene_accel_raw(epsm_ctx *ctx, float **nodes, uint64_t *n_node_floats, float **tris, uint64_t *n_tri_floats) {
+    if (!ctx) return EPSM_E_INVALID;
+    if (!ctx->have_scene) return fail(ctx, EPSM_E_NOSCENE, "no scene uploaded");
+    if (nodes) *nodes = reinterpret_cast<float *>(ctx->d_nodes.p);
+    if (n_node_floats) *n_node_floats = (uint64_t) ctx->sc.n_nodes * EPSM_NODE_F4 * 4;
+    if (tris) *tris = reinterpret_cast<float *>(ctx->d_tris.p);
+    if (n_tri_floats) *n_tri_floats = (uint64_t) ctx->sc.n_tris * EPSM_TRI_F4 * 4;
     return EPSM_OK;
 }
 

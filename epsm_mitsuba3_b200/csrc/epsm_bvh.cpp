@@ -88,7 +88,8 @@ struct Collapser {
     const Builder &B; Bvh4 &out; float pad;
     uint32_t max_depth = 0;
     // Emits binary subtree `b` as a wide node; returns its index.
-    uint32_t emit(uint32_t b, uint32_t depth) {
+    // `parent` = (parent node << 2) | slot, 0xffffffff for the root (kept in the node's pad word for the device refit).
+    uint32_t emit(uint32_t b, uint32_t depth, uint32_t parent = 0xffffffffu) {
         max_depth = std::max(max_depth, depth);
         uint32_t ch[4]; int nc = 0;
         ch[nc++] = B.nodes[b].left; ch[nc++] = B.nodes[b].right;
@@ -110,13 +111,16 @@ struct Collapser {
             for (int a = 0; a < 3; ++a) { lo[a][i] = c.box.lo[a] - pad; hi[a][i] = c.box.hi[a] + pad; }
             if (c.count > 0) ref[i] = ~(int32_t) ((emit_leaf(c) << 2) | (c.count - 1));
         }
+        uint32_t n_inner = 0;
         for (int i = 0; i < nc; ++i) {
-            if (B.nodes[ch[i]].count == 0) ref[i] = (int32_t) emit(ch[i], depth + 1);
+            if (B.nodes[ch[i]].count == 0) { ref[i] = (int32_t) emit(ch[i], depth + 1, (idx << 2) | (uint32_t) i); ++n_inner; }
         }
         f4 *n = &out.nodes[(size_t) idx * EPSM_NODE_F4];
         for (int a = 0; a < 3; ++a) { n[a] = f4{lo[a][0], lo[a][1], lo[a][2], lo[a][3]}; n[3 + a] = f4{hi[a][0], hi[a][1], hi[a][2], hi[a][3]}; }
         float rf[4]; memcpy(rf, ref, 16);
-        n[6] = f4{rf[0], rf[1], rf[2], rf[3]}; n[7] = f4{0, 0, 0, 0};
+        n[6] = f4{rf[0], rf[1], rf[2], rf[3]};
+        const uint32_t link[2] = {parent, n_inner}; float lf[2]; memcpy(lf, link, 8);
+        n[7] = f4{lf[0], lf[1], 0, 0};                          // never read by the traversal
         return idx;
     }
     uint32_t emit_leaf(const BNode &c) {
@@ -136,6 +140,23 @@ struct Collapser {
 };
 
 } // namespace
+
+// Σ over nodes of the half-area of the union of the node's child boxes: the traversal-cost proxy the refit policy watches.
+double epsm_bvh4_cost(const f4 *nodes, size_t n_nodes) {
+    double sum = 0;
+    for (size_t i = 0; i < n_nodes; ++i) {
+        const float *n = &nodes[i * EPSM_NODE_F4].x;
+        int32_t ref[4]; memcpy(ref, n + 24, 16);
+        float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
+        for (int s = 0; s < 4; ++s) {
+            if (ref[s] == 0x7fffffff) continue;
+            for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], n[4 * a + s]); hi[a] = std::max(hi[a], n[12 + 4 * a + s]); }
+        }
+        const float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+        if (dx >= 0 && dy >= 0 && dz >= 0) sum += (double) (dx * dy + dy * dz + dz * dx);
+    }
+    return sum;
+}
 
 void epsm_build_bvh4(const float *pos, const uint32_t *faces, size_t nf, Bvh4 &out) {
     auto t0 = std::chrono::steady_clock::now();
@@ -166,10 +187,13 @@ void epsm_build_bvh4(const float *pos, const uint32_t *faces, size_t nf, Bvh4 &o
         ref[0] = ~(int32_t) ((C.emit_leaf(B.nodes[0]) << 2) | (B.nodes[0].count - 1));
         f4 *n = &out.nodes[0];
         for (int a = 0; a < 3; ++a) { n[a] = f4{lo[a][0], lo[a][1], lo[a][2], lo[a][3]}; n[3 + a] = f4{hi[a][0], hi[a][1], hi[a][2], hi[a][3]}; }
-        float rf[4]; memcpy(rf, ref, 16); n[6] = f4{rf[0], rf[1], rf[2], rf[3]}; n[7] = f4{0, 0, 0, 0};
+        float rf[4]; memcpy(rf, ref, 16); n[6] = f4{rf[0], rf[1], rf[2], rf[3]};
+        const uint32_t root_link = 0xffffffffu; float lf; memcpy(&lf, &root_link, 4); n[7] = f4{lf, 0, 0, 0};
     } else {
         C.emit(0, 1);
     }
     out.depth = C.max_depth;
+    out.pad = pad;
+    out.cost = epsm_bvh4_cost(out.nodes.data(), out.nodes.size() / EPSM_NODE_F4);
     out.build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 }

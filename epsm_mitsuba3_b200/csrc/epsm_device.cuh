@@ -222,6 +222,62 @@ struct TStack {
 
 EPSM_HD void cswap(uint32_t &a, uint32_t &b) { uint32_t lo = a < b ? a : b, hi = a < b ? b : a; a = lo; b = hi; }
 
+// ------------------------------------------------------------------------------------------------
+//  BVH4 refit after a vertex update (the per-iteration scene update of EPSM/optim.py:110-123 →
+//  Mesh::parameters_changed, mesh.cpp:82-102 → Scene::parameters_changed, scene.cpp:304-336, which rebuilds
+//  the Embree / OptiX structure).  The topology of the last host build is kept; triangle records and boxes
+//  are recomputed with the host builder's expressions (epsm_bvh.cpp), so a refit with unchanged positions
+//  reproduces the build bit for bit.  Shared by k_refit_* (epsm_kernels.cu) and the test-only host harness.
+// ------------------------------------------------------------------------------------------------
+// Rewrites triangle slot `slot` (p0 | e1 | e2, prim id kept); returns max |coordinate| of its vertices.
+EPSM_HD float refit_tri_slot(f4 *tris, const uint32_t *faces, const float *pos, uint32_t slot) {
+    f4 *tp = tris + (size_t) slot * EPSM_TRI_F4;
+    const float pf = tp[0].w; const uint32_t prim = f2u(pf);
+    const uint32_t *f = faces + 3 * (size_t) prim;
+    const f3 p0 = ld3(pos, f[0]), p1 = ld3(pos, f[1]), p2 = ld3(pos, f[2]);
+    tp[0] = f4{p0.x, p0.y, p0.z, pf};
+    tp[1] = f4{p1.x - p0.x, p1.y - p0.y, p1.z - p0.z, p2.x - p0.x};
+    tp[2] = f4{p2.y - p0.y, p2.z - p0.z, 0.f, 0.f};
+    float m = fmaxf(fmaxf(fabsf(p0.x), fabsf(p0.y)), fabsf(p0.z));
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(p1.x), fabsf(p1.y)), fabsf(p1.z)));
+    return fmaxf(m, fmaxf(fmaxf(fabsf(p2.x), fabsf(p2.y)), fabsf(p2.z)));
+}
+// Recomputes the boxes of the leaf children of node `idx` (inner-child slots must already hold their subtree boxes),
+// stores them, and returns the union of all child boxes in lo/hi and its half-area.
+EPSM_HD float refit_node(f4 *nodes, uint32_t idx, const f4 *tris, const uint32_t *faces, const float *pos, float pad, float *lo, float *hi) {
+    volatile float *n = &nodes[(size_t) idx * EPSM_NODE_F4].x;                // slots written by other CTAs: no L1
+    for (int a = 0; a < 3; ++a) { lo[a] = 1e30f; hi[a] = -1e30f; }
+    for (int s = 0; s < 4; ++s) {
+        const int32_t ref = (int32_t) f2u(n[24 + s]);
+        if (ref == 0x7fffffff) continue;
+        float clo[3], chi[3];
+        if (ref < 0) {
+            const uint32_t code = ~(uint32_t) ref, first = code >> 2, cnt = (code & 3u) + 1u;
+            for (int a = 0; a < 3; ++a) { clo[a] = 3.402823466e38f; chi[a] = -3.402823466e38f; }
+            for (uint32_t i = 0; i < cnt; ++i) {
+                const uint32_t prim = f2u(tris[(size_t) (first + i) * EPSM_TRI_F4].w);
+                const uint32_t *f = faces + 3 * (size_t) prim;
+                for (int k = 0; k < 3; ++k) {
+                    const float *p = pos + 3 * (size_t) f[k];
+                    for (int a = 0; a < 3; ++a) { clo[a] = fminf(clo[a], p[a]); chi[a] = fmaxf(chi[a], p[a]); }
+                }
+            }
+            for (int a = 0; a < 3; ++a) { clo[a] = clo[a] - pad; chi[a] = chi[a] + pad; n[4 * a + s] = clo[a]; n[12 + 4 * a + s] = chi[a]; }
+        } else {
+            for (int a = 0; a < 3; ++a) { clo[a] = n[4 * a + s]; chi[a] = n[12 + 4 * a + s]; }
+        }
+        for (int a = 0; a < 3; ++a) { lo[a] = fminf(lo[a], clo[a]); hi[a] = fmaxf(hi[a], chi[a]); }
+    }
+    const float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+    return (dx >= 0.f && dy >= 0.f && dz >= 0.f) ? dx * dy + dy * dz + dz * dx : 0.f;
+}
+// Stores the subtree box of a finished node into its slot of the parent node.
+EPSM_HD void refit_store_parent(f4 *nodes, uint32_t parent_link, const float *lo, const float *hi) {
+    volatile float *pn = &nodes[(size_t) (parent_link >> 2) * EPSM_NODE_F4].x; const uint32_t s = parent_link & 3u;
+    for (int a = 0; a < 3; ++a) { pn[4 * a + s] = lo[a]; pn[12 + 4 * a + s] = hi[a]; }
+}
+EPSM_HD float refit_pad(float max_abs) { return 1e-5f * max_abs + 1e-7f; }    // epsm_bvh.cpp: Möller–Trumbore slack
+
 // Closest hit (ANY = false) or occlusion test (ANY = true) through the BVH4.
 // Ties in t are resolved towards the larger primitive index, which is what scanning primitives in
 // order with `t <= maxt` (mesh.h:363; kdtree.h:2188-2290) produces; box culling is inclusive and the

@@ -140,6 +140,8 @@ void host_scene_rebuild_accel(HostScene &hs) {
     build_area_tables(&hs);
 }
 
+void host_scene_rebuild_area_tables(HostScene &hs) { build_area_tables(&hs); }
+
 void host_scene_view(const HostScene &hs, DScene &sc) {
     sc.nodes = hs.bvh.nodes.data(); sc.tris = hs.bvh.tris.data(); sc.pos = hs.pos.data(); sc.nrm = hs.nrm.data();
     sc.faces = hs.faces.data(); sc.face_mesh = hs.face_mesh.data(); sc.meshes = hs.meshes.data(); sc.bsdfs = hs.bsdfs.data();

@@ -20,5 +20,7 @@ std::string host_scene_build(HostScene &hs, const epsm_mesh_desc *meshes, uint32
                              const epsm_emitter_desc *emitters, uint32_t n_emitters, const epsm_sensor_desc *sensors, uint32_t n_sensors);
 // (Re)builds the BVH4 and the emitter area tables from hs.pos.
 void host_scene_rebuild_accel(HostScene &hs);
+// Only the emitter area tables / per-mesh area fields (Mesh::build_pmf) from hs.pos.
+void host_scene_rebuild_area_tables(HostScene &hs);
 // DScene over the HOST arrays (hostsim only; the product fills a DScene with device pointers).
 void host_scene_view(const HostScene &hs, DScene &sc);

@@ -775,6 +775,47 @@ __global__ void k_zero_range(float *__restrict__ p, uint64_t off, uint64_t n) {
 }
 
 // ------------------------------------------------------------------------------------------------
+//  BVH4 refit on the device (per-iteration scene update; reference: Scene::parameters_changed rebuilds the
+//  Embree / OptiX structure, scene.cpp:304-336, scene_embree.inl:130-187).  Two launches:
+//    k_refit_tris   one thread per triangle slot: p0 | e1 | e2 from the new positions, max |coordinate|
+//    k_refit_nodes  one thread per node whose children are all leaves; a finished node stores its box into
+//                   its parent's slot and bumps the parent's arrival counter, the last arrival climbs on
+//  scratch: [0] max|coordinate| bits, [2..3] Σ half-area (double), [4 + i] arrival counter of node i.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_refit_tris(f4 *__restrict__ tris, uint32_t n_slots, const uint32_t *__restrict__ faces,
+                                                    const float *__restrict__ pos, uint32_t *__restrict__ scratch) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    float m = 0.f;
+    if (i < n_slots) m = refit_tri_slot(tris, faces, pos, i);
+    const uint32_t wm = __reduce_max_sync(0xffffffffu, __float_as_uint(m));        // non-negative floats order like their bits
+    if ((threadIdx.x & 31u) == 0 && wm != 0) atomicMax(scratch, wm);
+}
+__global__ void __launch_bounds__(256) k_refit_nodes(f4 *nodes, uint32_t n_nodes, const f4 *__restrict__ tris,
+                                                     const uint32_t *__restrict__ faces, const float *__restrict__ pos, uint32_t *__restrict__ scratch) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    double area = 0.0;
+    if (i < n_nodes && __float_as_uint(nodes[(size_t) i * EPSM_NODE_F4 + 7].y) == 0u) {
+        const float pad = refit_pad(__uint_as_float(*(volatile uint32_t *) scratch));
+        uint32_t *arrive = scratch + 4;
+        uint32_t cur = i;
+        for (;;) {
+            float lo[3], hi[3];
+            area += (double) refit_node(nodes, cur, tris, faces, pos, pad, lo, hi);
+            const uint32_t link = __float_as_uint(nodes[(size_t) cur * EPSM_NODE_F4 + 7].x);
+            if (link == 0xffffffffu) break;                                          // root
+            refit_store_parent(nodes, link, lo, hi);
+            __threadfence();
+            const uint32_t parent = link >> 2, need = __float_as_uint(nodes[(size_t) parent * EPSM_NODE_F4 + 7].y);
+            if (atomicAdd(arrive + parent, 1u) + 1u != need) break;                  // a sibling subtree is still open
+            __threadfence();
+            cur = parent;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) area += __shfl_xor_sync(0xffffffffu, area, o);
+    if ((threadIdx.x & 31u) == 0 && area != 0.0) atomicAdd(reinterpret_cast<double *>(scratch + 2), area);
+}
+
+// ------------------------------------------------------------------------------------------------
 //  Launchers
 // ------------------------------------------------------------------------------------------------
 static inline void tile_rows(DLaunch &ln) {
@@ -917,5 +958,16 @@ cudaError_t epsm_launch_vertex_normals(const float *pos, const uint32_t *faces, 
     k_zero_range<<<(3 * v_cnt + 255) / 256, 256, 0, s>>>(nrm, 3 * (uint64_t) v_off, 3 * (uint64_t) v_cnt);
     k_normals_accumulate<<<(f_cnt + 255) / 256, 256, 0, s>>>(pos, faces, f_off, f_cnt, nrm);
     k_normals_finish<<<(v_cnt + 255) / 256, 256, 0, s>>>(nrm, v_off, v_cnt);
+    return cudaGetLastError();
+}
+
+size_t epsm_refit_scratch_words(uint32_t n_nodes) { return 4 + (size_t) n_nodes; }
+cudaError_t epsm_launch_refit(f4 *nodes, uint32_t n_nodes, f4 *tris, uint32_t n_tris, const uint32_t *faces, const float *pos,
+                              uint32_t *scratch, cudaStream_t s) {
+    if (n_nodes == 0 || n_tris == 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(scratch, 0, epsm_refit_scratch_words(n_nodes) * sizeof(uint32_t), s);
+    if (e != cudaSuccess) return e;
+    k_refit_tris<<<(n_tris + 255) / 256, 256, 0, s>>>(tris, n_tris, faces, pos, scratch);
+    k_refit_nodes<<<(n_nodes + 255) / 256, 256, 0, s>>>(nodes, n_nodes, tris, faces, pos, scratch);
     return cudaGetLastError();
 }

@@ -17,6 +17,7 @@ or without the built library raises.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Callable, Dict, Optional
 
 import numpy as np
@@ -90,6 +91,12 @@ class Scene:
         self._check(self.lib.epsm_scene_upload(ctx, c.meshes, nm, c.bsdfs, nb, c.emitters, ne, c.sensors, ns))
         self.voff = data.vertex_offsets()
         self.n_vertices = int(self.voff[-1])
+        # how params.update() refreshes the BVH (apply_updates): 'auto' | 'refit' | 'rebuild'
+        self.accel_update = os.environ.get("EPSM_ACCEL_UPDATE", "auto")
+        if self.accel_update not in ("auto", "refit", "rebuild"):
+            raise EpsmError(f"EPSM_ACCEL_UPDATE must be auto, refit or rebuild, not {self.accel_update!r}")
+        self.rebuild_cost_ratio = 1.5
+        self.rebuild_every = 0
 
     # ---- plumbing --------------------------------------------------------------------------
     def _check(self, rc):
@@ -148,7 +155,7 @@ class Scene:
 
     # ---- scene updates ---------------------------------------------------------------------
     def update_vertices(self, mesh_id: int, positions, commit: bool = True):
-        """params['<mesh>.vertex_positions'] = positions; params.update()"""
+        """params['<mesh>.vertex_positions'] = positions; params.update().  `commit=True` applies `self.accel_update`."""
         if isinstance(positions, torch.Tensor):
             positions = positions.detach().to(torch.float32).contiguous()
             if positions.is_cuda:
@@ -159,10 +166,42 @@ class Scene:
         addr, mem = self._ptr(positions)
         self._check(self.lib.epsm_scene_update_vertices(self.ctx, mesh_id, addr, mem))
         if commit:
-            self.commit()
+            self.apply_updates()
 
     def commit(self):
+        """Host rebuild of the BVH (what the reference does on every parameters_changed, scene.cpp:304-336)."""
         self._check(self.lib.epsm_scene_commit(self.ctx))
+
+    def refit(self):
+        """Device refit of the BVH: topology of the last build kept, boxes and triangle records recomputed."""
+        self._check(self.lib.epsm_scene_refit(self.ctx))
+
+    def accel_cost(self):
+        """(cost of the tree as built, cost now, refits since the last build) — Σ node half-areas."""
+        b, n, r = C.c_double(), C.c_double(), C.c_uint64()
+        self._check(self.lib.epsm_scene_accel_cost(self.ctx, C.byref(b), C.byref(n), C.byref(r)))
+        return b.value, n.value, r.value
+
+    def accel_raw(self):
+        """Device views of the BVH4 nodes (n,32) and triangle slots (n,16), for tests."""
+        pn, nn, pt, nt = C.c_void_p(), C.c_uint64(), C.c_void_p(), C.c_uint64()
+        self._check(self.lib.epsm_scene_accel_raw(self.ctx, C.byref(pn), C.byref(nn), C.byref(pt), C.byref(nt)))
+        return _wrap_device(pn.value, (nn.value // 32, 32), self.device), _wrap_device(pt.value, (nt.value // 16, 16), self.device)
+
+    def apply_updates(self):
+        """Make pending vertex updates visible to the next render.  Policy `self.accel_update`:
+        'rebuild' — host SAH rebuild every time (the reference's behaviour);
+        'refit'   — device refit every time;
+        'auto'    — device refit, host rebuild once the refitted tree's cost exceeds `self.rebuild_cost_ratio` × the
+                    cost of the tree as built (default 1.5) or after `self.rebuild_every` refits (default 0 = never)."""
+        mode = self.accel_update
+        if mode == "rebuild":
+            return self.commit()
+        self.refit()
+        if mode == "auto":
+            built, now, refits = self.accel_cost()
+            if now > self.rebuild_cost_ratio * built or (self.rebuild_every and refits >= self.rebuild_every):
+                self.commit()                                  # commit after a refit = fresh build of the current positions
 
     # ---- low-level entry points (numpy or torch in, same kind out) --------------------------
     def trace(self, rays, any_hit: bool = False, counters: Optional[np.ndarray] = None):
@@ -389,7 +428,7 @@ class SceneParameters(dict):
         for key in sorted(self._dirty):
             self.scene.update_vertices(self._mesh_of[key], self[key].reshape(-1, 3), commit=False)
         if self._dirty:
-            self.scene.commit()
+            self.scene.apply_updates()
         self._dirty.clear()
 
     def accumulate_gradients(self, grad_pos: torch.Tensor, grad_nrm: torch.Tensor):

@@ -118,9 +118,25 @@ int epsm_scene_upload(epsm_ctx *ctx,
 /* params['<mesh>.vertex_positions'] = …; params.update()  (src/python/python/util.py:181-228 →
  * Mesh::parameters_changed, src/render/mesh.cpp:82-102 → Scene::parameters_changed, scene.cpp:304-336).
  * `positions` holds 3*vertex_count floats in `mem` space.  Vertex normals of meshes that have them
- * are recomputed (mesh.cpp:257-330), area tables and the BVH are rebuilt on commit. */
+ * are recomputed (mesh.cpp:257-330), area tables and the BVH are rebuilt on the host on commit.  epsm_scene_commit
+ * after epsm_scene_refit (no new updates) replaces the refitted tree by a fresh build of the current positions. */
 int epsm_scene_update_vertices(epsm_ctx *ctx, uint32_t mesh_id, const float *positions, int mem);
 int epsm_scene_commit(epsm_ctx *ctx);
+
+/* The same update with the acceleration structure REFITTED on the device instead of rebuilt on the host: the topology
+ * of the last build is kept, triangle records and every box are recomputed from the new positions by two kernels
+ * (k_refit_tris, k_refit_nodes), vertex normals as in commit; nothing is copied to the host unless an emitter mesh
+ * moved (its area tables, Mesh::build_pmf mesh.cpp:361-393, are small and rebuilt on the host).  The reference rebuilds
+ * its Embree / OptiX structure on every parameters_changed (scene.cpp:304-336, scene_embree.inl:130-187,
+ * scene_optix.inl:236-440); hit records do not depend on the structure (closest t, ties to the larger primitive index),
+ * so refit and rebuild return identical results and differ only in traversal cost.  A refit with unchanged positions
+ * reproduces the host build bit for bit. */
+int epsm_scene_refit(epsm_ctx *ctx);
+/* Traversal-cost proxy for the refit / rebuild decision: Σ over nodes of the half-area of the node's box, for the tree
+ * as last BUILT and as it is NOW (after refits; reads one double back).  Any pointer may be NULL. */
+int epsm_scene_accel_cost(epsm_ctx *ctx, double *cost_built, double *cost_now, uint64_t *refits_since_build);
+/* Library-owned device pointers to the BVH4 nodes (32 floats each) and triangle slots (16 floats each), for tests. */
+int epsm_scene_accel_raw(epsm_ctx *ctx, float **nodes, uint64_t *n_node_floats, float **tris, uint64_t *n_tri_floats);
 
 /* Scene::ray_intersect_preliminary / Scene::ray_test on a ray batch
  * (src/render/scene_embree.inl:202-426, scene_optix.inl:516-646, kdtree.h:2188-2290).

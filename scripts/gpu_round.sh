@@ -5,7 +5,7 @@ T=${1:-x}
 mkdir -p gpurun_out
 (timeout 900 python -m pytest tests -m gpu -x -q) > gpurun_out/${T}_pytest_gpu.log 2>&1; tail -3 gpurun_out/${T}_pytest_gpu.log
 timeout 600 python bench.py > gpurun_out/${T}_bench_room.json 2> gpurun_out/${T}_bench_room.err
-B="timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-full-replay-leg"
+B="timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-full-replay-leg --no-iteration-leg"
 for c in 23 24; do EPSM_WF_CHUNK=$((1<<c)) $B > gpurun_out/${T}_chunk$c.json 2> gpurun_out/${T}_chunk$c.err; done
 $B --workload glass > gpurun_out/${T}_bench_glass.json 2>&1
 $B --workload smpl > gpurun_out/${T}_bench_smpl.json 2>&1
@@ -17,7 +17,7 @@ try:
 except Exception as e: print(sys.argv[1], 'ERR', e)
 PY
 done
-NB="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-full-replay-leg"
+NB="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-full-replay-leg --no-iteration-leg"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/${T}_launches_room.csv $NB > gpurun_out/${T}_ncu_list.log 2>&1
 # full captures: the traversal launches of one chunk (warm-up pass) and two finish launches
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_wf_trace -c 12 -o gpurun_out/${T}_trace_full -f $NB > gpurun_out/${T}_ncu_trace.log 2>&1

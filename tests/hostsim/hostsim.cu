@@ -40,6 +40,31 @@ void sim_scene_update_vertices(sim_scene *s, uint32_t mesh_id, const float *posi
     memcpy(s->hs.pos.data() + 3 * (size_t) m.v_off, positions, 3 * (size_t) m.v_cnt * sizeof(float));
     host_scene_rebuild_accel(s->hs); host_scene_view(s->hs, s->sc);
 }
+// The device refit (k_refit_tris / k_refit_nodes) run serially: children are emitted after their parent by the builder,
+// so descending node order is a valid bottom-up schedule.  Returns the refitted tree's cost (Σ node half-areas).
+double sim_scene_refit(sim_scene *s, uint32_t mesh_id, const float *positions) {
+    const DMesh &m = s->hs.meshes[mesh_id];
+    memcpy(s->hs.pos.data() + 3 * (size_t) m.v_off, positions, 3 * (size_t) m.v_cnt * sizeof(float));
+    f4 *nodes = s->hs.bvh.nodes.data(), *tris = s->hs.bvh.tris.data();
+    const uint32_t n_nodes = (uint32_t) (s->hs.bvh.nodes.size() / EPSM_NODE_F4), n_slots = (uint32_t) (s->hs.bvh.tris.size() / EPSM_TRI_F4);
+    float max_abs = 0.f;
+    for (uint32_t i = 0; i < n_slots; ++i) max_abs = fmaxf(max_abs, refit_tri_slot(tris, s->hs.faces.data(), s->hs.pos.data(), i));
+    const float pad = refit_pad(max_abs);
+    double cost = 0;
+    for (uint32_t i = n_nodes; i-- > 0;) {
+        float lo[3], hi[3];
+        cost += (double) refit_node(nodes, i, tris, s->hs.faces.data(), s->hs.pos.data(), pad, lo, hi);
+        const uint32_t link = f2u(nodes[(size_t) i * EPSM_NODE_F4 + 7].x);
+        if (link != 0xffffffffu) refit_store_parent(nodes, link, lo, hi);
+    }
+    host_scene_rebuild_area_tables(s->hs); host_scene_view(s->hs, s->sc);
+    return cost;
+}
+double sim_scene_cost(sim_scene *s) { return epsm_bvh4_cost(s->hs.bvh.nodes.data(), s->hs.bvh.nodes.size() / EPSM_NODE_F4); }
+void sim_scene_copy_accel(sim_scene *s, float *nodes, float *tris) {
+    if (nodes) memcpy(nodes, s->hs.bvh.nodes.data(), s->hs.bvh.nodes.size() * sizeof(f4));
+    if (tris) memcpy(tris, s->hs.bvh.tris.data(), s->hs.bvh.tris.size() * sizeof(f4));
+}
 void sim_scene_stats(sim_scene *s, uint64_t *out) {
     out[0] = s->hs.faces.size() / 3; out[1] = s->hs.bvh.nodes.size() / EPSM_NODE_F4; out[2] = s->hs.bvh.depth;
 }

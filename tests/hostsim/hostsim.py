@@ -26,6 +26,9 @@ def lib():
         L.sim_scene_destroy.argtypes = [vp]
         L.sim_scene_update_vertices.argtypes = [vp, u32, vp]
         L.sim_scene_stats.argtypes = [vp, vp]
+        L.sim_scene_refit.argtypes = [vp, u32, vp]; L.sim_scene_refit.restype = C.c_double
+        L.sim_scene_cost.argtypes = [vp]; L.sim_scene_cost.restype = C.c_double
+        L.sim_scene_copy_accel.argtypes = [vp, vp, vp]
         L.sim_trace.argtypes = [vp, vp, u64, vp, i32, vp]
         L.sim_sampler_stream.argtypes = [u32, u64, u64, u32, vp]
         L.sim_sample_rays.argtypes = [vp, u32, u32, u32, u64, u64, vp]
@@ -58,6 +61,19 @@ class SimScene:
 
     def update_vertices(self, mesh_id, positions):
         p = np.ascontiguousarray(positions, np.float32); lib().sim_scene_update_vertices(self.h, mesh_id, p.ctypes.data)
+
+    def refit_vertices(self, mesh_id, positions):
+        """The device refit's per-node code, run serially on the host; returns the refitted tree's cost."""
+        p = np.ascontiguousarray(positions, np.float32); return lib().sim_scene_refit(self.h, mesh_id, p.ctypes.data)
+
+    def accel_cost(self):
+        return lib().sim_scene_cost(self.h)
+
+    def accel(self):
+        st = self.stats()
+        nodes = np.zeros((st["n_nodes"], 32), np.float32); tris = np.zeros((st["n_triangles"], 16), np.float32)
+        lib().sim_scene_copy_accel(self.h, nodes.ctypes.data, tris.ctypes.data)
+        return nodes, tris
 
     def trace(self, rays, any_hit=False, counters=None):
         rays = np.ascontiguousarray(rays, np.float32); n = rays.shape[0]
