@@ -142,12 +142,13 @@ def test_gpu_gradients_after_refit_equal_rebuild():
     p = moved(sd, mid, 1, amp=0.01)
     a.update_vertices(mid, p, commit=False); a.refit()
     b.update_vertices(mid, p, commit=False); b.commit()
-    nrm_a = a.accel_raw()  # keep the scene alive
     g = torch.from_numpy(parity.synthetic_grad_in(32)).cuda()
     outs = []
     for s in (a, b):
         gp = torch.zeros(s.n_vertices, 3, device="cuda"); gn = torch.zeros_like(gp)
+        torch.cuda.synchronize()                              # the library runs on its own stream: order torch's fills before it
         s.render_backward_raw("manifold_caustic", 2, 5, 4, 6, 5, g, gp, gn)
+        s.synchronize()
         outs.append((gp.cpu().numpy(), gn.cpu().numpy()))
     # same paths, same per-path values; only the atomic accumulation order differs between the two runs
     for x, y in zip(outs[0], outs[1]):
