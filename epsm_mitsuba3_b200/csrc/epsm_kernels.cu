@@ -288,29 +288,24 @@ struct WfBuffers {
     Hit *hits;                 // [C] path hits, then [MAXV·C] direct hits
     uint32_t *occl;            // [C]
     QRay *q_closest /* 2C */, *q_any /* C */;
-    uint32_t *counters;        // [0..15] closest-queue sizes, [16..31] closest heads, [32..47] any sizes, [48..63] any heads,
-                               // [64 + it] number of lanes entering stage B of iteration `it` (= size of the lane list below)
-    uint32_t *live0;           // [C] lanes that survive stage A of iteration 0: the domain of stage B(0) and of k_wf_finish
-    uint32_t *live[2];         // [C] each: lanes entering iteration it ≥ 1 (ping-pong on it & 1), appended by stage B(it − 1)
+    uint32_t *counters;        // [0..15] closest-queue sizes, [16..31] closest heads, [32..47] any sizes, [48..63] any heads
     uint32_t capacity;
 };
-#define WF_COUNTER_WORDS 96u
 
 size_t epsm_wf_workspace_bytes(uint32_t capacity) {
     size_t c = capacity;
     return c * (4 * (1 + WORDS_OF(WfState) + WORDS_OF(PathHead) + EPSM_MAXV * WORDS_OF(VLog)) + sizeof(Hit) * (1 + EPSM_MAXV)
-                + sizeof(uint32_t) + sizeof(QRay) * 3 + 3 * sizeof(uint32_t)) + WF_COUNTER_WORDS * sizeof(uint32_t) + 20 * 256;
+                + sizeof(uint32_t) + sizeof(QRay) * 3) + 64 * sizeof(uint32_t) + 16 * 256;
 }
 static WfBuffers wf_carve(void *base, uint32_t capacity) {
     WfBuffers w; char *p = (char *) base; size_t c = capacity;
     auto take = [&](size_t bytes) { char *r = p; p += (bytes + 255) & ~(size_t) 255; return r; };
-    w.counters = (uint32_t *) take(WF_COUNTER_WORDS * sizeof(uint32_t));
+    w.counters = (uint32_t *) take(64 * sizeof(uint32_t));
     w.status = (uint32_t *) take(c * 4);
     w.states = (uint32_t *) take(c * 4 * WORDS_OF(WfState)); w.heads = (uint32_t *) take(c * 4 * WORDS_OF(PathHead));
     w.vlogs = (uint32_t *) take(c * 4 * EPSM_MAXV * WORDS_OF(VLog));
     w.hits = (Hit *) take(c * sizeof(Hit) * (1 + EPSM_MAXV)); w.occl = (uint32_t *) take(c * sizeof(uint32_t));
     w.q_closest = (QRay *) take(2 * c * sizeof(QRay)); w.q_any = (QRay *) take(c * sizeof(QRay));
-    w.live0 = (uint32_t *) take(c * 4); w.live[0] = (uint32_t *) take(c * 4); w.live[1] = (uint32_t *) take(c * 4);
     w.capacity = capacity; return w;
 }
 
@@ -526,14 +521,9 @@ __global__ void __launch_bounds__(CTA) k_wf_trace(DScene sc, const QRay *__restr
 
 // `grad_pos` != NULL enables the first-vertex fast path (scatter passes; the record probe keeps every lane).
 __global__ void __launch_bounds__(128, EPSM_STAGE_MINBLOCKS) k_wf_stage_a(DScene sc, DLaunch ln, uint32_t it, uint32_t n, WfBuffers wb, float *__restrict__ grad_pos) {
-    // Iteration 0 runs over the chunk's slots; later iterations over the compacted list of lanes still on their path.
-    const uint32_t j = blockIdx.x * 128 + threadIdx.x;
-    const uint32_t cnt = it == 0 ? n : wb.counters[64 + it];
-    if (blockIdx.x * 128 >= cnt) return;
-    uint32_t i = j; bool have = j < cnt;
-    if (have) { if (it == 0) have = (wb.status[j] & 0xffu) == WF_LIVE; else i = wb.live[it & 1][j]; }
-    bool push = false, survive = false; Ray sr;
-    if (have) {
+    const uint32_t i = blockIdx.x * 128 + threadIdx.x;
+    bool push = false; Ray sr;
+    if (i < n && (wb.status[i] & 0xffu) == WF_LIVE) {
         WfState S; const Hit h = wb.hits[i];
         bool keep = true;
         if (it == 0) {
@@ -548,7 +538,6 @@ __global__ void __launch_bounds__(128, EPSM_STAGE_MINBLOCKS) k_wf_stage_a(DScene
                 for (int c = 0; c < 3; ++c) scatter3(grad_pos, si.fi[c], dg * si.bw[c], sel);
                 wb.status[i] = WF_SCATTERED; keep = false; push = false;
             } else soa_store(H, wb.heads, wb.capacity, i);
-            survive = keep;
         } else {
             soa_load(S, wb.states, wb.capacity, i);
             PathHead H;                                   // only written at the first hit
@@ -558,19 +547,12 @@ __global__ void __launch_bounds__(128, EPSM_STAGE_MINBLOCKS) k_wf_stage_a(DScene
     }
     const uint32_t q = queue_push(wb.counters + 32 + it, push);
     if (push) queue_write(wb.q_any, q, sr, i);
-    if (it == 0) {
-        const uint32_t l = queue_push(wb.counters + 64, survive);
-        if (survive) wb.live0[l] = i;
-    }
 }
 
 __global__ void __launch_bounds__(128, EPSM_STAGE_MINBLOCKS) k_wf_stage_b(DScene sc, DLaunch ln, uint32_t it, uint32_t max_iter, uint32_t n, WfBuffers wb, bool keep_state) {
-    const uint32_t j = blockIdx.x * 128 + threadIdx.x;
-    const uint32_t cnt = wb.counters[64 + it];               // lanes that went through stage A of this iteration
-    if (blockIdx.x * 128 >= cnt) return;
-    const uint32_t i = j < cnt ? (it == 0 ? wb.live0 : wb.live[it & 1])[j] : 0u;
+    const uint32_t i = blockIdx.x * 128 + threadIdx.x;
     bool push_direct = false, push_next = false; Ray direct, next;
-    if (j < cnt) {
+    if (i < n && (wb.status[i] & 0xffu) == WF_LIVE) {
         WfState S; soa_load(S, wb.states, wb.capacity, i);
         const Hit h = wb.hits[i];
         const bool occluded = S.need_shadow && wb.occl[i] != 0u;
@@ -586,8 +568,6 @@ __global__ void __launch_bounds__(128, EPSM_STAGE_MINBLOCKS) k_wf_stage_b(DScene
     if (push_direct) queue_write(wb.q_closest, qd, direct, wb.capacity + it * wb.capacity + i);
     const uint32_t qn = queue_push(wb.counters + (it + 1), push_next);
     if (push_next) queue_write(wb.q_closest, qn, next, i);
-    const uint32_t l = queue_push(wb.counters + 64 + (it + 1), push_next);
-    if (push_next) wb.live[(it + 1) & 1][l] = i;
 }
 
 __global__ void k_count_lanes(uint32_t n, WfBuffers wb, unsigned long long *counters) {
@@ -608,10 +588,10 @@ __device__ __forceinline__ void vlog_inactive(VLog &v) {
 template <bool RECORD>
 __global__ void __launch_bounds__(128, EPSM_STAGE_MINBLOCKS) k_wf_finish(DScene sc, DLaunch ln, uint64_t work_base, uint32_t n, WfBuffers wb,
                                                    float *__restrict__ grad_pos, float *__restrict__ grad_nrm, float *__restrict__ records) {
-    const uint32_t j = blockIdx.x * 128 + threadIdx.x;
-    if (j >= wb.counters[64]) return;                        // the lanes that survived stage A(0); the rest are scattered already
-    const uint32_t i = wb.live0[j];
-    const uint32_t status = wb.status[i];
+    const uint32_t i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t status = wb.status[i], code = status & 0xffu;
+    if (code == WF_NONE || code == WF_SCATTERED) return;
     const int n_written = (int) (status >> 8);
     PathLog P;
     soa_load(static_cast<PathHead &>(P), wb.heads, wb.capacity, i);
@@ -938,7 +918,7 @@ cudaError_t epsm_launch_backward(const DScene &sc, DLaunch ln, const float *grad
     for (uint64_t base = 0; base < total; base += capacity) {
         const uint32_t n = (uint32_t) ((total - base) < capacity ? (total - base) : capacity);
         const uint32_t grid = (n + 127) / 128;
-        cudaMemsetAsync(wb.counters, 0, WF_COUNTER_WORDS * sizeof(uint32_t), s);
+        cudaMemsetAsync(wb.counters, 0, 64 * sizeof(uint32_t), s);
         k_wf_init<<<grid, 128, 0, s>>>(ln, base, n, grad_in, wb); ++launches;
         for (uint32_t it = 0; it <= max_iter; ++it) {
             // closest-hit queue `it`: path rays of iteration `it` and the direct rays of iteration `it − 1`

@@ -238,9 +238,8 @@ def test_primal_render_at_full_film_size_conserves_filter_weight():
     scene.synchronize()
     film = scene.film_raw(1).cpu().numpy().astype(np.float64)
     assert np.isfinite(film).all()
-    # weight a sample would deposit on an unbounded film: (Σ_k f(x_k))² averaged over the jitter; compare interior pixels
     inner = film[8:-8, 8:-8, 3]
-    assert abs(inner.mean() / film[512, 512, 3] - 1) < 0.05
+    assert abs(inner.mean() / film[..., 3].mean() - 1) < 0.01 and inner.min() > 0       # only the cropped border loses weight
     o_total = film[..., 3].sum()
     # second seed: same expected total within sampling noise of the border pixels only
     scene.film_clear(1); scene.render_accumulate(1, 4, 8, 6, 5); scene.synchronize()
