@@ -244,11 +244,18 @@ int pull_stale_positions(epsm_ctx *ctx) {
     return EPSM_OK;
 }
 int recompute_dirty_normals(epsm_ctx *ctx) {
-    for (size_t i = 0; i < ctx->hs.meshes.size(); ++i) {
+    // meshes are concatenated in the vertex / face arrays: one launch triple per run of adjacent dirty meshes with normals
+    const size_t nm = ctx->hs.meshes.size();
+    for (size_t i = 0; i < nm;) {
         const DMesh &m = ctx->hs.meshes[i];
-        if (!ctx->mesh_dirty[i] || !m.has_normals) continue;
-        CK(epsm_launch_vertex_normals(ctx->d_pos.p, ctx->d_faces.p, m.f_off, m.f_cnt, m.v_off, m.v_cnt, ctx->d_nrm.p, ctx->stream), "vertex normals");
+        if (!ctx->mesh_dirty[i] || !m.has_normals) { ++i; continue; }
+        size_t j = i + 1;
+        while (j < nm && ctx->mesh_dirty[j] && ctx->hs.meshes[j].has_normals) ++j;
+        const DMesh &l = ctx->hs.meshes[j - 1];
+        CK(epsm_launch_vertex_normals(ctx->d_pos.p, ctx->d_faces.p, m.f_off, l.f_off + l.f_cnt - m.f_off, m.v_off, l.v_off + l.v_cnt - m.v_off,
+                                      ctx->d_nrm.p, ctx->stream), "vertex normals");
         ctx->launches += 3;
+        i = j;
     }
     return EPSM_OK;
 }

@@ -154,11 +154,12 @@ class Scene:
         self._check(self.lib.epsm_set_sample_range(self.ctx, s_begin, s_end))
 
     # ---- scene updates ---------------------------------------------------------------------
-    def update_vertices(self, mesh_id: int, positions, commit: bool = True):
-        """params['<mesh>.vertex_positions'] = positions; params.update().  `commit=True` applies `self.accel_update`."""
+    def update_vertices(self, mesh_id: int, positions, commit: bool = True, synced: bool = False):
+        """params['<mesh>.vertex_positions'] = positions; params.update().  `commit=True` applies `self.accel_update`.
+        `synced=True`: the caller has already ordered torch's stream before the library's (one sync for many meshes)."""
         if isinstance(positions, torch.Tensor):
             positions = positions.detach().to(torch.float32).contiguous()
-            if positions.is_cuda:
+            if positions.is_cuda and not synced:
                 torch.cuda.current_stream(self.device).synchronize()
         else:
             positions = np.ascontiguousarray(positions, np.float32)
@@ -425,8 +426,12 @@ class SceneParameters(dict):
         if values:
             for k, v in values.items():
                 self[k] = v
-        for key in sorted(self._dirty):
-            self.scene.update_vertices(self._mesh_of[key], self[key].reshape(-1, 3), commit=False)
+        staged = [(self._mesh_of[key], torch.as_tensor(self[key]).detach().to(torch.float32).reshape(-1, 3).contiguous()) for key in self._dirty]
+        staged.sort(key=lambda t: t[0])
+        if any(t.is_cuda for _, t in staged):
+            torch.cuda.current_stream(self.scene.device).synchronize()      # once: the tensors above are complete
+        for mesh_id, t in staged:
+            self.scene.update_vertices(mesh_id, t, commit=False, synced=True)
         if self._dirty:
             self.scene.apply_updates()
         self._dirty.clear()

@@ -4,7 +4,7 @@ wavefront and the rest is closed by identities the path must satisfy:
 
   * hit records of sampled rays bit-exact against the oracle (brute-force semantics through its own BVH);
   * per-path records of sampled lane windows of the FULL wavefront against the oracle + the reference's torch calc_grad;
-  * linearity of the gradient pass in grad_in (the path is linear in the image gradient: epsm.py:250-272);
+  * additivity of the gradient pass over images with disjoint pixel support (each path reads its own pixel: epsm.py:250-257);
   * the pruned replay equals the full replay, lane / sample shards sum to the whole, the wavefront chunk size does not
     matter, refit equals rebuild — all on the full wavefront."""
 import os
@@ -59,17 +59,19 @@ def test_fullsize_path_records_of_sampled_windows(room):
         assert stats["nonzero"] >= 0
 
 
-def test_fullsize_gradient_pass_is_linear_in_grad_in(room):
+def test_fullsize_gradient_pass_is_additive_over_pixels(room):
+    """Each path reads grad_in at its own pixel only (epsm.py:250-257) and everything downstream is per path, so the pass
+    is additive over images with disjoint pixel support — exactly, ±0.1 outlier zeroing (epsm.py:933-944) included
+    (plain linearity in grad_in does not hold because of that zeroing)."""
     sd, scene, o = room
-    g1 = torch.from_numpy(parity.synthetic_grad_in(RES, seed=7)).cuda()
-    g2 = torch.from_numpy(parity.synthetic_grad_in(RES, seed=8)).cuda()
-    a, b = backward(scene, "manifold", 1, 31, SPP, MD, g1), backward(scene, "manifold", 1, 31, SPP, MD, g2)
-    c = backward(scene, "manifold", 1, 31, SPP, MD, 2.0 * g1 - 0.5 * g2)
-    # ±0.1 outlier zeroing (epsm.py:933-944) is the one non-linear step: it acts per path on a handful of paths
-    ref = 2.0 * a - 0.5 * b
-    err = (c - ref).abs().double(); scale = float(ref.abs().max())
-    assert float((err > 1e-3 * scale).double().mean()) < 1e-3
-    assert float(a.abs().sum()) > 0
+    g = torch.from_numpy(parity.synthetic_grad_in(RES, seed=7)).cuda()
+    yy, xx = torch.meshgrid(torch.arange(RES, device="cuda"), torch.arange(RES, device="cuda"), indexing="ij")
+    mask = (((yy // 8) + (xx // 8)) % 2 == 0)[..., None].float()
+    whole = backward(scene, "manifold", 1, 31, SPP, MD, g)
+    a, b = backward(scene, "manifold", 1, 31, SPP, MD, g * mask), backward(scene, "manifold", 1, 31, SPP, MD, g * (1 - mask))
+    assert close(a + b, whole) and float(a.abs().sum()) > 0 and float(b.abs().sum()) > 0
+    # and a zero image gradient reaches no parameter
+    assert float(backward(scene, "manifold", 1, 31, SPP, MD, torch.zeros_like(g)).abs().sum()) == 0.0
 
 
 def test_fullsize_pruned_equals_full_and_shards_sum(room):
