@@ -58,6 +58,7 @@ EXPORTS = [
     "epsm_render_accumulate", "epsm_film_clear", "epsm_film_raw", "epsm_film_develop", "epsm_render",
     "epsm_render_backward", "epsm_path_records", "epsm_sampler_stream", "epsm_sample_rays",
     "epsm_set_sample_range", "epsm_set_full_replay", "epsm_set_trace_profiling", "epsm_get_trace_profile", "epsm_scene_get_stats", "epsm_launch_count", "epsm_stream", "epsm_synchronize",
+    "epsm_sinkhorn_grad",
 ]
 
 _LIB = None
@@ -113,6 +114,7 @@ def load_library() -> C.CDLL:
     lib.epsm_stream.argtypes = [vp]
     lib.epsm_stream.restype = vp
     lib.epsm_synchronize.argtypes = [vp]
+    lib.epsm_sinkhorn_grad.argtypes = [vp, fp, u32, fp, u32, C.c_float, C.c_float, C.c_float, fp, C.POINTER(C.c_double), C.POINTER(u32), i32]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if name not in ("epsm_last_error", "epsm_launch_count", "epsm_stream"):

@@ -12,6 +12,7 @@
 #include "epsm_types.h"
 #include "epsm_host_scene.h"
 #include "epsm_launch.h"
+#include "epsm_sinkhorn.h"
 
 namespace {
 
@@ -60,6 +61,8 @@ struct epsm_ctx {
     DevBuf<unsigned char> d_workspace; uint32_t wf_capacity = 0, trace_grid = 0;   // wavefront workspace (one chunk of lanes)
     DScene sc;
     bool trace_profiling = false; EpsmEventList trace_events;
+    DevBuf<float> d_sink;                           // Sinkhorn matcher: clouds (host-memory calls), potentials ×2, barycentres
+    DevBuf<double> d_sink_loss; DevBuf<int> d_sink_bbox;
 };
 
 namespace {
@@ -175,7 +178,7 @@ int epsm_destroy(epsm_ctx *ctx) {
     ctx->d_nodes.release(); ctx->d_tris.release(); ctx->d_pos.release(); ctx->d_nrm.release(); ctx->d_cdf.release(); ctx->d_pmf.release();
     ctx->d_faces.release(); ctx->d_face_mesh.release(); ctx->d_meshes.release(); ctx->d_bsdfs.release(); ctx->d_emitters.release();
     for (auto &f : ctx->d_films) f.release();
-    ctx->stage_a.release(); ctx->stage_b.release(); ctx->stage_c.release(); ctx->d_counters.release(); ctx->d_workspace.release();
+    ctx->stage_a.release(); ctx->stage_b.release(); ctx->stage_c.release(); ctx->d_counters.release(); ctx->d_workspace.release(); ctx->d_sink.release(); ctx->d_sink_loss.release(); ctx->d_sink_bbox.release();
     cudaStreamDestroy(ctx->stream);
     delete ctx; return EPSM_OK;
 }
@@ -539,6 +542,82 @@ int epsm_set_sample_range(epsm_ctx *ctx, uint32_t s_begin, uint32_t s_end) {
 int epsm_set_full_replay(epsm_ctx *ctx, int enable) {
     if (!ctx) return EPSM_E_INVALID;
     ctx->full_replay = enable != 0;
+    return EPSM_OK;
+}
+
+int epsm_sinkhorn_grad(epsm_ctx *ctx, const float *x, uint32_t n, const float *y, uint32_t m, float blur, float scaling, float scale,
+                       float *grad_x, double *loss, uint32_t *n_steps, int mem) {
+    if (!ctx) return EPSM_E_INVALID;
+    if (!x || !y || n == 0 || m == 0) return fail(ctx, EPSM_E_INVALID, "sinkhorn: empty point cloud");
+    if (!(blur > 0.f) || !(scaling > 0.f && scaling < 1.f)) return fail(ctx, EPSM_E_INVALID, "sinkhorn: blur must be > 0 and 0 < scaling < 1");
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    cudaStream_t s = ctx->stream;
+    // device layout of d_sink: [x 5n | y 5m]? (host calls only) then f_ba, f_aa (n) ×2, g_ab, g_bb (m) ×2, bary_xy, bary_xx (5n), grad (5n, host calls)
+    const size_t cloud = mem == EPSM_MEM_HOST ? 5 * ((size_t) n + m) : 0, pots = 4 * ((size_t) n + m), bary = 10 * (size_t) n;
+    const size_t gout = mem == EPSM_MEM_HOST ? 5 * (size_t) n : 0;
+    CK(ctx->d_sink.alloc(cloud + pots + bary + gout), "sinkhorn alloc");
+    CK(ctx->d_sink_loss.alloc(1), "sinkhorn alloc"); CK(ctx->d_sink_bbox.alloc(10), "sinkhorn alloc");
+    float *base = ctx->d_sink.p;
+    const float *dx = x, *dy = y;
+    if (mem == EPSM_MEM_HOST) {
+        CK(cudaMemcpyAsync(base, x, 5 * (size_t) n * sizeof(float), cudaMemcpyHostToDevice, s), "H2D x");
+        CK(cudaMemcpyAsync(base + 5 * (size_t) n, y, 5 * (size_t) m * sizeof(float), cudaMemcpyHostToDevice, s), "H2D y");
+        dx = base; dy = base + 5 * (size_t) n;
+    }
+    float *p = base + cloud;
+    float *f_ba[2] = {p, p + n}, *f_aa[2] = {p + 2 * (size_t) n, p + 3 * (size_t) n}; p += 4 * (size_t) n;
+    float *g_ab[2] = {p, p + m}, *g_bb[2] = {p + 2 * (size_t) m, p + 3 * (size_t) m}; p += 4 * (size_t) m;
+    float *bary_xy = p, *bary_xx = p + 5 * (size_t) n; p += bary;
+    float *d_grad = mem == EPSM_MEM_HOST ? p : grad_x;
+    // ε-schedule (geomloss epsilon_schedule, p = 2) from the diameter of the joint bounding box (max_diameter)
+    CK(epsm_launch_sink_bbox(dx, n, dy, m, ctx->d_sink_bbox.p, s), "k_sink_bbox"); ctx->launches += 2;
+    int hb[10];
+    CK(cudaMemcpyAsync(hb, ctx->d_sink_bbox.p, sizeof(hb), cudaMemcpyDeviceToHost, s), "bbox D2H");
+    CK(cudaStreamSynchronize(s), "bbox sync");
+    float d2 = 0.f;
+    for (int d = 0; d < 5; ++d) { const float e = epsm_sink_ord_to_float(hb[5 + d]) - epsm_sink_ord_to_float(hb[d]); d2 += e * e; }
+    const double diameter = (double) sqrtf(d2);
+    if (!(diameter > 0.0)) return fail(ctx, EPSM_E_INVALID, "sinkhorn: degenerate point clouds (zero diameter)");
+    std::vector<double> eps_list; eps_list.push_back(diameter * diameter);
+    {   // numpy.arange(2 ln d, 2 ln blur, 2 ln scaling): ceil((stop − start)/step) values start + k·step
+        const double start = 2.0 * log(diameter), stop = 2.0 * log((double) blur), step = 2.0 * log((double) scaling);
+        const long cnt = (long) ceil((stop - start) / step);
+        for (long k = 0; k < cnt; ++k) eps_list.push_back(exp(start + (double) k * step));
+    }
+    eps_list.push_back((double) blur * (double) blur);
+    const float la = -logf((float) n), lb = -logf((float) m);
+    auto make = [&](int cur, int nxt, bool init) {
+        SinkStep st; memset(&st, 0, sizeof(st));
+        // f_ba: rows x, cols y, carries g_ab;  g_ab: rows y, cols x, carries f_ba;  f_aa: x,x carries f_aa;  g_bb: y,y carries g_bb
+        st.job[0] = SinkJob{dx, dy, init ? nullptr : g_ab[cur], f_ba[cur], f_ba[nxt], nullptr, n, m, lb, 0};
+        st.job[1] = SinkJob{dy, dx, init ? nullptr : f_ba[cur], g_ab[cur], g_ab[nxt], nullptr, m, n, la, 0};
+        st.job[2] = SinkJob{dx, dx, init ? nullptr : f_aa[cur], f_aa[cur], f_aa[nxt], nullptr, n, n, la, 0};
+        st.job[3] = SinkJob{dy, dy, init ? nullptr : g_bb[cur], g_bb[cur], g_bb[nxt], nullptr, m, m, lb, 0};
+        return st;
+    };
+    int cur = 0;
+    {   // initialisation at ε₀: potentials ← softmin(ε₀, C, ln weight)
+        SinkStep st = make(1, 0, true); st.eps = (float) eps_list[0]; st.average = 0;
+        CK(epsm_launch_sink_step(st, 4, false, s), "k_sink_softmin"); ctx->launches += 1;
+    }
+    for (double eps : eps_list) {
+        SinkStep st = make(cur, cur ^ 1, false); st.eps = (float) eps; st.average = 1;
+        CK(epsm_launch_sink_step(st, 4, false, s), "k_sink_softmin"); ctx->launches += 1;
+        cur ^= 1;
+    }
+    {   // last extrapolation (un-averaged) + the softmax-weighted barycentres the gradient needs
+        SinkStep st = make(cur, cur ^ 1, false); st.eps = (float) eps_list.back(); st.average = 0;
+        st.job[0].bary = bary_xy; st.job[2].bary = bary_xx;
+        CK(epsm_launch_sink_step(st, 4, true, s), "k_sink_softmin"); ctx->launches += 1;
+        cur ^= 1;
+    }
+    CK(epsm_launch_sink_finish(bary_xx, bary_xy, scale / (float) n, n, grad_x ? d_grad : nullptr, f_ba[cur], f_aa[cur], g_ab[cur], g_bb[cur], m,
+                               ctx->d_sink_loss.p, s), "k_sink_finish");
+    ctx->launches += 1;
+    if (n_steps) *n_steps = (uint32_t) eps_list.size();
+    if (mem == EPSM_MEM_HOST && grad_x) CK(cudaMemcpyAsync(grad_x, d_grad, 5 * (size_t) n * sizeof(float), cudaMemcpyDeviceToHost, s), "D2H grad");
+    if (loss) CK(cudaMemcpyAsync(loss, ctx->d_sink_loss.p, sizeof(double), cudaMemcpyDeviceToHost, s), "D2H loss");
+    if (loss || mem == EPSM_MEM_HOST) CK(cudaStreamSynchronize(s), "sinkhorn sync");
     return EPSM_OK;
 }
 

@@ -1,0 +1,178 @@
+// epsm_sinkhorn.cu — the matcher that turns (rendered image, target image) into grad_in for the manifold integrators:
+// Matcher.match_Sinkhorn (EPSM/utils/matcher.py:51-63) = geomloss SamplesLoss("sinkhorn", blur, scaling), p = 2,
+// debias, balanced, uniform weights, differentiated w.r.t. the rendered 5-D cloud.
+//
+// geomloss is absent from the reference tree (README.md:11, unpinned); the algorithm restated here is geomloss 0.2.x
+// `sinkhorn_loop` / `sinkhorn_cost` / `epsilon_schedule` (oracle/sinkhorn_ref.py holds the literal restatement):
+//
+//   ε-schedule  [d², exp(arange(2 ln d, 2 ln blur, 2 ln scaling)) …, blur²],  d = |bbox(x ∪ y)|
+//   init        f_ba = softmin(ε₀, C_xy, ln b)   g_ab = softmin(ε₀, C_yx, ln a)   f_aa, g_bb likewise on (x,x), (y,y)
+//   per ε       four softmins from the OLD potentials, then averaged with them (symmetric Sinkhorn)
+//   last        one more un-averaged step at blur²; loss = ⟨a, f_ba − f_aa⟩ + ⟨b, g_ab − g_bb⟩
+//   gradient    ∂loss/∂x_i = a_i (Σ_j w^xx_ij x_j − Σ_j w^xy_ij y_j),  w = softmax_j(h_j − C_ij/ε)   (potentials detached)
+//
+// with softmin(ε, C, h)_i = −ε ln Σ_j exp(h_j − C_ij/ε), C_ij = |x_i − y_j|²/2.  The reference materialises N×N matrices
+// (tensorized backend) or streams them through KeOps; here one kernel evaluates all four softmins of a step as an online
+// log-sum-exp over column tiles staged in shared memory — nothing of size N² ever exists.  FP32 FMA + SFU ex2: K = 5 is
+// far too thin for tensor cores, and C/ε at ε = 1e-4 needs the full fp32 mantissa, so distances are formed from
+// coordinate differences (no |x|² + |y|² − 2x·y cancellation).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include "epsm_sinkhorn.h"
+
+namespace {
+
+constexpr int SK_THREADS = 256;          // 8 warps: each takes a column slice of every tile
+constexpr int SK_ROWS = 64;              // rows per CTA: 2 per lane
+constexpr int SK_TILE = 1024;            // columns per shared-memory tile (8 floats each = 32 KB)
+constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+
+__device__ __forceinline__ float ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+struct RowAcc { float m, s, a[5]; };
+
+template <bool GRAD>
+__device__ __forceinline__ void visit(RowAcc &r, const float *x, const float4 y0, const float4 y1, float halfk) {
+    const float d0 = x[0] - y0.x, d1 = x[1] - y0.y, d2 = x[2] - y0.z, d3 = x[3] - y0.w, d4 = x[4] - y1.x;
+    const float q = fmaf(d4, d4, fmaf(d3, d3, fmaf(d2, d2, fmaf(d1, d1, d0 * d0))));
+    const float t = fmaf(-halfk, q, y1.y);                 // log2 of the term: (h_j − C_ij/ε)·log2 e
+    if (t > r.m) {                                          // rare once the running maximum has settled
+        const float c = ex2(r.m - t);
+        r.s *= c;
+        if (GRAD) { r.a[0] *= c; r.a[1] *= c; r.a[2] *= c; r.a[3] *= c; r.a[4] *= c; }
+        r.m = t;
+    }
+    const float e = ex2(t - r.m);
+    r.s += e;
+    if (GRAD) {
+        r.a[0] = fmaf(e, y0.x, r.a[0]); r.a[1] = fmaf(e, y0.y, r.a[1]); r.a[2] = fmaf(e, y0.z, r.a[2]);
+        r.a[3] = fmaf(e, y0.w, r.a[3]); r.a[4] = fmaf(e, y1.x, r.a[4]);
+    }
+}
+
+// One Sinkhorn step: blockIdx.y selects the softmin (job), blockIdx.x a block of SK_ROWS rows.
+template <bool GRAD>
+__global__ void __launch_bounds__(SK_THREADS, 2) k_sink_softmin(SinkStep st) {
+    const SinkJob job = st.job[blockIdx.y];
+    const uint32_t row0 = blockIdx.x * SK_ROWS;
+    if (row0 >= job.n_rows) return;
+    __shared__ float4 tile[SK_TILE][2];
+    __shared__ float red[SK_THREADS / 32][SK_ROWS][GRAD ? 7 : 2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float inv_eps = 1.0f / st.eps, halfk = 0.5f * LOG2E * inv_eps;
+    float x[2][5]; RowAcc acc[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        uint32_t i = row0 + 32 * r + lane; if (i >= job.n_rows) i = job.n_rows - 1;
+#pragma unroll
+        for (int d = 0; d < 5; ++d) x[r][d] = job.rows[5 * (size_t) i + d];
+        acc[r].m = -INFINITY; acc[r].s = 0.f;
+#pragma unroll
+        for (int d = 0; d < 5; ++d) acc[r].a[d] = 0.f;
+    }
+    for (uint32_t j0 = 0; j0 < job.n_cols; j0 += SK_TILE) {
+        const uint32_t nt = job.n_cols - j0 < SK_TILE ? job.n_cols - j0 : SK_TILE;
+        __syncthreads();
+        for (uint32_t k = threadIdx.x; k < nt; k += SK_THREADS) {
+            const float *c = job.cols + 5 * (size_t) (j0 + k);
+            const float h = job.pot_cols ? fmaf(job.pot_cols[j0 + k], inv_eps, job.w_log) : job.w_log;
+            tile[k][0] = make_float4(c[0], c[1], c[2], c[3]);
+            tile[k][1] = make_float4(c[4], h * LOG2E, 0.f, 0.f);
+        }
+        __syncthreads();
+        // warp w walks columns w, w + 8, … of the tile: every lane reads the same address (broadcast)
+        for (uint32_t k = warp; k < nt; k += SK_THREADS / 32) {
+            const float4 y0 = tile[k][0], y1 = tile[k][1];
+            visit<GRAD>(acc[0], x[0], y0, y1, halfk);
+            visit<GRAD>(acc[1], x[1], y0, y1, halfk);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        float *o = red[warp][32 * r + lane];
+        o[0] = acc[r].m; o[1] = acc[r].s;
+        if (GRAD) { for (int d = 0; d < 5; ++d) o[2 + d] = acc[r].a[d]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < SK_ROWS) {
+        const uint32_t i = row0 + threadIdx.x;
+        if (i < job.n_rows) {
+            float M = -INFINITY;
+#pragma unroll
+            for (int w = 0; w < SK_THREADS / 32; ++w) M = fmaxf(M, red[w][threadIdx.x][0]);
+            float S = 0.f, A[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int w = 0; w < SK_THREADS / 32; ++w) {
+                const float c = ex2(red[w][threadIdx.x][0] - M);
+                S = fmaf(red[w][threadIdx.x][1], c, S);
+                if (GRAD) { for (int d = 0; d < 5; ++d) A[d] = fmaf(red[w][threadIdx.x][2 + d], c, A[d]); }
+            }
+            float val = -st.eps * LN2 * (M + lg2(S));       // softmin(ε, C, h)_i
+            if (st.average && job.pot_rows_old) val = 0.5f * (job.pot_rows_old[i] + val);
+            job.pot_rows_new[i] = val;
+            if (GRAD && job.bary) {
+                const float inv = 1.0f / S;
+                for (int d = 0; d < 5; ++d) job.bary[5 * (size_t) i + d] = A[d] * inv;
+            }
+        }
+    }
+}
+
+// Bounding box of x ∪ y (geomloss max_diameter): out[0..4] = min, out[5..9] = max, as ordered-int atomics.
+__device__ __forceinline__ int f2ord(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
+__global__ void k_sink_bbox(const float *x, uint32_t n, const float *y, uint32_t m, int *out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const float *p = i < n ? x + 5 * (size_t) i : (i < n + m ? y + 5 * (size_t) (i - n) : nullptr);
+#pragma unroll
+    for (int d = 0; d < 5; ++d) {
+        int lo = p ? f2ord(p[d]) : 0x7fffffff, hi = p ? lo : (int) 0x80000000;
+        lo = __reduce_min_sync(0xffffffffu, lo); hi = __reduce_max_sync(0xffffffffu, hi);
+        if ((threadIdx.x & 31) == 0) { atomicMin(out + d, lo); atomicMax(out + 5 + d, hi); }
+    }
+}
+__global__ void k_sink_bbox_init(int *out) { if (threadIdx.x < 5) { out[threadIdx.x] = 0x7fffffff; out[5 + threadIdx.x] = (int) 0x80000000; } }
+
+// g_i = factor·(bary_xx_i − bary_xy_i);  loss = Σ_i (f_ba − f_aa)_i / n + Σ_j (g_ab − g_bb)_j / m
+__global__ void k_sink_finish(const float *bary_xx, const float *bary_xy, float factor, uint32_t n, float *grad,
+                              const float *f_ba, const float *f_aa, const float *g_ab, const float *g_bb, uint32_t m, double *loss) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && grad) {
+#pragma unroll
+        for (int d = 0; d < 5; ++d) grad[5 * (size_t) i + d] = factor * (bary_xx[5 * (size_t) i + d] - bary_xy[5 * (size_t) i + d]);
+    }
+    double l = 0.0;
+    if (i < n) l += ((double) f_ba[i] - (double) f_aa[i]) / (double) n;
+    if (i < m) l += ((double) g_ab[i] - (double) g_bb[i]) / (double) m;
+    for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+    if ((threadIdx.x & 31) == 0 && l != 0.0) atomicAdd(loss, l);
+}
+
+} // namespace
+
+cudaError_t epsm_launch_sink_bbox(const float *x, uint32_t n, const float *y, uint32_t m, int *out10, cudaStream_t s) {
+    k_sink_bbox_init<<<1, 32, 0, s>>>(out10);
+    k_sink_bbox<<<(n + m + 255) / 256, 256, 0, s>>>(x, n, y, m, out10);
+    return cudaGetLastError();
+}
+float epsm_sink_ord_to_float(int o) { int i = o >= 0 ? o : o ^ 0x7fffffff; float f; memcpy(&f, &i, 4); return f; }
+
+cudaError_t epsm_launch_sink_step(const SinkStep &st, int n_jobs, bool grad, cudaStream_t s) {
+    uint32_t max_rows = 0;
+    for (int k = 0; k < n_jobs; ++k) max_rows = st.job[k].n_rows > max_rows ? st.job[k].n_rows : max_rows;
+    if (max_rows == 0) return cudaSuccess;
+    const dim3 grid((max_rows + SK_ROWS - 1) / SK_ROWS, n_jobs);
+    if (grad) k_sink_softmin<true><<<grid, SK_THREADS, 0, s>>>(st); else k_sink_softmin<false><<<grid, SK_THREADS, 0, s>>>(st);
+    return cudaGetLastError();
+}
+
+cudaError_t epsm_launch_sink_finish(const float *bary_xx, const float *bary_xy, float factor, uint32_t n, float *grad,
+                                    const float *f_ba, const float *f_aa, const float *g_ab, const float *g_bb, uint32_t m, double *loss,
+                                    cudaStream_t s) {
+    cudaError_t e = cudaMemsetAsync(loss, 0, sizeof(double), s);
+    if (e != cudaSuccess) return e;
+    const uint32_t k = n > m ? n : m;
+    k_sink_finish<<<(k + 255) / 256, 256, 0, s>>>(bary_xx, bary_xy, factor, n, grad, f_ba, f_aa, g_ab, g_bb, m, loss);
+    return cudaGetLastError();
+}

@@ -219,6 +219,18 @@ int epsm_set_sample_range(epsm_ctx *ctx, uint32_t s_begin, uint32_t s_end);
  * reference does; epsm_path_records always does.  Environment override at context creation: EPSM_FULL_REPLAY=1. */
 int epsm_set_full_replay(epsm_ctx *ctx, int enable);
 
+/* The matcher that produces grad_in: Matcher.match_Sinkhorn (EPSM/utils/matcher.py:51-63) =
+ * geomloss.SamplesLoss("sinkhorn", blur, scaling) (p = 2, debias, balanced, uniform weights) between the point clouds
+ * x (n × 5) and y (m × 5), differentiated w.r.t. x:  grad_x = scale · ∂loss/∂x  (the reference passes scale = res²,
+ * matcher.py:60).  geomloss is an unpinned third-party dependency absent from the reference tree; the algorithm is the
+ * published sinkhorn_loop of geomloss 0.2.x (ε-scaling from the clouds' diameter down to blur², symmetric averaged
+ * updates, one un-averaged extrapolation, debiased cost) — see oracle/sinkhorn_ref.py.  No scene is needed.
+ * grad_x: n × 5 floats in `mem` space (may be NULL); loss (HOST pointer, may be NULL): the Sinkhorn divergence;
+ * n_steps (HOST, may be NULL): length of the ε-schedule.  With device pointers and loss == NULL the call does not
+ * wait for the result (one host read-back of the 10-float bounding box happens inside). */
+int epsm_sinkhorn_grad(epsm_ctx *ctx, const float *x, uint32_t n, const float *y, uint32_t m,
+                       float blur, float scaling, float scale, float *grad_x, double *loss, uint32_t *n_steps, int mem);
+
 /* Scene statistics for the roofline accounting: bytes per BVH node / triangle record, counts. */
 typedef struct epsm_scene_stats {
     uint64_t n_triangles, n_vertices, n_nodes;
