@@ -31,7 +31,33 @@ constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
 __device__ __forceinline__ float ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
+// Packed FP32x2 arithmetic (sm_100a FFMA2 / FADD2 / FMUL2: two fp32 lanes per issue slot).
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk(float a, float b) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk(u64 v, float &a, float &b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
 struct RowAcc { float m, s, a[5]; };
+
+// Packed columns: `x` holds (x_d, x_d), the tile holds (y_d[j], y_d[j+1]); log2 of the two terms comes back packed.
+struct RowAcc2 { float m; u64 s; };
+__device__ __forceinline__ u64 term2(const u64 *x, const ulonglong2 t0, const ulonglong2 t1, const ulonglong2 t2, u64 neg_halfk) {
+    const u64 d0 = sub2(x[0], t0.x), d1 = sub2(x[1], t0.y), d2 = sub2(x[2], t1.x), d3 = sub2(x[3], t1.y), d4 = sub2(x[4], t2.x);
+    const u64 q = fma2(d4, d4, fma2(d3, d3, fma2(d2, d2, fma2(d1, d1, mul2(d0, d0)))));
+    return fma2(neg_halfk, q, t2.y);
+}
+// Four columns (two packed pairs) into one row's running log-sum-exp: one maximum test per four terms.
+__device__ __forceinline__ void fold4(RowAcc2 &r, u64 ta, u64 tb) {
+    float a0, a1, b0, b1; upk(ta, a0, a1); upk(tb, b0, b1);
+    const float tm = fmaxf(fmaxf(a0, a1), fmaxf(b0, b1));
+    if (tm > r.m) { const float c = ex2(r.m - tm); r.s = mul2(r.s, pk(c, c)); r.m = tm; }     // rare once the maximum has settled
+    const u64 nm = pk(-r.m, -r.m);
+    upk(add2(ta, nm), a0, a1); upk(add2(tb, nm), b0, b1);
+    r.s = add2(r.s, add2(pk(ex2(a0), ex2(a1)), pk(ex2(b0), ex2(b1))));
+}
 
 template <bool GRAD>
 __device__ __forceinline__ void visit(RowAcc &r, const float *x, const float4 y0, const float4 y1, float halfk) {
@@ -54,11 +80,11 @@ __device__ __forceinline__ void visit(RowAcc &r, const float *x, const float4 y0
 
 // One Sinkhorn step: blockIdx.y selects the softmin (job), blockIdx.x a block of SK_ROWS rows.
 template <bool GRAD>
-__global__ void __launch_bounds__(SK_THREADS, 2) k_sink_softmin(SinkStep st) {
+__global__ void __launch_bounds__(SK_THREADS, GRAD ? 2 : 3) k_sink_softmin(SinkStep st) {
     const SinkJob job = st.job[blockIdx.y];
     const uint32_t row0 = blockIdx.x * SK_ROWS;
     if (row0 >= job.n_rows) return;
-    __shared__ float4 tile[SK_TILE][2];
+    __shared__ float4 tile[2 * SK_TILE];
     __shared__ float red[SK_THREADS / 32][SK_ROWS][GRAD ? 7 : 2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float inv_eps = 1.0f / st.eps, halfk = 0.5f * LOG2E * inv_eps;
@@ -72,22 +98,60 @@ __global__ void __launch_bounds__(SK_THREADS, 2) k_sink_softmin(SinkStep st) {
 #pragma unroll
         for (int d = 0; d < 5; ++d) acc[r].a[d] = 0.f;
     }
-    for (uint32_t j0 = 0; j0 < job.n_cols; j0 += SK_TILE) {
-        const uint32_t nt = job.n_cols - j0 < SK_TILE ? job.n_cols - j0 : SK_TILE;
-        __syncthreads();
-        for (uint32_t k = threadIdx.x; k < nt; k += SK_THREADS) {
-            const float *c = job.cols + 5 * (size_t) (j0 + k);
-            const float h = job.pot_cols ? fmaf(job.pot_cols[j0 + k], inv_eps, job.w_log) : job.w_log;
-            tile[k][0] = make_float4(c[0], c[1], c[2], c[3]);
-            tile[k][1] = make_float4(c[4], h * LOG2E, 0.f, 0.f);
+    if (GRAD) {
+        for (uint32_t j0 = 0; j0 < job.n_cols; j0 += SK_TILE) {
+            const uint32_t nt = job.n_cols - j0 < SK_TILE ? job.n_cols - j0 : SK_TILE;
+            __syncthreads();
+            for (uint32_t k = threadIdx.x; k < nt; k += SK_THREADS) {
+                const float *c = job.cols + 5 * (size_t) (j0 + k);
+                const float h = job.pot_cols ? fmaf(job.pot_cols[j0 + k], inv_eps, job.w_log) : job.w_log;
+                tile[2 * k] = make_float4(c[0], c[1], c[2], c[3]);
+                tile[2 * k + 1] = make_float4(c[4], h * LOG2E, 0.f, 0.f);
+            }
+            __syncthreads();
+            // warp w walks columns w, w + 8, … of the tile: every lane reads the same address (broadcast)
+            for (uint32_t k = warp; k < nt; k += SK_THREADS / 32) {
+                const float4 y0 = tile[2 * k], y1 = tile[2 * k + 1];
+                visit<GRAD>(acc[0], x[0], y0, y1, halfk);
+                visit<GRAD>(acc[1], x[1], y0, y1, halfk);
+            }
         }
-        __syncthreads();
-        // warp w walks columns w, w + 8, … of the tile: every lane reads the same address (broadcast)
-        for (uint32_t k = warp; k < nt; k += SK_THREADS / 32) {
-            const float4 y0 = tile[k][0], y1 = tile[k][1];
-            visit<GRAD>(acc[0], x[0], y0, y1, halfk);
-            visit<GRAD>(acc[1], x[1], y0, y1, halfk);
+    } else {
+        u64 xp[2][5]; RowAcc2 a2[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+#pragma unroll
+            for (int d = 0; d < 5; ++d) xp[r][d] = pk(x[r][d], x[r][d]);
+            a2[r].m = -INFINITY; a2[r].s = pk(0.f, 0.f);
         }
+        const u64 neg_halfk = pk(-halfk, -halfk);
+        float *tf = reinterpret_cast<float *>(tile);
+        const ulonglong2 *tp = reinterpret_cast<const ulonglong2 *>(tile);
+        for (uint32_t j0 = 0; j0 < job.n_cols; j0 += SK_TILE) {
+            const uint32_t nt = job.n_cols - j0 < SK_TILE ? job.n_cols - j0 : SK_TILE, nq = (nt + 3) / 4;
+            __syncthreads();
+            // column pair p = (2p, 2p+1) → 12 floats: (y0a y0b y1a y1b | y2a y2b y3a y3b | y4a y4b ha hb); the tail of the last
+            // group of four columns is padded with h = −∞ (a term of weight zero)
+            for (uint32_t k = threadIdx.x; k < 4 * nq; k += SK_THREADS) {
+                float *o = tf + 12 * (k >> 1) + (k & 1);
+                if (k < nt) {
+                    const float *c = job.cols + 5 * (size_t) (j0 + k);
+                    const float h = job.pot_cols ? fmaf(job.pot_cols[j0 + k], inv_eps, job.w_log) : job.w_log;
+                    o[0] = c[0]; o[2] = c[1]; o[4] = c[2]; o[6] = c[3]; o[8] = c[4]; o[10] = h * LOG2E;
+                } else { o[0] = o[2] = o[4] = o[6] = o[8] = 0.f; o[10] = -INFINITY; }
+            }
+            __syncthreads();
+            // warp w walks groups w, w + 8, … of four columns: every lane reads the same 96 bytes (broadcast)
+            for (uint32_t k = warp; k < nq; k += SK_THREADS / 32) {
+                const ulonglong2 t0 = tp[6 * k], t1 = tp[6 * k + 1], t2 = tp[6 * k + 2], u0 = tp[6 * k + 3], u1 = tp[6 * k + 4], u2 = tp[6 * k + 5];
+                const u64 a0 = term2(xp[0], t0, t1, t2, neg_halfk), b0 = term2(xp[0], u0, u1, u2, neg_halfk);
+                const u64 a1 = term2(xp[1], t0, t1, t2, neg_halfk), b1 = term2(xp[1], u0, u1, u2, neg_halfk);
+                fold4(a2[0], a0, b0);
+                fold4(a2[1], a1, b1);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) { float sa, sb; upk(a2[r].s, sa, sb); acc[r].m = a2[r].m; acc[r].s = sa + sb; }
     }
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
