@@ -828,9 +828,12 @@ struct VLog {
     f3 light, p0, p1, p2, n0, n1, n2, hf, p;
 };
 struct PathHead { f3 cam, d, dldp1, L; float dlduv0, dlduv1; };
-struct PathLog : PathHead {
-    VLog v[EPSM_MAXV];
+// NV = vertex slots held: EPSM_MAXV in general; the short-chain instantiation of the gradient pass (k_wf_finish) holds 3
+// (two logged vertices + the inactive terminator), which lets the compiler keep the whole solve in registers.
+template <int NV> struct PathLogT : PathHead {
+    VLog v[NV];
 };
+typedef PathLogT<EPSM_MAXV> PathLog;
 
 // Per-lane path state that persists between the wavefront stages (k_wf_* in epsm_kernels.cu).  The stages are
 // cut exactly where sample_path queries the scene, so the trace kernels run between them on compacted queues:
@@ -1008,7 +1011,7 @@ EPSM_HDN void wf_stage_b(const DScene &sc, WfState &S, VLog &v, const Hit &h_in,
 
 // Closest hit of the ray towards the light sample (FollowShape): barycentric weights on the hit triangle, the
 // shadow-term distance ratio of epsm.py:614-615.
-EPSM_HDN void wf_direct_hit(const DScene &sc, VLog &v, const Hit &hd) {
+EPSM_HD void wf_direct_hit(const DScene &sc, VLog &v, const Hit &hd) {
     if (hd.prim == 0xffffffffu) return;
     const uint32_t g0 = sc.faces[3 * hd.prim], g1 = sc.faces[3 * hd.prim + 1], g2 = sc.faces[3 * hd.prim + 2];
     const float w1 = hd.u, w2 = hd.v, w0 = 1.f - w1 - w2;
@@ -1067,7 +1070,7 @@ EPSM_HD f3 frame_backward(f3 t, f3 nh, float inv_ln, float inv_lv, f3 gt, f3 gb,
     return (gnh - nh * dot3(nh, gnh)) * inv_ln;
 }
 // half-vector constraint rows.  `attached`: differentiate through the frame (false in caustic section A, epsm.py:1022)
-EPSM_HDN void halfvector_jac(f3 xp, f3 xc, f3 xn, f3 n, float eta, bool attached, RowJac &J) {
+EPSM_HD void halfvector_jac(f3 xp, f3 xc, f3 xn, f3 n, float eta, bool attached, RowJac &J) {
     f3 t, b, nh; float inv_ln, inv_lv; frame_from_normal(n, t, b, nh, inv_ln, inv_lv);
     f3 di = xp - xc, dO = xn - xc;
     float ili = 1.0f / len3(di), ilo = 1.0f / len3(dO);
@@ -1092,7 +1095,7 @@ EPSM_HDN void halfvector_jac(f3 xp, f3 xc, f3 xn, f3 n, float eta, bool attached
     }
 }
 // res2 = R·ŵo − const (epsm.py:1028,1116): rows of the "outgoing direction stays fixed" constraint
-EPSM_HDN void outdir_jac(f3 xc, f3 xn, f3 n, bool attached, RowJac &J) {
+EPSM_HD void outdir_jac(f3 xc, f3 xn, f3 n, bool attached, RowJac &J) {
     f3 t, b, nh; float inv_ln, inv_lv; frame_from_normal(n, t, b, nh, inv_ln, inv_lv);
     f3 dO = xn - xc; float ilo = 1.0f / len3(dO); f3 wo = dO * ilo;
 #pragma unroll
@@ -1120,11 +1123,15 @@ EPSM_HD V2 v2_add(V2 a, V2 b) { return V2{a.x + b.x, a.y + b.y}; }
 EPSM_HD M2 uv_block(const f3 g[2], f3 a0, f3 a1) { return M2{dot3(g[0], a0), dot3(g[0], a1), dot3(g[1], a0), dot3(g[1], a1)}; }
 
 
-struct PathGrads {
-    f3 pg[EPSM_MAXV][5];         // path_grad[5k + {0,1,2: p0 p1 p2, 3: n, 4: m}]
-    f3 lg[EPSM_MAXV];            // light_grad[k]
-    f3 dg[EPSM_MAXV];            // diffuse_grad[k]
+template <int NV> struct PathGradsT {
+    f3 pg[NV][5];                // path_grad[5k + {0,1,2: p0 p1 p2, 3: n, 4: m}]
+    f3 lg[NV];                   // light_grad[k]
+    f3 dg[NV];                   // diffuse_grad[k]
 };
+typedef PathGradsT<EPSM_MAXV> PathGrads;
+// Loops over the vertex slots are fully unrolled: in the short-chain instantiation every index becomes static and the
+// whole solve lives in registers (244, no stack frame); a counted `unroll (N)` keeps the loop and the local arrays.
+#define EPSM_UNROLL_NV _Pragma("unroll")
 
 EPSM_HD f3 vpoint(const VLog &v) { return v.p0 * v.b0 + v.p1 * v.b1 + v.p2 * (1.f - v.b0 - v.b1); }
 EPSM_HD f3 vnormal(const VLog &v) { return v.n0 * v.b0 + v.n1 * v.b1 + v.n2 * (1.f - v.b0 - v.b1); }
@@ -1132,11 +1139,14 @@ EPSM_HD f3 vnormal(const VLog &v) { return v.n0 * v.b0 + v.n1 * v.b1 + v.n2 * (1
 struct RowStore { RowJac J; M2 Lb, Db, Ub; };            // a stored section-B row block
 
 // manifold: ManifoldIntegrator.calc_grad (epsm.py:745-946)
-EPSM_HDN void calc_grad_manifold(const PathLog &P, int n_logged, PathGrads &G) {
-    RowStore rows[EPSM_MAXV];                             // rows[r-1]: B-row of vertex r
+template <int NV>
+EPSM_HD void calc_grad_manifold(const PathLogT<NV> &P, int n_logged, PathGradsT<NV> &G) {
+    RowStore rows[NV];                                    // rows[r-1]: B-row of vertex r
     int hasdiffuse = 0; bool valid = true;
     const V2 rhs = V2{P.dlduv0, P.dlduv1};
-    for (int id = 1; id <= n_logged; ++id) {
+    EPSM_UNROLL_NV
+    for (int id = 1; id <= NV; ++id) {
+        if (id > n_logged) break;
         const VLog &v = P.v[id - 1];
         const bool isdiffuse = (v.flags & EPSM_BF_DIFFUSE) != 0;
         if (id == 1) { G.dg[0] = isdiffuse ? P.dldp1 : mk3(0, 0, 0); valid = v.ismesh > 0; }
@@ -1150,7 +1160,7 @@ EPSM_HDN void calc_grad_manifold(const PathLog &P, int n_logged, PathGrads &G) {
         const f3 a0 = v.p0 - v.p2, a1 = v.p1 - v.p2, nn0 = v.n0 - v.n2, nn1 = v.n1 - v.n2;
         for (int sec = 0; sec < 2; ++sec) {
             const bool secB = sec == 1;
-            if (secB && id >= n_logged) break;            // id < len(path_info) − 1 (epsm.py:868)
+            if (secB && (id >= n_logged || id >= NV)) break;   // id < len(path_info) − 1 (epsm.py:868); NV: slots held
             const f3 xn = secB ? vpoint(P.v[id]) : v.light;
             RowStore cur;
             halfvector_jac(xp, xc, xn, n, v.eta, true, cur.J);
@@ -1163,17 +1173,20 @@ EPSM_HDN void calc_grad_manifold(const PathLog &P, int n_logged, PathGrads &G) {
             if (ok) {
                 // Solve Cᵀ w = (dlduv, 0, …) for the block-tridiagonal C = [B-rows 1..id−1 ; this row]:
                 // eliminate from the last block upwards (S_j = D_jᵀ + L_{j+1}ᵀ G_{j+1}, G_j = −S_j⁻¹ U_{j−1}ᵀ).
-                M2 Gm[EPSM_MAXV + 1];
+                M2 Gm[NV + 1];
                 M2 S = m2_T(cur.Db);
+                EPSM_UNROLL_NV
                 for (int j = id; j >= 2; --j) {
                     Gm[j] = m2_neg(m2_mul(m2_inv(S), m2_T(rows[j - 2].Ub)));
                     const M2 Lj = j == id ? cur.Lb : rows[j - 1].Lb;
                     S = m2_add(m2_T(rows[j - 2].Db), m2_mul(m2_T(Lj), Gm[j]));
                 }
-                V2 w[EPSM_MAXV + 1];
+                V2 w[NV + 1];
                 w[1] = m2_mv(m2_inv(S), rhs);
+                EPSM_UNROLL_NV
                 for (int j = 2; j <= id; ++j) w[j] = m2_mv(Gm[j], w[j - 1]);
                 // parameter gradients: θ ∈ {p0,p1,p2,n,m} of vertices 1..id
+                EPSM_UNROLL_NV
                 for (int j = 1; j <= id; ++j) {
                     const RowJac &Jj = j == id ? cur.J : rows[j - 1].J;
                     f3 a = Jj.gc[0] * w[j].x + Jj.gc[1] * w[j].y;
@@ -1197,15 +1210,18 @@ EPSM_HDN void calc_grad_manifold(const PathLog &P, int n_logged, PathGrads &G) {
 // output (dlduv is zeroed unless vertex 1 is diffuse, epsm.py:999, and section A masks hasdiffuse > 0,
 // epsm.py:1083,1090), so only section B is evaluated: rows 2..id are half-vector rows, row 1 (the diffuse
 // vertex) is replaced by the fixed-outgoing-direction constraint of the current vertex (epsm.py:1141-1163).
-EPSM_HDN void calc_grad_caustic(const PathLog &P, int n_logged, PathGrads &G) {
-    RowStore rows[EPSM_MAXV];
+template <int NV>
+EPSM_HD void calc_grad_caustic(const PathLogT<NV> &P, int n_logged, PathGradsT<NV> &G) {
+    RowStore rows[NV];
     const VLog &v1 = P.v[0];
     const bool d1 = (v1.flags & EPSM_BF_DIFFUSE) != 0;
     G.dg[0] = d1 ? P.dldp1 : mk3(0, 0, 0);
     if (!d1) return;
     const V2 rhs = V2{P.dlduv0, P.dlduv1};
     int hasdiffuse = 0; bool valid = true;
-    for (int id = 1; id < n_logged; ++id) {
+    EPSM_UNROLL_NV
+    for (int id = 1; id < NV; ++id) {
+        if (id >= n_logged) break;
         const VLog &v = P.v[id - 1];
         hasdiffuse += (v.flags & EPSM_BF_DIFFUSE) ? 1 : 0;
         valid = valid && (v.ismesh > 0) && hasdiffuse < 2;
@@ -1226,11 +1242,12 @@ EPSM_HDN void calc_grad_caustic(const PathLog &P, int n_logged, PathGrads &G) {
         if (!nx.active || !(nd || nnull)) continue;
         // Solve wᵀC = (dlduv, 0, …): with the rows ordered [2, 3, …, id, 1] the matrix is block upper
         // triangular with diagonal blocks L_2 … L_id, E — forward substitution over column blocks.
-        V2 w[EPSM_MAXV + 1];
+        V2 w[NV + 1];
         if (id == 1) {
             w[1] = m2_mv(m2_inv(m2_T(E)), rhs);
         } else {
             w[2] = m2_mv(m2_inv(m2_T(rows[1].Lb)), rhs);
+            EPSM_UNROLL_NV
             for (int j = 2; j < id; ++j) {
                 V2 acc = m2_mv(m2_T(rows[j - 1].Db), w[j]);
                 if (j - 1 >= 2) acc = v2_add(acc, m2_mv(m2_T(rows[j - 2].Ub), w[j - 1]));
@@ -1241,6 +1258,7 @@ EPSM_HDN void calc_grad_caustic(const PathLog &P, int n_logged, PathGrads &G) {
             w[1] = v2_neg(m2_mv(m2_inv(m2_T(E)), acc));
         }
         if (nd) {
+            EPSM_UNROLL_NV
             for (int j = 1; j <= id; ++j) {
                 // half-vector rows exist for r ≥ 2 (r = 1 only when id == 1 … then row 1 is the res2 row)
                 f3 a = mk3(0, 0, 0), gn = mk3(0, 0, 0), gm = mk3(0, 0, 0);
@@ -1266,9 +1284,12 @@ EPSM_HDN void calc_grad_caustic(const PathLog &P, int n_logged, PathGrads &G) {
 
 // `n_avail` (optional): only vertices 0 … n_avail−1 of the log are active — outputs are produced for those alone, so the
 // zero-fill and the outlier pass stop there (the gradient pass passes the loaded prefix; default: all).
-EPSM_HDN void calc_grad(const PathLog &P, int variant, int n_logged, PathGrads &G, int n_avail = EPSM_MAXV) {
-    for (int k = 0; k < EPSM_MAXV && k < n_avail; ++k) { for (int c = 0; c < 5; ++c) G.pg[k][c] = mk3(0, 0, 0); G.lg[k] = G.dg[k] = mk3(0, 0, 0); }
-    if (variant == EPSM_VARIANT_MANIFOLD) calc_grad_manifold(P, n_logged, G);
-    else calc_grad_caustic(P, n_logged, G);
-    for (int k = 0; k < EPSM_MAXV && k < n_avail; ++k) { for (int c = 0; c < 5; ++c) G.pg[k][c] = outlier3(G.pg[k][c]); G.lg[k] = outlier3(G.lg[k]); G.dg[k] = outlier3(G.dg[k]); }
+template <int NV>
+EPSM_HD void calc_grad(const PathLogT<NV> &P, int variant, int n_logged, PathGradsT<NV> &G, int n_avail = NV) {
+    EPSM_UNROLL_NV
+    for (int k = 0; k < NV; ++k) { if (k >= n_avail) break; for (int c = 0; c < 5; ++c) G.pg[k][c] = mk3(0, 0, 0); G.lg[k] = G.dg[k] = mk3(0, 0, 0); }
+    if (variant == EPSM_VARIANT_MANIFOLD) calc_grad_manifold<NV>(P, n_logged, G);
+    else calc_grad_caustic<NV>(P, n_logged, G);
+    EPSM_UNROLL_NV
+    for (int k = 0; k < NV; ++k) { if (k >= n_avail) break; for (int c = 0; c < 5; ++c) G.pg[k][c] = outlier3(G.pg[k][c]); G.lg[k] = outlier3(G.lg[k]); G.dg[k] = outlier3(G.dg[k]); }
 }

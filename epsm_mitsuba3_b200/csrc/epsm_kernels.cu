@@ -164,12 +164,15 @@ __device__ __forceinline__ void scatter3(float *__restrict__ buf, uint32_t idx, 
 
 // The Backward-mode replay seeds of sample_path (epsm.py:559-562, 609-627, 644-645)
 // `n_avail`: vertices 0 … n_avail−1 of the log are present; the rest are inactive and contribute nothing.
-__device__ void scatter_path(const PathLog &P, const PathGrads &G, int variant, int n_logged, int n_avail, uint32_t max_depth_prop,
+template <int NV>
+__device__ void scatter_path(const PathLogT<NV> &P, const PathGradsT<NV> &G, int variant, int n_logged, int n_avail, uint32_t max_depth_prop,
                              float *__restrict__ grad_pos, float *__restrict__ grad_nrm) {
     // len(path_grad) = 5·n_logged (manifold) or 5·(n_logged−1)+3 (caustic: n, m of the last vertex are never added)
     const int n_pg = variant == EPSM_VARIANT_MANIFOLD ? 5 * n_logged : 5 * (n_logged - 1) + 3;
     const bool shadow_term = (max_depth_prop < EPSM_MAX_ITER ? max_depth_prop : EPSM_MAX_ITER) <= 3;
-    for (int k = 0; k < n_logged && k < n_avail; ++k) {
+    EPSM_UNROLL_NV
+    for (int k = 0; k < NV; ++k) {
+        if (k >= n_logged || k >= n_avail) break;
         const VLog &v = P.v[k];
         const bool sel = v.active && (v.mesh_flags & EPSM_MESH_GRAD);
         if (5 * k + 4 < n_pg) {
@@ -585,15 +588,26 @@ __device__ __forceinline__ void vlog_inactive(VLog &v) {
     v.p0 = v.p1 = v.p2 = mk3(0, 0, 0); v.b0 = v.b1 = 0.f;
 }
 
-template <bool RECORD>
-__global__ void __launch_bounds__(128, EPSM_STAGE_MINBLOCKS) k_wf_finish(DScene sc, DLaunch ln, uint64_t work_base, uint32_t n, WfBuffers wb,
-                                                   float *__restrict__ grad_pos, float *__restrict__ grad_nrm, float *__restrict__ records) {
+// NV = vertex slots held per lane.  The scatter pass runs twice: NV = WF_SHORT_NV takes the lanes whose replay logged at
+// most WF_SHORT_NV − 1 vertices (the gradient chain of most paths ends at their second vertex; with static slot indices
+// the solve stays in registers), NV = EPSM_MAXV takes the rest (`skip_short`).  The record probe uses NV = EPSM_MAXV alone.
+#define WF_SHORT_NV 3
+#ifndef EPSM_FINISH_SHORT_BLOCKS
+#define EPSM_FINISH_SHORT_BLOCKS 4
+#endif
+#ifndef EPSM_FINISH_LONG_BLOCKS
+#define EPSM_FINISH_LONG_BLOCKS 3
+#endif
+template <bool RECORD, int NV>
+__global__ void __launch_bounds__(128, NV < EPSM_MAXV ? EPSM_FINISH_SHORT_BLOCKS : EPSM_FINISH_LONG_BLOCKS) k_wf_finish(DScene sc, DLaunch ln, uint64_t work_base, uint32_t n, WfBuffers wb,
+                                                   float *__restrict__ grad_pos, float *__restrict__ grad_nrm, float *__restrict__ records, bool skip_short) {
     const uint32_t i = blockIdx.x * 128 + threadIdx.x;
     if (i >= n) return;
     const uint32_t status = wb.status[i], code = status & 0xffu;
     if (code == WF_NONE || code == WF_SCATTERED) return;
     const int n_written = (int) (status >> 8);
-    PathLog P;
+    if (NV < EPSM_MAXV ? n_written > NV - 1 : (skip_short && n_written <= WF_SHORT_NV - 1)) return;
+    PathLogT<NV> P;
     soa_load(static_cast<PathHead &>(P), wb.heads, wb.capacity, i);
     const uint32_t max_iter = wf_iterations(ln.max_depth);
     const int n_logged = (int) (max_iter < EPSM_MAXV ? max_iter : EPSM_MAXV);      // len(path_info) − 1 (independent of pruning)
@@ -601,7 +615,8 @@ __global__ void __launch_bounds__(128, EPSM_STAGE_MINBLOCKS) k_wf_finish(DScene 
     // (manifold, epsm.py:855,920) or at the second one (caustic: vertex 1 must be diffuse, epsm.py:999,1008), at a
     // non-mesh vertex or where the path left the scene; every output beyond it is masked to zero by calc_grad.
     bool chain = true; int n_diffuse = 0, n_avail = 0;
-    for (int k = 0; k < EPSM_MAXV; ++k) {
+    EPSM_UNROLL_NV
+    for (int k = 0; k < NV; ++k) {
         if (k < n_logged && k < n_written && (chain || RECORD)) {
             soa_load(P.v[k], wb.vlogs + (size_t) k * WORDS_OF(VLog) * wb.capacity, wb.capacity, i);
             VLog &v = P.v[k];
@@ -617,14 +632,14 @@ __global__ void __launch_bounds__(128, EPSM_STAGE_MINBLOCKS) k_wf_finish(DScene 
             memset(&P.v[k], 0, sizeof(VLog)); P.v[k].prim = 0xffffffffu;
         } else {
             vlog_inactive(P.v[k]);                        // the gradient-dead tail starts here; nothing behind it is read
-            break;
+            if (NV == EPSM_MAXV) break;                   // (the short instantiation fills its few slots: static indices)
         }
     }
-    if (RECORD) { WfState S; soa_load(S, wb.states, wb.capacity, i); P.L = S.L; n_avail = EPSM_MAXV; }
-    PathGrads G;
-    calc_grad(P, ln.variant, n_logged, G, n_avail);
-    if (RECORD) { const WorkItem wi = wf_work_item(ln, work_base + i); write_record(P, G, n_logged, records + (wi.lane - ln.lane_begin) * EPSM_REC_FLOATS); }
-    else scatter_path(P, G, ln.variant, n_logged, n_avail, ln.max_depth, grad_pos, grad_nrm);
+    if (RECORD) { WfState S; soa_load(S, wb.states, wb.capacity, i); P.L = S.L; n_avail = NV; }
+    PathGradsT<NV> G;
+    calc_grad<NV>(P, ln.variant, n_logged, G, n_avail);
+    if (RECORD) { if (NV == EPSM_MAXV) { const WorkItem wi = wf_work_item(ln, work_base + i); write_record(reinterpret_cast<const PathLog &>(P), reinterpret_cast<const PathGrads &>(G), n_logged, records + (wi.lane - ln.lane_begin) * EPSM_REC_FLOATS); } }
+    else scatter_path<NV>(P, G, ln.variant, n_logged, n_avail, ln.max_depth, grad_pos, grad_nrm);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -936,9 +951,12 @@ cudaError_t epsm_launch_backward(const DScene &sc, DLaunch ln, const float *grad
             ++launches;
             k_wf_stage_b<<<grid, 128, 0, s>>>(sc, ln, it, max_iter, n, wb, records != nullptr); ++launches;
         }
-        if (records) k_wf_finish<true><<<grid, 128, 0, s>>>(sc, ln, base, n, wb, nullptr, nullptr, records);
-        else k_wf_finish<false><<<grid, 128, 0, s>>>(sc, ln, base, n, wb, grad_pos, grad_nrm, nullptr);
-        ++launches;
+        if (records) { k_wf_finish<true, EPSM_MAXV><<<grid, 128, 0, s>>>(sc, ln, base, n, wb, nullptr, nullptr, records, false); ++launches; }
+        else {
+            k_wf_finish<false, WF_SHORT_NV><<<grid, 128, 0, s>>>(sc, ln, base, n, wb, grad_pos, grad_nrm, nullptr, false);
+            k_wf_finish<false, EPSM_MAXV><<<grid, 128, 0, s>>>(sc, ln, base, n, wb, grad_pos, grad_nrm, nullptr, true);
+            launches += 2;
+        }
         if (counters) { k_count_lanes<<<grid, 128, 0, s>>>(n, wb, counters); ++launches; }
     }
     if (n_launches) *n_launches += launches;
