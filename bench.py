@@ -143,6 +143,15 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, gpu=0):
         super().__init__(daemon=True); self.gpu = gpu; self.rows = []; self.stop_evt = threading.Event(); self.proc = None
+        self.t_begin = None
+
+    def wait_first(self, timeout):
+        t0 = time.time()
+        while not self.rows and time.time() - t0 < timeout:
+            time.sleep(0.02)
+
+    def begin(self):
+        self.t_begin = time.time()
 
     def run(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -151,21 +160,27 @@ class ClockSampler(threading.Thread):
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
-                self.rows.append([c.strip() for c in line.split(",")])
+                self.rows.append([c.strip() for c in line.split(",")] + [time.time()])
                 if self.stop_evt.is_set():
                     break
         except Exception:
             pass
 
     def finish(self):
+        t_end = time.time()
         self.stop_evt.set()
         if self.proc:
             try:
                 self.proc.terminate()
             except Exception:
                 pass
+        rows = [r for r in self.rows if self.t_begin is None or self.t_begin <= r[-1] <= t_end + 0.05]
+        if not rows:
+            # timed region shorter than the 200 ms sampling period: the last row before its end (the GPU has been under
+            # the same load since the warm-up steps)
+            rows = [r for r in self.rows if r[-1] <= t_end + 0.05][-1:]
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
@@ -301,12 +316,14 @@ def main():
             ms += e2.elapsed_time(e3)
         return ms
 
+    clk = ClockSampler(local); clk.start()                  # nvidia-smi takes a while to start on an 8-GPU box: launch it before the warm-up
     for k in range(args.warmup):
         step(k, False)
+    clk.wait_first(2.0)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    clk = ClockSampler(local); clk.start()
+    clk.begin()
     launches0 = scene.launch_count()
     t_wall0 = time.perf_counter()
     ms_steps = [step(args.warmup + k, True) for k in range(args.steps)]
