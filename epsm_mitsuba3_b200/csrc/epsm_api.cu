@@ -112,10 +112,21 @@ int zero_counters(epsm_ctx *ctx) {
     return EPSM_OK;
 }
 
-// Workspace for one chunk of the wavefront: at most EPSM_WF_CHUNK lanes (default 2^22 ≈ 6 GB of the 180 GB HBM).
+// Workspace for one chunk of the wavefront.  Bigger chunks mean fewer, fuller launches (the late iterations of a chunk are
+// latency floors of a few thousand rays): the room pass takes 61.1 / 57.7 / 55.4 / 54.2 ms at 2^22 / 2^23 / 2^24 / 2^25 lanes
+// (profiles/r01_h_*).  Default: the largest power of two whose workspace (≈ 1.5 KB per lane) fits a third of the free device
+// memory, at most 2^25 lanes (48 GB of the B200's 180 GB), at least 2^20.  EPSM_WF_CHUNK overrides.
 int ensure_workspace(epsm_ctx *ctx, uint64_t lanes) {
     uint64_t cap = 1ull << 22;
     if (const char *e = getenv("EPSM_WF_CHUNK")) { uint64_t v = strtoull(e, nullptr, 10); if (v >= 1024) cap = v; }
+    else {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+            free_b += ctx->d_workspace.n;                                   // what this context already holds counts as available
+            cap = 1ull << 25;
+            while (cap > (1ull << 20) && epsm_wf_workspace_bytes((uint32_t) cap) > free_b / 3) cap >>= 1;
+        }
+    }
     if (lanes < cap) cap = (lanes + 1023) & ~1023ull;
     if (cap < 1024) cap = 1024;
     if (ctx->wf_capacity >= cap && ctx->d_workspace.p) return EPSM_OK;

@@ -91,6 +91,21 @@ EPSM_HD float mulsign_neg(float a, float b) { return u2f(f2u(a) ^ (~f2u(b) & 0x8
 EPSM_HD float safe_sqrt(float x) { return sqrtf(fmaxf(x, 0.0f)); }
 EPSM_HD float sqr(float x) { return x * x; }
 EPSM_HD float max3(f3 a) { return fmaxf(fmaxf(a.x, a.y), a.z); }
+// Three-input min / max: one FMNMX3 on sm_100a (the slab tests are ALU-pipe heavy); same value as the nested form.
+EPSM_HD float fmax3(float a, float b, float c) {
+#ifdef __CUDA_ARCH__
+    float r; asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r;
+#else
+    return fmaxf(fmaxf(a, b), c);
+#endif
+}
+EPSM_HD float fmin3(float a, float b, float c) {
+#ifdef __CUDA_ARCH__
+    float r; asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r;
+#else
+    return fminf(fminf(a, b), c);
+#endif
+}
 EPSM_HD f3 ld3(const float *p, uint32_t i) { return mk3(p[3 * i], p[3 * i + 1], p[3 * i + 2]); }
 EPSM_HD f3 a3(const float *p) { return mk3(p[0], p[1], p[2]); }
 
@@ -321,16 +336,14 @@ EPSM_HDN Hit bvh_trace(const DScene &sc, const Ray &ray, TStack &st, uint32_t &n
         const f4 lx = n0.a, ly = n0.b, lz = n1.a, hx = n1.b, hy = n2.a, hz = n2.b, ch = ldg4(np + 6);
         if (COUNT) ++n_nodes;
         uint32_t key[4];
-        float tmn[4];
         const uint32_t cref[4] = {f2u(ch.x), f2u(ch.y), f2u(ch.z), f2u(ch.w)};     // 0x7fffffff marks an empty slot
 #define EPSM_SLAB(k, LX, LY, LZ, HX, HY, HZ)                                                        \
         {                                                                                           \
             float ax = fmaf(LX, ix, -ox), bx = fmaf(HX, ix, -ox);                                   \
             float ay = fmaf(LY, iy, -oy), by = fmaf(HY, iy, -oy);                                   \
             float az = fmaf(LZ, iz, -oz), bz = fmaf(HZ, iz, -oz);                                   \
-            float t0 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));      \
-            float t1 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), hit.t));     \
-            tmn[k] = t0;                                                                            \
+            float t0 = fmaxf(fmax3(fminf(ax, bx), fminf(ay, by), fminf(az, bz)), 0.0f);             \
+            float t1 = fminf(fmin3(fmaxf(ax, bx), fmaxf(ay, by), fmaxf(az, bz)), hit.t);            \
             key[k] = (t0 <= t1 * 1.0000004f && cref[k] != 0x7fffffffu) ? ((f2u(t0) & ~3u) | (uint32_t) k) : 0xffffffffu; \
         }
         EPSM_SLAB(0, lx.x, ly.x, lz.x, hx.x, hy.x, hz.x)
@@ -345,7 +358,8 @@ EPSM_HDN Hit bvh_trace(const DScene &sc, const Ray &ray, TStack &st, uint32_t &n
             if (key[i] != 0xffffffffu) {
                 uint32_t k = key[i] & 3u;
                 uint32_t r = k == 0 ? cref[0] : k == 1 ? cref[1] : k == 2 ? cref[2] : cref[3];
-                float t = k == 0 ? tmn[0] : k == 1 ? tmn[1] : k == 2 ? tmn[2] : tmn[3];
+                // the key carries the entry distance (two mantissa bits cleared: never larger, so the pop test stays conservative)
+                float t = u2f(key[i] & ~3u);
                 st.push(r, t);
             }
         }

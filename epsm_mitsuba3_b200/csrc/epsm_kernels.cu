@@ -481,16 +481,15 @@ __global__ void __launch_bounds__(CTA) k_wf_trace(DScene sc, const QRay *__restr
         const f8 n0 = ldg8(np), n1 = ldg8(np + 2), n2 = ldg8(np + 4);
         const f4 lx = n0.a, ly = n0.b, lz = n1.a, hx = n1.b, hy = n2.a, hz = n2.b, ch = ldg4(np + 6);
         if (COUNT) ++c_nodes;
-        uint32_t key[4]; float tmn[4];
+        uint32_t key[4];
         const uint32_t cref[4] = {f2u(ch.x), f2u(ch.y), f2u(ch.z), f2u(ch.w)};
 #define WF_SLAB(k, LX, LY, LZ, HX, HY, HZ)                                                          \
         {                                                                                           \
             const float ax = fmaf(LX, ix, -ox), bx = fmaf(HX, ix, -ox);                             \
             const float ay = fmaf(LY, iy, -oy), by = fmaf(HY, iy, -oy);                             \
             const float az = fmaf(LZ, iz, -oz), bz = fmaf(HZ, iz, -oz);                             \
-            const float t0 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f)); \
-            const float t1 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), best_t)); \
-            tmn[k] = t0;                                                                            \
+            const float t0 = fmaxf(fmax3(fminf(ax, bx), fminf(ay, by), fminf(az, bz)), 0.0f);        \
+            const float t1 = fminf(fmin3(fmaxf(ax, bx), fmaxf(ay, by), fmaxf(az, bz)), best_t);      \
             key[k] = (t0 <= t1 * 1.0000004f && cref[k] != 0x7fffffffu) ? ((f2u(t0) & ~3u) | (uint32_t) k) : 0xffffffffu; \
         }
         WF_SLAB(0, lx.x, ly.x, lz.x, hx.x, hy.x, hz.x)
@@ -504,7 +503,8 @@ __global__ void __launch_bounds__(CTA) k_wf_trace(DScene sc, const QRay *__restr
             if (key[i] != 0xffffffffu) {
                 const uint32_t k = key[i] & 3u;
                 const uint32_t r = k == 0 ? cref[0] : k == 1 ? cref[1] : k == 2 ? cref[2] : cref[3];
-                const float t = k == 0 ? tmn[0] : k == 1 ? tmn[1] : k == 2 ? tmn[2] : tmn[3];
+                // the key carries the entry distance (two mantissa bits cleared: never larger, so the pop test stays conservative)
+                const float t = u2f(key[i] & ~3u);
                 const uint2 e = make_uint2(r, __float_as_uint(t));
                 if (sp < WF_STACK) sstack[sp][threadIdx.x] = e; else if (sp < WF_STACK + WF_LSTACK) lstack[sp - WF_STACK] = e;
                 if (sp < WF_STACK + WF_LSTACK) ++sp;
