@@ -278,6 +278,14 @@ template <uint32_t NW, typename T> __device__ __forceinline__ void soa_store_pre
 #ifndef EPSM_STAGE_MINBLOCKS
 #define EPSM_STAGE_MINBLOCKS 2
 #endif
+// Per-kernel choice measured on the B200 (room / glass pass, ms): stage A / B at 2,2 → 54.3 / 27.8; 3,3 → 52.3 / 26.5;
+// 4,3 → 81.4 / 26.0 (stage A spills at 128 registers); 4,4 → 58.1 / 41.1.
+#ifndef EPSM_STAGEB_MINBLOCKS
+#define EPSM_STAGEB_MINBLOCKS 3
+#endif
+#ifndef EPSM_STAGEA_MINBLOCKS
+#define EPSM_STAGEA_MINBLOCKS 3
+#endif
 #define WF_NONE 0u      // slot without a lane
 #define WF_LIVE 1u      // path still being traced
 #define WF_DONE 2u      // path has terminated (its remaining logged vertices are inactive)
@@ -291,24 +299,33 @@ struct WfBuffers {
     Hit *hits;                 // [C] path hits, then [MAXV·C] direct hits
     uint32_t *occl;            // [C]
     QRay *q_closest /* 2C */, *q_any /* C */;
-    uint32_t *counters;        // [0..15] closest-queue sizes, [16..31] closest heads, [32..47] any sizes, [48..63] any heads
+    uint32_t *counters;        // [0..15] closest-queue sizes, [16..31] closest heads, [32..47] any sizes, [48..63] any heads,
+                               // [64 + it] size of the lane list of iteration it ≥ WF_LIST_FROM
+    uint32_t *live[2];         // [C] each: lanes still on their path at iteration it (ping-pong on it & 1), appended by stage B(it − 1)
     uint32_t capacity;
 };
+#define WF_COUNTER_WORDS 96u
+// From this iteration on the stage kernels run over the compacted lane list instead of over all slots: by then a few
+// percent of the lanes are left and a full-grid launch is a 0.6 ms floor of status reads (33.5 M slots); in the dense
+// early iterations slot order (coalesced records) wins (profiles/r01_f_refit_iteration.md).
+#define WF_LIST_FROM 2u
+#define WF_LIST_SPARSE 8u   // … and only when fewer than 1/8 of the chunk's slots are still alive
 
 size_t epsm_wf_workspace_bytes(uint32_t capacity) {
     size_t c = capacity;
     return c * (4 * (1 + WORDS_OF(WfState) + WORDS_OF(PathHead) + EPSM_MAXV * WORDS_OF(VLog)) + sizeof(Hit) * (1 + EPSM_MAXV)
-                + sizeof(uint32_t) + sizeof(QRay) * 3) + 64 * sizeof(uint32_t) + 16 * 256;
+                + sizeof(uint32_t) + sizeof(QRay) * 3 + 2 * sizeof(uint32_t)) + WF_COUNTER_WORDS * sizeof(uint32_t) + 20 * 256;
 }
 static WfBuffers wf_carve(void *base, uint32_t capacity) {
     WfBuffers w; char *p = (char *) base; size_t c = capacity;
     auto take = [&](size_t bytes) { char *r = p; p += (bytes + 255) & ~(size_t) 255; return r; };
-    w.counters = (uint32_t *) take(64 * sizeof(uint32_t));
+    w.counters = (uint32_t *) take(WF_COUNTER_WORDS * sizeof(uint32_t));
     w.status = (uint32_t *) take(c * 4);
     w.states = (uint32_t *) take(c * 4 * WORDS_OF(WfState)); w.heads = (uint32_t *) take(c * 4 * WORDS_OF(PathHead));
     w.vlogs = (uint32_t *) take(c * 4 * EPSM_MAXV * WORDS_OF(VLog));
     w.hits = (Hit *) take(c * sizeof(Hit) * (1 + EPSM_MAXV)); w.occl = (uint32_t *) take(c * sizeof(uint32_t));
     w.q_closest = (QRay *) take(2 * c * sizeof(QRay)); w.q_any = (QRay *) take(c * sizeof(QRay));
+    w.live[0] = (uint32_t *) take(c * 4); w.live[1] = (uint32_t *) take(c * 4);
     w.capacity = capacity; return w;
 }
 
@@ -523,10 +540,16 @@ __global__ void __launch_bounds__(CTA) k_wf_trace(DScene sc, const QRay *__restr
 }
 
 // `grad_pos` != NULL enables the first-vertex fast path (scatter passes; the record probe keeps every lane).
-__global__ void __launch_bounds__(128, EPSM_STAGE_MINBLOCKS) k_wf_stage_a(DScene sc, DLaunch ln, uint32_t it, uint32_t n, WfBuffers wb, float *__restrict__ grad_pos) {
-    const uint32_t i = blockIdx.x * 128 + threadIdx.x;
+__global__ void __launch_bounds__(128, EPSM_STAGEA_MINBLOCKS) k_wf_stage_a(DScene sc, DLaunch ln, uint32_t it, uint32_t n, WfBuffers wb, float *__restrict__ grad_pos) {
+    // the lane list pays only when few lanes are left (its order is scrambled by the concurrent appends): otherwise slot order
+    const bool listed = it >= WF_LIST_FROM && wb.counters[64 + it] < n / WF_LIST_SPARSE;
+    const uint32_t cnt = listed ? wb.counters[64 + it] : n;
+    // listed iterations are launched with a small fixed grid (the list size lives on the device) and stride over the list
+    for (uint32_t base = blockIdx.x * 128; base < cnt; base += gridDim.x * 128) {
+    const uint32_t j = base + threadIdx.x;
+    const uint32_t i = listed ? (j < cnt ? wb.live[it & 1][j] : 0u) : j;
     bool push = false; Ray sr;
-    if (i < n && (wb.status[i] & 0xffu) == WF_LIVE) {
+    if (j < cnt && (listed || (wb.status[i] & 0xffu) == WF_LIVE)) {
         WfState S; const Hit h = wb.hits[i];
         bool keep = true;
         if (it == 0) {
@@ -550,12 +573,18 @@ __global__ void __launch_bounds__(128, EPSM_STAGE_MINBLOCKS) k_wf_stage_a(DScene
     }
     const uint32_t q = queue_push(wb.counters + 32 + it, push);
     if (push) queue_write(wb.q_any, q, sr, i);
+    }
 }
 
-__global__ void __launch_bounds__(128, EPSM_STAGE_MINBLOCKS) k_wf_stage_b(DScene sc, DLaunch ln, uint32_t it, uint32_t max_iter, uint32_t n, WfBuffers wb, bool keep_state) {
-    const uint32_t i = blockIdx.x * 128 + threadIdx.x;
+__global__ void __launch_bounds__(128, EPSM_STAGEB_MINBLOCKS) k_wf_stage_b(DScene sc, DLaunch ln, uint32_t it, uint32_t max_iter, uint32_t n, WfBuffers wb, bool keep_state) {
+    // the lane list pays only when few lanes are left (its order is scrambled by the concurrent appends): otherwise slot order
+    const bool listed = it >= WF_LIST_FROM && wb.counters[64 + it] < n / WF_LIST_SPARSE;
+    const uint32_t cnt = listed ? wb.counters[64 + it] : n;
+    for (uint32_t base = blockIdx.x * 128; base < cnt; base += gridDim.x * 128) {
+    const uint32_t j = base + threadIdx.x;
+    const uint32_t i = listed ? (j < cnt ? wb.live[it & 1][j] : 0u) : j;
     bool push_direct = false, push_next = false; Ray direct, next;
-    if (i < n && (wb.status[i] & 0xffu) == WF_LIVE) {
+    if (j < cnt && (listed || (wb.status[i] & 0xffu) == WF_LIVE)) {
         WfState S; soa_load(S, wb.states, wb.capacity, i);
         const Hit h = wb.hits[i];
         const bool occluded = S.need_shadow && wb.occl[i] != 0u;
@@ -571,6 +600,11 @@ __global__ void __launch_bounds__(128, EPSM_STAGE_MINBLOCKS) k_wf_stage_b(DScene
     if (push_direct) queue_write(wb.q_closest, qd, direct, wb.capacity + it * wb.capacity + i);
     const uint32_t qn = queue_push(wb.counters + (it + 1), push_next);
     if (push_next) queue_write(wb.q_closest, qn, next, i);
+    if (it + 1 >= WF_LIST_FROM) {                           // the lanes of the next iteration, for its stage kernels
+        const uint32_t l = queue_push(wb.counters + 64 + (it + 1), push_next);
+        if (push_next) wb.live[(it + 1) & 1][l] = i;
+    }
+    }
 }
 
 __global__ void k_count_lanes(uint32_t n, WfBuffers wb, unsigned long long *counters) {
@@ -596,7 +630,7 @@ __device__ __forceinline__ void vlog_inactive(VLog &v) {
 #define EPSM_FINISH_SHORT_BLOCKS 4
 #endif
 #ifndef EPSM_FINISH_LONG_BLOCKS
-#define EPSM_FINISH_LONG_BLOCKS 3
+#define EPSM_FINISH_LONG_BLOCKS 2
 #endif
 template <bool RECORD, int NV>
 __global__ void __launch_bounds__(128, NV < EPSM_MAXV ? EPSM_FINISH_SHORT_BLOCKS : EPSM_FINISH_LONG_BLOCKS) k_wf_finish(DScene sc, DLaunch ln, uint64_t work_base, uint32_t n, WfBuffers wb,
@@ -933,7 +967,7 @@ cudaError_t epsm_launch_backward(const DScene &sc, DLaunch ln, const float *grad
     for (uint64_t base = 0; base < total; base += capacity) {
         const uint32_t n = (uint32_t) ((total - base) < capacity ? (total - base) : capacity);
         const uint32_t grid = (n + 127) / 128;
-        cudaMemsetAsync(wb.counters, 0, 64 * sizeof(uint32_t), s);
+        cudaMemsetAsync(wb.counters, 0, WF_COUNTER_WORDS * sizeof(uint32_t), s);
         k_wf_init<<<grid, 128, 0, s>>>(ln, base, n, grad_in, wb); ++launches;
         for (uint32_t it = 0; it <= max_iter; ++it) {
             // closest-hit queue `it`: path rays of iteration `it` and the direct rays of iteration `it − 1`
@@ -943,13 +977,14 @@ cudaError_t epsm_launch_backward(const DScene &sc, DLaunch ln, const float *grad
             ev_end();
             ++launches;
             if (it == max_iter) break;
-            k_wf_stage_a<<<grid, 128, 0, s>>>(sc, ln, it, n, wb, records ? nullptr : grad_pos); ++launches;
+            const uint32_t sgrid = it >= WF_LIST_FROM && grid > trace_grid * 4 ? trace_grid * 4 : grid;   // listed: stride over the lane list
+            k_wf_stage_a<<<sgrid, 128, 0, s>>>(sc, ln, it, n, wb, records ? nullptr : grad_pos); ++launches;
             ev_begin();
             if (counters) k_wf_trace<true, true><<<trace_grid, CTA, 0, s>>>(sc, wb.q_any, wb.counters + 32 + it, wb.counters + 48 + it, nullptr, wb.occl, counters);
             else k_wf_trace<true, false><<<trace_grid, CTA, 0, s>>>(sc, wb.q_any, wb.counters + 32 + it, wb.counters + 48 + it, nullptr, wb.occl, nullptr);
             ev_end();
             ++launches;
-            k_wf_stage_b<<<grid, 128, 0, s>>>(sc, ln, it, max_iter, n, wb, records != nullptr); ++launches;
+            k_wf_stage_b<<<sgrid, 128, 0, s>>>(sc, ln, it, max_iter, n, wb, records != nullptr); ++launches;
         }
         if (records) { k_wf_finish<true, EPSM_MAXV><<<grid, 128, 0, s>>>(sc, ln, base, n, wb, nullptr, nullptr, records, false); ++launches; }
         else {
