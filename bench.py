@@ -438,7 +438,7 @@ def main():
                "roofline": roof, "cpu_baseline": cpu, "full_replay": full_leg, "iteration": iteration,
                "scene": {"triangles": int(stats["n_triangles"]), "vertices": int(stats["n_vertices"]), "bvh_nodes": int(stats["n_nodes"]),
                          "bvh_build_ms": stats["build_ms"]},
-               "wall_s_timed_region": t_wall}
+               "wall_s_timed_region": t_wall, "ms_steps": [round(float(x), 3) for x in ms_steps]}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

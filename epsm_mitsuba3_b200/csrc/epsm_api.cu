@@ -117,6 +117,7 @@ int zero_counters(epsm_ctx *ctx) {
 // (profiles/r01_h_*).  Default: the largest power of two whose workspace (≈ 1.5 KB per lane) fits a third of the free device
 // memory, at most 2^25 lanes (48 GB of the B200's 180 GB), at least 2^20.  EPSM_WF_CHUNK overrides.
 int ensure_workspace(epsm_ctx *ctx, uint64_t lanes) {
+    if (ctx->d_workspace.p && ctx->wf_capacity >= lanes) return EPSM_OK;       // the whole wavefront already fits: one chunk
     uint64_t cap = 1ull << 22;
     if (const char *e = getenv("EPSM_WF_CHUNK")) { uint64_t v = strtoull(e, nullptr, 10); if (v >= 1024) cap = v; }
     else {
