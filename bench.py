@@ -269,7 +269,9 @@ def main():
         v = float(np.mean([r["value"] for r in vals])) if vals else 0.0
         r = vals[-1] if vals else {"cores": os.cpu_count(), "kind": "port", "sample": "none"}
         out = {"impl": "reference", "metric": "gradient path samples/sec", "value": v, "unit": "samples/s", "n_gpus": args.gpus,
-               "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": args.scaling,
+               "steps": args.steps, "warmup": args.warmup, "ms_per_step": (res * res * spp / v * 1e3) if v else None,
+               "ms_per_step_note": "one whole pass of the workload at the sampled rate (each step times a bounded sample, see cpu_baseline.sample)",
+               "higher_is_better": True, "scaling": args.scaling,
                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                "cpu_baseline": {"value": v, "unit": "samples/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
                "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
