@@ -286,6 +286,7 @@ template <uint32_t NW, typename T> __device__ __forceinline__ void soa_store_pre
 #ifndef EPSM_STAGEA_MINBLOCKS
 #define EPSM_STAGEA_MINBLOCKS 3
 #endif
+#define WF_HEAD_INIT_WORDS 6   // PathHead::cam, d — all that k_wf_init knows
 #define WF_NONE 0u      // slot without a lane
 #define WF_LIVE 1u      // path still being traced
 #define WF_DONE 2u      // path has terminated (its remaining logged vertices are inactive)
@@ -336,9 +337,11 @@ struct WorkItem { uint32_t px, py, s; uint64_t lane; bool valid; };
 __device__ __forceinline__ WorkItem wf_work_item(const DLaunch &ln, uint64_t w) {
     const uint32_t W = ln.sensor.w, H = ln.sensor.h, S = ln.s_end - ln.s_begin;
     const uint32_t tiles_x = (W + TILE_W - 1) / TILE_W;
-    const uint64_t per_tile = 32ull * S;
-    const uint64_t tile = w / per_tile; const uint32_t r = (uint32_t) (w % per_tile);
-    const uint32_t tx = (uint32_t) (tile % tiles_x), ty = ln.tile_y0 + (uint32_t) (tile / tiles_x);
+    const uint32_t per_tile = 32u * S;
+    uint32_t tile, r;
+    if (w < 0x100000000ull) { const uint32_t w32 = (uint32_t) w; tile = w32 / per_tile; r = w32 - tile * per_tile; }   // 32-bit divisions: the common case
+    else { tile = (uint32_t) (w / per_tile); r = (uint32_t) (w % per_tile); }
+    const uint32_t ty_rel = tile / tiles_x, tx = tile - ty_rel * tiles_x, ty = ln.tile_y0 + ty_rel;
     WorkItem wi; wi.s = ln.s_begin + r / 32; const uint32_t pin = r & 31;
     wi.px = tx * TILE_W + (pin & (TILE_W - 1)); wi.py = ty * TILE_H + pin / TILE_W;
     wi.lane = ((uint64_t) wi.py * W + wi.px) * ln.spp + wi.s;
@@ -370,7 +373,8 @@ __global__ void __launch_bounds__(128) k_wf_init(DLaunch ln, uint64_t work_base,
             const uint64_t pixel = (uint64_t) wi.py * ln.sensor.w + wi.px;
             PathHead H;
             wf_begin(ln.sensor, wi.px, wi.py, ln.seed, (uint32_t) wi.lane, grad_in[pixel * 5 + 3], grad_in[pixel * 5 + 4], S, H);
-            soa_store_prefix<WF_INIT_WORDS>(S, wb.states, wb.capacity, i); soa_store(H, wb.heads, wb.capacity, i);
+            soa_store_prefix<WF_INIT_WORDS>(S, wb.states, wb.capacity, i);
+            soa_store_prefix<WF_HEAD_INIT_WORDS>(H, wb.heads, wb.capacity, i);       // cam, d: the rest is zero until the first hit
             push = true;
         }
         wb.status[i] = wi.valid ? WF_LIVE : WF_NONE;
@@ -554,7 +558,8 @@ __global__ void __launch_bounds__(128, EPSM_STAGEA_MINBLOCKS) k_wf_stage_a(DScen
         bool keep = true;
         if (it == 0) {
             soa_load_prefix<WF_INIT_WORDS>(S, wb.states, wb.capacity, i); wf_state_defaults(S);
-            PathHead H; soa_load(H, wb.heads, wb.capacity, i);
+            PathHead H; soa_load_prefix<WF_HEAD_INIT_WORDS>(H, wb.heads, wb.capacity, i);
+            H.dldp1 = H.L = mk3(0, 0, 0); H.dlduv0 = H.dlduv1 = 0.f;
             SI si;
             push = wf_stage_a(sc, S, H, h, it, ln.max_depth, ln.variant, ln.prune != 0, si);
             if (grad_pos && wf_first_vertex_final(S, it, ln.prune != 0)) {
