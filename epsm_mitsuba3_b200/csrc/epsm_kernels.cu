@@ -48,7 +48,7 @@ __device__ __forceinline__ void flush_counters(const Tracer &tr, uint32_t lanes,
 //  Ray batches
 // ------------------------------------------------------------------------------------------------
 template <bool ANY, bool COUNT>
-__global__ void __launch_bounds__(CTA) k_trace(DScene sc, const f4 *__restrict__ rays, uint64_t n, uint32_t *__restrict__ hits,
+__global__ void __launch_bounds__(CTA) k_trace(const __grid_constant__ DScene sc, const f4 *__restrict__ rays, uint64_t n, uint32_t *__restrict__ hits,
                                                unsigned long long *counters) {
     __shared__ SharedStack ss;
     TStack st; bind_stack(st, ss);
@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(CTA) k_trace(DScene sc, const f4 *__restrict__
 #define FT_H (TILE_H + 5)
 
 template <bool COUNT>
-__global__ void __launch_bounds__(CTA, EPSM_PATH_MINBLOCKS) k_render(DScene sc, DLaunch ln, float *__restrict__ film, unsigned long long *counters) {
+__global__ void __launch_bounds__(CTA, EPSM_PATH_MINBLOCKS) k_render(const __grid_constant__ DScene sc, const __grid_constant__ DLaunch ln, float *__restrict__ film, unsigned long long *counters) {
     __shared__ SharedStack ss;
     __shared__ float ftile[FT_H][FT_W][4];
     TStack st; bind_stack(st, ss);
@@ -302,7 +302,7 @@ struct WfBuffers {
     QRay *q_closest /* 2C */, *q_any /* C */;
     uint32_t *counters;        // [0..15] closest-queue sizes, [16..31] closest heads, [32..47] any sizes, [48..63] any heads,
                                // [64 + it] size of the lane list of iteration it ≥ WF_LIST_FROM
-    uint32_t *live[2];         // [C] each: lanes still on their path at iteration it (ping-pong on it & 1), appended by stage B(it − 1)
+    uint32_t *live0, *live1;   // [C] each: lanes still on their path at iteration it (ping-pong on it & 1), appended by stage B(it − 1)
     uint32_t capacity;
 };
 #define WF_COUNTER_WORDS 96u
@@ -326,7 +326,7 @@ static WfBuffers wf_carve(void *base, uint32_t capacity) {
     w.vlogs = (uint32_t *) take(c * 4 * EPSM_MAXV * WORDS_OF(VLog));
     w.hits = (Hit *) take(c * sizeof(Hit) * (1 + EPSM_MAXV)); w.occl = (uint32_t *) take(c * sizeof(uint32_t));
     w.q_closest = (QRay *) take(2 * c * sizeof(QRay)); w.q_any = (QRay *) take(c * sizeof(QRay));
-    w.live[0] = (uint32_t *) take(c * 4); w.live[1] = (uint32_t *) take(c * 4);
+    w.live0 = (uint32_t *) take(c * 4); w.live1 = (uint32_t *) take(c * 4);
     w.capacity = capacity; return w;
 }
 
@@ -364,7 +364,7 @@ __device__ __forceinline__ void queue_write(QRay *q, uint32_t idx, const Ray &r,
     d[0] = make_float4(r.o.x, r.o.y, r.o.z, r.maxt); d[1] = make_float4(r.d.x, r.d.y, r.d.z, __uint_as_float(out));
 }
 
-__global__ void __launch_bounds__(128) k_wf_init(DLaunch ln, uint64_t work_base, uint32_t n, const float *__restrict__ grad_in, WfBuffers wb) {
+__global__ void __launch_bounds__(128) k_wf_init(const __grid_constant__ DLaunch ln, uint64_t work_base, uint32_t n, const float *__restrict__ grad_in, WfBuffers wb) {
     const uint32_t i = blockIdx.x * 128 + threadIdx.x;
     bool push = false; WfState S;
     if (i < n) {
@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(128) k_wf_init(DLaunch ln, uint64_t work_base,
 #define WF_SPECULATE 1
 #endif
 template <bool ANY, bool COUNT>
-__global__ void __launch_bounds__(CTA) k_wf_trace(DScene sc, const QRay *__restrict__ queue, const uint32_t *__restrict__ count, uint32_t *head,
+__global__ void __launch_bounds__(CTA) k_wf_trace(const __grid_constant__ DScene sc, const QRay *__restrict__ queue, const uint32_t *__restrict__ count, uint32_t *head,
                                                   Hit *__restrict__ hits, uint32_t *__restrict__ occl, unsigned long long *counters) {
     __shared__ uint2 sstack[WF_STACK][CTA];
     uint2 lstack[WF_LSTACK];
@@ -544,14 +544,18 @@ __global__ void __launch_bounds__(CTA) k_wf_trace(DScene sc, const QRay *__restr
 }
 
 // `grad_pos` != NULL enables the first-vertex fast path (scatter passes; the record probe keeps every lane).
-__global__ void __launch_bounds__(128, EPSM_STAGEA_MINBLOCKS) k_wf_stage_a(DScene sc, DLaunch ln, uint32_t it, uint32_t n, WfBuffers wb, float *__restrict__ grad_pos) {
-    // the lane list pays only when few lanes are left (its order is scrambled by the concurrent appends): otherwise slot order
-    const bool listed = it >= WF_LIST_FROM && wb.counters[64 + it] < n / WF_LIST_SPARSE;
+// STRIDED (iterations ≥ WF_LIST_FROM): launched with a small fixed grid that strides over the compacted lane list when few
+// lanes are left (the list size lives on the device; its order is scrambled by the concurrent appends, so it pays only when
+// sparse) and over the slots otherwise.  The dense early iterations use the loop-free instantiation (one slot per thread).
+template <bool STRIDED>
+__global__ void __launch_bounds__(128, EPSM_STAGEA_MINBLOCKS) k_wf_stage_a(const __grid_constant__ DScene sc, const __grid_constant__ DLaunch ln, uint32_t it, uint32_t n, WfBuffers wb, float *__restrict__ grad_pos) {
+    const bool listed = STRIDED && wb.counters[64 + it] < n / WF_LIST_SPARSE;
     const uint32_t cnt = listed ? wb.counters[64 + it] : n;
-    // listed iterations are launched with a small fixed grid (the list size lives on the device) and stride over the list
-    for (uint32_t base = blockIdx.x * 128; base < cnt; base += gridDim.x * 128) {
+    uint32_t base = blockIdx.x * 128;
+    if (base >= cnt) return;
+    do {
     const uint32_t j = base + threadIdx.x;
-    const uint32_t i = listed ? (j < cnt ? wb.live[it & 1][j] : 0u) : j;
+    const uint32_t i = listed ? (j < cnt ? ((it & 1u) ? wb.live1 : wb.live0)[j] : 0u) : j;
     bool push = false; Ray sr;
     if (j < cnt && (listed || (wb.status[i] & 0xffu) == WF_LIVE)) {
         WfState S; const Hit h = wb.hits[i];
@@ -578,16 +582,19 @@ __global__ void __launch_bounds__(128, EPSM_STAGEA_MINBLOCKS) k_wf_stage_a(DScen
     }
     const uint32_t q = queue_push(wb.counters + 32 + it, push);
     if (push) queue_write(wb.q_any, q, sr, i);
-    }
+    base += gridDim.x * 128;
+    } while (STRIDED && base < cnt);
 }
 
-__global__ void __launch_bounds__(128, EPSM_STAGEB_MINBLOCKS) k_wf_stage_b(DScene sc, DLaunch ln, uint32_t it, uint32_t max_iter, uint32_t n, WfBuffers wb, bool keep_state) {
-    // the lane list pays only when few lanes are left (its order is scrambled by the concurrent appends): otherwise slot order
-    const bool listed = it >= WF_LIST_FROM && wb.counters[64 + it] < n / WF_LIST_SPARSE;
+template <bool STRIDED>
+__global__ void __launch_bounds__(128, EPSM_STAGEB_MINBLOCKS) k_wf_stage_b(const __grid_constant__ DScene sc, const __grid_constant__ DLaunch ln, uint32_t it, uint32_t max_iter, uint32_t n, WfBuffers wb, bool keep_state) {
+    const bool listed = STRIDED && wb.counters[64 + it] < n / WF_LIST_SPARSE;
     const uint32_t cnt = listed ? wb.counters[64 + it] : n;
-    for (uint32_t base = blockIdx.x * 128; base < cnt; base += gridDim.x * 128) {
+    uint32_t base = blockIdx.x * 128;
+    if (base >= cnt) return;
+    do {
     const uint32_t j = base + threadIdx.x;
-    const uint32_t i = listed ? (j < cnt ? wb.live[it & 1][j] : 0u) : j;
+    const uint32_t i = listed ? (j < cnt ? ((it & 1u) ? wb.live1 : wb.live0)[j] : 0u) : j;
     bool push_direct = false, push_next = false; Ray direct, next;
     if (j < cnt && (listed || (wb.status[i] & 0xffu) == WF_LIVE)) {
         WfState S; soa_load(S, wb.states, wb.capacity, i);
@@ -607,9 +614,10 @@ __global__ void __launch_bounds__(128, EPSM_STAGEB_MINBLOCKS) k_wf_stage_b(DScen
     if (push_next) queue_write(wb.q_closest, qn, next, i);
     if (it + 1 >= WF_LIST_FROM) {                           // the lanes of the next iteration, for its stage kernels
         const uint32_t l = queue_push(wb.counters + 64 + (it + 1), push_next);
-        if (push_next) wb.live[(it + 1) & 1][l] = i;
+        if (push_next) (((it + 1) & 1u) ? wb.live1 : wb.live0)[l] = i;       // (a select, not an index: indexing a kernel parameter forces a local copy of it)
     }
-    }
+    base += gridDim.x * 128;
+    } while (STRIDED && base < cnt);
 }
 
 __global__ void k_count_lanes(uint32_t n, WfBuffers wb, unsigned long long *counters) {
@@ -638,7 +646,7 @@ __device__ __forceinline__ void vlog_inactive(VLog &v) {
 #define EPSM_FINISH_LONG_BLOCKS 2
 #endif
 template <bool RECORD, int NV>
-__global__ void __launch_bounds__(128, NV < EPSM_MAXV ? EPSM_FINISH_SHORT_BLOCKS : EPSM_FINISH_LONG_BLOCKS) k_wf_finish(DScene sc, DLaunch ln, uint64_t work_base, uint32_t n, WfBuffers wb,
+__global__ void __launch_bounds__(128, NV < EPSM_MAXV ? EPSM_FINISH_SHORT_BLOCKS : EPSM_FINISH_LONG_BLOCKS) k_wf_finish(const __grid_constant__ DScene sc, const __grid_constant__ DLaunch ln, uint64_t work_base, uint32_t n, WfBuffers wb,
                                                    float *__restrict__ grad_pos, float *__restrict__ grad_nrm, float *__restrict__ records, bool skip_short) {
     const uint32_t i = blockIdx.x * 128 + threadIdx.x;
     if (i >= n) return;
@@ -689,7 +697,7 @@ __global__ void __launch_bounds__(128, NV < EPSM_MAXV ? EPSM_FINISH_SHORT_BLOCKS
 //  pass.  The film kernel owns one 8×4-pixel tile per CTA — work items are enumerated tile by tile, so a tile's samples
 //  are contiguous — accumulates the 5×5 Gaussian footprints in shared memory and flushes each film pixel once.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_pr_init(DLaunch ln, uint64_t work_base, uint32_t n, WfBuffers wb) {
+__global__ void __launch_bounds__(128) k_pr_init(const __grid_constant__ DLaunch ln, uint64_t work_base, uint32_t n, WfBuffers wb) {
     const uint32_t i = blockIdx.x * 128 + threadIdx.x;
     bool push = false; PrState S;
     if (i < n) {
@@ -707,7 +715,7 @@ __global__ void __launch_bounds__(128) k_pr_init(DLaunch ln, uint64_t work_base,
     if (push) queue_write(wb.q_closest, q, S.ray, i);
 }
 
-__global__ void __launch_bounds__(128, EPSM_STAGE_MINBLOCKS) k_pr_stage(DScene sc, DLaunch ln, uint32_t it, uint32_t n, WfBuffers wb) {
+__global__ void __launch_bounds__(128, EPSM_STAGE_MINBLOCKS) k_pr_stage(const __grid_constant__ DScene sc, const __grid_constant__ DLaunch ln, uint32_t it, uint32_t n, WfBuffers wb) {
     const uint32_t i = blockIdx.x * 128 + threadIdx.x;
     bool push_shadow = false, push_next = false; Ray shadow; PrState S;
     if (i < n && wb.status[i] == WF_LIVE) {
@@ -727,7 +735,7 @@ __global__ void __launch_bounds__(128, EPSM_STAGE_MINBLOCKS) k_pr_stage(DScene s
 
 // ImageBlock::put, coalesced branch (imageblock.cpp:414-494) into a tile-local RGBW block with a 2-pixel apron, then
 // HDRFilm::put_block (hdrfilm.cpp:286-320): pixels outside the film are the cropped border.
-__global__ void __launch_bounds__(128) k_pr_film(DScene sc, DLaunch ln, uint64_t work_base, uint32_t n, WfBuffers wb, float *__restrict__ film) {
+__global__ void __launch_bounds__(128) k_pr_film(const __grid_constant__ DScene sc, const __grid_constant__ DLaunch ln, uint64_t work_base, uint32_t n, WfBuffers wb, float *__restrict__ film) {
     __shared__ float ftile[FT_H][FT_W][4];
     for (int k = threadIdx.x; k < FT_H * FT_W * 4; k += 128) (&ftile[0][0][0])[k] = 0.f;
     __syncthreads();
@@ -982,14 +990,19 @@ cudaError_t epsm_launch_backward(const DScene &sc, DLaunch ln, const float *grad
             ev_end();
             ++launches;
             if (it == max_iter) break;
-            const uint32_t sgrid = it >= WF_LIST_FROM && grid > trace_grid * 4 ? trace_grid * 4 : grid;   // listed: stride over the lane list
-            k_wf_stage_a<<<sgrid, 128, 0, s>>>(sc, ln, it, n, wb, records ? nullptr : grad_pos); ++launches;
+            const bool strided = it >= WF_LIST_FROM && grid > trace_grid * 4;
+            const uint32_t sgrid = strided ? trace_grid * 4 : grid;
+            if (strided) k_wf_stage_a<true><<<sgrid, 128, 0, s>>>(sc, ln, it, n, wb, records ? nullptr : grad_pos);
+            else k_wf_stage_a<false><<<sgrid, 128, 0, s>>>(sc, ln, it, n, wb, records ? nullptr : grad_pos);
+            ++launches;
             ev_begin();
             if (counters) k_wf_trace<true, true><<<trace_grid, CTA, 0, s>>>(sc, wb.q_any, wb.counters + 32 + it, wb.counters + 48 + it, nullptr, wb.occl, counters);
             else k_wf_trace<true, false><<<trace_grid, CTA, 0, s>>>(sc, wb.q_any, wb.counters + 32 + it, wb.counters + 48 + it, nullptr, wb.occl, nullptr);
             ev_end();
             ++launches;
-            k_wf_stage_b<<<sgrid, 128, 0, s>>>(sc, ln, it, max_iter, n, wb, records != nullptr); ++launches;
+            if (strided) k_wf_stage_b<true><<<sgrid, 128, 0, s>>>(sc, ln, it, max_iter, n, wb, records != nullptr);
+            else k_wf_stage_b<false><<<sgrid, 128, 0, s>>>(sc, ln, it, max_iter, n, wb, records != nullptr);
+            ++launches;
         }
         if (records) { k_wf_finish<true, EPSM_MAXV><<<grid, 128, 0, s>>>(sc, ln, base, n, wb, nullptr, nullptr, records, false); ++launches; }
         else {
