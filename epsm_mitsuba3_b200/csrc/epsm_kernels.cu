@@ -15,6 +15,8 @@
 // the random stream (sampler.cpp:122-130) — is (pixel · spp + s) exactly as in the reference
 // wavefront (common.py:326-343).
 #include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
+#include <stdlib.h>
 #include <stdint.h>
 #include "epsm_device.cuh"
 #include "epsm_launch.h"
@@ -302,7 +304,8 @@ struct WfBuffers {
     QRay *q_closest /* 2C */, *q_any /* C */;
     uint32_t *counters;        // [0..15] closest-queue sizes, [16..31] closest heads, [32..47] any sizes, [48..63] any heads,
                                // [64 + it] size of the lane list of iteration it ≥ WF_LIST_FROM
-    uint32_t *live0, *live1;   // [C] each: lanes still on their path at iteration it (ping-pong on it & 1), appended by stage B(it − 1)
+    uint32_t *live0, *live1;   // [C] each: lanes still on their path at iteration it > 2 (ping-pong on it & 1), appended by stage B(it − 1)
+    uint32_t *live2;           // [C] the lanes of iteration 2, kept to the end: they are the lanes of the long-chain finish kernel
     uint32_t capacity;
 };
 #define WF_COUNTER_WORDS 96u
@@ -315,7 +318,7 @@ struct WfBuffers {
 size_t epsm_wf_workspace_bytes(uint32_t capacity) {
     size_t c = capacity;
     return c * (4 * (1 + WORDS_OF(WfState) + WORDS_OF(PathHead) + EPSM_MAXV * WORDS_OF(VLog)) + sizeof(Hit) * (1 + EPSM_MAXV)
-                + sizeof(uint32_t) + sizeof(QRay) * 3 + 2 * sizeof(uint32_t)) + WF_COUNTER_WORDS * sizeof(uint32_t) + 20 * 256;
+                + sizeof(uint32_t) + sizeof(QRay) * 3 + 3 * sizeof(uint32_t)) + WF_COUNTER_WORDS * sizeof(uint32_t) + 20 * 256;
 }
 static WfBuffers wf_carve(void *base, uint32_t capacity) {
     WfBuffers w; char *p = (char *) base; size_t c = capacity;
@@ -326,7 +329,7 @@ static WfBuffers wf_carve(void *base, uint32_t capacity) {
     w.vlogs = (uint32_t *) take(c * 4 * EPSM_MAXV * WORDS_OF(VLog));
     w.hits = (Hit *) take(c * sizeof(Hit) * (1 + EPSM_MAXV)); w.occl = (uint32_t *) take(c * sizeof(uint32_t));
     w.q_closest = (QRay *) take(2 * c * sizeof(QRay)); w.q_any = (QRay *) take(c * sizeof(QRay));
-    w.live0 = (uint32_t *) take(c * 4); w.live1 = (uint32_t *) take(c * 4);
+    w.live0 = (uint32_t *) take(c * 4); w.live1 = (uint32_t *) take(c * 4); w.live2 = (uint32_t *) take(c * 4);
     w.capacity = capacity; return w;
 }
 
@@ -348,6 +351,9 @@ __device__ __forceinline__ WorkItem wf_work_item(const DLaunch &ln, uint64_t w) 
     wi.valid = wi.px < W && wi.py < H && ty < ln.tile_y1 && wi.lane >= ln.lane_begin && wi.lane < ln.lane_end;
     return wi;
 }
+
+// Lane list of iteration `it` ≥ WF_LIST_FROM (selects, not an index: indexing a kernel parameter forces a local copy of it).
+__device__ __forceinline__ uint32_t *wf_lane_list(const WfBuffers &wb, uint32_t it) { return it == 2u ? wb.live2 : ((it & 1u) ? wb.live1 : wb.live0); }
 
 // Warp-aggregated queue append; returns the entry index (undefined when !pred).
 __device__ __forceinline__ uint32_t queue_push(uint32_t *count, bool pred) {
@@ -555,7 +561,7 @@ __global__ void __launch_bounds__(128, EPSM_STAGEA_MINBLOCKS) k_wf_stage_a(const
     if (base >= cnt) return;
     do {
     const uint32_t j = base + threadIdx.x;
-    const uint32_t i = listed ? (j < cnt ? ((it & 1u) ? wb.live1 : wb.live0)[j] : 0u) : j;
+    const uint32_t i = listed ? (j < cnt ? wf_lane_list(wb, it)[j] : 0u) : j;
     bool push = false; Ray sr;
     if (j < cnt && (listed || (wb.status[i] & 0xffu) == WF_LIVE)) {
         WfState S; const Hit h = wb.hits[i];
@@ -594,7 +600,7 @@ __global__ void __launch_bounds__(128, EPSM_STAGEB_MINBLOCKS) k_wf_stage_b(const
     if (base >= cnt) return;
     do {
     const uint32_t j = base + threadIdx.x;
-    const uint32_t i = listed ? (j < cnt ? ((it & 1u) ? wb.live1 : wb.live0)[j] : 0u) : j;
+    const uint32_t i = listed ? (j < cnt ? wf_lane_list(wb, it)[j] : 0u) : j;
     bool push_direct = false, push_next = false; Ray direct, next;
     if (j < cnt && (listed || (wb.status[i] & 0xffu) == WF_LIVE)) {
         WfState S; soa_load(S, wb.states, wb.capacity, i);
@@ -614,7 +620,7 @@ __global__ void __launch_bounds__(128, EPSM_STAGEB_MINBLOCKS) k_wf_stage_b(const
     if (push_next) queue_write(wb.q_closest, qn, next, i);
     if (it + 1 >= WF_LIST_FROM) {                           // the lanes of the next iteration, for its stage kernels
         const uint32_t l = queue_push(wb.counters + 64 + (it + 1), push_next);
-        if (push_next) (((it + 1) & 1u) ? wb.live1 : wb.live0)[l] = i;       // (a select, not an index: indexing a kernel parameter forces a local copy of it)
+        if (push_next) wf_lane_list(wb, it + 1)[l] = i;
     }
     base += gridDim.x * 128;
     } while (STRIDED && base < cnt);
@@ -646,10 +652,8 @@ __device__ __forceinline__ void vlog_inactive(VLog &v) {
 #define EPSM_FINISH_LONG_BLOCKS 2
 #endif
 template <bool RECORD, int NV>
-__global__ void __launch_bounds__(128, NV < EPSM_MAXV ? EPSM_FINISH_SHORT_BLOCKS : EPSM_FINISH_LONG_BLOCKS) k_wf_finish(const __grid_constant__ DScene sc, const __grid_constant__ DLaunch ln, uint64_t work_base, uint32_t n, WfBuffers wb,
-                                                   float *__restrict__ grad_pos, float *__restrict__ grad_nrm, float *__restrict__ records, bool skip_short) {
-    const uint32_t i = blockIdx.x * 128 + threadIdx.x;
-    if (i >= n) return;
+__device__ __forceinline__ void finish_lane(const DScene &sc, const DLaunch &ln, uint64_t work_base, uint32_t i, const WfBuffers &wb,
+                                            float *__restrict__ grad_pos, float *__restrict__ grad_nrm, float *__restrict__ records, bool skip_short) {
     const uint32_t status = wb.status[i], code = status & 0xffu;
     if (code == WF_NONE || code == WF_SCATTERED) return;
     const int n_written = (int) (status >> 8);
@@ -687,6 +691,17 @@ __global__ void __launch_bounds__(128, NV < EPSM_MAXV ? EPSM_FINISH_SHORT_BLOCKS
     calc_grad<NV>(P, ln.variant, n_logged, G, n_avail);
     if (RECORD) { if (NV == EPSM_MAXV) { const WorkItem wi = wf_work_item(ln, work_base + i); write_record(reinterpret_cast<const PathLog &>(P), reinterpret_cast<const PathGrads &>(G), n_logged, records + (wi.lane - ln.lane_begin) * EPSM_REC_FLOATS); } }
     else scatter_path<NV>(P, G, ln.variant, n_logged, n_avail, ln.max_depth, grad_pos, grad_nrm);
+}
+// LISTED (the long-chain scatter launch when those lanes are few): one thread per entry of `list`, the lanes that entered
+// iteration 2 — exactly the lanes with more than two logged vertices, appended by stage B(1) and sorted back into slot
+// order by the launcher (neighbouring pixels → similar control flow and neighbouring records).
+template <bool RECORD, int NV, bool LISTED>
+__global__ void __launch_bounds__(128, NV < EPSM_MAXV ? EPSM_FINISH_SHORT_BLOCKS : EPSM_FINISH_LONG_BLOCKS) k_wf_finish(const __grid_constant__ DScene sc, const __grid_constant__ DLaunch ln, uint64_t work_base, uint32_t n, WfBuffers wb,
+                                                   float *__restrict__ grad_pos, float *__restrict__ grad_nrm, float *__restrict__ records, bool skip_short,
+                                                   const uint32_t *__restrict__ list) {
+    const uint32_t j = blockIdx.x * 128 + threadIdx.x;
+    if (j >= n) return;                                       // LISTED: n = entries of the list
+    finish_lane<RECORD, NV>(sc, ln, work_base, LISTED ? list[j] : j, wb, grad_pos, grad_nrm, records, skip_short);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -977,6 +992,8 @@ cudaError_t epsm_launch_backward(const DScene &sc, DLaunch ln, const float *grad
     const uint32_t max_iter = wf_replay_iterations(ln.max_depth, ln.prune != 0);
     WfBuffers wb = wf_carve(workspace, capacity);
     uint64_t launches = 0;
+    uint32_t finish_sparse = WF_LIST_SPARSE;
+    if (const char *e = getenv("EPSM_FINISH_SPARSE")) finish_sparse = (uint32_t) strtoul(e, nullptr, 10);   // experiments: 0 never lists, 1 always
     for (uint64_t base = 0; base < total; base += capacity) {
         const uint32_t n = (uint32_t) ((total - base) < capacity ? (total - base) : capacity);
         const uint32_t grid = (n + 127) / 128;
@@ -1004,11 +1021,27 @@ cudaError_t epsm_launch_backward(const DScene &sc, DLaunch ln, const float *grad
             else k_wf_stage_b<false><<<sgrid, 128, 0, s>>>(sc, ln, it, max_iter, n, wb, records != nullptr);
             ++launches;
         }
-        if (records) { k_wf_finish<true, EPSM_MAXV><<<grid, 128, 0, s>>>(sc, ln, base, n, wb, nullptr, nullptr, records, false); ++launches; }
+        if (records) { k_wf_finish<true, EPSM_MAXV, false><<<grid, 128, 0, s>>>(sc, ln, base, n, wb, nullptr, nullptr, records, false, nullptr); ++launches; }
         else {
-            k_wf_finish<false, WF_SHORT_NV><<<grid, 128, 0, s>>>(sc, ln, base, n, wb, grad_pos, grad_nrm, nullptr, false);
-            k_wf_finish<false, EPSM_MAXV><<<grid, 128, 0, s>>>(sc, ln, base, n, wb, grad_pos, grad_nrm, nullptr, true);
-            launches += 2;
+            k_wf_finish<false, WF_SHORT_NV, false><<<grid, 128, 0, s>>>(sc, ln, base, n, wb, grad_pos, grad_nrm, nullptr, false, nullptr); ++launches;
+            if (max_iter > 2) {                               // lanes with more than two logged vertices exist only then
+                uint32_t n_long = 0;                          // = size of the lane list of iteration 2 (one 4-byte read-back per chunk)
+                cudaMemcpyAsync(&n_long, wb.counters + 64 + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, s);
+                cudaError_t e = cudaStreamSynchronize(s); if (e != cudaSuccess) return e;
+                const uint32_t *list = nullptr;
+                if (n_long != 0 && finish_sparse != 0 && n_long < n / finish_sparse) {
+                    // back into slot order: keys < n, sorted from live2 into live0 with live1 as scratch (all three are free now)
+                    int bits = 1; while (bits < 32 && (1ull << bits) < n) ++bits;
+                    size_t temp = 0;
+                    cub::DeviceRadixSort::SortKeys(nullptr, temp, wb.live2, wb.live0, (int) n_long, 0, bits, s);
+                    if (temp <= (size_t) capacity * sizeof(uint32_t) &&
+                        cub::DeviceRadixSort::SortKeys(wb.live1, temp, wb.live2, wb.live0, (int) n_long, 0, bits, s) == cudaSuccess) { list = wb.live0; launches += 3; }
+                    else list = wb.live2;
+                }
+                if (list) k_wf_finish<false, EPSM_MAXV, true><<<(n_long + 127) / 128, 128, 0, s>>>(sc, ln, base, n_long, wb, grad_pos, grad_nrm, nullptr, true, list);
+                else if (n_long != 0) k_wf_finish<false, EPSM_MAXV, false><<<grid, 128, 0, s>>>(sc, ln, base, n, wb, grad_pos, grad_nrm, nullptr, true, nullptr);
+                if (n_long != 0) ++launches;
+            }
         }
         if (counters) { k_count_lanes<<<grid, 128, 0, s>>>(n, wb, counters); ++launches; }
     }
