@@ -567,9 +567,12 @@ int epsm_sinkhorn_grad(epsm_ctx *ctx, const float *x, uint32_t n, const float *y
     // device layout of d_sink: [x 5n | y 5m]? (host calls only) then f_ba, f_aa (n) ×2, g_ab, g_bb (m) ×2, bary_xy, bary_xx (5n), grad (5n, host calls)
     const size_t cloud = mem == EPSM_MEM_HOST ? 5 * ((size_t) n + m) : 0, pots = 4 * ((size_t) n + m), bary = 10 * (size_t) n;
     const size_t gout = mem == EPSM_MEM_HOST ? 5 * (size_t) n : 0;
-    CK(ctx->d_sink.alloc(cloud + pots + bary + gout), "sinkhorn alloc");
+    const size_t packed = 2 * (epsm_sink_packed_floats(n) + epsm_sink_packed_floats(m));       // four jobs: columns y, x, x, y (16-byte aligned: first)
+    CK(ctx->d_sink.alloc(packed + cloud + pots + bary + gout), "sinkhorn alloc");
     CK(ctx->d_sink_loss.alloc(1), "sinkhorn alloc"); CK(ctx->d_sink_bbox.alloc(10), "sinkhorn alloc");
-    float *base = ctx->d_sink.p;
+    float4 *pk_y0 = reinterpret_cast<float4 *>(ctx->d_sink.p), *pk_x0 = pk_y0 + epsm_sink_packed_floats(m) / 4,
+           *pk_x1 = pk_x0 + epsm_sink_packed_floats(n) / 4, *pk_y1 = pk_x1 + epsm_sink_packed_floats(n) / 4;
+    float *base = ctx->d_sink.p + packed;
     const float *dx = x, *dy = y;
     if (mem == EPSM_MEM_HOST) {
         CK(cudaMemcpyAsync(base, x, 5 * (size_t) n * sizeof(float), cudaMemcpyHostToDevice, s), "H2D x");
@@ -601,20 +604,20 @@ int epsm_sinkhorn_grad(epsm_ctx *ctx, const float *x, uint32_t n, const float *y
     auto make = [&](int cur, int nxt, bool init) {
         SinkStep st; memset(&st, 0, sizeof(st));
         // f_ba: rows x, cols y, carries g_ab;  g_ab: rows y, cols x, carries f_ba;  f_aa: x,x carries f_aa;  g_bb: y,y carries g_bb
-        st.job[0] = SinkJob{dx, dy, init ? nullptr : g_ab[cur], f_ba[cur], f_ba[nxt], nullptr, n, m, lb, 0};
-        st.job[1] = SinkJob{dy, dx, init ? nullptr : f_ba[cur], g_ab[cur], g_ab[nxt], nullptr, m, n, la, 0};
-        st.job[2] = SinkJob{dx, dx, init ? nullptr : f_aa[cur], f_aa[cur], f_aa[nxt], nullptr, n, n, la, 0};
-        st.job[3] = SinkJob{dy, dy, init ? nullptr : g_bb[cur], g_bb[cur], g_bb[nxt], nullptr, m, m, lb, 0};
+        st.job[0] = SinkJob{dx, dy, init ? nullptr : g_ab[cur], f_ba[cur], f_ba[nxt], nullptr, n, m, lb, 0, pk_y0};
+        st.job[1] = SinkJob{dy, dx, init ? nullptr : f_ba[cur], g_ab[cur], g_ab[nxt], nullptr, m, n, la, 0, pk_x0};
+        st.job[2] = SinkJob{dx, dx, init ? nullptr : f_aa[cur], f_aa[cur], f_aa[nxt], nullptr, n, n, la, 0, pk_x1};
+        st.job[3] = SinkJob{dy, dy, init ? nullptr : g_bb[cur], g_bb[cur], g_bb[nxt], nullptr, m, m, lb, 0, pk_y1};
         return st;
     };
     int cur = 0;
     {   // initialisation at ε₀: potentials ← softmin(ε₀, C, ln weight)
         SinkStep st = make(1, 0, true); st.eps = (float) eps_list[0]; st.average = 0;
-        CK(epsm_launch_sink_step(st, 4, false, s), "k_sink_softmin"); ctx->launches += 1;
+        CK(epsm_launch_sink_step(st, 4, false, s), "k_sink_softmin"); ctx->launches += 2;
     }
     for (double eps : eps_list) {
         SinkStep st = make(cur, cur ^ 1, false); st.eps = (float) eps; st.average = 1;
-        CK(epsm_launch_sink_step(st, 4, false, s), "k_sink_softmin"); ctx->launches += 1;
+        CK(epsm_launch_sink_step(st, 4, false, s), "k_sink_softmin"); ctx->launches += 2;
         cur ^= 1;
     }
     {   // last extrapolation (un-averaged) + the softmax-weighted barycentres the gradient needs

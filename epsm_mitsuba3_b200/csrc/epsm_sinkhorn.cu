@@ -125,20 +125,15 @@ __global__ void __launch_bounds__(SK_THREADS, GRAD ? 2 : 3) k_sink_softmin(SinkS
             a2[r].m = -INFINITY; a2[r].s = pk(0.f, 0.f);
         }
         const u64 neg_halfk = pk(-halfk, -halfk);
-        float *tf = reinterpret_cast<float *>(tile);
         const ulonglong2 *tp = reinterpret_cast<const ulonglong2 *>(tile);
         for (uint32_t j0 = 0; j0 < job.n_cols; j0 += SK_TILE) {
             const uint32_t nt = job.n_cols - j0 < SK_TILE ? job.n_cols - j0 : SK_TILE, nq = (nt + 3) / 4;
             __syncthreads();
-            // column pair p = (2p, 2p+1) → 12 floats: (y0a y0b y1a y1b | y2a y2b y3a y3b | y4a y4b ha hb); the tail of the last
-            // group of four columns is padded with h = −∞ (a term of weight zero)
-            for (uint32_t k = threadIdx.x; k < 4 * nq; k += SK_THREADS) {
-                float *o = tf + 12 * (k >> 1) + (k & 1);
-                if (k < nt) {
-                    const float *c = job.cols + 5 * (size_t) (j0 + k);
-                    const float h = job.pot_cols ? fmaf(job.pot_cols[j0 + k], inv_eps, job.w_log) : job.w_log;
-                    o[0] = c[0]; o[2] = c[1]; o[4] = c[2]; o[6] = c[3]; o[8] = c[4]; o[10] = h * LOG2E;
-                } else { o[0] = o[2] = o[4] = o[6] = o[8] = 0.f; o[10] = -INFINITY; }
+            // the columns arrive packed by k_sink_pack: group of four columns = 6 float4
+            // (y0a y0b y1a y1b | y2a y2b y3a y3b | y4a y4b ha hb) × 2 pairs, h = (ln w + pot/ε)·log2 e, tail padded with h = −∞
+            {
+                const float4 *src = job.packed + (size_t) (j0 / 4) * 6;
+                for (uint32_t k = threadIdx.x; k < 6 * nq; k += SK_THREADS) tile[k] = src[k];
             }
             __syncthreads();
             // warp w walks groups w, w + 8, … of four columns: every lane reads the same 96 bytes (broadcast)
@@ -184,6 +179,19 @@ __global__ void __launch_bounds__(SK_THREADS, GRAD ? 2 : 3) k_sink_softmin(SinkS
     }
 }
 
+// Columns of every softmin of a step in the layout the packed inner loop reads (one thread per column, blockIdx.y = job).
+__global__ void k_sink_pack(SinkStep st) {
+    const SinkJob job = st.job[blockIdx.y];
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x, padded = (job.n_cols + 3u) & ~3u;
+    if (k >= padded) return;
+    float *o = reinterpret_cast<float *>(job.packed) + 12 * (size_t) (k >> 1) + (k & 1);
+    if (k < job.n_cols) {
+        const float *c = job.cols + 5 * (size_t) k;
+        const float h = job.pot_cols ? fmaf(job.pot_cols[k], 1.0f / st.eps, job.w_log) : job.w_log;
+        o[0] = c[0]; o[2] = c[1]; o[4] = c[2]; o[6] = c[3]; o[8] = c[4]; o[10] = h * LOG2E;
+    } else { o[0] = o[2] = o[4] = o[6] = o[8] = 0.f; o[10] = -INFINITY; }
+}
+
 // Bounding box of x ∪ y (geomloss max_diameter): out[0..4] = min, out[5..9] = max, as ordered-int atomics.
 __device__ __forceinline__ int f2ord(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
 __global__ void k_sink_bbox(const float *x, uint32_t n, const float *y, uint32_t m, int *out) {
@@ -227,7 +235,13 @@ cudaError_t epsm_launch_sink_step(const SinkStep &st, int n_jobs, bool grad, cud
     for (int k = 0; k < n_jobs; ++k) max_rows = st.job[k].n_rows > max_rows ? st.job[k].n_rows : max_rows;
     if (max_rows == 0) return cudaSuccess;
     const dim3 grid((max_rows + SK_ROWS - 1) / SK_ROWS, n_jobs);
-    if (grad) k_sink_softmin<true><<<grid, SK_THREADS, 0, s>>>(st); else k_sink_softmin<false><<<grid, SK_THREADS, 0, s>>>(st);
+    if (grad) k_sink_softmin<true><<<grid, SK_THREADS, 0, s>>>(st);
+    else {
+        uint32_t max_cols = 0;
+        for (int k = 0; k < n_jobs; ++k) max_cols = st.job[k].n_cols > max_cols ? st.job[k].n_cols : max_cols;
+        k_sink_pack<<<dim3((max_cols + 3 + 255) / 256, n_jobs), 256, 0, s>>>(st);
+        k_sink_softmin<false><<<grid, SK_THREADS, 0, s>>>(st);
+    }
     return cudaGetLastError();
 }
 

@@ -14,7 +14,9 @@ struct SinkJob {
     uint32_t n_rows, n_cols;
     float w_log;                       // ln of the uniform column weight
     uint32_t _pad;
+    float4 *packed;                    // scratch of 6·ceil(n_cols/4) float4: the columns as k_sink_pack lays them out for this step
 };
+inline size_t epsm_sink_packed_floats(uint32_t n_cols) { return 24 * (size_t) ((n_cols + 3) / 4); }
 struct SinkStep { SinkJob job[4]; float eps; int average; };
 
 cudaError_t epsm_launch_sink_bbox(const float *x, uint32_t n, const float *y, uint32_t m, int *out10, cudaStream_t s);
