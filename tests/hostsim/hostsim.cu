@@ -65,6 +65,16 @@ void sim_scene_copy_accel(sim_scene *s, float *nodes, float *tris) {
     if (nodes) memcpy(nodes, s->hs.bvh.nodes.data(), s->hs.bvh.nodes.size() * sizeof(f4));
     if (tris) memcpy(tris, s->hs.bvh.tris.data(), s->hs.bvh.tris.size() * sizeof(f4));
 }
+// The product's BSDF code on its own (for the known answers of the reference's BSDF tests).
+void sim_bsdf_sample(sim_scene *s, uint32_t bsdf_id, const float *wi, float s1, float s2x, float s2y, float *out12) {
+    BSample bs; bsdf_sample(s->hs.bsdfs[bsdf_id], mk3(wi[0], wi[1], wi[2]), s1, s2x, s2y, true, bs);
+    const float v[12] = {bs.wo.x, bs.wo.y, bs.wo.z, bs.pdf, bs.eta, (float) bs.type, bs.weight.x, bs.weight.y, bs.weight.z, bs.hf.x, bs.hf.y, bs.hf.z};
+    memcpy(out12, v, sizeof(v));
+}
+void sim_bsdf_eval_pdf(sim_scene *s, uint32_t bsdf_id, const float *wi, const float *wo, float *out4) {
+    f3 value; float pdf; bsdf_eval_pdf(s->hs.bsdfs[bsdf_id], mk3(wi[0], wi[1], wi[2]), mk3(wo[0], wo[1], wo[2]), value, pdf);
+    out4[0] = value.x; out4[1] = value.y; out4[2] = value.z; out4[3] = pdf;
+}
 void sim_scene_stats(sim_scene *s, uint64_t *out) {
     out[0] = s->hs.faces.size() / 3; out[1] = s->hs.bvh.nodes.size() / EPSM_NODE_F4; out[2] = s->hs.bvh.depth;
 }

@@ -29,6 +29,8 @@ def lib():
         L.sim_scene_refit.argtypes = [vp, u32, vp]; L.sim_scene_refit.restype = C.c_double
         L.sim_scene_cost.argtypes = [vp]; L.sim_scene_cost.restype = C.c_double
         L.sim_scene_copy_accel.argtypes = [vp, vp, vp]
+        L.sim_bsdf_sample.argtypes = [vp, u32, vp, C.c_float, C.c_float, C.c_float, vp]
+        L.sim_bsdf_eval_pdf.argtypes = [vp, u32, vp, vp, vp]
         L.sim_trace.argtypes = [vp, vp, u64, vp, i32, vp]
         L.sim_sampler_stream.argtypes = [u32, u64, u64, u32, vp]
         L.sim_sample_rays.argtypes = [vp, u32, u32, u32, u64, u64, vp]
@@ -74,6 +76,16 @@ class SimScene:
         nodes = np.zeros((st["n_nodes"], 32), np.float32); tris = np.zeros((st["n_triangles"], 16), np.float32)
         lib().sim_scene_copy_accel(self.h, nodes.ctypes.data, tris.ctypes.data)
         return nodes, tris
+
+    def bsdf_sample(self, bsdf_id, wi, s1, s2):
+        wi = np.asarray(wi, np.float32); out = np.zeros(12, np.float32)
+        lib().sim_bsdf_sample(self.h, bsdf_id, wi.ctypes.data, s1, s2[0], s2[1], out.ctypes.data)
+        return dict(wo=out[0:3], pdf=out[3], eta=out[4], type=int(out[5]), weight=out[6:9], hf=out[9:12])
+
+    def bsdf_eval_pdf(self, bsdf_id, wi, wo):
+        wi = np.asarray(wi, np.float32); wo = np.asarray(wo, np.float32); out = np.zeros(4, np.float32)
+        lib().sim_bsdf_eval_pdf(self.h, bsdf_id, wi.ctypes.data, wo.ctypes.data, out.ctypes.data)
+        return out[:3], out[3]
 
     def trace(self, rays, any_hit=False, counters=None):
         rays = np.ascontiguousarray(rays, np.float32); n = rays.shape[0]
