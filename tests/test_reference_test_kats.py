@@ -171,3 +171,24 @@ def test_area_emitter_direction_sample(orc):   # area.cpp:82-200 / test_area.py 
             assert np.isclose(ds["pdf"], ds["dist"] ** 2 / (cos_l * area), rtol=1e-4)       # shape.cpp:352-383: area → solid angle
             n_checked += 1
     assert n_checked > 0
+
+
+def test_imageblock_put_against_brute_force(orc):     # src/render/tests/test_imageblock.py:37-120
+    """ImageBlock::put against the brute-force reference the reference's test builds: gaussian filter, no border (HDRFilm crops
+    it, hdrfilm.cpp:286-320), offset (0, 0), normalize False — the configuration EPSMIntegrator.render uses."""
+    o = orc.OracleScene(S.cornell_box(8, 1, 8))
+    for j in range(5):
+        for i in range(5):
+            pos = (np.float32(3.3 + 0.25 * i), np.float32(3 + 0.25 * j))      # one of the points is exactly on a boundary
+            film = np.zeros((6, 6, 4), np.float32)
+            o.film_put(film, pos, [1.0, 0.5, 0.25])
+            fx = np.array([o.filter_eval(float(np.float32(x + 0.5) - pos[0])) for x in range(6)])
+            fy = np.array([o.filter_eval(float(np.float32(y + 0.5) - pos[1])) for y in range(6)])
+            ref = np.outer(fy, fx)
+            assert np.allclose(film[..., 3], ref, atol=1e-5), (i, j)
+            assert np.allclose(film[..., 0], ref, atol=1e-5) and np.allclose(film[..., 2], 0.25 * ref, atol=1e-5)
+    # the filter itself: gaussian, stddev 0.5, zero at the radius 2 (gaussian.cpp:48-103)
+    assert abs(o.filter_eval(2.0)) < 1e-5 and o.filter_eval(-2.5) == 0.0          # max(poly, 0): the radius is where the polynomial crosses zero
+    g = lambda x: np.exp(-x * x / (2 * 0.25)) - np.exp(-4 / (2 * 0.25))
+    for x in (0.0, 0.3, 1.0, 1.7):
+        assert abs(o.filter_eval(x) - g(x)) < 1e-3          # degree-9 Remez fit of the Gaussian (gaussian.cpp:57-89)
