@@ -310,8 +310,8 @@ struct WfBuffers {
 };
 #define WF_COUNTER_WORDS 96u
 // From this iteration on the stage kernels run over the compacted lane list instead of over all slots: by then a few
-// percent of the lanes are left and a full-grid launch is a 0.6 ms floor of status reads (33.5 M slots); in the dense
-// early iterations slot order (coalesced records) wins (profiles/r01_f_refit_iteration.md).
+// percent of the lanes are left and a full-grid launch is a 0.6 ms floor (262 144 CTAs that read one status word each);
+// in the dense early iterations slot order (coalesced records) wins (profiles/r01_f_refit_iteration.md).
 #define WF_LIST_FROM 2u
 #define WF_LIST_SPARSE 8u   // … and only when fewer than 1/8 of the chunk's slots are still alive
 
