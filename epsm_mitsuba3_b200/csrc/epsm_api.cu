@@ -568,11 +568,14 @@ int epsm_sinkhorn_grad(epsm_ctx *ctx, const float *x, uint32_t n, const float *y
     const size_t cloud = mem == EPSM_MEM_HOST ? 5 * ((size_t) n + m) : 0, pots = 4 * ((size_t) n + m), bary = 10 * (size_t) n;
     const size_t gout = mem == EPSM_MEM_HOST ? 5 * (size_t) n : 0;
     const size_t packed = 2 * (epsm_sink_packed_floats(n) + epsm_sink_packed_floats(m));       // four jobs: columns y, x, x, y (16-byte aligned: first)
-    CK(ctx->d_sink.alloc(packed + cloud + pots + bary + gout), "sinkhorn alloc");
+    const size_t tinfo = 2 * (epsm_sink_tile_floats(n) + epsm_sink_tile_floats(m));
+    CK(ctx->d_sink.alloc(packed + tinfo + cloud + pots + bary + gout), "sinkhorn alloc");
     CK(ctx->d_sink_loss.alloc(1), "sinkhorn alloc"); CK(ctx->d_sink_bbox.alloc(10), "sinkhorn alloc");
     float4 *pk_y0 = reinterpret_cast<float4 *>(ctx->d_sink.p), *pk_x0 = pk_y0 + epsm_sink_packed_floats(m) / 4,
            *pk_x1 = pk_x0 + epsm_sink_packed_floats(n) / 4, *pk_y1 = pk_x1 + epsm_sink_packed_floats(n) / 4;
-    float *base = ctx->d_sink.p + packed;
+    float *ti_y0 = ctx->d_sink.p + packed, *ti_x0 = ti_y0 + epsm_sink_tile_floats(m), *ti_x1 = ti_x0 + epsm_sink_tile_floats(n),
+          *ti_y1 = ti_x1 + epsm_sink_tile_floats(n);
+    float *base = ctx->d_sink.p + packed + tinfo;
     const float *dx = x, *dy = y;
     if (mem == EPSM_MEM_HOST) {
         CK(cudaMemcpyAsync(base, x, 5 * (size_t) n * sizeof(float), cudaMemcpyHostToDevice, s), "H2D x");
@@ -604,10 +607,10 @@ int epsm_sinkhorn_grad(epsm_ctx *ctx, const float *x, uint32_t n, const float *y
     auto make = [&](int cur, int nxt, bool init) {
         SinkStep st; memset(&st, 0, sizeof(st));
         // f_ba: rows x, cols y, carries g_ab;  g_ab: rows y, cols x, carries f_ba;  f_aa: x,x carries f_aa;  g_bb: y,y carries g_bb
-        st.job[0] = SinkJob{dx, dy, init ? nullptr : g_ab[cur], f_ba[cur], f_ba[nxt], nullptr, n, m, lb, 0, pk_y0};
-        st.job[1] = SinkJob{dy, dx, init ? nullptr : f_ba[cur], g_ab[cur], g_ab[nxt], nullptr, m, n, la, 0, pk_x0};
-        st.job[2] = SinkJob{dx, dx, init ? nullptr : f_aa[cur], f_aa[cur], f_aa[nxt], nullptr, n, n, la, 0, pk_x1};
-        st.job[3] = SinkJob{dy, dy, init ? nullptr : g_bb[cur], g_bb[cur], g_bb[nxt], nullptr, m, m, lb, 0, pk_y1};
+        st.job[0] = SinkJob{dx, dy, init ? nullptr : g_ab[cur], f_ba[cur], f_ba[nxt], nullptr, n, m, lb, 0, pk_y0, ti_y0};
+        st.job[1] = SinkJob{dy, dx, init ? nullptr : f_ba[cur], g_ab[cur], g_ab[nxt], nullptr, m, n, la, 0, pk_x0, ti_x0};
+        st.job[2] = SinkJob{dx, dx, init ? nullptr : f_aa[cur], f_aa[cur], f_aa[nxt], nullptr, n, n, la, 0, pk_x1, ti_x1};
+        st.job[3] = SinkJob{dy, dy, init ? nullptr : g_bb[cur], g_bb[cur], g_bb[nxt], nullptr, m, m, lb, 0, pk_y1, ti_y1};
         return st;
     };
     int cur = 0;

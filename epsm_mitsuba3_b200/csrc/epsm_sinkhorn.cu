@@ -126,9 +126,45 @@ __global__ void __launch_bounds__(SK_THREADS, GRAD ? 2 : 3) k_sink_softmin(SinkS
         }
         const u64 neg_halfk = pk(-halfk, -halfk);
         const ulonglong2 *tp = reinterpret_cast<const ulonglong2 *>(tile);
-        for (uint32_t j0 = 0; j0 < job.n_cols; j0 += SK_TILE) {
-            const uint32_t nt = job.n_cols - j0 < SK_TILE ? job.n_cols - j0 : SK_TILE, nq = (nt + 3) / 4;
+        // Far-tile test.  Every term of a tile is at most hmax − halfk·d², d = distance between the boxes of this CTA's rows and
+        // of the tile's points; once that is 40 binary orders below the running maximum of every row, the tile cannot change an
+        // fp32 sum and is skipped (ε-scaling makes the kernel narrow: at ε = blur² most tiles of a pixel-grid cloud are far).
+        // Tiles are visited from the nearest outwards so that the maxima are set early.
+        float rlo[5], rhi[5];
+#pragma unroll
+        for (int d = 0; d < 5; ++d) {
+            rlo[d] = fminf(x[0][d], x[1][d]); rhi[d] = fmaxf(x[0][d], x[1][d]);
+            for (int of = 16; of > 0; of >>= 1) { rlo[d] = fminf(rlo[d], __shfl_xor_sync(0xffffffffu, rlo[d], of)); rhi[d] = fmaxf(rhi[d], __shfl_xor_sync(0xffffffffu, rhi[d], of)); }
+        }
+        const uint32_t n_tiles = (job.n_cols + SK_TILE - 1) / SK_TILE;
+        auto tile_bound = [&](uint32_t t) {
+            const float *ti = job.tile_info + 12 * (size_t) t;
+            float d2 = 0.f;
+#pragma unroll
+            for (int d = 0; d < 5; ++d) { const float g = fmaxf(fmaxf(ti[d] - rhi[d], rlo[d] - ti[5 + d]), 0.f); d2 = fmaf(g, g, d2); }
+            return fmaf(-halfk, d2, ti[10]);
+        };
+        uint32_t t_near = 0; float b_near = -INFINITY;
+        for (uint32_t t = 0; t < n_tiles; ++t) { const float b = tile_bound(t); if (b > b_near) { b_near = b; t_near = t; } }
+        __shared__ float s_mmin[2];
+        uint32_t visited = 0;
+        for (uint32_t step = 0; step < 2 * n_tiles; ++step) {
+            // step 0: the nearest tile; step 2o − 1: o tiles further; step 2o: o tiles nearer the start (all CTA-uniform)
+            const uint32_t off = (step + 1) >> 1;
+            uint32_t t;
+            if (step == 0u) t = t_near;
+            else if (step & 1u) { if (t_near + off >= n_tiles) continue; t = t_near + off; }
+            else { if (off > t_near) continue; t = t_near - off; }
+            const uint32_t slot = visited++ & 1u;                               // double-buffered: a skip has no second barrier
+            if (warp == 0) {
+                float mm = fminf(a2[0].m, a2[1].m);
+                for (int of = 16; of > 0; of >>= 1) mm = fminf(mm, __shfl_xor_sync(0xffffffffu, mm, of));
+                if (lane == 0) s_mmin[slot] = mm;
+            }
             __syncthreads();
+            if (tile_bound(t) < s_mmin[slot] - 40.f) continue;                  // CTA-uniform
+            const uint32_t j0 = t * SK_TILE;
+            const uint32_t nt = job.n_cols - j0 < SK_TILE ? job.n_cols - j0 : SK_TILE, nq = (nt + 3) / 4;
             // the columns arrive packed by k_sink_pack: group of four columns = 6 float4
             // (y0a y0b y1a y1b | y2a y2b y3a y3b | y4a y4b ha hb) × 2 pairs, h = (ln w + pot/ε)·log2 e, tail padded with h = −∞
             {
@@ -179,17 +215,42 @@ __global__ void __launch_bounds__(SK_THREADS, GRAD ? 2 : 3) k_sink_softmin(SinkS
     }
 }
 
-// Columns of every softmin of a step in the layout the packed inner loop reads (one thread per column, blockIdx.y = job).
-__global__ void k_sink_pack(SinkStep st) {
+// Columns of every softmin of a step in the layout the packed inner loop reads: one CTA per tile of SK_TILE columns
+// (blockIdx.y = job).  Also writes the tile's record for the far-tile test of k_sink_softmin: bounding box of its points
+// and the largest h·log2 e among them (12 floats: lo[5], hi[5], hmax, –).
+__global__ void __launch_bounds__(256) k_sink_pack(SinkStep st) {
     const SinkJob job = st.job[blockIdx.y];
-    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x, padded = (job.n_cols + 3u) & ~3u;
-    if (k >= padded) return;
-    float *o = reinterpret_cast<float *>(job.packed) + 12 * (size_t) (k >> 1) + (k & 1);
-    if (k < job.n_cols) {
-        const float *c = job.cols + 5 * (size_t) k;
-        const float h = job.pot_cols ? fmaf(job.pot_cols[k], 1.0f / st.eps, job.w_log) : job.w_log;
-        o[0] = c[0]; o[2] = c[1]; o[4] = c[2]; o[6] = c[3]; o[8] = c[4]; o[10] = h * LOG2E;
-    } else { o[0] = o[2] = o[4] = o[6] = o[8] = 0.f; o[10] = -INFINITY; }
+    const uint32_t j0 = blockIdx.x * SK_TILE;
+    if (j0 >= job.n_cols) return;
+    const uint32_t padded = (job.n_cols + 3u) & ~3u;
+    const float inv_eps = 1.0f / st.eps;
+    float lo[5], hi[5], hmax = -INFINITY;
+#pragma unroll
+    for (int d = 0; d < 5; ++d) { lo[d] = INFINITY; hi[d] = -INFINITY; }
+    for (uint32_t k = j0 + threadIdx.x; k < j0 + SK_TILE && k < padded; k += 256) {
+        float *o = reinterpret_cast<float *>(job.packed) + 12 * (size_t) (k >> 1) + (k & 1);
+        if (k < job.n_cols) {
+            const float *c = job.cols + 5 * (size_t) k;
+            const float h = (job.pot_cols ? fmaf(job.pot_cols[k], inv_eps, job.w_log) : job.w_log) * LOG2E;
+            o[0] = c[0]; o[2] = c[1]; o[4] = c[2]; o[6] = c[3]; o[8] = c[4]; o[10] = h;
+#pragma unroll
+            for (int d = 0; d < 5; ++d) { lo[d] = fminf(lo[d], c[d]); hi[d] = fmaxf(hi[d], c[d]); }
+            hmax = fmaxf(hmax, h);
+        } else { o[0] = o[2] = o[4] = o[6] = o[8] = 0.f; o[10] = -INFINITY; }
+    }
+    __shared__ float red[8][11];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 0; d < 5; ++d)
+        for (int of = 16; of > 0; of >>= 1) { lo[d] = fminf(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], of)); hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], of)); }
+    for (int of = 16; of > 0; of >>= 1) hmax = fmaxf(hmax, __shfl_xor_sync(0xffffffffu, hmax, of));
+    if (lane == 0) { for (int d = 0; d < 5; ++d) { red[warp][d] = lo[d]; red[warp][5 + d] = hi[d]; } red[warp][10] = hmax; }
+    __syncthreads();
+    if (threadIdx.x < 11) {
+        float v = red[0][threadIdx.x];
+        for (int w = 1; w < 8; ++w) v = threadIdx.x < 5 ? fminf(v, red[w][threadIdx.x]) : fmaxf(v, red[w][threadIdx.x]);
+        job.tile_info[12 * (size_t) blockIdx.x + threadIdx.x] = v;
+    }
 }
 
 // Bounding box of x ∪ y (geomloss max_diameter): out[0..4] = min, out[5..9] = max, as ordered-int atomics.
@@ -239,7 +300,7 @@ cudaError_t epsm_launch_sink_step(const SinkStep &st, int n_jobs, bool grad, cud
     else {
         uint32_t max_cols = 0;
         for (int k = 0; k < n_jobs; ++k) max_cols = st.job[k].n_cols > max_cols ? st.job[k].n_cols : max_cols;
-        k_sink_pack<<<dim3((max_cols + 3 + 255) / 256, n_jobs), 256, 0, s>>>(st);
+        k_sink_pack<<<dim3((max_cols + SK_TILE - 1) / SK_TILE, n_jobs), 256, 0, s>>>(st);
         k_sink_softmin<false><<<grid, SK_THREADS, 0, s>>>(st);
     }
     return cudaGetLastError();

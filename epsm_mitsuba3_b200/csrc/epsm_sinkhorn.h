@@ -15,7 +15,9 @@ struct SinkJob {
     float w_log;                       // ln of the uniform column weight
     uint32_t _pad;
     float4 *packed;                    // scratch of 6·ceil(n_cols/4) float4: the columns as k_sink_pack lays them out for this step
+    float *tile_info;                  // scratch of 12 floats per 1024-column tile: box of its points and largest h·log2 e
 };
+inline size_t epsm_sink_tile_floats(uint32_t n_cols) { return 12 * (size_t) ((n_cols + 1023) / 1024); }
 inline size_t epsm_sink_packed_floats(uint32_t n_cols) { return 24 * (size_t) ((n_cols + 3) / 4); }
 struct SinkStep { SinkJob job[4]; float eps; int average; };
 
