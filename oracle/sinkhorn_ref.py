@@ -99,7 +99,7 @@ def match_sinkhorn(render_rgb, target_rgb, res, blur=0.01, scaling=0.9, dtype=to
     x.requires_grad_(True)
     loss = sinkhorn_loss(x, y, blur, scaling)
     (g,) = torch.autograd.grad(loss * res * res, [x])
-    return g.numpy(), float(loss)
+    return g.numpy(), float(loss.detach())
 
 
 def grad_barycentric(render_rgb, target_rgb, res, blur=0.01, scaling=0.9, dtype=torch.float64):
