@@ -8,6 +8,10 @@
 #include <cstring>
 #include <thread>
 
+#ifndef EPSM_SAH_BINS
+#define EPSM_SAH_BINS 32   // measured on the room: 16 → 43.4 nodes per path, 32 → 42.4 (traversal −2 %), 64 → 42.8
+#endif
+
 namespace {
 
 struct Box {
@@ -38,7 +42,7 @@ struct Builder {
         n.first = first; n.count = count; n.left = n.right = 0;
         if (count <= 1) return;
         // binned SAH over the three axes
-        const int NB = 16;
+        const int NB = EPSM_SAH_BINS;
         float best_cost = FLT_MAX; int best_axis = -1, best_bin = -1;
         for (int a = 0; a < 3; ++a) {
             float lo = cb.lo[a], ext = cb.hi[a] - lo;
