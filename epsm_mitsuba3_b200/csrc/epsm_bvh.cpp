@@ -12,6 +12,10 @@
 #define EPSM_SAH_BINS 32   // measured on the room: 16 → 43.4 nodes per path, 32 → 42.4 (traversal −2 %), 64 → 42.8
 #endif
 
+#ifndef EPSM_SAH_CT
+#define EPSM_SAH_CT 2.0f     // cost of visiting a node relative to one triangle test; measured on the room (nodes / triangles per path, traversal ms): 0.5 → 42.3 / 7.4, 21.7; 1 → 40.9 / 10.3, 20.9; 2 → 38.7 / 16.5, 20.7; ≥ 3 saturates (every leaf full); 8-triangle leaves lose
+#endif
+
 namespace {
 
 struct Box {
@@ -65,7 +69,7 @@ struct Builder {
             }
         }
         float leaf_cost = n.box.half_area() * count;
-        if (count <= EPSM_MAX_LEAF && (best_axis < 0 || leaf_cost <= best_cost + 0.5f * n.box.half_area())) return;   // leaf
+        if (count <= EPSM_MAX_LEAF && (best_axis < 0 || leaf_cost <= best_cost + EPSM_SAH_CT * n.box.half_area())) return;   // leaf
         uint32_t mid;
         if (best_axis >= 0) {
             float lo = cb.lo[best_axis], scale = NB / (cb.hi[best_axis] - lo);
@@ -113,7 +117,7 @@ struct Collapser {
         for (int i = 0; i < nc; ++i) {
             const BNode &c = B.nodes[ch[i]];
             for (int a = 0; a < 3; ++a) { lo[a][i] = c.box.lo[a] - pad; hi[a][i] = c.box.hi[a] + pad; }
-            if (c.count > 0) ref[i] = ~(int32_t) ((emit_leaf(c) << 2) | (c.count - 1));
+            if (c.count > 0) ref[i] = ~(int32_t) ((emit_leaf(c) << EPSM_LEAF_BITS) | (c.count - 1));
         }
         uint32_t n_inner = 0;
         for (int i = 0; i < nc; ++i) {
@@ -188,7 +192,7 @@ void epsm_build_bvh4(const float *pos, const uint32_t *faces, size_t nf, Bvh4 &o
         float lo[3][4], hi[3][4]; int32_t ref[4];
         for (int i = 0; i < 4; ++i) { for (int a = 0; a < 3; ++a) { lo[a][i] = 1e30f; hi[a][i] = -1e30f; } ref[i] = 0x7fffffff; }
         for (int a = 0; a < 3; ++a) { lo[a][0] = B.nodes[0].box.lo[a] - pad; hi[a][0] = B.nodes[0].box.hi[a] + pad; }
-        ref[0] = ~(int32_t) ((C.emit_leaf(B.nodes[0]) << 2) | (B.nodes[0].count - 1));
+        ref[0] = ~(int32_t) ((C.emit_leaf(B.nodes[0]) << EPSM_LEAF_BITS) | (B.nodes[0].count - 1));
         f4 *n = &out.nodes[0];
         for (int a = 0; a < 3; ++a) { n[a] = f4{lo[a][0], lo[a][1], lo[a][2], lo[a][3]}; n[3 + a] = f4{hi[a][0], hi[a][1], hi[a][2], hi[a][3]}; }
         float rf[4]; memcpy(rf, ref, 16); n[6] = f4{rf[0], rf[1], rf[2], rf[3]};

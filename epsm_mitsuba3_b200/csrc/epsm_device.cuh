@@ -267,7 +267,7 @@ EPSM_HD float refit_node(f4 *nodes, uint32_t idx, const f4 *tris, const uint32_t
         if (ref == 0x7fffffff) continue;
         float clo[3], chi[3];
         if (ref < 0) {
-            const uint32_t code = ~(uint32_t) ref, first = code >> 2, cnt = (code & 3u) + 1u;
+            const uint32_t code = ~(uint32_t) ref, first = code >> EPSM_LEAF_BITS, cnt = (code & (EPSM_MAX_LEAF - 1u)) + 1u;
             for (int a = 0; a < 3; ++a) { clo[a] = 3.402823466e38f; chi[a] = -3.402823466e38f; }
             for (uint32_t i = 0; i < cnt; ++i) {
                 const uint32_t prim = f2u(tris[(size_t) (first + i) * EPSM_TRI_F4].w);
@@ -316,7 +316,7 @@ EPSM_HDN Hit bvh_trace(const DScene &sc, const Ray &ray, TStack &st, uint32_t &n
         if (tn > hit.t) continue;
         if ((int32_t) ref < 0) {
             // ---- leaf: up to 4 triangles, one 256-bit + one 64-bit load each ----
-            uint32_t code = ~ref, first = code >> 2, cnt = (code & 3u) + 1u;
+            uint32_t code = ~ref, first = code >> EPSM_LEAF_BITS, cnt = (code & (EPSM_MAX_LEAF - 1u)) + 1u;
             for (uint32_t i = 0; i < cnt; ++i) {
                 const f4 *tp = sc.tris + (size_t) (first + i) * EPSM_TRI_F4;
                 const f8 ab = ldg8(tp); const f2 c = ldg2(tp + 2); const f4 a = ab.a, b = ab.b;

@@ -484,7 +484,7 @@ __global__ void __launch_bounds__(CTA) k_wf_trace(const __grid_constant__ DScene
         if (m_leaf != 0u && (m_in == 0u || __popc(m_leaf) >= WF_LEAF_MIN)) {
             // ---- leaf phase ----
             if (has_leaf) {
-                const uint32_t code = ~leaf, first = code >> 2, cnt = (code & 3u) + 1u;
+                const uint32_t code = ~leaf, first = code >> EPSM_LEAF_BITS, cnt = (code & (EPSM_MAX_LEAF - 1u)) + 1u;
                 bool done = false;
                 for (uint32_t k = 0; k < cnt; ++k) {
                     const f4 *tp = sc.tris + (size_t) (first + k) * EPSM_TRI_F4;

@@ -3,7 +3,7 @@
 // HBM layout:
 //   nodes      BVH4, 128 B per node, SoA inside the node: 8 × float4
 //                [0] lo.x[4] [1] lo.y[4] [2] lo.z[4] [3] hi.x[4] [4] hi.y[4] [5] hi.z[4] [6] child[4] [7] pad
-//              child >= 0: inner node index; child < 0: leaf, ~child = (first_tri << 2) | (count-1);
+//              child >= 0: inner node index; child < 0: leaf, ~child = (first_tri << EPSM_LEAF_BITS) | (count-1);
 //              empty slots have child == 0x7fffffff and are skipped.  One node = one 128-byte line, fetched
 //              as three 256-bit loads (sm_100a LDG.E.256) for the boxes + one 128-bit load for the children.
 //   tris       64-byte slots (32-byte aligned), 48 B of payload per triangle in BVH leaf order: 4 × float4
@@ -30,7 +30,10 @@ struct f4 { float x, y, z, w; };
 #define EPSM_NODE_F4   8      // float4 per BVH node
 #define EPSM_TRI_F4    4      // float4 per triangle slot (3 used: EPSM_TRI_BYTES of payload)
 #define EPSM_TRI_BYTES 48     // algorithmic bytes per triangle test
-#define EPSM_MAX_LEAF  4
+#ifndef EPSM_LEAF_BITS
+#define EPSM_LEAF_BITS 2      // bits of a leaf reference that hold (count − 1)
+#endif
+#define EPSM_MAX_LEAF  (1 << EPSM_LEAF_BITS)
 #define EPSM_MAXV      5      // logged vertices per path (epsm.py:648)
 #define EPSM_MAX_ITER  6      // sample_path iteration cap (epsm.py:549)
 
