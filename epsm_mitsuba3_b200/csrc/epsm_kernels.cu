@@ -730,7 +730,10 @@ __global__ void __launch_bounds__(128) k_pr_init(const __grid_constant__ DLaunch
     if (push) queue_write(wb.q_closest, q, S.ray, i);
 }
 
-__global__ void __launch_bounds__(128, EPSM_STAGE_MINBLOCKS) k_pr_stage(const __grid_constant__ DScene sc, const __grid_constant__ DLaunch ln, uint32_t it, uint32_t n, WfBuffers wb) {
+#ifndef EPSM_PR_MINBLOCKS
+#define EPSM_PR_MINBLOCKS 5    // measured (room primal, ms): 4 CTAs/SM (113 registers) 188.4, 5 → 186.5, 6 → 186.7, 8 → 186.9
+#endif
+__global__ void __launch_bounds__(128, EPSM_PR_MINBLOCKS) k_pr_stage(const __grid_constant__ DScene sc, const __grid_constant__ DLaunch ln, uint32_t it, uint32_t n, WfBuffers wb) {
     const uint32_t i = blockIdx.x * 128 + threadIdx.x;
     bool push_shadow = false, push_next = false; Ray shadow; PrState S;
     if (i < n && wb.status[i] == WF_LIVE) {
