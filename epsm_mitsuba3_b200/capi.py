@@ -54,9 +54,9 @@ class SceneStats(C.Structure):
 # Every symbol include/epsm_b200.h declares (tests/test_capi.py checks the library exports all of them).
 EXPORTS = [
     "epsm_create", "epsm_destroy", "epsm_last_error", "epsm_scene_upload",
-    "epsm_scene_update_vertices", "epsm_scene_commit", "epsm_scene_refit", "epsm_scene_accel_cost", "epsm_scene_accel_raw", "epsm_trace",
+    "epsm_scene_update_vertices", "epsm_scene_update_normals", "epsm_scene_vertex_buffers", "epsm_scene_commit", "epsm_scene_refit", "epsm_scene_accel_cost", "epsm_scene_accel_raw", "epsm_trace",
     "epsm_render_accumulate", "epsm_film_clear", "epsm_film_raw", "epsm_film_develop", "epsm_render",
-    "epsm_render_backward", "epsm_path_records", "epsm_sampler_stream", "epsm_sample_rays",
+    "epsm_render_backward", "epsm_vertex_normals_backward", "epsm_path_records", "epsm_sampler_stream", "epsm_sample_rays",
     "epsm_set_sample_range", "epsm_set_full_replay", "epsm_set_trace_profiling", "epsm_get_trace_profile", "epsm_scene_get_stats", "epsm_launch_count", "epsm_stream", "epsm_synchronize",
     "epsm_sinkhorn_grad",
 ]
@@ -90,6 +90,8 @@ def load_library() -> C.CDLL:
     lib.epsm_scene_upload.argtypes = [vp, C.POINTER(MeshDesc), u32, C.POINTER(BsdfDesc), u32,
                                       C.POINTER(EmitterDesc), u32, C.POINTER(SensorDesc), u32]
     lib.epsm_scene_update_vertices.argtypes = [vp, u32, fp, i32]
+    lib.epsm_scene_update_normals.argtypes = [vp, u32, fp, i32]
+    lib.epsm_scene_vertex_buffers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(u64)]
     lib.epsm_scene_commit.argtypes = [vp]
     lib.epsm_scene_refit.argtypes = [vp]
     lib.epsm_scene_accel_cost.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(u64)]
@@ -101,6 +103,7 @@ def load_library() -> C.CDLL:
     lib.epsm_film_develop.argtypes = [vp, u32, fp, i32]
     lib.epsm_render.argtypes = [vp, u32, u32, u32, u32, u32, fp, i32]
     lib.epsm_render_backward.argtypes = [vp, i32, u32, u32, u32, u32, u32, fp, fp, fp, i32, u64, u64, vp]
+    lib.epsm_vertex_normals_backward.argtypes = [vp, fp, fp, i32]
     lib.epsm_path_records.argtypes = [vp, i32, u32, u32, u32, u32, u32, fp, u64, u64, fp, i32]
     lib.epsm_sampler_stream.argtypes = [vp, u32, u64, u64, u32, fp, i32]
     lib.epsm_sample_rays.argtypes = [vp, u32, u32, u32, u64, u64, fp, i32]

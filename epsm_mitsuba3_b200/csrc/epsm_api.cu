@@ -244,6 +244,31 @@ int epsm_scene_update_vertices(epsm_ctx *ctx, uint32_t mesh_id, const float *pos
     return EPSM_OK;
 }
 
+int epsm_scene_update_normals(epsm_ctx *ctx, uint32_t mesh_id, const float *normals, int mem) {
+    if (!ctx) return EPSM_E_INVALID;
+    if (!ctx->have_scene) return fail(ctx, EPSM_E_NOSCENE, "no scene uploaded");
+    if (mesh_id >= ctx->hs.meshes.size() || !normals) return fail(ctx, EPSM_E_INVALID, "bad mesh id / normals");
+    const DMesh &m = ctx->hs.meshes[mesh_id];
+    if (!m.has_normals)                                                  // mesh.cpp:258-260
+        return fail(ctx, EPSM_E_INVALID, "Storing new normals in a Mesh that didn't have normals at construction time is not implemented yet.");
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    const size_t nb = 3 * (size_t) m.v_cnt * sizeof(float);
+    float *dst = ctx->d_nrm.p + 3 * (size_t) m.v_off;
+    CK(cudaMemcpyAsync(dst, normals, nb, mem == EPSM_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream), "normals copy");
+    CK(cudaMemcpyAsync(ctx->hs.nrm.data() + 3 * (size_t) m.v_off, dst, nb, cudaMemcpyDeviceToHost, ctx->stream), "normals mirror");
+    CK(cudaStreamSynchronize(ctx->stream), "normals sync");
+    return EPSM_OK;
+}
+
+int epsm_scene_vertex_buffers(epsm_ctx *ctx, float **positions, float **normals, uint64_t *n_floats) {
+    if (!ctx) return EPSM_E_INVALID;
+    if (!ctx->have_scene) return fail(ctx, EPSM_E_NOSCENE, "no scene uploaded");
+    if (positions) *positions = ctx->d_pos.p;
+    if (normals) *normals = ctx->d_nrm.p;
+    if (n_floats) *n_floats = ctx->hs.pos.size();
+    return EPSM_OK;
+}
+
 namespace {
 // Bring the host mirror of the positions up to date (device-pointer updates are mirrored lazily).
 int pull_stale_positions(epsm_ctx *ctx) {
@@ -469,6 +494,39 @@ int epsm_render_backward(epsm_ctx *ctx, int variant, uint32_t sensor, uint32_t s
         CK(cudaStreamSynchronize(ctx->stream), "backward sync");
     }
     if (counters) return fetch_counters(ctx, counters);
+    return EPSM_OK;
+}
+
+int epsm_vertex_normals_backward(epsm_ctx *ctx, const float *grad_nrm, float *grad_pos, int mem) {
+    if (!ctx) return EPSM_E_INVALID;
+    if (!ctx->have_scene) return fail(ctx, EPSM_E_NOSCENE, "no scene uploaded");
+    if (!grad_nrm || !grad_pos) return fail(ctx, EPSM_E_INVALID, "grad_nrm / grad_pos is NULL");
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    const size_t n_v = ctx->hs.pos.size();
+    const float *d_gn; int rc = to_device(ctx, grad_nrm, n_v, mem, ctx->stage_c, &d_gn); if (rc) return rc;
+    float *d_gp = grad_pos;
+    if (mem == EPSM_MEM_HOST) {
+        CK(ctx->stage_b.alloc(n_v), "stage alloc"); d_gp = ctx->stage_b.p;
+        CK(cudaMemcpyAsync(d_gp, grad_pos, n_v * sizeof(float), cudaMemcpyHostToDevice, ctx->stream), "H2D grad_pos");
+    }
+    CK(ctx->stage_a.alloc(n_v), "scratch alloc");
+    const size_t nm = ctx->hs.meshes.size();
+    auto wants = [&](const DMesh &m) { return m.has_normals && (m.flags & EPSM_MESH_GRAD); };
+    for (size_t i = 0; i < nm;) {                       // one launch group per run of adjacent differentiable meshes with normals
+        const DMesh &m = ctx->hs.meshes[i];
+        if (!wants(m)) { ++i; continue; }
+        size_t j = i + 1;
+        while (j < nm && wants(ctx->hs.meshes[j])) ++j;
+        const DMesh &l = ctx->hs.meshes[j - 1];
+        CK(epsm_launch_vertex_normals_backward(ctx->d_pos.p, ctx->d_faces.p, m.f_off, l.f_off + l.f_cnt - m.f_off, m.v_off, l.v_off + l.v_cnt - m.v_off,
+                                               d_gn, d_gp, ctx->stage_a.p, ctx->stream), "vertex normals backward");
+        ctx->launches += 4;
+        i = j;
+    }
+    if (mem == EPSM_MEM_HOST) {
+        CK(cudaMemcpyAsync(grad_pos, d_gp, n_v * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream), "D2H grad_pos");
+        CK(cudaStreamSynchronize(ctx->stream), "normals backward sync");
+    }
     return EPSM_OK;
 }
 

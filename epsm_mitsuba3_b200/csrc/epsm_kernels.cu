@@ -16,6 +16,8 @@
 // wavefront (common.py:326-343).
 #include <cuda_runtime.h>
 #include <cub/device/device_radix_sort.cuh>
+#include <cooperative_groups.h>
+#include <cooperative_groups/reduce.h>
 #include <stdlib.h>
 #include <stdint.h>
 #include "epsm_device.cuh"
@@ -145,20 +147,18 @@ __global__ void k_film_develop(const float *__restrict__ film, uint64_t n_pixels
 //  codegen, ext/drjit/ext/drjit-core/src/cuda_eval.cpp:808-905)
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void scatter3(float *__restrict__ buf, uint32_t idx, f3 v, bool pred) {
+    namespace cg = cooperative_groups;
     pred = pred && (v.x != 0.f || v.y != 0.f || v.z != 0.f);
     if (!pred) return;
-    const unsigned act = __activemask();
-    const unsigned peers = __match_any_sync(act, idx);
-    const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
-    if (peers != (1u << lane)) {
-        f3 sum = mk3(0, 0, 0);
-        for (unsigned rem = peers; rem; rem &= rem - 1) {
-            const int src = __ffs(rem) - 1;
-            sum.x += __shfl_sync(peers, v.x, src); sum.y += __shfl_sync(peers, v.y, src); sum.z += __shfl_sync(peers, v.z, src);
-        }
-        v = sum;
+    // Opportunistic aggregation: the lanes that reached this point together (coalesced_threads — the supported way to
+    // name them; a bare __activemask() guarantees nothing about who arrives at the following intrinsic) are
+    // partitioned by target vertex (match.any), each partition is summed and its first lane issues the atomics.
+    const cg::coalesced_group g = cg::coalesced_threads();
+    const cg::coalesced_group peers = cg::labeled_partition(g, idx);
+    if (peers.size() > 1) {
+        v.x = cg::reduce(peers, v.x, cg::plus<float>()); v.y = cg::reduce(peers, v.y, cg::plus<float>()); v.z = cg::reduce(peers, v.z, cg::plus<float>());
     }
-    if (lane == leader) {
+    if (peers.thread_rank() == 0) {
         float *d = buf + 3 * (size_t) idx;
         atomicAdd(d, v.x); atomicAdd(d + 1, v.y); atomicAdd(d + 2, v.z);          // red.global.add.f32
     }
@@ -357,13 +357,11 @@ __device__ __forceinline__ uint32_t *wf_lane_list(const WfBuffers &wb, uint32_t 
 
 // Warp-aggregated queue append; returns the entry index (undefined when !pred).
 __device__ __forceinline__ uint32_t queue_push(uint32_t *count, bool pred) {
-    const unsigned m = __ballot_sync(__activemask(), pred);
     if (!pred) return 0;
-    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    const cooperative_groups::coalesced_group g = cooperative_groups::coalesced_threads();      // the lanes that push now
     uint32_t base = 0;
-    if (lane == leader) base = atomicAdd(count, __popc(m));
-    base = __shfl_sync(m, base, leader);
-    return base + __popc(m & ((1u << lane) - 1));
+    if (g.thread_rank() == 0) base = atomicAdd(count, g.size());
+    return g.shfl(base, 0) + g.thread_rank();
 }
 __device__ __forceinline__ void queue_write(QRay *q, uint32_t idx, const Ray &r, uint32_t out) {
     float4 *d = reinterpret_cast<float4 *>(q + idx);
@@ -851,6 +849,63 @@ __global__ void k_normals_finish(float *__restrict__ nrm, uint32_t v_off, uint32
     n = l != 0.f ? n * (1.0f / l) : mk3(1, 0, 0);
     d[0] = n.x; d[1] = n.y; d[2] = n.z;
 }
+// Adjoint of the two kernels above (the reference differentiates recompute_vertex_normals through Dr.Jit's AD when
+// params.update() re-derives the normals from AD-attached positions, mesh.cpp:82-87,311-330, so the sh_frame.n·g3 seed
+// of epsm.py:644-645 reaches vertex_positions).  `acc` holds the un-normalised sums Σ n·angle (k_normals_accumulate);
+// k_normals_bwd_vertex turns it in place into dL/d(sum) = (g − n̂ (n̂·g)) / |sum|; k_normals_bwd_face pushes that through
+// n = normalize(cross(e1, e2)) and angle_k = safe_acos(dot(normalize(a), normalize(b))) into the positions.
+__global__ void k_normals_bwd_vertex(float *__restrict__ acc, const float *__restrict__ grad_nrm, uint32_t v_off, uint32_t v_cnt) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= v_cnt) return;
+    float *d = acc + 3 * (size_t) (v_off + i);
+    const f3 s = mk3(d[0], d[1], d[2]), g = ld3(grad_nrm, v_off + i);
+    const float l = len3(s);
+    f3 o = mk3(0, 0, 0);
+    if (l != 0.f) { const f3 n = s * (1.0f / l); o = (g - n * dot3(n, g)) * (1.0f / l); }      // the bogus (1,0,0) normal is a constant
+    d[0] = o.x; d[1] = o.y; d[2] = o.z;
+}
+__device__ __forceinline__ void normalize_bwd(const f3 &v, const f3 &g_unit, f3 &g_v) {      // u = v/|v|: g_v = (g_u − u (u·g_u)) / |v|
+    const float l = len3(v);
+    if (!(l > 0.f)) { g_v = mk3(0, 0, 0); return; }
+    const f3 u = v * (1.0f / l);
+    g_v = (g_unit - u * dot3(u, g_unit)) * (1.0f / l);
+}
+__global__ void k_normals_bwd_face(const float *__restrict__ pos, const uint32_t *__restrict__ faces, uint32_t f_off, uint32_t f_cnt,
+                                   const float *__restrict__ g_sum, float *__restrict__ grad_pos) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= f_cnt) return;
+    const uint32_t *f = faces + 3 * (size_t) (f_off + i);
+    const uint32_t fi[3] = {f[0], f[1], f[2]};
+    const f3 v[3] = {ld3(pos, fi[0]), ld3(pos, fi[1]), ld3(pos, fi[2])};
+    const f3 e1 = v[1] - v[0], e2 = v[2] - v[0], c = cross3(e1, e2), n = norm3(c);
+    f3 gv[3] = {mk3(0, 0, 0), mk3(0, 0, 0), mk3(0, 0, 0)};
+    f3 g_n = mk3(0, 0, 0);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int k1 = (k + 1) % 3, k2 = (k + 2) % 3;
+        const f3 a = v[k1] - v[k], b = v[k2] - v[k], d0 = norm3(a), d1 = norm3(b);
+        const float x = dot3(d0, d1), xc = fminf(fmaxf(x, -1.f), 1.f), ang = acosf(xc);
+        const f3 nn = n * ang;
+        if (!(nn.x == nn.x && nn.y == nn.y && nn.z == nn.z)) continue;               // the forward skipped this corner
+        const f3 gs = ld3(g_sum, fi[k]);
+        g_n = g_n + gs * ang;
+        const float g_ang = dot3(n, gs);
+        if (x > -1.f && x < 1.f) {                                                     // safe_acos: no gradient in the clamped range
+            const float g_x = -g_ang / sqrtf(1.f - x * x);
+            f3 g_a, g_b; normalize_bwd(a, d1 * g_x, g_a); normalize_bwd(b, d0 * g_x, g_b);
+            gv[k1] = gv[k1] + g_a; gv[k2] = gv[k2] + g_b; gv[k] = gv[k] - g_a - g_b;
+        }
+    }
+    f3 g_c; normalize_bwd(c, g_n, g_c);
+    const f3 g_e1 = cross3(e2, g_c), g_e2 = cross3(g_c, e1);
+    gv[1] = gv[1] + g_e1; gv[2] = gv[2] + g_e2; gv[0] = gv[0] - g_e1 - g_e2;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        if (!(gv[k].x == gv[k].x && gv[k].y == gv[k].y && gv[k].z == gv[k].z)) continue;
+        float *d = grad_pos + 3 * (size_t) fi[k];
+        atomicAdd(d, gv[k].x); atomicAdd(d + 1, gv[k].y); atomicAdd(d + 2, gv[k].z);
+    }
+}
 __global__ void k_zero_range(float *__restrict__ p, uint64_t off, uint64_t n) {
     uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[off + i] = 0.f;
@@ -1067,6 +1122,16 @@ cudaError_t epsm_launch_vertex_normals(const float *pos, const uint32_t *faces, 
     k_zero_range<<<(3 * v_cnt + 255) / 256, 256, 0, s>>>(nrm, 3 * (uint64_t) v_off, 3 * (uint64_t) v_cnt);
     k_normals_accumulate<<<(f_cnt + 255) / 256, 256, 0, s>>>(pos, faces, f_off, f_cnt, nrm);
     k_normals_finish<<<(v_cnt + 255) / 256, 256, 0, s>>>(nrm, v_off, v_cnt);
+    return cudaGetLastError();
+}
+
+cudaError_t epsm_launch_vertex_normals_backward(const float *pos, const uint32_t *faces, uint32_t f_off, uint32_t f_cnt, uint32_t v_off, uint32_t v_cnt,
+                                                const float *grad_nrm, float *grad_pos, float *scratch, cudaStream_t s) {
+    if (v_cnt == 0 || f_cnt == 0) return cudaSuccess;
+    k_zero_range<<<(3 * v_cnt + 255) / 256, 256, 0, s>>>(scratch, 3 * (uint64_t) v_off, 3 * (uint64_t) v_cnt);
+    k_normals_accumulate<<<(f_cnt + 255) / 256, 256, 0, s>>>(pos, faces, f_off, f_cnt, scratch);
+    k_normals_bwd_vertex<<<(v_cnt + 255) / 256, 256, 0, s>>>(scratch, grad_nrm, v_off, v_cnt);
+    k_normals_bwd_face<<<(f_cnt + 255) / 256, 256, 0, s>>>(pos, faces, f_off, f_cnt, scratch, grad_pos);
     return cudaGetLastError();
 }
 

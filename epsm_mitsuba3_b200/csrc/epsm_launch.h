@@ -22,6 +22,9 @@ cudaError_t epsm_launch_sampler_stream(uint32_t seed, uint64_t lane_begin, uint6
 cudaError_t epsm_launch_sample_rays(const DSensor &se, uint32_t seed, uint32_t spp, uint64_t lane_begin, uint64_t n_lanes, float *out, cudaStream_t s);
 cudaError_t epsm_launch_vertex_normals(const float *pos, const uint32_t *faces, uint32_t f_off, uint32_t f_cnt, uint32_t v_off, uint32_t v_cnt,
                                        float *nrm, cudaStream_t s);
+// grad_pos += Jᵀ·grad_nrm for the vertex range: adjoint of epsm_launch_vertex_normals.  `scratch`: 3·(total vertices) floats.
+cudaError_t epsm_launch_vertex_normals_backward(const float *pos, const uint32_t *faces, uint32_t f_off, uint32_t f_cnt, uint32_t v_off, uint32_t v_cnt,
+                                                const float *grad_nrm, float *grad_pos, float *scratch, cudaStream_t s);
 // Device refit of the BVH4 (topology of the last host build kept): rewrites triangle records and all boxes from `pos`.
 // `scratch` holds epsm_refit_scratch_words(n_nodes) uint32; after the launch scratch[0] = bits of max|coordinate| and the
 // double at scratch + 2 = epsm_bvh4_cost of the refitted tree.

@@ -163,11 +163,34 @@ class Scene:
                 torch.cuda.current_stream(self.device).synchronize()
         else:
             positions = np.ascontiguousarray(positions, np.float32)
-        assert positions.size if isinstance(positions, np.ndarray) else positions.numel() == 3 * self.data.meshes[mesh_id].positions.shape[0]
+        n = positions.size if isinstance(positions, np.ndarray) else positions.numel()
+        if n != 3 * self.data.meshes[mesh_id].positions.shape[0]:
+            raise EpsmError(f"mesh {mesh_id}: vertex_positions has {n} values, expected {3 * self.data.meshes[mesh_id].positions.shape[0]}")
         addr, mem = self._ptr(positions)
         self._check(self.lib.epsm_scene_update_vertices(self.ctx, mesh_id, addr, mem))
         if commit:
             self.apply_updates()
+
+    def update_normals(self, mesh_id: int, normals):
+        """params['<mesh>.vertex_normals'] = normals; params.update() (epsm_scene_update_normals)."""
+        if isinstance(normals, torch.Tensor):
+            normals = normals.detach().to(torch.float32).contiguous()
+            if normals.is_cuda:
+                torch.cuda.current_stream(self.device).synchronize()
+        else:
+            normals = np.ascontiguousarray(normals, np.float32)
+        n = normals.size if isinstance(normals, np.ndarray) else normals.numel()
+        if n != 3 * self.data.meshes[mesh_id].positions.shape[0]:
+            raise EpsmError(f"mesh {mesh_id}: vertex_normals has {n} values, expected {3 * self.data.meshes[mesh_id].positions.shape[0]}")
+        addr, mem = self._ptr(normals)
+        self._check(self.lib.epsm_scene_update_normals(self.ctx, mesh_id, addr, mem))
+
+    def vertex_buffers(self):
+        """Zero-copy (V,3) device views of the scene's current vertex positions and normals."""
+        pp, pn, n = C.c_void_p(), C.c_void_p(), C.c_uint64()
+        self._check(self.lib.epsm_scene_vertex_buffers(self.ctx, C.byref(pp), C.byref(pn), C.byref(n)))
+        shape = (n.value // 3, 3)
+        return _wrap_device(pp.value, shape, self.device), _wrap_device(pn.value, shape, self.device)
 
     def commit(self):
         """Host rebuild of the BVH (what the reference does on every parameters_changed, scene.cpp:304-336)."""
@@ -272,6 +295,15 @@ class Scene:
                                                   self._ptr(grad_pos)[0], self._ptr(grad_nrm)[0], mem, lane_begin, lane_end, cp))
         return grad_pos, grad_nrm
 
+    def vertex_normals_backward(self, grad_nrm, grad_pos):
+        """grad_pos += Jᵀ·grad_nrm: the adjoint of Mesh::recompute_vertex_normals (mesh.cpp:311-330) for every
+        differentiable mesh with vertex normals (epsm_vertex_normals_backward).  Same memory space for both."""
+        a, mem = self._ptr(grad_nrm); b, mem2 = self._ptr(grad_pos)
+        if mem != mem2:
+            raise EpsmError("grad_nrm and grad_pos must live in the same memory space")
+        self._check(self.lib.epsm_vertex_normals_backward(self.ctx, a, b, mem))
+        return grad_pos
+
     def path_records(self, variant, sensor, seed, spp, max_depth, rr_depth, grad_in, lane_begin, lane_end):
         grad_in = np.ascontiguousarray(grad_in, np.float32)
         out = np.zeros((lane_end - lane_begin, capi.REC_FLOATS), np.float32)
@@ -327,12 +359,16 @@ class EPSMIntegrator:
             s0, s1 = sample_shard(spp, dist.get_rank(), dist.get_world_size())
             if s1 > s0:
                 scene.set_sample_range(s0, s1)
-                scene.render_accumulate(sensor, seed, spp, self.max_depth, self.rr_depth)
-                scene.set_sample_range(0, 0)
+                try:
+                    scene.render_accumulate(sensor, seed, spp, self.max_depth, self.rr_depth)
+                finally:
+                    scene.set_sample_range(0, 0)      # never leave the context sharded for later calls
             film = scene.film_raw(sensor)
             scene.synchronize()
             dist.all_reduce(film)                     # every rank splatted its samples of every pixel: sum the RGBW film
-            _sync_torch(scene.device)
+        # the library's stream writes into a fresh torch allocation: order torch's stream first (the caching allocator
+        # may hand back a block with pending torch-stream work)
+        _sync_torch(scene.device)
         self.primal_image = scene.film_develop(sensor)
         scene.synchronize()
         return self.primal_image
@@ -361,8 +397,10 @@ class EPSMIntegrator:
         _sync_torch(scene.device)
         if s1 > s0:
             scene.set_sample_range(s0, s1)
-            scene.render_backward_raw(self.variant, sensor, seed, spp, self.max_depth, self.rr_depth, g, buf[0], buf[1])
-            scene.set_sample_range(0, 0)
+            try:
+                scene.render_backward_raw(self.variant, sensor, seed, spp, self.max_depth, self.rr_depth, g, buf[0], buf[1])
+            finally:
+                scene.set_sample_range(0, 0)
         scene.synchronize()
         if dist is not None:
             dist.all_reduce(buf)                        # one NCCL allreduce of the mesh-gradient buffer per step
@@ -402,19 +440,27 @@ def load_dict(d: dict):
 #  SceneParameters / mi.render
 # ------------------------------------------------------------------------------------------------
 class SceneParameters(dict):
-    """mi.traverse(scene) restricted to mesh vertex data (util.py:24-228)."""
+    """mi.traverse(scene) restricted to mesh vertex data (util.py:24-228): `<mesh>.vertex_positions` for every mesh and
+    `<mesh>.vertex_normals` for the meshes that have vertex normals (mesh.cpp:71-75), flat float32 tensors like the
+    reference's buffers."""
 
     def __init__(self, scene: Scene):
         super().__init__()
         self.scene = scene
         self._dirty = set()
+        self._mesh_of = {}          # vertex_positions key → mesh id
+        self._nrm_of = {}           # vertex_normals key   → mesh id
+        seen = set()
         for i, m in enumerate(scene.data.meshes):
-            key = f"{m.name}.vertex_positions"
-            if key in self:
-                key = f"{m.name}_{i}.vertex_positions"
+            name = m.name if m.name not in seen else f"{m.name}_{i}"
+            seen.add(name)
+            key = f"{name}.vertex_positions"
             super().__setitem__(key, torch.from_numpy(m.positions.copy()).to(scene.device))
-            self._mesh_of = getattr(self, "_mesh_of", {})
             self._mesh_of[key] = i
+            if m.normals is not None:
+                nkey = f"{name}.vertex_normals"
+                super().__setitem__(nkey, torch.from_numpy(m.normals.copy()).to(scene.device))
+                self._nrm_of[nkey] = i
 
     def __setitem__(self, key, value):
         if key not in self:
@@ -426,24 +472,53 @@ class SceneParameters(dict):
         if values:
             for k, v in values.items():
                 self[k] = v
-        staged = [(self._mesh_of[key], torch.as_tensor(self[key]).detach().to(torch.float32).reshape(-1, 3).contiguous()) for key in self._dirty]
-        staged.sort(key=lambda t: t[0])
-        if any(t.is_cuda for _, t in staged):
+        stage = lambda key: torch.as_tensor(self[key]).detach().to(torch.float32).reshape(-1, 3).contiguous()
+        staged = sorted(((self._mesh_of[k], stage(k)) for k in self._dirty if k in self._mesh_of), key=lambda t: t[0])
+        staged_n = sorted(((self._nrm_of[k], stage(k)) for k in self._dirty if k in self._nrm_of), key=lambda t: t[0])
+        if any(t.is_cuda for _, t in staged + staged_n):
             torch.cuda.current_stream(self.scene.device).synchronize()      # once: the tensors above are complete
         for mesh_id, t in staged:
             self.scene.update_vertices(mesh_id, t, commit=False, synced=True)
-        if self._dirty:
-            self.scene.apply_updates()
+        if staged:
+            self.scene.apply_updates()          # positions changed: normals re-derived (mesh.cpp:82-87), BVH refreshed
+            _, nrm = self.scene.vertex_buffers()
+            voff = self.scene.voff
+            moved = {i for i, _ in staged}
+            for nkey, i in self._nrm_of.items():
+                if i in moved and nkey not in self._dirty:
+                    dict.__setitem__(self, nkey, nrm[int(voff[i]):int(voff[i + 1])].clone())
+            self.scene.synchronize()
+        for mesh_id, t in staged_n:             # explicit normals win over the recomputed ones (keys = [vertex_normals])
+            self.scene.update_normals(mesh_id, t)
         self._dirty.clear()
 
     def accumulate_gradients(self, grad_pos: torch.Tensor, grad_nrm: torch.Tensor):
+        """dr.grad of the parameters after render_backward: `vertex_normals` entries that require grad receive grad_nrm;
+        `vertex_positions` entries receive grad_pos plus grad_nrm pulled back through recompute_vertex_normals — the
+        normals are a differentiable function of the positions after params.update() (mesh.cpp:82-87,311-330)."""
         voff = self.scene.voff
+        for key, i in self._nrm_of.items():
+            t = self[key]
+            if isinstance(t, torch.Tensor) and t.requires_grad:
+                g = grad_nrm[int(voff[i]):int(voff[i + 1])].reshape(t.shape)
+                t.grad = g.clone() if t.grad is None else t.grad + g
+        total = total_position_gradient(self.scene, grad_pos, grad_nrm)
         for key, i in self._mesh_of.items():
             t = self[key]
             if not (isinstance(t, torch.Tensor) and t.requires_grad):
                 continue
-            g = grad_pos[int(voff[i]):int(voff[i + 1])].reshape(t.shape)
+            g = total[int(voff[i]):int(voff[i + 1])].reshape(t.shape)
             t.grad = g.clone() if t.grad is None else t.grad + g
+
+
+def total_position_gradient(scene: Scene, grad_pos: torch.Tensor, grad_nrm: torch.Tensor) -> torch.Tensor:
+    """grad_pos + Jᵀ·grad_nrm (adjoint of Mesh::recompute_vertex_normals, epsm_vertex_normals_backward)."""
+    total = grad_pos.clone()
+    if any(m.normals is not None and m.grad for m in scene.data.meshes):
+        _sync_torch(scene.device)
+        scene.vertex_normals_backward(grad_nrm.contiguous(), total)
+        scene.synchronize()
+    return total
 
 
 def traverse(scene: Scene) -> SceneParameters:
@@ -467,6 +542,7 @@ class _RenderOp(torch.autograd.Function):
         s2 = scene.sensors()[2]
         g = grad_out[:s2.width, :s2.width, :].to(torch.float32).contiguous()
         gp, gn = integ.backward_buffers(scene, g, 2, seed_grad, 8)
+        gp = total_position_gradient(scene, gp, gn)          # + the normals' dependence on the positions (mesh.cpp:82-87)
         voff = scene.voff
         outs = []
         for mesh_id, shape in zip(ctx.keys, ctx.shapes):

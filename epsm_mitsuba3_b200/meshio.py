@@ -33,7 +33,9 @@ def _apply(to_world: Optional[Transform4f], positions: np.ndarray, normals: Opti
     p = (positions.astype(np.float64) @ m[:3, :3].T + m[:3, 3]).astype(np.float32)
     n = None
     if normals is not None:
-        n = normals.astype(np.float64) @ m[:3, :3].T + m[:3, 3]            # transform_affine on a normal, as obj.cpp:247 / ply.cpp:214 do
+        # transform_affine(InputNormal3f) dispatches to the Normal overload: inverse_transpose · n, no translation
+        # (include/mitsuba/core/transform.h:98-100,146-155; obj.cpp:253, ply.cpp:298)
+        n = normals.astype(np.float64) @ np.linalg.inv(m[:3, :3])
         ln = np.linalg.norm(n, axis=1, keepdims=True); ln[ln == 0] = 1
         n = (n / ln).astype(np.float32)
     return p, n

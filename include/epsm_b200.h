@@ -122,6 +122,14 @@ int epsm_scene_upload(epsm_ctx *ctx,
  * after epsm_scene_refit (no new updates) replaces the refitted tree by a fresh build of the current positions. */
 int epsm_scene_update_vertices(epsm_ctx *ctx, uint32_t mesh_id, const float *positions, int mem);
 int epsm_scene_commit(epsm_ctx *ctx);
+/* params['<mesh>.vertex_normals'] = …; params.update() (mesh.cpp:71-75: the key is exposed as differentiable; a change of
+ * the normals alone triggers no recomputation, mesh.cpp:82-83).  3*vertex_count floats in `mem` space.  Fails for meshes
+ * created without vertex normals, as the reference does (mesh.cpp:258-260).  The next epsm_scene_update_vertices of the
+ * mesh re-derives the normals from the positions again. */
+int epsm_scene_update_normals(epsm_ctx *ctx, uint32_t mesh_id, const float *normals, int mem);
+/* Library-owned device pointers to the concatenated vertex positions / normals (3·total vertex count floats each;
+ * meshes without normals hold zeros) — the current values of the `vertex_positions` / `vertex_normals` parameters. */
+int epsm_scene_vertex_buffers(epsm_ctx *ctx, float **positions, float **normals, uint64_t *n_floats);
 
 /* The same update with the acceleration structure REFITTED on the device instead of rebuilt on the host: the topology
  * of the last build is kept, triangle records and every box are recomputed from the new positions by two kernels
@@ -176,6 +184,14 @@ int epsm_render_backward(epsm_ctx *ctx, int variant, uint32_t sensor, uint32_t s
                          uint32_t max_depth, uint32_t rr_depth,
                          const float *grad_in_hw5, float *grad_pos, float *grad_nrm, int mem,
                          uint64_t lane_begin, uint64_t lane_end, uint64_t *counters);
+
+/* Adjoint of Mesh::recompute_vertex_normals (src/render/mesh.cpp:311-330).  In the reference params.update() re-derives the
+ * vertex normals of a mesh from its (AD-attached) positions inside Mesh::parameters_changed (mesh.cpp:82-87), so the
+ * `si_follow.sh_frame.n · g3` seed of epsm.py:644-645 continues from vertex_normals into vertex_positions.  This entry
+ * point does that step for every EPSM_MESH_GRAD mesh that has vertex normals: grad_pos += Jᵀ · grad_nrm, both
+ * 3·(total vertex count) floats in `mem` space, J evaluated at the scene's current positions.  grad_nrm is not modified
+ * (it stays dr.grad of `<mesh>.vertex_normals` for callers that set the normals directly). */
+int epsm_vertex_normals_backward(epsm_ctx *ctx, const float *grad_nrm, float *grad_pos, int mem);
 
 /* Per-path records for parity tests (the data the reference logs in epsm.py:547,648-654 and the
  * calc_grad outputs).  One record per lane in [lane_begin, lane_end); layout EPSM_REC_* below.

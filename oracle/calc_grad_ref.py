@@ -8,10 +8,14 @@ system `constraint[:, :2id, 2:2id+2]` is inverted densely with `torch.linalg.inv
 `nan_to_num` and the final ±0.1 outlier zeroing.  Runs on CPU (the reference hard-codes `.cuda()`,
 epsm.py:768-773) in float32 or float64.
 
-PARITY UNPINNED: the reference has no test, golden vector or fixture for calc_grad (SURVEY.md F5,
-§8c) and its own path cannot run in this image, so this restatement is checked only by review
-against the cited lines — it is deliberately written with the same autograd + dense-inverse method
-so that it is methodologically independent of the CUDA path (analytic Jacobians + block solves).
+PINNED TO THE REFERENCE ITSELF: the reference has no test, golden vector or fixture for calc_grad
+(SURVEY.md F5, §8c), but its calc_grad source needs only torch, so tests/golden/make_calc_grad_vectors.py
+`exec`s epsm.py:744-946 / :951-1200 where they lie under /root/reference (with `.cuda()` and the four
+`mi.` symbols stubbed) on the path logs of the parity scenes and commits what the reference returns
+(tests/golden/calc_grad_reference.npz, float32 and float64).  tests/test_calc_grad_pinned.py holds this
+restatement to those vectors (float64: 1e-12 relative) and, where /root/reference is present, re-executes
+the reference live.  The restatement uses the reference's own method (autograd rows + dense inverse), so it
+is methodologically independent of the CUDA path (analytic Jacobians + block solves).
 """
 from __future__ import annotations
 
@@ -74,7 +78,7 @@ def _halfvector(frame, prev, cur, nxt, eta):
     return res / torch.norm(res, dim=-1, keepdim=True), wo2
 
 
-def calc_grad(paths: np.ndarray, variant: str, n_logged: int, dtype=torch.float32):
+def calc_grad(paths: np.ndarray, variant: str, n_logged: int, dtype=torch.float32, keep_dtype: bool = False):
     """paths: structured array from OracleScene.path_log; n_logged = len(path_info) − 1.
 
     Returns (path_grad [5 per vertex (manifold) / 5 per vertex but 3 for the last (caustic)],
@@ -268,7 +272,7 @@ def calc_grad(paths: np.ndarray, variant: str, n_logged: int, dtype=torch.float3
     def outlier(t):                                                         # epsm.py:933-944 / 1187-1198
         t = t.detach().clone()
         t[t > 0.1] = 0; t[t < -0.1] = 0
-        return t.to(torch.float32).numpy()
+        return t.numpy() if keep_dtype else t.to(torch.float32).numpy()
 
     return [outlier(t) for t in final], [outlier(t) for t in light_grad], [outlier(t) for t in diffuse_grad]
 

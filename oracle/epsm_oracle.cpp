@@ -948,6 +948,7 @@ void orc_bsdf_sample(const epsm_bsdf_desc *b, const float *wi, float s1, float s
     out[0] = bs.wo.x; out[1] = bs.wo.y; out[2] = bs.wo.z; out[3] = bs.pdf; out[4] = bs.eta; out[5] = (float) bs.type;
     out[6] = bs.weight.x; out[7] = bs.weight.y; out[8] = bs.weight.z; out[9] = bs.hf.x; out[10] = bs.hf.y; out[11] = bs.hf.z;
 }
+uint32_t orc_bsdf_flags(const epsm_bsdf_desc *b) { return bsdf_flags(*b); }
 void orc_bsdf_eval_pdf(const epsm_bsdf_desc *b, const float *wi, const float *wo, float *out) {
     V3 v; float p; bsdf_eval_pdf(*b, mk(wi[0], wi[1], wi[2]), mk(wo[0], wo[1], wo[2]), true, &v, &p);
     out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = p;
@@ -960,6 +961,16 @@ void orc_sample_emitter(orc_scene *s, const float *r, float sx, float sy, float 
     DS ds; V3 w; sample_emitter_direction(s->sc, si, sx, sy, si.valid, &ds, &w);
     float *o = out; auto put3 = [&](V3 v) { *o++ = v.x; *o++ = v.y; *o++ = v.z; };
     put3(ds.p); put3(ds.n); put3(ds.d); *o++ = ds.pdf; *o++ = ds.dist; put3(w);
+}
+// pdf_emitter_direction + Emitter::eval probe (scene.cpp:279-290, area.cpp:82-89, :173-200): the ray r starts at the
+// reference point; out = [pdf, Le(3)] for the surface it hits (0 when that is no emitter)
+void orc_pdf_emitter(orc_scene *s, const float *r, float *out) {
+    g_accel_owner = s;
+    Ray ray{mk(r[0], r[1], r[2]), mk(r[4], r[5], r[6]), r[3]};
+    PI pi = scene_closest(s->sc, ray); SI si = compute_si(s->sc, ray, pi);
+    out[0] = si.valid ? pdf_emitter_direction(s->sc, si, ray.o, true) : 0.f;
+    V3 le = si.valid ? emitter_eval(s->sc, si) : mk(0, 0, 0);
+    out[1] = le.x; out[2] = le.y; out[3] = le.z;
 }
 
 void orc_sample_rays(orc_scene *s, uint32_t sensor, uint32_t seed, uint32_t spp, uint64_t lane_begin, uint64_t lane_end, float *out) {

@@ -71,6 +71,8 @@ def lib() -> C.CDLL:
         L.orc_bsdf_sample.argtypes = [C.POINTER(capi.BsdfDesc), C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_void_p]
         L.orc_bsdf_eval_pdf.argtypes = [C.POINTER(capi.BsdfDesc), C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_sample_emitter.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p]
+        L.orc_bsdf_flags.argtypes = [C.POINTER(capi.BsdfDesc)]; L.orc_bsdf_flags.restype = C.c_uint32
+        L.orc_pdf_emitter.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_sample_rays.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_void_p]
         L.orc_camera_ray.argtypes = [C.c_void_p, C.c_uint32, C.c_float, C.c_float, C.c_void_p]
         L.orc_render_accumulate.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
@@ -120,6 +122,10 @@ def bsdf_sample(bsdf, wi, s1, s2):
 def bsdf_eval_pdf(bsdf, wi, wo):
     d = _bsdf_desc(bsdf); wi = np.asarray(wi, np.float32); wo = np.asarray(wo, np.float32); out = np.zeros(4, np.float32)
     lib().orc_bsdf_eval_pdf(C.byref(d), _p(wi), _p(wo), _p(out)); return out[:3], out[3]
+
+
+def bsdf_flags(bsdf):
+    d = _bsdf_desc(bsdf); return int(lib().orc_bsdf_flags(C.byref(d)))
 
 
 def _bsdf_desc(b):
@@ -174,6 +180,12 @@ class OracleScene:
         r = np.array([o[0], o[1], o[2], 3.4e38, d[0], d[1], d[2], 0], np.float32); out = np.zeros(14, np.float32)
         lib().orc_sample_emitter(self.h, _p(r), sample[0], sample[1], _p(out))
         return dict(p=out[0:3], n=out[3:6], d=out[6:9], pdf=out[9], dist=out[10], weight=out[11:14])
+
+    def pdf_emitter(self, ref_p, d):
+        """(pdf_emitter_direction, Emitter::eval) for the surface seen from ref_p along d."""
+        r = np.array([ref_p[0], ref_p[1], ref_p[2], 3.4e38, d[0], d[1], d[2], 0], np.float32); out = np.zeros(4, np.float32)
+        lib().orc_pdf_emitter(self.h, _p(r), _p(out))
+        return float(out[0]), out[1:4]
 
     def camera_ray(self, sensor, u, v):
         out = np.zeros(13, np.float32); lib().orc_camera_ray(self.h, sensor, u, v, _p(out))

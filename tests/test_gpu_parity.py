@@ -46,15 +46,7 @@ class GpuBackend:
         self.scene.update_vertices(mesh_id, p)
 
 
-CASES = {
-    "mirror": (lambda: S.mirror_plane_scene(32, 4, 24), "manifold", 6),
-    "rough": (lambda: S.mirror_plane_scene(32, 4, 24, rough=True), "manifold", 6),
-    "glass": (lambda: S.glass_sphere_caustic(32, 4, 24, subdiv=3), "manifold_caustic", 6),
-    "cbox_d3": (lambda: S.cornell_box(32, 4, 24), "manifold", 3),
-    "cbox_mirror": (lambda: S.cornell_box(32, 4, 24, box_bsdf=S.Bsdf.conductor()), "manifold", 6),
-    "cbox_glass": (lambda: S.cornell_box(32, 4, 24, box_bsdf=S.Bsdf.dielectric(1.5)), "manifold_caustic", 5),
-    "room": (lambda: S.indoor_room(20000, 32, 4, 24), "manifold", 6),
-}
+from tests.cases import CASES  # noqa: E402
 
 
 @pytest.fixture(scope="module", params=sorted(CASES))

@@ -15,6 +15,7 @@ CASES = {
     "cbox_mirror": (lambda: S.cornell_box(16, 4, 12, box_bsdf=S.Bsdf.conductor()), "manifold", 6),
     "cbox_glass": (lambda: S.cornell_box(16, 4, 12, box_bsdf=S.Bsdf.dielectric(1.5)), "manifold_caustic", 5),
     "room": (lambda: S.indoor_room(6000, 16, 4, 16), "manifold", 6),
+    "stage": (lambda: S.articulated_stage(16, 4, 16), "manifold_caustic", 3),      # BASELINE configs[3] at test size
 }
 
 

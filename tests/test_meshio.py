@@ -104,3 +104,24 @@ def test_loaded_mesh_feeds_the_scene_and_the_oracle(tmp_path, orc):
     sd2.meshes[0] = m
     rays = parity.random_rays(sd, 2000)
     assert np.array_equal(orc.OracleScene(sd).trace(rays).view(np.uint32), orc.OracleScene(sd2).trace(rays).view(np.uint32))
+
+
+def test_file_normals_use_the_inverse_transpose_and_no_translation(tmp_path):
+    """transform_affine on a Normal3f = inverse_transpose · n without the translation (transform.h:146-155; obj.cpp:253,
+    ply.cpp:298): a translated, non-uniformly scaled to_world must keep normals perpendicular to the transformed surface."""
+    p = tmp_path / "slope.obj"
+    # a 45° slope: plane x + z = 0 … normal (1,0,1)/√2, given in the file
+    p.write_text("v 0 0 0\nv 1 0 -1\nv 0 1 0\nvn 0.70710678 0 0.70710678\nf 1//1 2//1 3//1\n")
+    tw = S.T().translate([5.0, -3.0, 2.0]).scale([2.0, 1.0, 0.5])
+    m = meshio.load_obj(str(p), to_world=tw)
+    e1, e2 = m.positions[1] - m.positions[0], m.positions[2] - m.positions[0]
+    for n in m.normals:
+        assert abs(np.linalg.norm(n) - 1) < 1e-6
+        assert abs(np.dot(n, e1)) < 1e-6 and abs(np.dot(n, e2)) < 1e-6         # still the surface normal
+    expect = np.array([0.5, 0, 2.0]) / np.linalg.norm([0.5, 0, 2.0])            # M^-T (1,0,1) ∝ (1/2, 0, 2)
+    assert np.allclose(m.normals[0], expect, atol=1e-6)
+    # same through PLY
+    src = meshio.load_obj(str(p))
+    q = tmp_path / "slope.ply"; meshio.save_ply(str(q), src)
+    m2 = meshio.load_ply(str(q), to_world=tw)
+    assert np.allclose(m2.normals, m.normals, atol=1e-6) and np.allclose(m2.positions, m.positions, atol=1e-6)
