@@ -17,7 +17,6 @@
 #include <cuda_runtime.h>
 #include <cub/device/device_radix_sort.cuh>
 #include <cooperative_groups.h>
-#include <cooperative_groups/reduce.h>
 #include <stdlib.h>
 #include <stdint.h>
 #include "epsm_device.cuh"
@@ -147,18 +146,26 @@ __global__ void k_film_develop(const float *__restrict__ film, uint64_t n_pixels
 //  codegen, ext/drjit/ext/drjit-core/src/cuda_eval.cpp:808-905)
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void scatter3(float *__restrict__ buf, uint32_t idx, f3 v, bool pred) {
-    namespace cg = cooperative_groups;
     pred = pred && (v.x != 0.f || v.y != 0.f || v.z != 0.f);
     if (!pred) return;
-    // Opportunistic aggregation: the lanes that reached this point together (coalesced_threads — the supported way to
-    // name them; a bare __activemask() guarantees nothing about who arrives at the following intrinsic) are
-    // partitioned by target vertex (match.any), each partition is summed and its first lane issues the atomics.
-    const cg::coalesced_group g = cg::coalesced_threads();
-    const cg::coalesced_group peers = cg::labeled_partition(g, idx);
-    if (peers.size() > 1) {
-        v.x = cg::reduce(peers, v.x, cg::plus<float>()); v.y = cg::reduce(peers, v.y, cg::plus<float>()); v.z = cg::reduce(peers, v.z, cg::plus<float>());
+    // Opportunistic aggregation over the lanes that arrived together, partitioned by target vertex (match.any); each
+    // partition is summed and its first lane issues the atomics.  This is what cooperative_groups' coalesced_threads() +
+    // labeled_partition() expand to (an __activemask() followed by __match_any_sync on it, then shuffles on the partition's
+    // own mask) written out: cg::reduce / cg shuffles over a non-contiguous partition pay a rank→lane search per shuffle —
+    // measured on the room pass (profiles/r02_b_warp_aggregation.md): this form 44.6 ms, cg::reduce 49.8 ms, rank-rotating
+    // cg shuffles 159.8 ms.  Every lane named in `peers` executes the same shuffles (the loop runs popc(peers) times for
+    // all of them), and nothing between the mask query and the match can split the lanes.
+    const unsigned peers = __match_any_sync(__activemask(), idx);
+    const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+    if (peers != (1u << lane)) {
+        f3 sum = mk3(0, 0, 0);
+        for (unsigned rem = peers; rem; rem &= rem - 1) {
+            const int src = __ffs(rem) - 1;
+            sum.x += __shfl_sync(peers, v.x, src); sum.y += __shfl_sync(peers, v.y, src); sum.z += __shfl_sync(peers, v.z, src);
+        }
+        v = sum;
     }
-    if (peers.thread_rank() == 0) {
+    if (lane == leader) {
         float *d = buf + 3 * (size_t) idx;
         atomicAdd(d, v.x); atomicAdd(d + 1, v.y); atomicAdd(d + 2, v.z);          // red.global.add.f32
     }

