@@ -6,12 +6,12 @@ host-side mirror of the reference's integrator interface (`engine`), the seeded 
 generators (`scenes`), the hybrid schedule helper (`schedule`) the matcher that produces the image gradient (`matcher`) and OBJ / PLY mesh ingestion (`meshio`).
 """
 from . import capi, scenes, meshio  # noqa: F401
-from .engine import (EpsmError, Scene, SceneParameters, EPSMIntegrator, ManifoldIntegrator,  # noqa: F401
+from .engine import (EpsmError, Scene, SceneParameters, Integrator, PathIntegrator, EPSMIntegrator, ManifoldIntegrator,  # noqa: F401
                      ManifoldCausticIntegrator, load_dict, register_integrator, traverse, render,
                      sample_tea_32, band_lanes, sample_shard)
 from .schedule import HybridSchedule, Phase  # noqa: F401
 from .matcher import Matcher  # noqa: F401
 
-__all__ = ["capi", "scenes", "meshio", "EpsmError", "Scene", "SceneParameters", "EPSMIntegrator", "ManifoldIntegrator",
+__all__ = ["capi", "scenes", "meshio", "EpsmError", "Scene", "SceneParameters", "Integrator", "PathIntegrator", "EPSMIntegrator", "ManifoldIntegrator",
            "ManifoldCausticIntegrator", "load_dict", "register_integrator", "traverse", "render", "sample_tea_32",
            "band_lanes", "sample_shard", "HybridSchedule", "Phase", "Matcher"]

@@ -42,7 +42,7 @@ class EmitterDesc(C.Structure):
 class SensorDesc(C.Structure):
     _fields_ = [("to_world", C.c_float * 16), ("fov_x", C.c_float),
                 ("near_clip", C.c_float), ("far_clip", C.c_float),
-                ("width", C.c_uint32), ("height", C.c_uint32)]
+                ("width", C.c_uint32), ("height", C.c_uint32), ("flags", C.c_uint32)]
 
 
 class SceneStats(C.Structure):
@@ -52,6 +52,8 @@ class SceneStats(C.Structure):
 
 
 # Every symbol include/epsm_b200.h declares (tests/test_capi.py checks the library exports all of them).
+SENSOR_SAMPLE_BORDER = 1
+
 EXPORTS = [
     "epsm_create", "epsm_destroy", "epsm_last_error", "epsm_scene_upload",
     "epsm_scene_update_vertices", "epsm_scene_update_normals", "epsm_scene_vertex_buffers", "epsm_scene_commit", "epsm_scene_refit", "epsm_scene_accel_cost", "epsm_scene_accel_raw", "epsm_trace",

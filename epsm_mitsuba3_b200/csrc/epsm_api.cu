@@ -207,7 +207,7 @@ int epsm_scene_upload(epsm_ctx *ctx, const epsm_mesh_desc *meshes, uint32_t n_me
     ctx->d_films.assign(n_sensors, DevBuf<float>());
     for (uint32_t i = 0; i < n_sensors; ++i) {
         const DSensor &s = ctx->hs.sensors[i];
-        const size_t nf = (size_t) s.w * s.h * 4;
+        const size_t nf = (size_t) s.fw * s.fh * 4;
         CK(ctx->d_films[i].alloc(nf), "film alloc");
         CK(cudaMemsetAsync(ctx->d_films[i].p, 0, nf * sizeof(float), ctx->stream), "film memset");
     }
@@ -403,7 +403,7 @@ int epsm_film_clear(epsm_ctx *ctx, uint32_t sensor) {
     if (sensor >= ctx->hs.sensors.size()) return fail(ctx, EPSM_E_INVALID, "sensor index out of range");
     CK(cudaSetDevice(ctx->device), "cudaSetDevice");
     const DSensor &s = ctx->hs.sensors[sensor];
-    CK(cudaMemsetAsync(ctx->d_films[sensor].p, 0, (size_t) s.w * s.h * 4 * sizeof(float), ctx->stream), "film memset");
+    CK(cudaMemsetAsync(ctx->d_films[sensor].p, 0, (size_t) s.fw * s.fh * 4 * sizeof(float), ctx->stream), "film memset");
     return EPSM_OK;
 }
 
@@ -412,7 +412,7 @@ int epsm_film_raw(epsm_ctx *ctx, uint32_t sensor, float **device_ptr, uint64_t *
     if (!ctx->have_scene) return fail(ctx, EPSM_E_NOSCENE, "no scene uploaded");
     if (sensor >= ctx->hs.sensors.size() || !device_ptr || !n_floats) return fail(ctx, EPSM_E_INVALID, "bad arguments");
     const DSensor &s = ctx->hs.sensors[sensor];
-    *device_ptr = ctx->d_films[sensor].p; *n_floats = (uint64_t) s.w * s.h * 4;
+    *device_ptr = ctx->d_films[sensor].p; *n_floats = (uint64_t) s.fw * s.fh * 4;
     return EPSM_OK;
 }
 
@@ -445,7 +445,7 @@ int epsm_film_develop(epsm_ctx *ctx, uint32_t sensor, float *out_hw5, int mem) {
     if (!ctx->have_scene) return fail(ctx, EPSM_E_NOSCENE, "no scene uploaded");
     if (sensor >= ctx->hs.sensors.size() || !out_hw5) return fail(ctx, EPSM_E_INVALID, "bad arguments");
     CK(cudaSetDevice(ctx->device), "cudaSetDevice");
-    const DSensor &s = ctx->hs.sensors[sensor]; const uint64_t np = (uint64_t) s.w * s.h;
+    const DSensor &s = ctx->hs.sensors[sensor]; const uint64_t np = (uint64_t) s.fw * s.fh;
     float *d_out = out_hw5;
     if (mem == EPSM_MEM_HOST) { CK(ctx->stage_b.alloc(np * 5), "stage alloc"); d_out = ctx->stage_b.p; }
     CK(epsm_launch_develop(ctx->d_films[sensor].p, np, d_out, ctx->stream), "k_film_develop");
@@ -472,7 +472,7 @@ int epsm_render_backward(epsm_ctx *ctx, int variant, uint32_t sensor, uint32_t s
     DLaunch ln; int rc = make_launch(ctx, sensor, seed, spp, max_depth, rr_depth, lane_begin, lane_end, variant, ln);
     if (rc) return rc;
     CK(cudaSetDevice(ctx->device), "cudaSetDevice");
-    const size_t n_img = (size_t) ln.sensor.w * ln.sensor.h * 5, n_v = ctx->hs.pos.size();
+    const size_t n_img = (size_t) ln.sensor.fw * ln.sensor.fh * 5, n_v = ctx->hs.pos.size();
     const float *d_gin; rc = to_device(ctx, grad_in_hw5, n_img, mem, ctx->stage_a, &d_gin); if (rc) return rc;
     float *d_gp = grad_pos, *d_gn = grad_nrm;
     if (mem == EPSM_MEM_HOST) {
@@ -539,7 +539,7 @@ int epsm_path_records(epsm_ctx *ctx, int variant, uint32_t sensor, uint32_t seed
     if (rc) return rc;
     ln.prune = 0;                                    // records are those of the full replay (every logged vertex of epsm.py:648-654)
     CK(cudaSetDevice(ctx->device), "cudaSetDevice");
-    const size_t n_img = (size_t) ln.sensor.w * ln.sensor.h * 5, n_rec = (size_t) (ln.lane_end - ln.lane_begin) * EPSM_REC_FLOATS;
+    const size_t n_img = (size_t) ln.sensor.fw * ln.sensor.fh * 5, n_rec = (size_t) (ln.lane_end - ln.lane_begin) * EPSM_REC_FLOATS;
     const float *d_gin; rc = to_device(ctx, grad_in_hw5, n_img, mem, ctx->stage_a, &d_gin); if (rc) return rc;
     float *d_rec = records;
     if (mem == EPSM_MEM_HOST) { CK(ctx->stage_b.alloc(n_rec), "stage alloc"); d_rec = ctx->stage_b.p; }

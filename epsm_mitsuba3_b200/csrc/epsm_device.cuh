@@ -672,8 +672,8 @@ EPSM_HD f3 xform_vec(const float *m, f3 v) {
 // Lane → pixel → jittered film position → ray + differentials.  The lane's first two random numbers are the jitter.
 EPSM_HDN void camera_ray(const DSensor &s, uint32_t px, uint32_t py, Pcg &rng, CamRay &c) {
     float jx = pcg_f32(rng), jy = pcg_f32(rng);
-    float pos_x = (float) px + jx, pos_y = (float) py + jy;
-    float sx = 1.0f / (float) s.w, sy = 1.0f / (float) s.h;
+    float pos_x = (float) ((int) px - s.border) + jx, pos_y = (float) ((int) py - s.border) + jy;     // pos -= border_size (common.py:337-338)
+    float sx = 1.0f / (float) s.fw, sy = 1.0f / (float) s.fh;
     float ax = fmaf(pos_x, sx, -0.f * sx), ay = fmaf(pos_y, sy, -0.f * sy);
     f3 near_p = xform_point(s.s2c, mk3(ax, ay, 0.f));
     f3 d = norm3(near_p);

@@ -30,7 +30,9 @@ f3 project(const float *m, float x, float y, float z) {
 // ProjectiveCamera transforms: perspective_projection (include/mitsuba/render/sensor.h:227-262) inverted analytically,
 // position differentials as in PerspectiveCamera::update_camera_transforms (src/sensors/perspective.cpp:173-186)
 void make_sensor(const epsm_sensor_desc &d, DSensor &s) {
-    s.w = d.width; s.h = d.height; s.near_clip = d.near_clip; s.far_clip = d.far_clip;
+    s.fw = d.width; s.fh = d.height; s.near_clip = d.near_clip; s.far_clip = d.far_clip;
+    s.border = (d.flags & EPSM_SENSOR_SAMPLE_BORDER) ? 2 : 0;        // ReconstructionFilter::border_size = ceil(radius − ½) (rfilter.h), radius 2
+    s.w = s.fw + 2 * (uint32_t) s.border; s.h = s.fh + 2 * (uint32_t) s.border;
     memcpy(s.to_world, d.to_world, sizeof(s.to_world));
     const double aspect = (double) d.width / (double) d.height, n = d.near_clip, f = d.far_clip;
     const double recip = 1.0 / (f - n), cot = 1.0 / tan(0.5 * (double) d.fov_x * M_PI / 180.0);

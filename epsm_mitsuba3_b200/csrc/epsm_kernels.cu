@@ -87,7 +87,8 @@ __global__ void __launch_bounds__(CTA, EPSM_PATH_MINBLOCKS) k_render(const __gri
     Tracer tr(sc, st);
     for (int i = threadIdx.x; i < FT_H * FT_W * 4; i += CTA) (&ftile[0][0][0])[i] = 0.f;
     __syncthreads();
-    const uint32_t W = ln.sensor.w, H = ln.sensor.h;
+    const uint32_t W = ln.sensor.w, H = ln.sensor.h;                  // sampling grid (film + border)
+    const int B = ln.sensor.border, FW = (int) ln.sensor.fw, FH = (int) ln.sensor.fh;
     const uint32_t tiles_x = (W + TILE_W - 1) / TILE_W;
     const uint32_t tx = blockIdx.x % tiles_x, ty = ln.tile_y0 + blockIdx.x / tiles_x;
     const uint32_t pin = threadIdx.x & 31, slot = threadIdx.x >> 5;
@@ -109,7 +110,7 @@ __global__ void __launch_bounds__(CTA, EPSM_PATH_MINBLOCKS) k_render(const __gri
             float wx[5], wy[5];
 #pragma unroll
             for (int k = 0; k < 5; ++k) { wx[k] = filter_eval(sc.filter, rel_x); wy[k] = filter_eval(sc.filter, rel_y); rel_x += 1; rel_y += 1; }
-            const int lx = pix - (int) (tx * TILE_W) + 2, ly = piy - (int) (ty * TILE_H) + 2;   // tile-local, 2-px apron
+            const int lx = pix - ((int) (tx * TILE_W) - B) + 2, ly = piy - ((int) (ty * TILE_H) - B) + 2;   // tile-local, 2-px apron
 #pragma unroll
             for (int ys = 0; ys < 5; ++ys)
 #pragma unroll
@@ -123,11 +124,11 @@ __global__ void __launch_bounds__(CTA, EPSM_PATH_MINBLOCKS) k_render(const __gri
     __syncthreads();
     // flush the tile (with apron) into the RGBW film; pixels outside the film are the cropped border
     for (int i = threadIdx.x; i < FT_H * FT_W; i += CTA) {
-        const int fy = (int) (ty * TILE_H) + i / FT_W - 2, fx = (int) (tx * TILE_W) + i % FT_W - 2;
-        if (fx < 0 || fy < 0 || fx >= (int) W || fy >= (int) H) continue;
+        const int fy = (int) (ty * TILE_H) - B + i / FT_W - 2, fx = (int) (tx * TILE_W) - B + i % FT_W - 2;      // film coordinates
+        if (fx < 0 || fy < 0 || fx >= FW || fy >= FH) continue;
         const float *s = ftile[i / FT_W][i % FT_W];
         if (s[3] == 0.f && s[0] == 0.f && s[1] == 0.f && s[2] == 0.f) continue;
-        float *d = film + ((size_t) fy * W + fx) * 4;
+        float *d = film + ((size_t) fy * FW + fx) * 4;
         atomicAdd(d + 0, s[0]); atomicAdd(d + 1, s[1]); atomicAdd(d + 2, s[2]); atomicAdd(d + 3, s[3]);
     }
     if (COUNT) flush_counters(tr, lanes, counters);
@@ -381,9 +382,12 @@ __global__ void __launch_bounds__(128) k_wf_init(const __grid_constant__ DLaunch
     if (i < n) {
         const WorkItem wi = wf_work_item(ln, work_base + i);
         if (wi.valid) {
-            const uint64_t pixel = (uint64_t) wi.py * ln.sensor.w + wi.px;
+            // grad_in is film-sized; samples of the border (sample_border sensors) carry no pixel-motion gradient
+            const int fx = (int) wi.px - ln.sensor.border, fy = (int) wi.py - ln.sensor.border;
+            const bool in_film = fx >= 0 && fy >= 0 && fx < (int) ln.sensor.fw && fy < (int) ln.sensor.fh;
+            const uint64_t pixel = in_film ? (uint64_t) fy * ln.sensor.fw + fx : 0;
             PathHead H;
-            wf_begin(ln.sensor, wi.px, wi.py, ln.seed, (uint32_t) wi.lane, grad_in[pixel * 5 + 3], grad_in[pixel * 5 + 4], S, H);
+            wf_begin(ln.sensor, wi.px, wi.py, ln.seed, (uint32_t) wi.lane, in_film ? grad_in[pixel * 5 + 3] : 0.f, in_film ? grad_in[pixel * 5 + 4] : 0.f, S, H);
             soa_store_prefix<WF_INIT_WORDS>(S, wb.states, wb.capacity, i);
             soa_store_prefix<WF_HEAD_INIT_WORDS>(H, wb.heads, wb.capacity, i);       // cam, d: the rest is zero until the first hit
             push = true;
@@ -762,7 +766,8 @@ __global__ void __launch_bounds__(128) k_pr_film(const __grid_constant__ DScene 
     __shared__ float ftile[FT_H][FT_W][4];
     for (int k = threadIdx.x; k < FT_H * FT_W * 4; k += 128) (&ftile[0][0][0])[k] = 0.f;
     __syncthreads();
-    const uint32_t W = ln.sensor.w, H = ln.sensor.h, S = ln.s_end - ln.s_begin;
+    const uint32_t W = ln.sensor.w, S = ln.s_end - ln.s_begin;          // sampling grid (film + border)
+    const int B = ln.sensor.border, FW = (int) ln.sensor.fw, FH = (int) ln.sensor.fh;
     const uint32_t tiles_x = (W + TILE_W - 1) / TILE_W;
     const uint64_t per_tile = 32ull * S;
     const uint64_t tile = work_base / per_tile + blockIdx.x;
@@ -778,13 +783,14 @@ __global__ void __launch_bounds__(128) k_pr_film(const __grid_constant__ DScene 
         pr_resolve_pending(St, wb.occl[i] != 0u);
         const f3 L = St.L;
         Pcg rng = pcg_for_lane(ln.seed, (uint32_t) wi.lane);
-        const float pos_x = (float) wi.px + pcg_f32(rng), pos_y = (float) wi.py + pcg_f32(rng);     // camera_ray's jitter
+        const float jx = pcg_f32(rng), jy = pcg_f32(rng);
+        const float pos_x = (float) ((int) wi.px - B) + jx, pos_y = (float) ((int) wi.py - B) + jy;     // camera_ray's film position
         const int pix = (int) floorf(pos_x) - 2, piy = (int) floorf(pos_y) - 2;
         float rel_x = (float) pix + .5f - pos_x, rel_y = (float) piy + .5f - pos_y;
         float wx[5], wy[5];
 #pragma unroll
         for (int k = 0; k < 5; ++k) { wx[k] = filter_eval(sc.filter, rel_x); wy[k] = filter_eval(sc.filter, rel_y); rel_x += 1; rel_y += 1; }
-        const int lx = pix - (int) (tx * TILE_W) + 2, ly = piy - (int) (ty * TILE_H) + 2;
+        const int lx = pix - ((int) (tx * TILE_W) - B) + 2, ly = piy - ((int) (ty * TILE_H) - B) + 2;
 #pragma unroll
         for (int ys = 0; ys < 5; ++ys)
 #pragma unroll
@@ -796,11 +802,11 @@ __global__ void __launch_bounds__(128) k_pr_film(const __grid_constant__ DScene 
     }
     __syncthreads();
     for (int k = threadIdx.x; k < FT_H * FT_W; k += 128) {
-        const int fy = (int) (ty * TILE_H) + k / FT_W - 2, fx = (int) (tx * TILE_W) + k % FT_W - 2;
-        if (fx < 0 || fy < 0 || fx >= (int) W || fy >= (int) H) continue;
+        const int fy = (int) (ty * TILE_H) - B + k / FT_W - 2, fx = (int) (tx * TILE_W) - B + k % FT_W - 2;      // film coordinates
+        if (fx < 0 || fy < 0 || fx >= FW || fy >= FH) continue;
         const float *sv = ftile[k / FT_W][k % FT_W];
         if (sv[3] == 0.f && sv[0] == 0.f && sv[1] == 0.f && sv[2] == 0.f) continue;
-        float *d = film + ((size_t) fy * W + fx) * 4;
+        float *d = film + ((size_t) fy * FW + fx) * 4;
         atomicAdd(d + 0, sv[0]); atomicAdd(d + 1, sv[1]); atomicAdd(d + 2, sv[2]); atomicAdd(d + 3, sv[3]);
     }
 }

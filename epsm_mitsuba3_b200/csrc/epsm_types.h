@@ -60,7 +60,9 @@ struct DSensor {
     float s2c[16], to_world[16];
     f3 dx, dy;
     float near_clip, far_clip;
-    uint32_t w, h;
+    uint32_t w, h;               // sampling grid = film + 2·border: what lane → pixel enumerates (common.py:318-343)
+    uint32_t fw, fh;             // film (= crop) size
+    int32_t  border;             // rfilter border when hdrfilm.sample_border is set (2 for the Gaussian), else 0
 };
 
 struct DScene {

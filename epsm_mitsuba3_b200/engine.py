@@ -332,12 +332,15 @@ def _wrap_device(ptr: int, shape, device) -> torch.Tensor:
 # ------------------------------------------------------------------------------------------------
 #  Integrator plugins
 # ------------------------------------------------------------------------------------------------
-class EPSMIntegrator:
-    """EPSMIntegrator (epsm.py:12) with the property handling of ADIntegrator (common.py:28-43)."""
-    variant: str = None
+class Integrator:
+    """Property handling of ADIntegrator (common.py:28-43) and the primal render every integrator of this path shares:
+    the PRB loop of EPSMIntegrator.sample (epsm.py:308-501) is the estimator of `path` (src/integrators/path.cpp:1-324)
+    and of `prb` / `prb_reparam` in primal mode (NEE + BSDF sampling, MIS, Russian roulette from rr_depth)."""
+    channels: int = 3                                        # RGB; the EPSM integrators append two zero channels (epsm.py:76-82)
+    type_name: str = None
 
     def __init__(self, props: dict):
-        max_depth = int(props.get("max_depth", 6))
+        max_depth = int(props.get("max_depth", self.default_max_depth))
         if max_depth < 0 and max_depth != -1:
             raise Exception("\"max_depth\" must be set to -1 (infinite) or a value >= 0")
         self.max_depth = max_depth if max_depth != -1 else 0xffffffff
@@ -345,33 +348,63 @@ class EPSMIntegrator:
         if self.rr_depth <= 0:
             raise Exception("\"rr_depth\" must be set to a value greater than zero!")
 
-    # epsm.py:13-82
+    default_max_depth = 6
+
     def render(self, scene: Scene, sensor: int = 0, seed: int = 0, spp: int = 0, develop: bool = True, evaluate: bool = True) -> torch.Tensor:
         if not develop:
             raise Exception("develop=True must be specified when invoking AD integrators")
         s = scene.sensors()[sensor]
         spp = spp if spp != 0 else s.spp
         scene.film_clear(sensor)
+        # Mitsuba renders wavefronts of at most 2^32 samples and splits larger jobs into passes with successive seeds
+        # (common.py:468-475 / integrator.cpp); the 8192-spp target renders of optim.py:56-58 stay below the limit at 512².
+        passes = 1
+        while s.wavefront(spp) // passes > (1 << 32) or spp % passes:
+            passes += 1
         dist = _dist()
-        if dist is None:
-            scene.render_accumulate(sensor, seed, spp, self.max_depth, self.rr_depth)
-        else:
-            s0, s1 = sample_shard(spp, dist.get_rank(), dist.get_world_size())
-            if s1 > s0:
-                scene.set_sample_range(s0, s1)
-                try:
-                    scene.render_accumulate(sensor, seed, spp, self.max_depth, self.rr_depth)
-                finally:
-                    scene.set_sample_range(0, 0)      # never leave the context sharded for later calls
+        for p in range(passes):
+            spp_p = spp // passes
+            if dist is None:
+                scene.render_accumulate(sensor, seed + p, spp_p, self.max_depth, self.rr_depth)
+            else:
+                s0, s1 = sample_shard(spp_p, dist.get_rank(), dist.get_world_size())
+                if s1 > s0:
+                    scene.set_sample_range(s0, s1)
+                    try:
+                        scene.render_accumulate(sensor, seed + p, spp_p, self.max_depth, self.rr_depth)
+                    finally:
+                        scene.set_sample_range(0, 0)      # never leave the context sharded for later calls
+        if dist is not None:
             film = scene.film_raw(sensor)
             scene.synchronize()
             dist.all_reduce(film)                     # every rank splatted its samples of every pixel: sum the RGBW film
         # the library's stream writes into a fresh torch allocation: order torch's stream first (the caching allocator
         # may hand back a block with pending torch-stream work)
         _sync_torch(scene.device)
-        self.primal_image = scene.film_develop(sensor)
+        img = scene.film_develop(sensor)
         scene.synchronize()
+        self.primal_image = img if self.channels == 5 else img[..., :self.channels].contiguous()
         return self.primal_image
+
+    def render_backward(self, scene: Scene, params, grad_in: torch.Tensor, sensor: int = 0, seed: int = 0, spp: int = 0) -> None:
+        raise NotImplementedError(f"{type(self).__name__}.render_backward")          # Integrator::render_backward (integrator.h) for non-AD plugins
+
+    def position_gradient(self, scene: Scene, grad_out: torch.Tensor, sensor: int, seed: int, spp: int) -> torch.Tensor:
+        """(V,3) gradient of Σ image·grad_out w.r.t. the concatenated vertex positions (what _RenderOp.backward routes)."""
+        raise NotImplementedError(f"{type(self).__name__} is not differentiable")
+
+
+class PathIntegrator(Integrator):
+    """`path` (src/integrators/path.cpp:1-324): the primal path tracer the drivers use for target / reference images
+    (optim.py:56-58,80,160).  max_depth defaults to -1 (path.cpp / integrator.cpp MonteCarloIntegrator)."""
+    type_name = "path"
+    default_max_depth = -1
+
+
+class EPSMIntegrator(Integrator):
+    """EPSMIntegrator (epsm.py:12)."""
+    variant: str = None
+    channels = 5
 
     # epsm.py:84-306
     def render_backward(self, scene: Scene, params, grad_in: torch.Tensor, sensor: int = 0, seed: int = 0, spp: int = 0) -> None:
@@ -388,6 +421,14 @@ class EPSMIntegrator:
         _sync_torch(scene.device)
         gp, gn = self.backward_buffers(scene, g, sensor, seed, spp)
         params.accumulate_gradients(gp, gn)
+
+    def position_gradient(self, scene: Scene, grad_out: torch.Tensor, sensor: int, seed: int, spp: int) -> torch.Tensor:
+        s2 = scene.sensors()[2]                         # sensor / spp ignored: sensors()[2] at 8 spp (epsm.py:142-145)
+        if grad_out.shape[-1] == 3:
+            return torch.zeros((scene.n_vertices, 3), dtype=torch.float32, device=scene.device)
+        g = grad_out[:s2.width, :s2.width, :].to(torch.float32).contiguous()
+        gp, gn = self.backward_buffers(scene, g, 2, seed, 8)
+        return total_position_gradient(scene, gp, gn)   # + the normals' dependence on the positions (mesh.cpp:82-87)
 
     def backward_buffers(self, scene: Scene, g: torch.Tensor, sensor: int, seed: int, spp: int):
         s = scene.sensors()[sensor]
@@ -409,11 +450,11 @@ class EPSMIntegrator:
 
 
 class ManifoldIntegrator(EPSMIntegrator):              # epsm.py:744
-    variant = "manifold"
+    variant = type_name = "manifold"
 
 
 class ManifoldCausticIntegrator(EPSMIntegrator):       # epsm.py:951
-    variant = "manifold_caustic"
+    variant = type_name = "manifold_caustic"
 
 
 _REGISTRY: Dict[str, Callable[[dict], EPSMIntegrator]] = {}
@@ -424,6 +465,7 @@ def register_integrator(name: str, factory: Callable[[dict], EPSMIntegrator]) ->
     _REGISTRY[name] = factory
 
 
+register_integrator("path", lambda props: PathIntegrator(props))                         # src/integrators/path.cpp
 register_integrator("manifold", lambda props: ManifoldIntegrator(props))                 # epsm.py:948
 register_integrator("manifold_caustic", lambda props: ManifoldCausticIntegrator(props))  # epsm.py:1202
 
@@ -538,11 +580,8 @@ class _RenderOp(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         scene, integ = ctx.scene, ctx.integrator
-        seed_grad = sample_tea_32(ctx.seed, 1)[0]
-        s2 = scene.sensors()[2]
-        g = grad_out[:s2.width, :s2.width, :].to(torch.float32).contiguous()
-        gp, gn = integ.backward_buffers(scene, g, 2, seed_grad, 8)
-        gp = total_position_gradient(scene, gp, gn)          # + the normals' dependence on the positions (mesh.cpp:82-87)
+        seed_grad = sample_tea_32(ctx.seed, 1)[0]           # util.py:510-515; spp_grad = spp (util.py:505-506)
+        gp = integ.position_gradient(scene, grad_out, ctx.sensor, seed_grad, ctx.spp)
         voff = scene.voff
         outs = []
         for mesh_id, shape in zip(ctx.keys, ctx.shapes):

@@ -234,3 +234,100 @@ def save_ply(path: str, mesh: Mesh, binary: bool = True):
                 f.write((" ".join(repr(float(x)) for x in row) + "\n").encode())
             for t in mesh.faces:
                 f.write(f"3 {t[0]} {t[1]} {t[2]}\n".encode())
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+#  Mitsuba `.serialized` meshes (src/shapes/serialized.cpp:198-400): header 0x041C, version 3 | 4, then one deflate
+#  stream per sub-mesh: flags u32, [name\0 (v4)], vertex_count u64, face_count u64, positions, [normals], [texcoords],
+#  [colours] (float32 or float64 per flags), uint32 indices.  Multi-mesh files end with the sub-stream offsets
+#  (u64 for v4, u32 for v3) and the u32 mesh count.
+# ---------------------------------------------------------------------------------------------------------------------
+_SER_HEADER, _SER_V3, _SER_V4 = 0x041C, 3, 4
+_SER_NORMALS, _SER_TEXCOORDS, _SER_COLORS, _SER_FACENORMALS, _SER_SINGLE, _SER_DOUBLE = 0x1, 0x2, 0x8, 0x10, 0x1000, 0x2000
+
+
+def load_serialized(path: str, shape_index: int = 0, to_world: Optional[Transform4f] = None, face_normals: bool = False,
+                    name: Optional[str] = None, return_texcoords: bool = False, **mesh_kw):
+    import struct
+    import zlib
+
+    def fail(msg):
+        raise MeshIOError(f'Error while loading serialized file "{path}": {msg}!')
+    try:
+        data = open(path, "rb").read()
+    except OSError:
+        fail("file not found")
+    if len(data) < 4:
+        fail("encountered an invalid file format")
+    fmt, version = struct.unpack_from("<HH", data, 0)
+    if fmt != _SER_HEADER:
+        fail("encountered an invalid file format")
+    if version not in (_SER_V3, _SER_V4):
+        fail("encountered an incompatible file version")
+    start = 4
+    if shape_index != 0:
+        (count,) = struct.unpack_from("<I", data, len(data) - 4)
+        if shape_index < 0 or shape_index >= count:
+            fail(f"Unable to unserialize mesh, shape index is out of range! (requested {shape_index} out of 0..{count - 1})")
+        if version == _SER_V4:
+            (off,) = struct.unpack_from("<Q", data, len(data) - 8 * (count - shape_index) - 4)
+        else:
+            (off,) = struct.unpack_from("<I", data, len(data) - 4 * (count - shape_index + 1))
+        start = off + 4                                                   # skip the sub-stream's own header
+    try:
+        body = zlib.decompressobj().decompress(data[start:])
+    except zlib.error as e:
+        fail(f"zlib: {e}")
+    pos = 0
+    (flags,) = struct.unpack_from("<I", body, pos); pos += 4
+    ser_name = ""
+    if version == _SER_V4:
+        end = body.index(b"\0", pos); ser_name = body[pos:end].decode("utf-8", "replace"); pos = end + 1
+    nv, nf = struct.unpack_from("<QQ", body, pos); pos += 16
+    dt = "<f8" if flags & _SER_DOUBLE else "<f4"
+    isz = 8 if flags & _SER_DOUBLE else 4
+
+    def block(dim):
+        nonlocal pos
+        a = np.frombuffer(body, dt, nv * dim, pos).astype(np.float32).reshape(nv, dim); pos += nv * dim * isz
+        return a
+    positions = block(3)
+    normals = block(3) if flags & _SER_NORMALS else None
+    uvs = block(2) if flags & _SER_TEXCOORDS else None
+    if flags & _SER_COLORS:
+        block(3)
+    faces = np.frombuffer(body, "<u4", nf * 3, pos).reshape(nf, 3).copy()
+    if faces.size and faces.max() >= nv:
+        fail("face references a vertex out of range")
+    if face_normals:
+        normals = None
+    positions, normals = _apply(to_world, positions, normals)
+    mesh = _finish(name or ser_name or f"{path.split('/')[-1]}@{shape_index}", positions, faces, normals, face_normals, mesh_kw)
+    return (mesh, uvs) if return_texcoords else mesh
+
+
+def save_serialized(path: str, meshes, version: int = _SER_V4, double: bool = False):
+    """Writer for tests / exports: one or several meshes into one `.serialized` file."""
+    import struct
+    import zlib
+    meshes = [meshes] if isinstance(meshes, Mesh) else list(meshes)
+    out = bytearray(); offsets = []
+    for m in meshes:
+        offsets.append(len(out))
+        out += struct.pack("<HH", _SER_HEADER, version)
+        flags = (_SER_DOUBLE if double else _SER_SINGLE) | (_SER_NORMALS if m.normals is not None else 0)
+        raw = bytearray(struct.pack("<I", flags))
+        if version == _SER_V4:
+            raw += m.name.encode() + b"\0"
+        raw += struct.pack("<QQ", m.positions.shape[0], m.faces.shape[0])
+        dt = "<f8" if double else "<f4"
+        raw += np.ascontiguousarray(m.positions, dt).tobytes()
+        if m.normals is not None:
+            raw += np.ascontiguousarray(m.normals, dt).tobytes()
+        raw += np.ascontiguousarray(m.faces, "<u4").tobytes()
+        out += zlib.compress(bytes(raw))
+    for o in offsets:
+        out += struct.pack("<Q" if version == _SER_V4 else "<I", o)
+    out += struct.pack("<I", len(meshes))
+    with open(path, "wb") as f:
+        f.write(bytes(out))

@@ -155,6 +155,11 @@ class Sensor:
     spp: int = 4
     sample_border: bool = False
 
+    def wavefront(self, spp: int = 0) -> int:
+        """Lanes of one render: (film + the rfilter border on each side when sample_border) × spp (common.py:318-324)."""
+        b = 2 if self.sample_border else 0
+        return (self.width + 2 * b) * (self.height + 2 * b) * (spp or self.spp)
+
 
 @dataclass
 class SceneData:
@@ -233,6 +238,7 @@ class _CScene:
             d = self.sensors[i]
             d.to_world[:] = [float(x) for x in s.to_world.matrix.astype(np.float32).ravel()]
             d.fov_x, d.near_clip, d.far_clip, d.width, d.height = s.fov, s.near_clip, s.far_clip, s.width, s.height
+            d.flags = capi.SENSOR_SAMPLE_BORDER if s.sample_border else 0
         self.counts = (len(sd.meshes), len(sd.bsdfs), len(sd.emitters), len(sd.sensors))
 
 

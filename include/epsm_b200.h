@@ -87,11 +87,18 @@ typedef struct epsm_emitter_desc {   /* src/emitters/area.cpp, uniform radiance 
     int32_t mesh_id;
 } epsm_emitter_desc;
 
+/* epsm_sensor_desc.flags */
+#define EPSM_SENSOR_SAMPLE_BORDER 1u /* hdrfilm `sample_border` (src/render/film.cpp; common.py:318-343): the wavefront also covers the
+                                        reconstruction filter's border (2 pixels for the Gaussian) around the film, lane → pixel
+                                        uses the enlarged grid, splats outside the film are cropped.  The EPSM drivers set it
+                                        on sensor 0 (PRB / reference renders), not on sensors 1 and 2 (EPSM/exp/shadow.py:98-153) */
+
 typedef struct epsm_sensor_desc {    /* src/sensors/perspective.cpp + hdrfilm + gaussian rfilter */
     float    to_world[16];       /* row-major camera-to-world, no scale                      */
     float    fov_x;              /* degrees, horizontal                                      */
     float    near_clip, far_clip;
     uint32_t width, height;      /* film size == crop size (no crop window)                  */
+    uint32_t flags;              /* EPSM_SENSOR_*                                            */
 } epsm_sensor_desc;
 
 typedef struct epsm_ctx epsm_ctx;

@@ -163,7 +163,10 @@ struct Mesh {
     std::vector<float> pmf;
 };
 struct Sensor {
-    float s2c[16], to_world[16]; V3 dx, dy; float near_clip, far_clip; uint32_t w, h;
+    float s2c[16], to_world[16]; V3 dx, dy; float near_clip, far_clip;
+    uint32_t w, h;          // sampling grid: film + 2·border when the film has sample_border (common.py:318-324)
+    uint32_t fw, fh;        // film / crop size
+    int border;             // rfilter.border_size() = 2 for the Gaussian, 0 without sample_border
 };
 struct Scene {
     std::vector<V3> pos, nrm;
@@ -212,7 +215,9 @@ V3 xform_vec(const float *m, V3 v) {
     return mk(m[0] * v.x + m[1] * v.y + m[2] * v.z, m[4] * v.x + m[5] * v.y + m[6] * v.z, m[8] * v.x + m[9] * v.y + m[10] * v.z);
 }
 void init_sensor(Sensor &s, const epsm_sensor_desc &d) {
-    s.w = d.width; s.h = d.height; s.near_clip = d.near_clip; s.far_clip = d.far_clip;
+    s.fw = d.width; s.fh = d.height; s.near_clip = d.near_clip; s.far_clip = d.far_clip;
+    s.border = (d.flags & EPSM_SENSOR_SAMPLE_BORDER) ? 2 : 0;
+    s.w = s.fw + 2 * s.border; s.h = s.fh + 2 * s.border;
     memcpy(s.to_world, d.to_world, sizeof(s.to_world));
     double aspect = (double) d.width / (double) d.height;
     double recip = 1.0 / ((double) d.far_clip - (double) d.near_clip);
@@ -750,8 +755,8 @@ CamRay sample_camera_ray(const Sensor &s, uint32_t lane, uint32_t spp, PCG32 &rn
     uint32_t idx = lane / spp;
     uint32_t py = idx / s.w, px = idx - py * s.w;
     float jx = rng.next_f32(), jy = rng.next_f32();
-    float pos_x = (float) px + jx, pos_y = (float) py + jy;
-    float sx = 1.0f / (float) s.w, sy = 1.0f / (float) s.h;
+    float pos_x = (float) ((int) px - s.border) + jx, pos_y = (float) ((int) py - s.border) + jy;       // common.py:337-338
+    float sx = 1.0f / (float) s.fw, sy = 1.0f / (float) s.fh;
     float ax = fmaf(pos_x, sx, -0.f * sx), ay = fmaf(pos_y, sy, -0.f * sy);      // offset = -crop_offset*scale = -0
     V3 near_p = xform_point(s.s2c, mk(ax, ay, 0.f));
     V3 d = normalize(near_p);
@@ -1009,8 +1014,8 @@ void orc_render_accumulate(orc_scene *s, uint32_t sensor, uint32_t seed, uint32_
         bool valid; V3 L = sample_primal(sc, c.ray, rng, max_depth, rr_depth, &valid);
         Ls[5 * i] = L.x; Ls[5 * i + 1] = L.y; Ls[5 * i + 2] = L.z; Ls[5 * i + 3] = c.pos_x; Ls[5 * i + 4] = c.pos_y;
     }
-    std::vector<float> film((size_t) se.w * se.h * 4, 0.f);
-    for (size_t i = 0; i < n; ++i) film_put(sc, film, se.w, se.h, Ls[5 * i + 3], Ls[5 * i + 4], mk(Ls[5 * i], Ls[5 * i + 1], Ls[5 * i + 2]));
+    std::vector<float> film((size_t) se.fw * se.fh * 4, 0.f);
+    for (size_t i = 0; i < n; ++i) film_put(sc, film, se.fw, se.fh, Ls[5 * i + 3], Ls[5 * i + 4], mk(Ls[5 * i], Ls[5 * i + 1], Ls[5 * i + 2]));
     for (size_t i = 0; i < film.size(); ++i) film_rgbw[i] += film[i];
     if (per_lane_L) for (size_t i = 0; i < n; ++i) { per_lane_L[3 * i] = Ls[5 * i]; per_lane_L[3 * i + 1] = Ls[5 * i + 1]; per_lane_L[3 * i + 2] = Ls[5 * i + 2]; }
 }
@@ -1044,7 +1049,9 @@ void orc_path_log(orc_scene *s, uint32_t sensor, uint32_t seed, uint32_t spp, ui
         Ray ray = c.ray;
         P.cam[0] = ray.o.x; P.cam[1] = ray.o.y; P.cam[2] = ray.o.z; P.d[0] = ray.d.x; P.d[1] = ray.d.y; P.d[2] = ray.d.z;
         // (2) pixel motion → direction tangent, epsm.py:250-257
-        const float *g = grad_in + ((size_t) c.py * se.w + c.px) * 5;
+        static const float g_zero[5] = {0, 0, 0, 0, 0};
+        const int gfx = (int) c.px - se.border, gfy = (int) c.py - se.border;
+        const float *g = (gfx >= 0 && gfy >= 0 && gfx < (int) se.fw && gfy < (int) se.fh) ? grad_in + ((size_t) gfy * se.fw + gfx) * 5 : g_zero;
         V3 grad_d = (c.d_x - ray.d) * g[3] + (c.d_y - ray.d) * g[4];
         uint32_t depth = 0; V3 L = mk(0, 0, 0), beta = mk(1, 1, 1); float eta = 1.f; bool active = true;
         V3 prev_p = mk(0, 0, 0); float prev_pdf = 1.f; bool prev_delta = true;

@@ -192,7 +192,7 @@ class OracleScene:
         return dict(o=out[0:3], d=out[3:6], d_x=out[6:9], d_y=out[9:12], maxt=out[12])
 
     def sample_rays(self, sensor, seed, spp, lane_begin=0, lane_end=None):
-        s = self.sd.sensors[sensor]; lane_end = s.width * s.height * spp if lane_end is None else lane_end
+        s = self.sd.sensors[sensor]; lane_end = s.wavefront(spp) if lane_end is None else lane_end
         out = np.zeros((lane_end - lane_begin, 14), np.float32)
         lib().orc_sample_rays(self.h, sensor, seed, spp, lane_begin, lane_end, _p(out)); return out
 
@@ -204,7 +204,7 @@ class OracleScene:
         lib().orc_film_put(self.h, _p(film), W, H, pos[0], pos[1], _p(rgb))
 
     def render_raw(self, sensor, seed, spp, max_depth=6, rr_depth=5, lane_begin=0, lane_end=None, per_lane=False):
-        s = self.sd.sensors[sensor]; lane_end = s.width * s.height * spp if lane_end is None else lane_end
+        s = self.sd.sensors[sensor]; lane_end = s.wavefront(spp) if lane_end is None else lane_end
         film = np.zeros((s.height, s.width, 4), np.float32)
         L = np.zeros((lane_end - lane_begin, 3), np.float32) if per_lane else None
         lib().orc_render_accumulate(self.h, sensor, seed, spp, max_depth, rr_depth, lane_begin, lane_end, _p(film),
@@ -221,7 +221,7 @@ class OracleScene:
         return self.develop(self.render_raw(sensor, seed, spp, max_depth, rr_depth))
 
     def path_log(self, sensor, seed, spp, max_depth, rr_depth, grad_in, lane_begin=0, lane_end=None):
-        s = self.sd.sensors[sensor]; lane_end = s.width * s.height * spp if lane_end is None else lane_end
+        s = self.sd.sensors[sensor]; lane_end = s.wavefront(spp) if lane_end is None else lane_end
         g = np.ascontiguousarray(grad_in, np.float32)
         assert g.shape == (s.height, s.width, 5)
         n = lane_end - lane_begin

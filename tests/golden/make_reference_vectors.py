@@ -288,10 +288,11 @@ def normal_cases():
     return {"body": body, "mirror": mirror, "blob": blob}
 
 
-def dump_path_render(dr, mi, sd, tmpdir, out, key, spp, max_depth):
-    """Converged `path` image on sensor 1 (sample_border False): the statistical oracle of the whole primal loop."""
+def dump_path_render(dr, mi, sd, tmpdir, out, key, spp, max_depth, sensor=1):
+    """Converged `path` image on sensor 1 (sample_border False) — or sensor 0 (sample_border True, the target-render
+    sensor of EPSM/optim.py:56-58): the statistical oracle of the whole primal loop."""
     scene = to_reference_scene(mi, sd, tmpdir, integrator={"type": "path", "max_depth": max_depth, "rr_depth": 5})
-    img = mi.render(scene, sensor=1, spp=spp, seed=0)
+    img = mi.render(scene, sensor=sensor, spp=spp, seed=0)
     out[f"path/{key}/image"] = np.array(img, np.float32)
     out[f"path/{key}/meta"] = np.array([spp, max_depth], np.int32)
 
@@ -339,6 +340,7 @@ def main():
         dump_path_render(dr, mi, cases["mirror"], tmp, out, "mirror", 4096, 6)
         dump_path_render(dr, mi, cases["glass"], tmp, out, "glass", 4096, 6)
         dump_path_render(dr, mi, cases["rough"], tmp, out, "rough", 4096, 3)
+        dump_path_render(dr, mi, cases["cbox"], tmp, out, "cbox_border", 4096, 6, sensor=0)
     np.savez_compressed(FIXTURE, **out)
     print("wrote", FIXTURE, os.path.getsize(FIXTURE) // 1024, "KiB,", len(out), "arrays")
 

@@ -116,7 +116,8 @@ void sim_sample_rays(sim_scene *s, uint32_t sensor, uint32_t seed, uint32_t spp,
 void sim_render_accumulate(sim_scene *s, uint32_t sensor, uint32_t seed, uint32_t spp, uint32_t max_depth, uint32_t rr_depth,
                            uint64_t lane_begin, uint64_t lane_end, float *film, int staged) {
     DLaunch ln = make_launch(s, sensor, seed, spp, max_depth, rr_depth, 0);
-    const uint32_t W = ln.sensor.w, H = ln.sensor.h;
+    const uint32_t W = ln.sensor.w;                                   // sampling grid width (lane → pixel)
+    const uint32_t FW = ln.sensor.fw, FH = ln.sensor.fh;               // film
     const int64_t n = (int64_t) (lane_end - lane_begin);
     std::vector<float> tmp((size_t) n * 5);
     #pragma omp parallel for schedule(dynamic, 64)
@@ -146,8 +147,8 @@ void sim_render_accumulate(sim_scene *s, uint32_t sensor, uint32_t seed, uint32_
         float rel_x = (float) pix + .5f - pos_x, rel_y = (float) piy + .5f - pos_y, wx[5], wy[5];
         for (int k = 0; k < 5; ++k) { wx[k] = filter_eval(s->sc.filter, rel_x); wy[k] = filter_eval(s->sc.filter, rel_y); rel_x += 1; rel_y += 1; }
         for (int ys = 0; ys < 5; ++ys) for (int xs = 0; xs < 5; ++xs) {
-            int x = pix + xs, y = piy + ys; if (x < 0 || y < 0 || x >= (int) W || y >= (int) H) continue;
-            float w = wy[ys] * wx[xs]; float *d = film + ((size_t) y * W + x) * 4;
+            int x = pix + xs, y = piy + ys; if (x < 0 || y < 0 || x >= (int) FW || y >= (int) FH) continue;
+            float w = wy[ys] * wx[xs]; float *d = film + ((size_t) y * FW + x) * 4;
             d[0] += tmp[5 * i] * w; d[1] += tmp[5 * i + 1] * w; d[2] += tmp[5 * i + 2] * w; d[3] += 1.0f * w;
         }
     }
@@ -168,7 +169,10 @@ void sim_backward(sim_scene *s, int variant, uint32_t sensor, uint32_t seed, uin
     for (int64_t i = 0; i < n; ++i) {
         uint64_t lane = lane_begin + i; uint32_t pixel = (uint32_t) (lane / spp);
         LocalStack ls; TStack st; bind(st, ls); Tracer tr(s->sc, st);
-        const float gx = grad_in[(size_t) pixel * 5 + 3], gy = grad_in[(size_t) pixel * 5 + 4];
+        const int fx = (int) (pixel % W) - ln.sensor.border, fy = (int) (pixel / W) - ln.sensor.border;
+        const bool in_film = fx >= 0 && fy >= 0 && fx < (int) ln.sensor.fw && fy < (int) ln.sensor.fh;
+        const size_t fpix = in_film ? (size_t) fy * ln.sensor.fw + fx : 0;
+        const float gx = in_film ? grad_in[fpix * 5 + 3] : 0.f, gy = in_film ? grad_in[fpix * 5 + 4] : 0.f;
         PathLog P;
         if (prune == 2 && !records) {
             // the production schedule of the gradient pass: first-vertex fast path (k_wf_stage_a) and a log that holds

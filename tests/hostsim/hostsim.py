@@ -101,7 +101,7 @@ class SimScene:
         out = np.zeros((le - lb, 14), np.float32); lib().sim_sample_rays(self.h, sensor, seed, spp, lb, le, out.ctypes.data); return out
 
     def render_raw(self, sensor, seed, spp, max_depth=6, rr_depth=5, lb=0, le=None, staged=False):
-        s = self.data.sensors[sensor]; le = s.width * s.height * spp if le is None else le
+        s = self.data.sensors[sensor]; le = s.wavefront(spp) if le is None else le
         film = np.zeros((s.height, s.width, 4), np.float32)
         lib().sim_render_accumulate(self.h, sensor, seed, spp, max_depth, rr_depth, lb, le, film.ctypes.data, 1 if staged else 0)
         return film
@@ -112,7 +112,7 @@ class SimScene:
         return out
 
     def backward(self, variant, sensor, seed, spp, max_depth, rr_depth, grad_in, lb=0, le=None, prune=True):
-        s = self.data.sensors[sensor]; le = s.width * s.height * spp if le is None else le
+        s = self.data.sensors[sensor]; le = s.wavefront(spp) if le is None else le
         g = np.ascontiguousarray(grad_in, np.float32)
         gp = np.zeros((self.n_vertices, 3), np.float32); gn = np.zeros((self.n_vertices, 3), np.float32)
         lib().sim_backward(self.h, _vid(variant), sensor, seed, spp, max_depth, rr_depth, g.ctypes.data, lb, le,

@@ -304,6 +304,55 @@ def test_primal_render_converges_to_the_reference_path_integrator(key, scene_dat
     _stat_check(img, V[f"path/{key}/image"], 512, spp_ref)
 
 
+def _edge_weight_check(img, ref):
+    """sample_border: the border samples splat into the edge pixels, so edge rows/columns must not be darker or noisier
+    than the reference's (without the border they lose ≈ half their filter weight and the mean of colour/weight drifts)."""
+    e = lambda a: np.concatenate([a[0].ravel(), a[-1].ravel(), a[:, 0].ravel(), a[:, -1].ravel()]).astype(np.float64)
+    assert abs(e(img).mean() / e(ref).mean() - 1) < 0.03
+
+
+def test_sample_border_sensor_against_the_reference(scene_data, orc):
+    """Sensor 0 of the trio (hdrfilm sample_border = true; EPSM/exp/shadow.py:24-38): (W+4)·(H+4)·spp lanes, film
+    positions shifted by the border, splats outside the film cropped (common.py:318-343)."""
+    sd = scene_data["cbox"]
+    assert sd.sensors[0].sample_border and sd.sensors[0].wavefront(3) == (32 + 4) * (32 + 4) * 3
+    o = orc.OracleScene(sd, accel=True)
+    rays = o.sample_rays(0, 5, 2)                                    # every lane of the bordered wavefront
+    pos = rays[:, 12:14]
+    assert rays.shape[0] == 36 * 36 * 2 and pos.min() >= -2 and pos.max() < 34 and (pos < 0).any() and (pos >= 32).any()
+    assert np.all(np.floor(pos[::2]) == np.stack(np.meshgrid(np.arange(36), np.arange(36), indexing="xy"), -1).reshape(-1, 2) - 2)
+    spp_ref, max_depth = (int(x) for x in V["path/cbox_border/meta"])
+    img = o.render(0, 0, 512, max_depth, 5)[..., :3]
+    _stat_check(img, V["path/cbox_border/image"], 512, spp_ref)
+    _edge_weight_check(img, V["path/cbox_border/image"])
+
+
+def test_product_device_code_on_the_border_sensor(scene_data, orc):
+    from tests.hostsim.hostsim import SimScene
+    sd = scene_data["cbox"]
+    sim, o = SimScene(sd), orc.OracleScene(sd, accel=True)
+    assert np.allclose(sim.sample_rays(0, 9, 2, 0, sd.sensors[0].wavefront(2)), o.sample_rays(0, 9, 2), rtol=1e-6, atol=1e-7)
+    parity.check_film(sim.render_raw(0, 3, 2, 6, 5), o.render_raw(0, 3, 2, 6, 5))
+
+
+@pytest.mark.gpu
+def test_gpu_border_sensor(scene_data, orc):
+    import epsm_mitsuba3_b200 as ep
+    sd = scene_data["cbox"]
+    scene = ep.Scene(sd, device=0)
+    o = orc.OracleScene(sd, accel=True)
+    n = sd.sensors[0].wavefront(2)
+    assert np.allclose(scene.sample_rays(0, 9, 2, 0, n), o.sample_rays(0, 9, 2), rtol=1e-6, atol=1e-7)
+    scene.film_clear(0); scene.render_accumulate(0, 3, 2, 6, 5); scene.synchronize()
+    parity.check_film(scene.film_raw(0).cpu().numpy(), o.render_raw(0, 3, 2, 6, 5))
+    scene.primal_megakernel_check = True
+    spp_ref, max_depth = (int(x) for x in V["path/cbox_border/meta"])
+    img = ep.load_dict({"type": "path", "max_depth": max_depth}).render(scene, sensor=0, seed=0, spp=4096).cpu().numpy()
+    assert img.shape == (32, 32, 3)                                   # the stock integrators return RGB, the EPSM ones RGB + 2 (epsm.py:76-82)
+    _stat_check(img, V["path/cbox_border/image"], 4096, spp_ref)
+    _edge_weight_check(img, V["path/cbox_border/image"])
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("key", ("cbox", "mirror", "glass", "rough"))
 def test_gpu_primal_render_converges_to_the_reference_path_integrator(key, scene_data):
