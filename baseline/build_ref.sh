@@ -32,3 +32,8 @@ else
   build kd -DMI_ENABLE_PYTHON=ON -DMI_ENABLE_EMBREE=OFF "-DPython_EXECUTABLE=$(which python3)"
 fi
 echo "reference built"
+# The reference's Python drivers (EPSM/optim.py, utils/, exp/) — installed next to the binaries so that the GPU box, which has
+# no /root/reference, can run them UNMODIFIED against the stand-in modules (tests/test_shim_optim.py).  baseline/_ref is
+# git-ignored: nothing of this enters the repository's history.
+mkdir -p "$ROOT/baseline/_ref/EPSM"
+cp -r "$REF/EPSM/optim.py" "$REF/EPSM/optim_human.py" "$REF/EPSM/utils" "$REF/EPSM/exp" "$ROOT/baseline/_ref/EPSM/"

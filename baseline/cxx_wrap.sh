@@ -8,4 +8,7 @@
 #   * -ffp-contract=off → GCC fuses nothing else (the JIT emits fma only for explicit fmadd),
 #   * -include immintrin.h → the intrinsic headers Dr.Jit pulls in one by one (packet_intrin.h:34-60) find their types,
 #   * -march=x86-64-v3 instead of native → the binaries also run on the GPU box's host CPU.
+# Embree compiles one translation unit per ISA with its own -mavx/-mavx2/-mavx512 flags and dispatches at run time: it
+# must keep them (and has no Dr.Jit code), so its sources pass through untouched.
+case "$*" in *ext/embree/*) exec /usr/bin/g++ "$@" ;; esac
 exec /usr/bin/g++ "$@" -march=x86-64-v3 -mno-sse4.2 -DDRJIT_X86_FMA=1 -include immintrin.h -ffp-contract=off

@@ -56,7 +56,7 @@ SENSOR_SAMPLE_BORDER = 1
 
 EXPORTS = [
     "epsm_create", "epsm_destroy", "epsm_last_error", "epsm_scene_upload",
-    "epsm_scene_update_vertices", "epsm_scene_update_normals", "epsm_scene_vertex_buffers", "epsm_scene_commit", "epsm_scene_refit", "epsm_scene_accel_cost", "epsm_scene_accel_raw", "epsm_trace",
+    "epsm_scene_update_vertices", "epsm_scene_update_normals", "epsm_scene_update_sensor", "epsm_scene_vertex_buffers", "epsm_scene_commit", "epsm_scene_refit", "epsm_scene_accel_cost", "epsm_scene_accel_raw", "epsm_trace",
     "epsm_render_accumulate", "epsm_film_clear", "epsm_film_raw", "epsm_film_develop", "epsm_render",
     "epsm_render_backward", "epsm_vertex_normals_backward", "epsm_path_records", "epsm_sampler_stream", "epsm_sample_rays",
     "epsm_set_sample_range", "epsm_set_full_replay", "epsm_set_trace_profiling", "epsm_get_trace_profile", "epsm_scene_get_stats", "epsm_launch_count", "epsm_stream", "epsm_synchronize",
@@ -93,6 +93,7 @@ def load_library() -> C.CDLL:
                                       C.POINTER(EmitterDesc), u32, C.POINTER(SensorDesc), u32]
     lib.epsm_scene_update_vertices.argtypes = [vp, u32, fp, i32]
     lib.epsm_scene_update_normals.argtypes = [vp, u32, fp, i32]
+    lib.epsm_scene_update_sensor.argtypes = [vp, u32, C.POINTER(SensorDesc)]
     lib.epsm_scene_vertex_buffers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(u64)]
     lib.epsm_scene_commit.argtypes = [vp]
     lib.epsm_scene_refit.argtypes = [vp]

@@ -260,6 +260,15 @@ int epsm_scene_update_normals(epsm_ctx *ctx, uint32_t mesh_id, const float *norm
     return EPSM_OK;
 }
 
+int epsm_scene_update_sensor(epsm_ctx *ctx, uint32_t sensor, const epsm_sensor_desc *desc) {
+    if (!ctx) return EPSM_E_INVALID;
+    if (!ctx->have_scene) return fail(ctx, EPSM_E_NOSCENE, "no scene uploaded");
+    if (!desc) return fail(ctx, EPSM_E_INVALID, "null sensor descriptor");
+    std::string err = host_scene_set_sensor(ctx->hs, sensor, *desc);      // sensors live in the launch descriptor: host state only
+    if (!err.empty()) return fail(ctx, EPSM_E_INVALID, err.c_str());
+    return EPSM_OK;
+}
+
 int epsm_scene_vertex_buffers(epsm_ctx *ctx, float **positions, float **normals, uint64_t *n_floats) {
     if (!ctx) return EPSM_E_INVALID;
     if (!ctx->have_scene) return fail(ctx, EPSM_E_NOSCENE, "no scene uploaded");

@@ -144,6 +144,14 @@ void host_scene_rebuild_accel(HostScene &hs) {
 
 void host_scene_rebuild_area_tables(HostScene &hs) { build_area_tables(&hs); }
 
+std::string host_scene_set_sensor(HostScene &hs, uint32_t index, const epsm_sensor_desc &d) {
+    if (index >= hs.sensors.size()) return "sensor index out of range";
+    if (d.width != hs.sensors[index].fw || d.height != hs.sensors[index].fh) return "a sensor update cannot change the film size";
+    if (!(d.fov_x > 0.f && d.fov_x < 180.f) || !(d.far_clip > d.near_clip)) return "bad sensor parameters";
+    make_sensor(d, hs.sensors[index]);
+    return "";
+}
+
 void host_scene_view(const HostScene &hs, DScene &sc) {
     sc.nodes = hs.bvh.nodes.data(); sc.tris = hs.bvh.tris.data(); sc.pos = hs.pos.data(); sc.nrm = hs.nrm.data();
     sc.faces = hs.faces.data(); sc.face_mesh = hs.face_mesh.data(); sc.meshes = hs.meshes.data(); sc.bsdfs = hs.bsdfs.data();

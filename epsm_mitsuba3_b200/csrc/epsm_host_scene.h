@@ -22,5 +22,7 @@ std::string host_scene_build(HostScene &hs, const epsm_mesh_desc *meshes, uint32
 void host_scene_rebuild_accel(HostScene &hs);
 // Only the emitter area tables / per-mesh area fields (Mesh::build_pmf) from hs.pos.
 void host_scene_rebuild_area_tables(HostScene &hs);
+// params['<sensor>.to_world'] = …; params.update(): recomputes the camera transforms of sensor `index` (same film size).
+std::string host_scene_set_sensor(HostScene &hs, uint32_t index, const epsm_sensor_desc &d);
 // DScene over the HOST arrays (hostsim only; the product fills a DScene with device pointers).
 void host_scene_view(const HostScene &hs, DScene &sc);

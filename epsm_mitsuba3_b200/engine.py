@@ -185,6 +185,12 @@ class Scene:
         addr, mem = self._ptr(normals)
         self._check(self.lib.epsm_scene_update_normals(self.ctx, mesh_id, addr, mem))
 
+    def update_sensors(self):
+        """params['<sensor>.to_world'] = …; params.update(): push the poses in `self.data.sensors` (epsm_scene_update_sensor)."""
+        c = self.data.to_c()
+        for i in range(len(self.data.sensors)):
+            self._check(self.lib.epsm_scene_update_sensor(self.ctx, i, C.byref(c.sensors[i])))
+
     def vertex_buffers(self):
         """Zero-copy (V,3) device views of the scene's current vertex positions and normals."""
         pp, pn, n = C.c_void_p(), C.c_void_p(), C.c_uint64()
@@ -304,6 +310,19 @@ class Scene:
         self._check(self.lib.epsm_vertex_normals_backward(self.ctx, a, b, mem))
         return grad_pos
 
+    def prb_reparam_backward_raw(self, sensor, seed, spp, integ, grad_in, grad_pos, grad_nrm, lane_begin=0, lane_end=0):
+        """epsm_prb_reparam_backward: accumulates into grad_pos / grad_nrm ((V,3) each, memory space of grad_in)."""
+        if isinstance(grad_in, np.ndarray):
+            grad_in = np.ascontiguousarray(grad_in, np.float32)
+        else:
+            grad_in = grad_in.detach().to(torch.float32).contiguous()
+        a_in, mem = self._ptr(grad_in)
+        cfg = capi.ReparamConfig(max_depth=integ.max_depth, rr_depth=integ.rr_depth, reparam_max_depth=min(integ.reparam_max_depth, 0xffffffff),
+                                 reparam_rays=integ.reparam_rays, reparam_kappa=integ.reparam_kappa, reparam_exp=integ.reparam_exp)
+        self._check(self.lib.epsm_prb_reparam_backward(self.ctx, sensor, seed, spp, C.byref(cfg), a_in, self._ptr(grad_pos)[0],
+                                                       self._ptr(grad_nrm)[0], mem, lane_begin, lane_end))
+        return grad_pos, grad_nrm
+
     def path_records(self, variant, sensor, seed, spp, max_depth, rr_depth, grad_in, lane_begin, lane_end):
         grad_in = np.ascontiguousarray(grad_in, np.float32)
         out = np.zeros((lane_end - lane_begin, capi.REC_FLOATS), np.float32)
@@ -389,9 +408,15 @@ class Integrator:
     def render_backward(self, scene: Scene, params, grad_in: torch.Tensor, sensor: int = 0, seed: int = 0, spp: int = 0) -> None:
         raise NotImplementedError(f"{type(self).__name__}.render_backward")          # Integrator::render_backward (integrator.h) for non-AD plugins
 
-    def position_gradient(self, scene: Scene, grad_out: torch.Tensor, sensor: int, seed: int, spp: int) -> torch.Tensor:
-        """(V,3) gradient of Σ image·grad_out w.r.t. the concatenated vertex positions (what _RenderOp.backward routes)."""
+    def vertex_gradients(self, scene: Scene, grad_out: torch.Tensor, sensor: int, seed: int, spp: int):
+        """(grad_pos, grad_nrm), (V,3) each: gradient of Σ image·grad_out w.r.t. the concatenated vertex positions (normals
+        held fixed) and vertex normals (what _RenderOp.backward routes)."""
         raise NotImplementedError(f"{type(self).__name__} is not differentiable")
+
+    def position_gradient(self, scene: Scene, grad_out: torch.Tensor, sensor: int, seed: int, spp: int) -> torch.Tensor:
+        """Total (V,3) gradient w.r.t. the vertex positions, incl. the normals' dependence on them (mesh.cpp:82-87)."""
+        gp, gn = self.vertex_gradients(scene, grad_out, sensor, seed, spp)
+        return total_position_gradient(scene, gp, gn)
 
 
 class PathIntegrator(Integrator):
@@ -422,13 +447,13 @@ class EPSMIntegrator(Integrator):
         gp, gn = self.backward_buffers(scene, g, sensor, seed, spp)
         params.accumulate_gradients(gp, gn)
 
-    def position_gradient(self, scene: Scene, grad_out: torch.Tensor, sensor: int, seed: int, spp: int) -> torch.Tensor:
+    def vertex_gradients(self, scene: Scene, grad_out: torch.Tensor, sensor: int, seed: int, spp: int):
         s2 = scene.sensors()[2]                         # sensor / spp ignored: sensors()[2] at 8 spp (epsm.py:142-145)
         if grad_out.shape[-1] == 3:
-            return torch.zeros((scene.n_vertices, 3), dtype=torch.float32, device=scene.device)
+            z = torch.zeros((2, scene.n_vertices, 3), dtype=torch.float32, device=scene.device)
+            return z[0], z[1]
         g = grad_out[:s2.width, :s2.width, :].to(torch.float32).contiguous()
-        gp, gn = self.backward_buffers(scene, g, 2, seed, 8)
-        return total_position_gradient(scene, gp, gn)   # + the normals' dependence on the positions (mesh.cpp:82-87)
+        return self.backward_buffers(scene, g, 2, seed, 8)
 
     def backward_buffers(self, scene: Scene, g: torch.Tensor, sensor: int, seed: int, spp: int):
         s = scene.sensors()[sensor]
@@ -457,6 +482,50 @@ class ManifoldCausticIntegrator(EPSMIntegrator):       # epsm.py:951
     variant = type_name = "manifold_caustic"
 
 
+class PRBReparamIntegrator(Integrator):
+    """`prb_reparam` (src/python/python/ad/integrators/prb_reparam.py:8-609 over RBIntegrator, common.py:574-975): hybrid
+    phase 2 of the EPSM drivers (optim.py:89-92,113-119), sensor 0, L2 loss.  Properties of prb_reparam.py:225-247."""
+    type_name = "prb_reparam"
+
+    def __init__(self, props: dict):
+        super().__init__(props)
+        self.reparam_max_depth = int(props.get("reparam_max_depth", self.max_depth))
+        self.reparam_rays = int(props.get("reparam_rays", 16))
+        self.reparam_kappa = float(props.get("reparam_kappa", 1e5))
+        self.reparam_exp = float(props.get("reparam_exp", 3.0))
+        self.reparam_antithetic = bool(props.get("reparam_antithetic", False))
+        self.reparam_unroll = bool(props.get("reparam_unroll", False))
+        if self.reparam_antithetic:
+            raise NotImplementedError("prb_reparam: reparam_antithetic=True is not built (default False; no EPSM driver sets it)")
+
+    def vertex_gradients(self, scene: Scene, grad_out: torch.Tensor, sensor: int, seed: int, spp: int):
+        """RBIntegrator.render_backward (common.py:803-975): grad_out is (H,W,3) for the film of `sensor`."""
+        s = scene.sensors()[sensor]
+        spp = spp if spp != 0 else s.spp
+        g = grad_out[..., :3].to(device=scene.device, dtype=torch.float32).contiguous()
+        if tuple(g.shape) != (s.height, s.width, 3):
+            raise EpsmError(f"prb_reparam: grad_in has shape {tuple(g.shape)}, the film of sensor {sensor} is {(s.height, s.width, 3)}")
+        dist = _dist()
+        s0, s1 = (0, spp) if dist is None else sample_shard(spp, dist.get_rank(), dist.get_world_size())
+        buf = torch.zeros((2, scene.n_vertices, 3), dtype=torch.float32, device=scene.device)
+        _sync_torch(scene.device)
+        if s1 > s0:
+            scene.set_sample_range(s0, s1)
+            try:
+                scene.prb_reparam_backward_raw(sensor, seed, spp, self, g, buf[0], buf[1])
+            finally:
+                scene.set_sample_range(0, 0)
+        scene.synchronize()
+        if dist is not None:
+            dist.all_reduce(buf)
+            _sync_torch(scene.device)
+        return buf[0], buf[1]
+
+    def render_backward(self, scene: Scene, params, grad_in: torch.Tensor, sensor: int = 0, seed: int = 0, spp: int = 0) -> None:
+        gp, gn = self.vertex_gradients(scene, grad_in, sensor, seed, spp)
+        params.accumulate_gradients(gp, gn)
+
+
 _REGISTRY: Dict[str, Callable[[dict], EPSMIntegrator]] = {}
 
 
@@ -466,6 +535,7 @@ def register_integrator(name: str, factory: Callable[[dict], EPSMIntegrator]) ->
 
 
 register_integrator("path", lambda props: PathIntegrator(props))                         # src/integrators/path.cpp
+register_integrator("prb_reparam", lambda props: PRBReparamIntegrator(props))           # prb_reparam.py:609
 register_integrator("manifold", lambda props: ManifoldIntegrator(props))                 # epsm.py:948
 register_integrator("manifold_caustic", lambda props: ManifoldCausticIntegrator(props))  # epsm.py:1202
 
@@ -567,33 +637,56 @@ def traverse(scene: Scene) -> SceneParameters:
     return SceneParameters(scene)
 
 
+trace_hook: Optional[Callable[[dict], None]] = None      # set by the stand-in `mitsuba` module when EPSM_SHIM_TRACE is given (tests)
+
+
 class _RenderOp(torch.autograd.Function):
     """mi.render's custom op (util.py:352-403): forward = integrator.render, backward = render_backward with
-    seed_grad = sample_tea_32(seed, 1)[0] (util.py:510-515)."""
+    seed_grad = sample_tea_32(seed, 1)[0] unless given, spp_grad = spp unless given (util.py:505-515).
+    `keys` lists (kind, mesh id) per differentiable input tensor: 'p' vertex_positions, 'n' vertex_normals."""
 
     @staticmethod
-    def forward(ctx, scene, integrator, sensor, seed, spp, keys, *tensors):
-        ctx.scene, ctx.integrator, ctx.sensor, ctx.seed, ctx.spp, ctx.keys = scene, integrator, sensor, seed, spp, keys
+    def forward(ctx, scene, integrator, sensor, seed, spp, seed_grad, spp_grad, keys, *tensors):
+        ctx.scene, ctx.integrator, ctx.sensor, ctx.keys = scene, integrator, sensor, keys
+        ctx.seed_grad = seed_grad if seed_grad != 0 else sample_tea_32(seed, 1)[0]
+        ctx.spp_grad = spp_grad if spp_grad != 0 else spp
         ctx.shapes = [t.shape for t in tensors]
+        if trace_hook:
+            trace_hook({"op": "render", "integrator": integrator.type_name, "sensor": sensor, "seed": seed, "spp": spp})
         return integrator.render(scene, sensor=sensor, seed=seed, spp=spp).clone()
 
     @staticmethod
     def backward(ctx, grad_out):
         scene, integ = ctx.scene, ctx.integrator
-        seed_grad = sample_tea_32(ctx.seed, 1)[0]           # util.py:510-515; spp_grad = spp (util.py:505-506)
-        gp = integ.position_gradient(scene, grad_out, ctx.sensor, seed_grad, ctx.spp)
+        gp, gn = integ.vertex_gradients(scene, grad_out, ctx.sensor, ctx.seed_grad, ctx.spp_grad)
+        if trace_hook:
+            trace_hook({"op": "backward", "integrator": integ.type_name, "sensor": ctx.sensor, "seed_grad": ctx.seed_grad,
+                        "spp_grad": ctx.spp_grad, "grad_abs_sum": float(gp.abs().sum() + gn.abs().sum())})
+        # the normals of a mesh whose vertex_normals are not an input are a function of its positions (mesh.cpp:82-87)
+        explicit = {m for kind, m in ctx.keys if kind == "n"}
+        if explicit:
+            gn_implicit = gn.clone()
+            for m in explicit:
+                gn_implicit[int(scene.voff[m]):int(scene.voff[m + 1])] = 0
+        else:
+            gn_implicit = gn
+        total = total_position_gradient(scene, gp, gn_implicit)
         voff = scene.voff
         outs = []
-        for mesh_id, shape in zip(ctx.keys, ctx.shapes):
-            outs.append(gp[int(voff[mesh_id]):int(voff[mesh_id + 1])].reshape(shape).clone())
-        return (None, None, None, None, None, None, *outs)
+        for (kind, mesh_id), shape in zip(ctx.keys, ctx.shapes):
+            src = total if kind == "p" else gn
+            outs.append(src[int(voff[mesh_id]):int(voff[mesh_id + 1])].reshape(shape).clone())
+        return (None,) * 8 + tuple(outs)
 
 
-def render(scene: Scene, params: SceneParameters, sensor: int = 0, integrator: EPSMIntegrator = None, seed: int = 0, spp: int = 0) -> torch.Tensor:
-    """mi.render(scene, params, sensor, integrator, seed, spp): differentiable w.r.t. the vertex_positions in `params`."""
+def render(scene: Scene, params: SceneParameters, sensor: int = 0, integrator: Integrator = None, seed: int = 0, spp: int = 0,
+           seed_grad: int = 0, spp_grad: int = 0) -> torch.Tensor:
+    """mi.render(scene, params, sensor, integrator, seed, seed_grad, spp, spp_grad): differentiable w.r.t. the
+    vertex_positions / vertex_normals tensors in `params` that require grad."""
     keys, tensors = [], []
-    for key, mesh_id in params._mesh_of.items():
-        t = params[key]
-        if isinstance(t, torch.Tensor) and t.requires_grad:
-            keys.append(mesh_id); tensors.append(t)
-    return _RenderOp.apply(scene, integrator, sensor, seed, spp, keys, *tensors)
+    for kind, table in (("p", params._mesh_of), ("n", params._nrm_of)):
+        for key, mesh_id in table.items():
+            t = params[key]
+            if isinstance(t, torch.Tensor) and t.requires_grad:
+                keys.append((kind, mesh_id)); tensors.append(t)
+    return _RenderOp.apply(scene, integrator, sensor, seed, spp, seed_grad, spp_grad, keys, *tensors)

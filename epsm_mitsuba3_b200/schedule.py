@@ -2,9 +2,9 @@
 
 `METHOD` strings ending in `hybrid` strip the 7-character suffix (`manifold_hybrid` → `manifold`,
 `manifold_caustic_hybrid` → `manifold_caustic`), run the EPSM integrator on sensor 1 for iterations `it < thres`,
-then reset the optimiser state once and switch to `prb_reparam` on sensor 0 with an L2 image loss.  Phase 2's
-integrator is SURVEY.md §8f rank 1 and is not built here: asking for it raises the plugin-not-found error the
-reference's plugin manager would raise (src/core/plugin.cpp:174-211).
+then reset the optimiser state once and switch to `prb_reparam` (engine.PRBReparamIntegrator over
+`epsm_prb_reparam_backward`) on sensor 0 with an L2 image loss.  examples/ and bench.py's `iteration` leg drive their loops
+through this class; EPSM/optim.py itself runs unmodified through the stand-in modules (epsm_mitsuba3_b200/shim).
 """
 from __future__ import annotations
 
@@ -18,7 +18,7 @@ NO_SWITCH = 10000                                  # optim.py:95: `thres = 10000
 
 @dataclass
 class Phase:
-    integrator: Optional[EPSMIntegrator]           # None ⇒ the phase-2 plugin is not available
+    integrator: Optional[EPSMIntegrator]
     integrator_type: str
     sensor: int                                    # optim.py:103-106: EPSM integrators render sensor 1, PRB sensor 0
     loss: str                                      # 'matcher' (5-channel image, optim.py:130-136) or 'l2' (optim.py:137-141)

@@ -5,6 +5,7 @@ Layout: `Float` is a 1-D array of width W; `Vector3f` / `Point3f` hold (W, 3) an
 structure-of-arrays vectors (`v[1] = 0` clears y, `v.x`); `TensorXf` is an N-d tensor with NumPy-style indexing."""
 from __future__ import annotations
 
+import builtins as _b
 import math as _math
 
 import numpy as _np
@@ -23,9 +24,9 @@ def _raw(x, dtype=_torch.float32):
         return x.t
     if isinstance(x, _torch.Tensor):
         return x.to(device=_device(), dtype=dtype) if x.dtype.is_floating_point or dtype != _torch.float32 else x.to(_device())
-    if isinstance(x, (list, tuple)) and any(isinstance(e, (ArrayBase, _torch.Tensor)) for e in x):
+    if isinstance(x, (list, tuple)) and _b.any(isinstance(e, (ArrayBase, _torch.Tensor)) for e in x):
         parts = [_raw(e, dtype).reshape(-1) for e in x]
-        w = max(p.shape[0] for p in parts)
+        w = _b.max(p.shape[0] for p in parts)
         return _torch.stack([p.expand(w) for p in parts], dim=-1)
     return _torch.as_tensor(_np.asarray(x), dtype=dtype, device=_device())
 
@@ -168,6 +169,9 @@ class TensorXf(ArrayBase):
     def _wrap(self, t):
         return TensorXf(t)
 
+    def __len__(self):                       # Tensor::size: number of entries (ext/drjit/src/python/tensor.h:41)
+        return self.t.numel()
+
     @property
     def array(self):
         return Float(self.t.reshape(-1))
@@ -202,9 +206,16 @@ class _VecBase(ArrayBase):
             if not -self.Size <= i < self.Size:
                 raise IndexError(i)                  # lets list(v) / unpacking terminate
             return Float(self.t[:, i])
+        if isinstance(i, tuple) and len(i) == 2 and isinstance(i[0], int):      # v[component, lane]
+            return Float(self.t[i[1], i[0]].reshape(-1))
         return super().__getitem__(i)
 
     def __setitem__(self, i, v):
+        if isinstance(i, tuple) and len(i) == 2 and isinstance(i[0], int):      # v[component, lane] = x
+            val = float(v) if isinstance(v, (int, float)) else _raw(v).reshape(-1)
+            with _torch.no_grad():
+                self.t[i[1], i[0]] = val
+            return
         if isinstance(i, int):
             v = _raw(v).reshape(-1) if not isinstance(v, (int, float)) else v
             if self.t.requires_grad and self.t.is_leaf:
@@ -306,7 +317,7 @@ def atan2(y, x):
 
 def clamp(x, lo, hi):
     if isinstance(x, (int, float)):
-        return min(max(x, lo), hi)
+        return _b.min(_b.max(x, lo), hi)
     return x._wrap(_torch.maximum(_torch.minimum(x.t, _raw(hi).to(x.t)), _raw(lo).to(x.t)))
 
 
@@ -534,7 +545,6 @@ def wrap_ad(source: str, target: str):
     return deco
 
 
-import builtins as _b
 builtins_any = _b.any
 
 

@@ -129,6 +129,9 @@ int epsm_scene_upload(epsm_ctx *ctx,
  * after epsm_scene_refit (no new updates) replaces the refitted tree by a fresh build of the current positions. */
 int epsm_scene_update_vertices(epsm_ctx *ctx, uint32_t mesh_id, const float *positions, int mem);
 int epsm_scene_commit(epsm_ctx *ctx);
+/* params['<sensor>.to_world'] = …; params.update() (src/sensors/perspective.cpp:134-171 parameters_changed →
+ * update_camera_transforms): replaces the pose / fov / clip planes of sensor `sensor`; the film size must not change. */
+int epsm_scene_update_sensor(epsm_ctx *ctx, uint32_t sensor, const epsm_sensor_desc *desc);
 /* params['<mesh>.vertex_normals'] = …; params.update() (mesh.cpp:71-75: the key is exposed as differentiable; a change of
  * the normals alone triggers no recomputation, mesh.cpp:82-83).  3*vertex_count floats in `mem` space.  Fails for meshes
  * created without vertex normals, as the reference does (mesh.cpp:258-260).  The next epsm_scene_update_vertices of the

@@ -76,8 +76,10 @@ def test_hybrid_schedule_follows_optim_py():
     assert (s.method, s.thres, s.integrator1.variant, s.integrator1.max_depth) == ("manifold_caustic", 3, "manifold_caustic", 4)
     p = s.phase(2)
     assert (p.integrator_type, p.sensor, p.loss, p.reset_optimizer) == ("manifold_caustic", 1, "matcher", False)
-    with pytest.raises(ep.EpsmError, match="prb_reparam"):
-        s.phase(3)                                          # phase 2 is SURVEY §8f rank 1: not built, fails like a missing plugin
+    p2 = s.phase(3)                                         # phase 2: prb_reparam on sensor 0, L2 loss, optimiser reset (optim.py:113-119)
+    assert (p2.integrator_type, p2.sensor, p2.loss, p2.reset_optimizer) == ("prb_reparam", 0, "l2", True)
+    assert (p2.integrator.max_depth, p2.integrator.reparam_rays, p2.integrator.reparam_kappa, p2.integrator.reparam_exp) == (4, 16, 1e5, 3.0)
+    assert p2.integrator.reparam_max_depth == 4             # prb_reparam.py:232: defaults to max_depth
     made = []
     s2 = ep.HybridSchedule("manifold_hybrid", 6, thres=5, phase2_factory=lambda props: made.append(props) or "prb")
     assert s2.phase(5).reset_optimizer and not s2.phase(6).reset_optimizer and s2.phase(6).sensor == 0 and s2.phase(6).loss == "l2"
