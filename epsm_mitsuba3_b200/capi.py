@@ -45,6 +45,11 @@ class SensorDesc(C.Structure):
                 ("width", C.c_uint32), ("height", C.c_uint32), ("flags", C.c_uint32)]
 
 
+class ReparamConfig(C.Structure):
+    _fields_ = [("max_depth", C.c_uint32), ("rr_depth", C.c_uint32), ("reparam_max_depth", C.c_uint32), ("reparam_rays", C.c_uint32),
+                ("reparam_kappa", C.c_float), ("reparam_exp", C.c_float)]
+
+
 class SceneStats(C.Structure):
     _fields_ = [("n_triangles", C.c_uint64), ("n_vertices", C.c_uint64), ("n_nodes", C.c_uint64),
                 ("node_bytes", C.c_uint32), ("tri_bytes", C.c_uint32),
@@ -56,7 +61,7 @@ SENSOR_SAMPLE_BORDER = 1
 
 EXPORTS = [
     "epsm_create", "epsm_destroy", "epsm_last_error", "epsm_scene_upload",
-    "epsm_scene_update_vertices", "epsm_scene_update_normals", "epsm_scene_update_sensor", "epsm_scene_vertex_buffers", "epsm_scene_commit", "epsm_scene_refit", "epsm_scene_accel_cost", "epsm_scene_accel_raw", "epsm_trace",
+    "epsm_scene_update_vertices", "epsm_scene_update_normals", "epsm_scene_update_sensor", "epsm_scene_set_mesh_grad", "epsm_prb_reparam_backward", "epsm_scene_vertex_buffers", "epsm_scene_commit", "epsm_scene_refit", "epsm_scene_accel_cost", "epsm_scene_accel_raw", "epsm_trace",
     "epsm_render_accumulate", "epsm_film_clear", "epsm_film_raw", "epsm_film_develop", "epsm_render",
     "epsm_render_backward", "epsm_vertex_normals_backward", "epsm_path_records", "epsm_sampler_stream", "epsm_sample_rays",
     "epsm_set_sample_range", "epsm_set_full_replay", "epsm_set_trace_profiling", "epsm_get_trace_profile", "epsm_scene_get_stats", "epsm_launch_count", "epsm_stream", "epsm_synchronize",
@@ -93,6 +98,8 @@ def load_library() -> C.CDLL:
                                       C.POINTER(EmitterDesc), u32, C.POINTER(SensorDesc), u32]
     lib.epsm_scene_update_vertices.argtypes = [vp, u32, fp, i32]
     lib.epsm_scene_update_normals.argtypes = [vp, u32, fp, i32]
+    lib.epsm_prb_reparam_backward.argtypes = [vp, u32, u32, u32, C.POINTER(ReparamConfig), fp, fp, fp, i32, u64, u64, i32]
+    lib.epsm_scene_set_mesh_grad.argtypes = [vp, u32, i32]
     lib.epsm_scene_update_sensor.argtypes = [vp, u32, C.POINTER(SensorDesc)]
     lib.epsm_scene_vertex_buffers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(u64)]
     lib.epsm_scene_commit.argtypes = [vp]

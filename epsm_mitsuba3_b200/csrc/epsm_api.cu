@@ -260,6 +260,20 @@ int epsm_scene_update_normals(epsm_ctx *ctx, uint32_t mesh_id, const float *norm
     return EPSM_OK;
 }
 
+int epsm_scene_set_mesh_grad(epsm_ctx *ctx, uint32_t mesh_id, int enable) {
+    if (!ctx) return EPSM_E_INVALID;
+    if (!ctx->have_scene) return fail(ctx, EPSM_E_NOSCENE, "no scene uploaded");
+    if (mesh_id >= ctx->hs.meshes.size()) return fail(ctx, EPSM_E_INVALID, "bad mesh id");
+    DMesh &m = ctx->hs.meshes[mesh_id];
+    const uint32_t f = enable ? (m.flags | EPSM_MESH_GRAD) : (m.flags & ~(uint32_t) EPSM_MESH_GRAD);
+    if (f == m.flags) return EPSM_OK;
+    m.flags = f;
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    CK(cudaMemcpyAsync(ctx->d_meshes.p + mesh_id, &m, sizeof(DMesh), cudaMemcpyHostToDevice, ctx->stream), "mesh flags");
+    CK(cudaStreamSynchronize(ctx->stream), "mesh flags sync");
+    return EPSM_OK;
+}
+
 int epsm_scene_update_sensor(epsm_ctx *ctx, uint32_t sensor, const epsm_sensor_desc *desc) {
     if (!ctx) return EPSM_E_INVALID;
     if (!ctx->have_scene) return fail(ctx, EPSM_E_NOSCENE, "no scene uploaded");
@@ -503,6 +517,42 @@ int epsm_render_backward(epsm_ctx *ctx, int variant, uint32_t sensor, uint32_t s
         CK(cudaStreamSynchronize(ctx->stream), "backward sync");
     }
     if (counters) return fetch_counters(ctx, counters);
+    return EPSM_OK;
+}
+
+int epsm_prb_reparam_backward(epsm_ctx *ctx, uint32_t sensor, uint32_t seed, uint32_t spp, const epsm_reparam_config *cfg,
+                              const float *grad_in_hw3, float *grad_pos, float *grad_nrm, int mem,
+                              uint64_t lane_begin, uint64_t lane_end, int film_ready) {
+    if (!ctx) return EPSM_E_INVALID;
+    if (!cfg || !grad_in_hw3 || !grad_pos || !grad_nrm) return fail(ctx, EPSM_E_INVALID, "cfg / grad_in / grad_pos / grad_nrm is NULL");
+    if (cfg->reparam_rays == 0 || cfg->reparam_rays > EPSM_PRB_MAX_RAYS) return fail(ctx, EPSM_E_INVALID, "reparam_rays must be in [1, 64]");
+    if (!(cfg->reparam_kappa > 0.f)) return fail(ctx, EPSM_E_INVALID, "reparam_kappa must be positive");
+    if (cfg->rr_depth == 0) return fail(ctx, EPSM_E_INVALID, "\"rr_depth\" must be set to a value greater than zero!");
+    int rc;
+    if (!film_ready) {                                   // primal pass of render_backward (common.py:905-935): the film of ALL lanes
+        rc = epsm_film_clear(ctx, sensor); if (rc) return rc;
+        rc = epsm_render_accumulate(ctx, sensor, seed, spp, cfg->max_depth, cfg->rr_depth, 0, 0, nullptr); if (rc) return rc;
+    }
+    DLaunch ln; rc = make_launch(ctx, sensor, seed, spp, cfg->max_depth, cfg->rr_depth, lane_begin, lane_end, 0, ln);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    const size_t n_img = (size_t) ln.sensor.fw * ln.sensor.fh * 3, n_v = ctx->hs.pos.size();
+    const float *d_gin; rc = to_device(ctx, grad_in_hw3, n_img, mem, ctx->stage_a, &d_gin); if (rc) return rc;
+    float *d_gp = grad_pos, *d_gn = grad_nrm;
+    if (mem == EPSM_MEM_HOST) {
+        CK(ctx->stage_b.alloc(n_v), "stage alloc"); CK(ctx->stage_c.alloc(n_v), "stage alloc");
+        d_gp = ctx->stage_b.p; d_gn = ctx->stage_c.p;
+        CK(cudaMemcpyAsync(d_gp, grad_pos, n_v * sizeof(float), cudaMemcpyHostToDevice, ctx->stream), "H2D grad_pos");
+        CK(cudaMemcpyAsync(d_gn, grad_nrm, n_v * sizeof(float), cudaMemcpyHostToDevice, ctx->stream), "H2D grad_nrm");
+    }
+    PrbConfig pc{cfg->max_depth, cfg->rr_depth, cfg->reparam_max_depth, cfg->reparam_rays, cfg->reparam_kappa, cfg->reparam_exp};
+    CK(epsm_launch_prb_backward(ctx->sc, ln, pc, ctx->d_films[sensor].p, d_gin, d_gp, d_gn, ctx->stream), "k_prb_backward");
+    ctx->launches += 1;
+    if (mem == EPSM_MEM_HOST) {
+        CK(cudaMemcpyAsync(grad_pos, d_gp, n_v * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream), "D2H grad_pos");
+        CK(cudaMemcpyAsync(grad_nrm, d_gn, n_v * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream), "D2H grad_nrm");
+        CK(cudaStreamSynchronize(ctx->stream), "prb backward sync");
+    }
     return EPSM_OK;
 }
 

@@ -42,6 +42,26 @@ void make_sensor(const epsm_sensor_desc &d, DSensor &s) {
     const double Sm[16] = {-2, 0, 0, 0, 0, -2 / aspect, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
     double t1[16], m[16]; mat4_mul(Tm, Sm, t1); mat4_mul(Pinv, t1, m);
     for (int i = 0; i < 16; ++i) s.s2c[i] = (float) m[i];
+    {   // camera_to_sample = scale(−½, −½·aspect, 1) · translate(−1, −1/aspect, 0) · perspective (perspective.cpp:173-180)
+        const double P[16] = {cot, 0, 0, 0, 0, cot, 0, 0, 0, 0, A, B, 0, 0, 1, 0};
+        const double Tr[16] = {1, 0, 0, -1, 0, 1, 0, -1 / aspect, 0, 0, 1, 0, 0, 0, 0, 1};
+        const double Sc[16] = {-0.5, 0, 0, 0, 0, -0.5 * aspect, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+        double t2[16], c2s[16]; mat4_mul(Tr, P, t2); mat4_mul(Sc, t2, c2s);
+        for (int i = 0; i < 16; ++i) s.c2s[i] = (float) c2s[i];
+        // to_world⁻¹ for an affine matrix: [R t]⁻¹ = [R⁻¹ −R⁻¹t]
+        double R[9]; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) R[3 * i + j] = d.to_world[4 * i + j];
+        const double det = R[0] * (R[4] * R[8] - R[5] * R[7]) - R[1] * (R[3] * R[8] - R[5] * R[6]) + R[2] * (R[3] * R[7] - R[4] * R[6]);
+        const double id = 1.0 / det;
+        const double Ri[9] = {(R[4] * R[8] - R[5] * R[7]) * id, (R[2] * R[7] - R[1] * R[8]) * id, (R[1] * R[5] - R[2] * R[4]) * id,
+                              (R[5] * R[6] - R[3] * R[8]) * id, (R[0] * R[8] - R[2] * R[6]) * id, (R[2] * R[3] - R[0] * R[5]) * id,
+                              (R[3] * R[7] - R[4] * R[6]) * id, (R[1] * R[6] - R[0] * R[7]) * id, (R[0] * R[4] - R[1] * R[3]) * id};
+        for (int i = 0; i < 3; ++i) {
+            double tt = 0;
+            for (int j = 0; j < 3; ++j) { s.w2c[4 * i + j] = (float) Ri[3 * i + j]; tt += Ri[3 * i + j] * d.to_world[4 * j + 3]; }
+            s.w2c[4 * i + 3] = (float) -tt;
+        }
+        s.w2c[12] = s.w2c[13] = s.w2c[14] = 0.f; s.w2c[15] = 1.f;
+    }
     f3 p0 = project(s.s2c, 0, 0, 0), px = project(s.s2c, 1.0f / d.width, 0, 0), py = project(s.s2c, 0, 1.0f / d.height, 0);
     s.dx = f3{px.x - p0.x, px.y - p0.y, px.z - p0.z}; s.dy = f3{py.x - p0.x, py.y - p0.y, py.z - p0.z};
 }

@@ -20,6 +20,7 @@
 #include <stdlib.h>
 #include <stdint.h>
 #include "epsm_device.cuh"
+#include "epsm_prb.cuh"
 #include "epsm_launch.h"
 
 #define TILE_W 8
@@ -1156,5 +1157,37 @@ cudaError_t epsm_launch_refit(f4 *nodes, uint32_t n_nodes, f4 *tris, uint32_t n_
     if (e != cudaSuccess) return e;
     k_refit_tris<<<(n_tris + 255) / 256, 256, 0, s>>>(tris, n_tris, faces, pos, scratch);
     k_refit_nodes<<<(n_nodes + 255) / 256, 256, 0, s>>>(nodes, n_nodes, tris, faces, pos, scratch);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+//  prb_reparam reverse pass (epsm_prb.cuh): one thread per lane.  Lanes are enumerated pixel-major over the launch's
+//  sample range, so that a warp holds neighbouring samples; the lane id (pixel·spp + s) fixes both random streams.
+// ------------------------------------------------------------------------------------------------
+struct AtomicSink {
+    float *gp, *gn;
+    __device__ __forceinline__ void pos(uint32_t v, f3 g) { atomicAdd(gp + 3 * v, g.x); atomicAdd(gp + 3 * v + 1, g.y); atomicAdd(gp + 3 * v + 2, g.z); }
+    __device__ __forceinline__ void nrm(uint32_t v, f3 g) { atomicAdd(gn + 3 * v, g.x); atomicAdd(gn + 3 * v + 1, g.y); atomicAdd(gn + 3 * v + 2, g.z); }
+};
+__global__ void __launch_bounds__(CTA) k_prb_backward(const __grid_constant__ DScene sc, const __grid_constant__ DLaunch ln, const __grid_constant__ PrbConfig cfg,
+                                                      const float *__restrict__ film, const float *__restrict__ grad_in, float *grad_pos, float *grad_nrm) {
+    __shared__ SharedStack ss;
+    TStack st; bind_stack(st, ss);
+    Tracer tr(sc, st);
+    const uint32_t S = ln.s_end - ln.s_begin;
+    const uint64_t i = (uint64_t) blockIdx.x * CTA + threadIdx.x, n_pix = (uint64_t) ln.sensor.w * ln.sensor.h;
+    if (i >= n_pix * S) return;
+    const uint64_t pixel = i / S; const uint32_t s = ln.s_begin + (uint32_t) (i - pixel * S);
+    const uint64_t lane = pixel * ln.spp + s;
+    if (lane < ln.lane_begin || lane >= ln.lane_end) return;
+    const uint32_t py = (uint32_t) (pixel / ln.sensor.w), px = (uint32_t) (pixel - (uint64_t) py * ln.sensor.w);
+    AtomicSink sink{grad_pos, grad_nrm};
+    prb_backward_lane<false>(sc, tr, ln.sensor, cfg, px, py, ln.seed, (uint32_t) lane, film, grad_in, sink);
+}
+cudaError_t epsm_launch_prb_backward(const DScene &sc, DLaunch ln, const PrbConfig &cfg, const float *film, const float *grad_in,
+                                     float *grad_pos, float *grad_nrm, cudaStream_t s) {
+    const uint64_t total = (uint64_t) ln.sensor.w * ln.sensor.h * (ln.s_end - ln.s_begin);
+    if (total == 0) return cudaSuccess;
+    k_prb_backward<<<(unsigned) ((total + CTA - 1) / CTA), CTA, 0, s>>>(sc, ln, cfg, film, grad_in, grad_pos, grad_nrm);
     return cudaGetLastError();
 }

@@ -31,3 +31,6 @@ cudaError_t epsm_launch_vertex_normals_backward(const float *pos, const uint32_t
 size_t epsm_refit_scratch_words(uint32_t n_nodes);
 cudaError_t epsm_launch_refit(f4 *nodes, uint32_t n_nodes, f4 *tris, uint32_t n_tris, const uint32_t *faces, const float *pos,
                               uint32_t *scratch, cudaStream_t s);
+// prb_reparam reverse pass (k_prb_backward): `film` = RGBW film of the primal pass over all lanes, grad_in (H,W,3).
+cudaError_t epsm_launch_prb_backward(const DScene &sc, DLaunch ln, const PrbConfig &cfg, const float *film, const float *grad_in,
+                                     float *grad_pos, float *grad_nrm, cudaStream_t s);

@@ -58,6 +58,7 @@ struct DEmitter { float radiance[3]; int32_t mesh; };
 
 struct DSensor {
     float s2c[16], to_world[16];
+    float c2s[16], w2c[16];      // camera_to_sample and to_world⁻¹ (Sensor::sample_direction, perspective.cpp:282-306): prb_reparam's film motion
     f3 dx, dy;
     float near_clip, far_clip;
     uint32_t w, h;               // sampling grid = film + 2·border: what lane → pixel enumerates (common.py:318-343)
@@ -85,3 +86,7 @@ struct DLaunch {
     int variant;
     uint32_t prune;              // gradient pass: stop each path where its gradient chain ends (epsm_device.cuh: wf_chain_vertex)
 };
+
+// prb_reparam properties (prb_reparam.py:225-247) as the kernels take them.
+#define EPSM_PRB_MAX_RAYS 64
+struct PrbConfig { uint32_t max_depth, rr_depth, reparam_max_depth, n_rays; float kappa, exponent; };

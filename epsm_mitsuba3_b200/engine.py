@@ -185,6 +185,12 @@ class Scene:
         addr, mem = self._ptr(normals)
         self._check(self.lib.epsm_scene_update_normals(self.ctx, mesh_id, addr, mem))
 
+    def set_mesh_grad(self, mesh_id: int, enable: bool = True):
+        """dr.enable_grad on a mesh's vertex buffers (epsm_scene_set_mesh_grad): the gradient passes scatter into it."""
+        if bool(self.data.meshes[mesh_id].grad) != bool(enable):
+            self._check(self.lib.epsm_scene_set_mesh_grad(self.ctx, mesh_id, 1 if enable else 0))
+            self.data.meshes[mesh_id].grad = bool(enable)
+
     def update_sensors(self):
         """params['<sensor>.to_world'] = …; params.update(): push the poses in `self.data.sensors` (epsm_scene_update_sensor)."""
         c = self.data.to_c()
@@ -310,7 +316,7 @@ class Scene:
         self._check(self.lib.epsm_vertex_normals_backward(self.ctx, a, b, mem))
         return grad_pos
 
-    def prb_reparam_backward_raw(self, sensor, seed, spp, integ, grad_in, grad_pos, grad_nrm, lane_begin=0, lane_end=0):
+    def prb_reparam_backward_raw(self, sensor, seed, spp, integ, grad_in, grad_pos, grad_nrm, lane_begin=0, lane_end=0, film_ready=False):
         """epsm_prb_reparam_backward: accumulates into grad_pos / grad_nrm ((V,3) each, memory space of grad_in)."""
         if isinstance(grad_in, np.ndarray):
             grad_in = np.ascontiguousarray(grad_in, np.float32)
@@ -320,7 +326,7 @@ class Scene:
         cfg = capi.ReparamConfig(max_depth=integ.max_depth, rr_depth=integ.rr_depth, reparam_max_depth=min(integ.reparam_max_depth, 0xffffffff),
                                  reparam_rays=integ.reparam_rays, reparam_kappa=integ.reparam_kappa, reparam_exp=integ.reparam_exp)
         self._check(self.lib.epsm_prb_reparam_backward(self.ctx, sensor, seed, spp, C.byref(cfg), a_in, self._ptr(grad_pos)[0],
-                                                       self._ptr(grad_nrm)[0], mem, lane_begin, lane_end))
+                                                       self._ptr(grad_nrm)[0], mem, lane_begin, lane_end, 1 if film_ready else 0))
         return grad_pos, grad_nrm
 
     def path_records(self, variant, sensor, seed, spp, max_depth, rr_depth, grad_in, lane_begin, lane_end):
@@ -689,4 +695,5 @@ def render(scene: Scene, params: SceneParameters, sensor: int = 0, integrator: I
             t = params[key]
             if isinstance(t, torch.Tensor) and t.requires_grad:
                 keys.append((kind, mesh_id)); tensors.append(t)
+                scene.set_mesh_grad(mesh_id, True)          # attached buffers receive gradients (dr.enable_grad semantics)
     return _RenderOp.apply(scene, integrator, sensor, seed, spp, seed_grad, spp_grad, keys, *tensors)

@@ -129,6 +129,10 @@ int epsm_scene_upload(epsm_ctx *ctx,
  * after epsm_scene_refit (no new updates) replaces the refitted tree by a fresh build of the current positions. */
 int epsm_scene_update_vertices(epsm_ctx *ctx, uint32_t mesh_id, const float *positions, int mem);
 int epsm_scene_commit(epsm_ctx *ctx);
+/* dr.enable_grad(params['<mesh>.vertex_positions']) at the boundary: sets / clears EPSM_MESH_GRAD of a mesh after upload, so
+ * that the gradient passes scatter into exactly the meshes whose buffers are attached (util.py:352-403 hands `params` to
+ * render_backward; only attached entries receive gradients). */
+int epsm_scene_set_mesh_grad(epsm_ctx *ctx, uint32_t mesh_id, int enable);
 /* params['<sensor>.to_world'] = …; params.update() (src/sensors/perspective.cpp:134-171 parameters_changed →
  * update_camera_transforms): replaces the pose / fov / clip planes of sensor `sensor`; the film size must not change. */
 int epsm_scene_update_sensor(epsm_ctx *ctx, uint32_t sensor, const epsm_sensor_desc *desc);
@@ -194,6 +198,24 @@ int epsm_render_backward(epsm_ctx *ctx, int variant, uint32_t sensor, uint32_t s
                          uint32_t max_depth, uint32_t rr_depth,
                          const float *grad_in_hw5, float *grad_pos, float *grad_nrm, int mem,
                          uint64_t lane_begin, uint64_t lane_end, uint64_t *counters);
+
+/* Integrator::render_backward for `prb_reparam` — hybrid phase 2 of the EPSM drivers (EPSM/optim.py:89-92,113-119):
+ * RBIntegrator.render_backward (src/python/python/ad/integrators/common.py:803-975) with PRBReparamIntegrator.sample
+ * (prb_reparam.py:277-607) and reparameterize_ray (ad/reparam.py:10-463).  Properties as in prb_reparam.py:225-247 (antithetic
+ * sampling and loop unrolling are evaluation strategies of the reference's AD graph and do not exist here; antithetic = false).
+ * grad_in: H·W·3 floats for the film of `sensor`; grad_pos / grad_nrm as in epsm_render_backward (accumulated into).
+ * film_ready = 0: the call first renders the primal film of all lanes of (sensor, seed, spp) into the context's film — the
+ * weights the image gradient is normalised with.  film_ready = 1: the caller has done that (epsm_film_clear +
+ * epsm_render_accumulate with the same seed / spp / depths, summed over ranks when the samples are sharded). */
+typedef struct epsm_reparam_config {
+    uint32_t max_depth, rr_depth;        /* ADIntegrator properties (common.py:28-43); max_depth −1 → 0xffffffff   */
+    uint32_t reparam_max_depth;          /* default = max_depth (prb_reparam.py:232)                                */
+    uint32_t reparam_rays;               /* auxiliary rays per reparameterisation, default 16, at most 64           */
+    float    reparam_kappa, reparam_exp; /* von Mises–Fisher concentration (1e5), harmonic-weight exponent (3)      */
+} epsm_reparam_config;
+int epsm_prb_reparam_backward(epsm_ctx *ctx, uint32_t sensor, uint32_t seed, uint32_t spp, const epsm_reparam_config *cfg,
+                              const float *grad_in_hw3, float *grad_pos, float *grad_nrm, int mem,
+                              uint64_t lane_begin, uint64_t lane_end, int film_ready);
 
 /* Adjoint of Mesh::recompute_vertex_normals (src/render/mesh.cpp:311-330).  In the reference params.update() re-derives the
  * vertex normals of a mesh from its (AD-attached) positions inside Mesh::parameters_changed (mesh.cpp:82-87), so the

@@ -1180,6 +1180,212 @@ int orc_probe(int fn, uint64_t n, const float *in_, int in_stride, float *out_, 
     return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+//  prb_reparam (src/python/python/ad/integrators/prb_reparam.py:277-607, reparam.py:10-463, common.py:291-422,
+//  803-975): the DETACHED half of the differential pass — the random walk, every sampled quantity and the auxiliary
+//  rays of the reparameterisation — logged per lane.  oracle/prb_reparam_ref.py re-evaluates the ATTACHED half on these
+//  records with torch autograd.  Record layout: PRB_* offsets below (mirrored in prb_reparam_ref.py).
+// ------------------------------------------------------------------------------------------------
+enum { PRB_AUX = 8, PRB_NAUX_MAX = 64, PRB_HDR = 16, PRB_IT = 72 };
+// aux record: hit, prim, b1, b2, w (= Z_i), d_w_omega(3)                                     reparam.py:83-118
+// header:  o(3) d(3) pos(2) L(3) valid n_iter cam_active spare(2)   then n_rays aux records of the camera ray
+// iteration: see the writes below; then n_rays aux records of the main ray and n_rays of the emitter ray
+
+// warp.h:546-583 (approach 1.2), κ ≠ 0
+static V3 square_to_von_mises_fisher(float sx, float sy_, float kappa) {
+    float sy = fmaxf(1.f - sy_, 1e-6f);
+    float cos_theta = 1.f + logf(fmaf(1.f - sy, expf(-2.f * kappa), sy)) / kappa;
+    float s, c; sincos_dr(6.283185307179586f * sx, &s, &c);
+    float sin_theta = safe_sqrt(1.f - cos_theta * cos_theta);
+    return mk(c * sin_theta, s * sin_theta, cos_theta);
+}
+// Mesh::compute_surface_interaction with RayFlags::BoundaryTest (mesh.cpp:823-886) / Rectangle (rectangle.cpp:319-320)
+static float boundary_test(const Scene &sc, const PI &pi, V3 ray_d) {
+    uint32_t mid = sc.face_mesh[pi.prim]; const Mesh &m = sc.meshes[mid];
+    const uint32_t *f = &sc.faces[3 * pi.prim];
+    V3 p0 = sc.pos[f[0]], p1 = sc.pos[f[1]], p2 = sc.pos[f[2]];
+    float b1 = pi.u, b2 = pi.v, b0 = 1.f - b1 - b2;
+    V3 p = fmadd(p0, b0, fmadd(p1, b1, p2 * b2));
+    if (m.flags & EPSM_MESH_RECTANGLE) {
+        V3 c0 = sc.pos[m.v_off], ex = sc.pos[m.v_off + 1] - c0, ey = sc.pos[m.v_off + 3] - c0, r = p - c0;
+        float u = dot(r, ex) / dot(ex, ex), v = dot(r, ey) / dot(ey, ey);
+        return fminf(0.5f - fabsf(u - 0.5f), 0.5f - fabsf(v - 0.5f));
+    }
+    V3 dp0 = p1 - p0, dp1 = p2 - p0, rel = p - p0;
+    float bb1 = dot(dp0, rel), bb2 = dot(dp1, rel), a11 = dot(dp0, dp0), a12 = dot(dp0, dp1), a22 = dot(dp1, dp1);
+    float inv_det = rcp_(a11 * a22 - a12 * a12);
+    float u = fmaf(a22, bb1, -(a12 * bb2)) * inv_det, v = fmaf(-a12, bb1, a11 * bb2) * inv_det, w = 1.f - u - v;
+    if (!m.has_normals) {
+        const float h = 0.5f * sqrtf(3.f);
+        float px = 0.f * w + 1.f * u + 0.5f * v, py = 0.f * w + 0.f * u + h * v;
+        const float tx[3] = {0.f, 1.f, 0.5f}, ty[3] = {0.f, 0.f, h};
+        const float ex[3] = {tx[1] - tx[0], tx[2] - tx[1], tx[0] - tx[2]}, ey[3] = {ty[1] - ty[0], ty[2] - ty[1], ty[0] - ty[2]};
+        float s = (ex[0] * ey[2] - ey[0] * ex[2]) < 0.f ? -1.f : 1.f;
+        float dx = INFINITY, dy = INFINITY;
+        for (int k = 0; k < 3; ++k) {
+            float vx = px - tx[k], vy = py - ty[k];
+            float tt = fminf(fmaxf((vx * ex[k] + vy * ey[k]) / (ex[k] * ex[k] + ey[k] * ey[k]), 0.f), 1.f);
+            float qx = vx - ex[k] * tt, qy = vy - ey[k] * tt;
+            dx = fminf(dx, qx * qx + qy * qy); dy = fminf(dy, s * (vx * ey[k] - vy * ex[k]));
+        }
+        return sqrtf(dx) / (sqrtf(3.f) / 6.f);
+    }
+    V3 n = fmadd(sc.nrm[f[0]], w, fmadd(sc.nrm[f[1]], u, sc.nrm[f[2]] * v));
+    float dp = dot(n, -ray_d);
+    return dp * dp;
+}
+// One auxiliary ray of _sample_warp_field (reparam.py:83-118), detached quantities only.
+static void warp_field_sample(const Scene &sc, const Ray &ray, float sx, float sy, float kappa, float exponent, float *rec) {
+    V3 om = square_to_von_mises_fisher(sx, sy, kappa);
+    V3 fs, ft; coordinate_system(ray.d, &fs, &ft);                                 // Frame3f(ray.d)
+    V3 ad = fmadd(ray.d, om.z, fmadd(ft, om.y, fs * om.x));                         // frame.to_world
+    Ray aux{ray.o, ad, FLT_MAX};
+    PI pi = scene_closest(sc, aux);
+    float B = pi.valid ? boundary_test(sc, pi, ad) : 1.0f;
+    float inv_vmf = rcp_(fmaf(sy, expf(-2.f * kappa), 1.f - sy));
+    float w_denom = inv_vmf - 1.f + B;
+    float w_denom_rcp = w_denom > 1e-4f ? rcp_(w_denom) : 0.f;
+    float w = powf(w_denom_rcp, exponent) * inv_vmf;
+    float tmp1 = inv_vmf * w * w_denom_rcp * kappa * exponent;
+    tmp1 = fminf(fmaxf(tmp1, -1e10f), 1e10f);
+    V3 tmp2 = fmadd(ray.d, 0.f, fmadd(ft, om.y, fs * om.x));
+    rec[0] = pi.valid ? 1.f : 0.f; rec[1] = pi.valid ? (float) pi.prim : 0.f; rec[2] = pi.u; rec[3] = pi.v; rec[4] = w;
+    rec[5] = tmp1 * tmp2.x; rec[6] = tmp1 * tmp2.y; rec[7] = tmp1 * tmp2.z;
+}
+static void reparam_log(const Scene &sc, const Ray &ray, bool active, PCG32 &rng, uint32_t n_rays, float kappa, float exponent, float *out) {
+    memset(out, 0, sizeof(float) * PRB_AUX * n_rays);
+    if (!active) return;                                                            // masked lanes do not advance the generator
+    for (uint32_t i = 0; i < n_rays; ++i) {
+        float sx = rng.next_f32(), sy = rng.next_f32();
+        warp_field_sample(sc, ray, sx, sy, kappa, exponent, out + PRB_AUX * i);
+    }
+}
+uint32_t orc_prb_record_floats(uint32_t n_iter, uint32_t n_rays) { return PRB_HDR + PRB_AUX * n_rays + n_iter * (PRB_IT + 2 * PRB_AUX * n_rays); }
+
+// Lanes [lane_begin, lane_end) of RBIntegrator.render_backward's two sample() passes for `prb_reparam`.  n_iter = record
+// capacity in iterations (≥ min(max_depth, what the test expects)); deeper iterations are still walked but not logged.
+void orc_prb_log(orc_scene *os, uint32_t sensor, uint32_t seed, uint32_t spp, uint32_t max_depth, uint32_t rr_depth,
+                 uint32_t reparam_max_depth, uint32_t n_rays, float kappa, float exponent,
+                 uint64_t lane_begin, uint64_t lane_end, uint32_t n_iter, float *out) {
+    const Scene &sc = os->sc; const Sensor &sn = sc.sensors[sensor];
+    g_accel_owner = os;
+    const uint32_t stride = orc_prb_record_floats(n_iter, n_rays);
+    #pragma omp parallel for schedule(dynamic, 16)
+    for (int64_t lane_ = (int64_t) lane_begin; lane_ < (int64_t) lane_end; ++lane_) {
+        uint32_t lane = (uint32_t) lane_;
+        float *R = out + (uint64_t) (lane - lane_begin) * stride; memset(R, 0, sizeof(float) * stride);
+        PCG32 rng = sampler_for_lane(seed, lane);
+        PCG32 aux = sampler_for_lane(0xffffffffu ^ seed, lane);                      // _ReparamWrapper, common.py:1200-1203
+        CamRay cr = sample_camera_ray(sn, lane, spp, rng);
+        // primal pass with the cloned sampler (common.py:905-915)
+        bool valid; PCG32 rng_p = rng;
+        V3 Ltot = sample_primal(sc, cr.ray, rng_p, max_depth, rr_depth, &valid);
+        R[0] = cr.ray.o.x; R[1] = cr.ray.o.y; R[2] = cr.ray.o.z; R[3] = cr.ray.d.x; R[4] = cr.ray.d.y; R[5] = cr.ray.d.z;
+        R[6] = cr.pos_x; R[7] = cr.pos_y; R[8] = Ltot.x; R[9] = Ltot.y; R[10] = Ltot.z; R[11] = valid ? 1.f : 0.f;
+        // sample_rays' reparameterisation of the camera ray (depth 0), common.py:372-397
+        bool cam_active = 0 < reparam_max_depth;
+        R[13] = cam_active ? 1.f : 0.f;
+        Ray cam_aux{cr.ray.o, cr.ray.d, FLT_MAX};
+        reparam_log(sc, cam_aux, cam_active, aux, n_rays, kappa, exponent, R + PRB_HDR);
+        // differential pass, prb_reparam.py:329-602 (detached quantities)
+        uint32_t depth = 0; V3 L = Ltot, beta = mk(1, 1, 1); float eta = 1.f, mis_em = 1.f; bool active = true;
+        Ray ray = cr.ray; PI pi = scene_closest(sc, ray);
+        uint32_t it = 0;
+        for (; it < max_depth && active; ++it) {
+            float *I = it < n_iter ? R + PRB_HDR + PRB_AUX * n_rays + (uint64_t) it * (PRB_IT + 2 * PRB_AUX * n_rays) : nullptr;
+            SI si = compute_si(sc, ray, pi);
+            V3 Le = beta * mis_em * emitter_eval(sc, si);
+            bool active_next = (depth + 1 < max_depth) && si.valid;
+            const epsm_bsdf_desc *b = si.valid ? &sc.bsdfs[sc.meshes[si.mesh].bsdf] : nullptr;
+            uint32_t flags = b ? bsdf_flags(*b) : 0u;
+            bool active_em = active_next && (flags & EPSM_BF_SMOOTH);
+            float e1 = rng.next_f32(), e2 = rng.next_f32();
+            DS ds; V3 em_weight;
+            sample_emitter_direction(sc, si, e1, e2, active_em, &ds, &em_weight);
+            active_em &= ds.pdf != 0.f;
+            Ray em_ray{mk(0, 0, 0), mk(0, 0, 1), 0.f};
+            V3 Lr_dir = mk(0, 0, 0); float mis_direct = 0.f;
+            if (active_em) {
+                em_ray = spawn_ray_to(si, ds.p);
+                V3 wo = to_local(si, ds.d); V3 val; float bpdf;
+                bsdf_eval_pdf(*b, si.wi, wo, true, &val, &bpdf);
+                mis_direct = mis_weight(ds.pdf, bpdf);
+                Lr_dir = beta * mis_direct * val * em_weight;
+            }
+            float s1 = rng.next_f32(), s2x = rng.next_f32(), s2y = rng.next_f32();
+            BSample bs; memset(&bs, 0, sizeof(bs));
+            if (b) bs = bsdf_sample(*b, si.wi, s1, s2x, s2y, active_next);
+            V3 beta_in = beta; float eta_in = eta;
+            eta *= bs.eta; beta = beta * bs.weight;
+            V3 L_prev = L; L = L - Le - Lr_dir;
+            float bmax = max3(beta);
+            active_next &= bmax != 0.f;
+            float rr_prob = fminf(bmax * eta * eta, .95f);
+            bool rr_active = depth >= rr_depth;
+            if (rr_active) beta = beta * rcp_(rr_prob);
+            bool rr_continue = rng.next_f32() < rr_prob;
+            active_next &= !rr_active || rr_continue;
+            Ray ray_next = ray; PI pi_next; memset(&pi_next, 0, sizeof(pi_next));
+            SI si_next; memset(&si_next, 0, sizeof(si_next));
+            if (si.valid) ray_next = spawn_ray(si, to_world(si, bs.wo));
+            if (active_next) pi_next = scene_closest(sc, ray_next);                  // ray_intersect_preliminary(ray_next, active=active_next)
+            si_next = compute_si(sc, ray_next, pi_next);
+            float pdf_em = pdf_emitter_direction(sc, si_next, si.p, !(bs.type & EPSM_BF_DELTA));
+            float mis_next = mis_weight(bs.pdf, pdf_em);
+            // run-ahead with a clone of the sampler, prb_reparam.py:484-520
+            PCG32 clone = rng;
+            bool active_next_next = active_next && si_next.valid && (depth + 2 < max_depth);
+            const epsm_bsdf_desc *bn = si_next.valid ? &sc.bsdfs[sc.meshes[si_next.mesh].bsdf] : nullptr;
+            bool active_em_next = active_next_next && bn && (bsdf_flags(*bn) & EPSM_BF_SMOOTH);
+            float c1 = clone.next_f32(), c2 = clone.next_f32();
+            DS dsn; V3 emw_n;
+            sample_emitter_direction(sc, si_next, c1, c2, active_em_next, &dsn, &emw_n);
+            active_em_next &= dsn.pdf != 0.f;
+            V3 Lr_dir_next = mk(0, 0, 0);
+            if (active_em_next) {
+                V3 won = to_local(si_next, dsn.d), valn; float bpdfn;
+                bsdf_eval_pdf(*bn, si_next.wi, won, true, &valn, &bpdfn);
+                Lr_dir_next = beta * mis_weight(dsn.pdf, bpdfn) * valn * emw_n;
+            }
+            float c3 = clone.next_f32(), c4 = clone.next_f32(), c5 = clone.next_f32();
+            BSample bsn; memset(&bsn, 0, sizeof(bsn));
+            if (bn) bsn = bsdf_sample(*bn, si_next.wi, c3, c4, c5, active_next_next);
+            V3 Le_next = active_next ? beta * mis_next * emitter_eval(sc, si_next) : mk(0, 0, 0);
+            V3 L_next = L - Le_next - Lr_dir_next;
+            // reparameterisations: the emitter ray's custom op is created later in the iteration, so its backward runs first
+            // (reverse traversal order of the AD graph); both draw from the wrapper's one generator.
+            bool em_rp_active = active_em && (depth + 1 < reparam_max_depth);
+            bool main_rp_active = depth < reparam_max_depth;
+            float *aux_main = I ? I + PRB_IT : nullptr, *aux_em = I ? I + PRB_IT + PRB_AUX * n_rays : nullptr;
+            std::vector<float> scratch(PRB_AUX * n_rays);
+            reparam_log(sc, Ray{em_ray.o, em_ray.d, FLT_MAX}, em_rp_active, aux, n_rays, kappa, exponent, aux_em ? aux_em : scratch.data());
+            reparam_log(sc, Ray{ray.o, ray.d, FLT_MAX}, main_rp_active, aux, n_rays, kappa, exponent, aux_main ? aux_main : scratch.data());
+            if (I) {
+                I[0] = si.valid ? 1.f : 0.f; I[1] = si.valid ? (float) pi.prim : 0.f; I[2] = pi.u; I[3] = pi.v; I[4] = pi.t;
+                I[5] = ray.o.x; I[6] = ray.o.y; I[7] = ray.o.z; I[8] = ray.d.x; I[9] = ray.d.y; I[10] = ray.d.z;
+                I[11] = beta_in.x; I[12] = beta_in.y; I[13] = beta_in.z; I[14] = mis_em; I[15] = eta_in;
+                I[16] = active_next ? 1.f : 0.f; I[17] = active_em ? 1.f : 0.f;
+                I[18] = ds.p.x; I[19] = ds.p.y; I[20] = ds.p.z; I[21] = ds.n.x; I[22] = ds.n.y; I[23] = ds.n.z; I[24] = ds.pdf;
+                I[25] = em_weight.x; I[26] = em_weight.y; I[27] = em_weight.z; I[28] = mis_direct;
+                I[29] = bs.wo.x; I[30] = bs.wo.y; I[31] = bs.wo.z; I[32] = bs.pdf; I[33] = bs.weight.x; I[34] = bs.weight.y; I[35] = bs.weight.z;
+                I[36] = (bs.type & EPSM_BF_DELTA) ? 1.f : 0.f; I[37] = ray_next.d.x; I[38] = ray_next.d.y; I[39] = ray_next.d.z;
+                I[40] = L_prev.x; I[41] = L_prev.y; I[42] = L_prev.z; I[43] = L.x; I[44] = L.y; I[45] = L.z;
+                I[46] = si_next.valid ? 1.f : 0.f; I[47] = si_next.valid ? (float) pi_next.prim : 0.f; I[48] = pi_next.u; I[49] = pi_next.v;
+                I[50] = L_next.x; I[51] = L_next.y; I[52] = L_next.z; I[53] = bsn.wo.x; I[54] = bsn.wo.y; I[55] = bsn.wo.z;
+                I[56] = active_next_next ? 1.f : 0.f; I[57] = main_rp_active ? 1.f : 0.f; I[58] = em_rp_active ? 1.f : 0.f;
+                I[59] = em_ray.o.x; I[60] = em_ray.o.y; I[61] = em_ray.o.z; I[62] = em_ray.d.x; I[63] = em_ray.d.y; I[64] = em_ray.d.z;
+                I[65] = Le.x; I[66] = Le.y; I[67] = Le.z; I[68] = Lr_dir.x; I[69] = Lr_dir.y; I[70] = Lr_dir.z; I[71] = (float) depth;
+            }
+            mis_em = mis_next;
+            pi = pi_next; ray = ray_next;
+            if (si.valid) depth += 1;
+            active = active_next;
+        }
+        R[12] = (float) it;
+    }
+}
+
 uint32_t orc_sizeof_path() { return (uint32_t) sizeof(orc_path); }
 uint32_t orc_sizeof_vertex() { return (uint32_t) sizeof(orc_vertex); }
 

@@ -7,6 +7,7 @@
 #include <string>
 #include <vector>
 #include "../../epsm_mitsuba3_b200/csrc/epsm_device.cuh"
+#include "../../epsm_mitsuba3_b200/csrc/epsm_prb.cuh"
 #include "../../epsm_mitsuba3_b200/csrc/epsm_host_scene.h"
 
 struct sim_scene { HostScene hs; DScene sc; std::string err; };
@@ -74,6 +75,11 @@ void sim_bsdf_sample(sim_scene *s, uint32_t bsdf_id, const float *wi, float s1, 
 void sim_bsdf_eval_pdf(sim_scene *s, uint32_t bsdf_id, const float *wi, const float *wo, float *out4) {
     f3 value; float pdf; bsdf_eval_pdf(s->hs.bsdfs[bsdf_id], mk3(wi[0], wi[1], wi[2]), mk3(wo[0], wo[1], wo[2]), value, pdf);
     out4[0] = value.x; out4[1] = value.y; out4[2] = value.z; out4[3] = pdf;
+}
+// Σ_c a_c·f_c and its gradient w.r.t. (wi, wo) from the 6-wide forward duals of epsm_prb.cuh: out = value(3), g_wi(3), g_wo(3)
+void sim_bsdf_grad(sim_scene *s, uint32_t bsdf_id, const float *wi, const float *wo, const float *a, float *out9) {
+    f3 gi, go, v; bsdf_grad(s->hs.bsdfs[bsdf_id], mk3(wi[0], wi[1], wi[2]), mk3(wo[0], wo[1], wo[2]), mk3(a[0], a[1], a[2]), gi, go, v);
+    const float o[9] = {v.x, v.y, v.z, gi.x, gi.y, gi.z, go.x, go.y, go.z}; memcpy(out9, o, sizeof(o));
 }
 void sim_scene_stats(sim_scene *s, uint64_t *out) {
     out[0] = s->hs.faces.size() / 3; out[1] = s->hs.bvh.nodes.size() / EPSM_NODE_F4; out[2] = s->hs.bvh.depth;
@@ -272,6 +278,21 @@ void sim_backward(sim_scene *s, int variant, uint32_t sensor, uint32_t seed, uin
             const f3 gl = G.lg[k] * v.lr_sum;
             for (int c = 0; c < 3; ++c) add3(grad_pos, v.dfi[c], gl * v.dbw[c], v.direct_valid && v.direct_grad);
         }
+    }
+}
+
+// k_prb_backward on the host: one lane at a time (serial, plain adds).  film = RGBW film of the primal pass over all lanes.
+struct HostSink { float *gp, *gn; EPSM_HD void pos(uint32_t v, f3 g) { gp[3 * v] += g.x; gp[3 * v + 1] += g.y; gp[3 * v + 2] += g.z; }
+                  EPSM_HD void nrm(uint32_t v, f3 g) { gn[3 * v] += g.x; gn[3 * v + 1] += g.y; gn[3 * v + 2] += g.z; } };
+void sim_prb_backward(sim_scene *s, uint32_t sensor, uint32_t seed, uint32_t spp, const epsm_reparam_config *cfg, const float *film,
+                      const float *grad_in, uint64_t lane_begin, uint64_t lane_end, float *grad_pos, float *grad_nrm) {
+    const DSensor &se = s->hs.sensors[sensor];
+    PrbConfig pc{cfg->max_depth, cfg->rr_depth, cfg->reparam_max_depth, cfg->reparam_rays, cfg->reparam_kappa, cfg->reparam_exp};
+    HostSink sink{grad_pos, grad_nrm};
+    for (uint64_t lane = lane_begin; lane < lane_end; ++lane) {
+        LocalStack ls; TStack st; bind(st, ls); Tracer tr(s->sc, st);
+        const uint32_t pixel = (uint32_t) (lane / spp);
+        prb_backward_lane<false>(s->sc, tr, se, pc, pixel % se.w, pixel / se.w, seed, (uint32_t) lane, film, grad_in, sink);
     }
 }
 

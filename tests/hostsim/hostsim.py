@@ -31,10 +31,12 @@ def lib():
         L.sim_scene_copy_accel.argtypes = [vp, vp, vp]
         L.sim_bsdf_sample.argtypes = [vp, u32, vp, C.c_float, C.c_float, C.c_float, vp]
         L.sim_bsdf_eval_pdf.argtypes = [vp, u32, vp, vp, vp]
+        L.sim_bsdf_grad.argtypes = [vp, u32, vp, vp, vp, vp]
         L.sim_trace.argtypes = [vp, vp, u64, vp, i32, vp]
         L.sim_sampler_stream.argtypes = [u32, u64, u64, u32, vp]
         L.sim_sample_rays.argtypes = [vp, u32, u32, u32, u64, u64, vp]
         L.sim_render_accumulate.argtypes = [vp, u32, u32, u32, u32, u32, u64, u64, vp, i32]
+        L.sim_prb_backward.argtypes = [vp, u32, u32, u32, C.POINTER(capi.ReparamConfig), vp, vp, u64, u64, vp, vp]
         L.sim_backward.argtypes = [vp, i32, u32, u32, u32, u32, u32, vp, u64, u64, vp, vp, vp, i32]
         _LIB = L
     return _LIB
@@ -87,6 +89,11 @@ class SimScene:
         lib().sim_bsdf_eval_pdf(self.h, bsdf_id, wi.ctypes.data, wo.ctypes.data, out.ctypes.data)
         return out[:3], out[3]
 
+    def bsdf_grad(self, bsdf_id, wi, wo, a):
+        wi, wo, a = (np.ascontiguousarray(x, np.float32) for x in (wi, wo, a)); out = np.zeros(9, np.float32)
+        lib().sim_bsdf_grad(self.h, bsdf_id, wi.ctypes.data, wo.ctypes.data, a.ctypes.data, out.ctypes.data)
+        return out[0:3], out[3:6], out[6:9]
+
     def trace(self, rays, any_hit=False, counters=None):
         rays = np.ascontiguousarray(rays, np.float32); n = rays.shape[0]
         hits = np.zeros(n if any_hit else (n, 4), np.uint32)
@@ -117,4 +124,14 @@ class SimScene:
         gp = np.zeros((self.n_vertices, 3), np.float32); gn = np.zeros((self.n_vertices, 3), np.float32)
         lib().sim_backward(self.h, _vid(variant), sensor, seed, spp, max_depth, rr_depth, g.ctypes.data, lb, le,
                            gp.ctypes.data, gn.ctypes.data, None, int(prune))     # 2 = production schedule (fast path + chain prefix)
+        return gp, gn
+
+    def prb_backward(self, sensor, seed, spp, cfg: dict, film, grad_in, lb=0, le=None):
+        """k_prb_backward's lane code (epsm_prb.cuh) on the host.  film: (H,W,4) primal film of all lanes; grad_in (H,W,3)."""
+        s = self.data.sensors[sensor]; le = s.wavefront(spp) if le is None else le
+        c = capi.ReparamConfig(**cfg)
+        film = np.ascontiguousarray(film, np.float32); g = np.ascontiguousarray(grad_in, np.float32)
+        assert film.shape == (s.height, s.width, 4) and g.shape == (s.height, s.width, 3)
+        gp = np.zeros((self.n_vertices, 3), np.float32); gn = np.zeros((self.n_vertices, 3), np.float32)
+        lib().sim_prb_backward(self.h, sensor, seed, spp, C.byref(c), film.ctypes.data, g.ctypes.data, lb, le, gp.ctypes.data, gn.ctypes.data)
         return gp, gn

@@ -38,7 +38,12 @@ def _run(tmp_path, method):
     env = dict(os.environ)
     env["PYTHONPATH"] = os.pathsep.join([shim.SHIM_DIR, ROOT, env.get("PYTHONPATH", "")])
     env["EPSM_SHIM_TRACE"] = str(tmp_path / "trace.jsonl")
-    r = subprocess.run([sys.executable, os.path.join(DRIVER, "optim.py"), method, "synth_shadow"], cwd=tmp_path, env=env,
+    # runpy executes the reference's source as __main__, exactly as `python optim.py <method> <config>` would; the one
+    # environment patch is for this image's headless OpenCV build, whose destroyAllWindows() (utils/logger.py:136) throws.
+    boot = ("import sys, runpy, cv2; cv2.destroyAllWindows = lambda: None; "
+            f"sys.argv = [{os.path.join(DRIVER, 'optim.py')!r}, {method!r}, 'synth_shadow']; "
+            f"runpy.run_path({os.path.join(DRIVER, 'optim.py')!r}, run_name='__main__')")
+    r = subprocess.run([sys.executable, "-c", boot], cwd=tmp_path, env=env,
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + "\n" + r.stderr[-6000:]
     assert "finish optim" in r.stdout
