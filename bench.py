@@ -3,10 +3,10 @@
 
 A "step" is one gradient pass (render_backward-equivalent: ray generation, sample_path replay, manifold solve,
 gradient scatter; epsm.py:84-306) over the W·H·spp wavefront of the workload, followed — for N > 1 — by the one
-NCCL allreduce of the mesh-gradient buffer.  Work is sharded across ranks by sample index.  Default `--scaling weak`:
-every rank traces the workload's spp samples of every pixel, i.e. N ranks render an (N·spp)-sample wavefront (rank r owns
-samples [r·spp, (r+1)·spp) of each pixel — BASELINE's resolution/spp sweep); `--scaling strong` keeps the wavefront at
-spp and gives each rank spp/N samples per pixel.
+NCCL allreduce of the mesh-gradient buffer.  Work is sharded across ranks by sample index.  Default `--scaling strong`:
+the workload's wavefront (BASELINE configs[2]: 1024²×32 spp, a fixed job) is split, each rank tracing spp/N samples of every
+pixel; the weak-scaling number (every rank traces spp samples per pixel, i.e. an (N·spp)-sample wavefront — BASELINE's
+resolution/spp sweep) is measured in the same run and printed under the key `weak`.  `--scaling weak` makes that the headline.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload room|glass|cbox|smpl]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N … bench.py --gpus N …
@@ -36,6 +36,8 @@ WORKLOADS = {
     # name: (builder kwargs, variant, max_depth, description)
     "room": dict(variant="manifold", max_depth=8, res=1024, spp=32,
                  desc="procedural 1M-triangle indoor scene, manifold(_hybrid phase 1), 1024x1024, 32 spp (BASELINE configs[2])"),
+    "room8m": dict(variant="manifold", max_depth=8, res=1024, spp=32, tris=8_000_000,
+                   desc="the procedural indoor scene at 8M triangles (~0.8 GB of BVH nodes + triangle slots: does NOT fit the 126 MB L2), manifold, 1024x1024, 32 spp"),
     "glass": dict(variant="manifold_caustic", max_depth=6, res=512, spp=64,
                   desc="glass icosphere (20480 tris) over diffuse plane + area light, manifold_caustic, 512x512, 64 spp (configs[1])"),
     "cbox": dict(variant="manifold", max_depth=6, res=128, spp=16, desc="mi.cornell_box() 128x128, 16 spp, manifold (configs[0])"),
@@ -46,7 +48,7 @@ WORKLOADS = {
 
 def build_scene(name, res, spp, tris):
     from epsm_mitsuba3_b200 import scenes as S
-    if name == "room":
+    if name in ("room", "room8m"):
         sd = S.indoor_room(tris, res, spp, res)
     elif name == "glass":
         sd = S.glass_sphere_caustic(res, spp, res)
@@ -138,6 +140,41 @@ def iteration_leg(ep, scene, sd, integ, wl, sensor, spp, g_dev, buf, n=5, warm=2
     return out
 
 
+def phase2_leg(ep, scene, sd, wl, spp, n=2):
+    """ms per optimisation iteration once the hybrid schedule has switched (optim.py:113-141): vertex update + BVH refresh, primal render of
+    sensor 0 (sample_border) with prb_reparam's estimator, L2 loss against a target, reverse pass (k_prb_backward: primal film, film adjoint,
+    16 auxiliary rays per reparameterised ray), vertex step."""
+    import torch
+    integ2 = ep.load_dict({"type": "prb_reparam", "max_depth": wl["max_depth"]})
+    params = ep.traverse(scene)
+    keys = [k for k, i in params._mesh_of.items() if sd.meshes[i].grad] or list(params._mesh_of)
+    base = {k: params[k].clone() for k in keys}
+    target = integ2.render(scene, sensor=0, seed=999, spp=spp).clone()
+    ts, parts = [], []
+    for it in range(1 + n):
+        torch.cuda.synchronize(); scene.synchronize()
+        t0 = time.perf_counter()
+        for k in keys:
+            params[k] = base[k] + 1e-3 * float(np.sin(it + 1.0))
+        params.update(); scene.synchronize()
+        t1 = time.perf_counter()
+        img = integ2.render(scene, sensor=0, seed=it, spp=spp); scene.synchronize()
+        t2 = time.perf_counter()
+        g = (2.0 * (img - target) / img.numel()).contiguous()                  # d/d img of sum(sqr(img − ref)) / len(img)  (optim.py:138)
+        gp, gn = integ2.vertex_gradients(scene, g, 0, ep.sample_tea_32(it, 1)[0], spp)
+        torch.cuda.synchronize()
+        t3 = time.perf_counter()
+        if it >= 1:
+            ts.append((t3 - t0) * 1e3); parts.append(((t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3))
+    for k in keys:
+        params[k] = base[k]
+    params.update()
+    pm = np.median(np.array(parts), axis=0)
+    return {"unit": "ms per iteration (wall, median)", "iterations": n, "integrator": "prb_reparam", "sensor": 0, "spp": spp, "reparam_rays": integ2.reparam_rays,
+            "ms": float(np.median(ts)), "update_ms": float(pm[0]), "primal_ms": float(pm[1]), "backward_ms": float(pm[2]),
+            "grad_abs_sum": float(gp.abs().sum())}
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
 
@@ -192,14 +229,19 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_port_throughput(sd, wl, grad_in, target_seconds=12.0):
-    """The CPU oracle (port of the reference's path) on a bounded sample of the workload, all host threads."""
+def cpu_port_throughput(sd, wl, grad_in, target_seconds=12.0, prune=True):
+    """The CPU oracle (port of the reference's path) on a bounded sample of the workload, all host threads.
+    prune=True: the replay stops where each path's gradient chain ends — the same work the GPU pass does (its default);
+    prune=False: the reference's full min(max_depth, 6)-iteration replay (compare with the GPU line's `full_replay`)."""
+    import ctypes as C
     import torch
     from oracle import oracle
     from oracle.calc_grad_ref import calc_grad, scatter_gradients
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     o = oracle.OracleScene(sd, accel=True)
+    oracle.lib().orc_set_prune.argtypes = [C.c_int]
+    oracle.lib().orc_set_prune(({"manifold": 0, "manifold_caustic": 1}[wl["variant"]]) if prune else -1)
     sensor, spp, md = 1, wl["spp"], wl["max_depth"]
     total = sd.sensors[sensor].width * sd.sensors[sensor].height * spp
     nl = min(min(md, 6), 5)
@@ -213,13 +255,64 @@ def cpu_port_throughput(sd, wl, grad_in, target_seconds=12.0):
         scatter_gradients(paths, wl["variant"], nl, pg, lg, dg, sd.n_vertices, md)
         return le - lb, time.perf_counter() - t0
 
-    n, dt = run(4096)
-    rate = n / dt
-    n2 = int(min(total // 4, max(4096, rate * target_seconds)))
-    n, dt = run(n2)
+    try:
+        n, dt = run(4096)
+        rate = n / dt
+        n2 = int(min(total // 4, max(4096, rate * target_seconds)))
+        n, dt = run(n2)
+    finally:
+        oracle.lib().orc_set_prune(-1)
     return {"value": n / dt, "unit": "gradient path samples/s", "cores": cores, "kind": "port",
+            "replay": "gradient-live prefix (same work as the GPU pass)" if prune else "full (the reference's min(max_depth,6) iterations per lane)",
             "sample": f"{n} consecutive lanes (whole pixels, image centre) of the same wavefront: oracle path_log (OpenMP, median-split BVH) "
                       f"+ torch calc_grad + NumPy scatter; {dt:.1f} s"}
+
+
+def reference_binary_throughput(sd, wl, res_sample=256, spp_sample=None, timeout=600):
+    """BASELINE.md §2 B-trav: the UNMODIFIED reference (baseline/_ref/{kd,embree}/mitsuba, scalar_rgb, built by baseline/build_ref.sh)
+    rendering the same scene with its `path` integrator on all host cores — the traversal-dominated primal half of the path
+    (the scalar build has no AD, so the manifold pass itself cannot run in it).  Bounded sample: res_sample² pixels at the
+    workload's spp.  Returns {variant: {...}}; entries say why when a binary is missing."""
+    import re
+    import shutil
+    import tempfile
+    from epsm_mitsuba3_b200 import export
+    cores = os.cpu_count() or 1
+    spp = spp_sample or wl["spp"]
+    out = {}
+    tmp = tempfile.mkdtemp(prefix="epsm_refscene_")
+    try:
+        xml = export.export_scene(sd, tmp, integrator={"type": "path", "max_depth": int(wl["max_depth"])}, sensors=[1], spp=spp, resolution=res_sample)
+        for variant, accel in (("kd", "SAH kd-tree (kdtree.h:2188-2290)"), ("embree", "Embree 3 (scene_embree.inl:202-426)")):
+            d = os.path.join(ROOT, "baseline", "_ref", variant)
+            exe = os.path.join(d, "mitsuba")
+            if not os.path.exists(exe):
+                out[variant] = {"unavailable": f"{exe} not built (baseline/build_ref.sh{' --embree' if variant == 'embree' else ''})"}
+                continue
+            env = dict(os.environ, LD_LIBRARY_PATH=d + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
+            try:
+                r = subprocess.run([exe, "-m", "scalar_rgb", "-t", str(cores), "-o", os.path.join(tmp, f"{variant}.exr"), xml], env=env,
+                                   capture_output=True, text=True, timeout=timeout)
+            except subprocess.TimeoutExpired:
+                out[variant] = {"unavailable": f"timed out after {timeout} s"}; continue
+            log = r.stdout + r.stderr
+
+            def secs(pat):
+                m = re.search(pat, log)
+                if not m:
+                    return None
+                v, u = float(m.group(1)), m.group(2)
+                return v * {"ms": 1e-3, "s": 1.0, "m": 60.0}[u]
+            t_render = secs(r"Rendering finished\. \(took ([0-9.]+)(ms|s|m)")
+            t_build = secs(r"(?:Finished\. \([^)]*took|Embree ready\. \(took) ([0-9.]+)(ms|s|m)")
+            if r.returncode != 0 or not t_render:
+                out[variant] = {"unavailable": f"exit code {r.returncode}: {log[-300:]}"}; continue
+            n = res_sample * res_sample * spp
+            out[variant] = {"value": n / t_render, "unit": "primal path samples/s", "cores": cores, "accel": accel, "accel_build_s": t_build,
+                            "render_s": t_render, "sample": f"`mitsuba -m scalar_rgb -t {cores}` path integrator, max_depth {wl['max_depth']}, {res_sample}x{res_sample}, {spp} spp of the exported scene"}
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    return out
 
 
 def main():
@@ -232,8 +325,11 @@ def main():
     ap.add_argument("--res", type=int, default=0)
     ap.add_argument("--spp", type=int, default=0)
     ap.add_argument("--tris", type=int, default=1_000_000)
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="weak: per-GPU work fixed (N ranks trace N*spp samples per pixel); strong: the spp-sample wavefront is split over the ranks")
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
+                    help="strong (default): the workload's spp-sample wavefront — BASELINE configs[2] is a fixed 1024x1024x32 job — is split over the ranks; "
+                         "weak: per-GPU work fixed (N ranks trace N*spp samples per pixel, BASELINE's resolution/spp sweep)")
+    ap.add_argument("--no-weak-leg", action="store_true", help="N > 1, strong scaling: skip the weak-scaling measurement printed beside the line")
+    ap.add_argument("--phase2-leg", action="store_true", help="also time one optimisation iteration of hybrid phase 2 (prb_reparam on sensor 0, L2 loss)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-iteration-leg", action="store_true", help="skip the ms-per-optimisation-iteration measurement (BASELINE.json's second metric)")
@@ -244,6 +340,8 @@ def main():
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     wl = dict(WORKLOADS[args.workload])
+    if "tris" in wl and args.tris == 1_000_000:
+        args.tris = wl["tris"]
     if args.res: wl["res"] = args.res
     if args.spp: wl["spp"] = args.spp
     res, spp = wl["res"], wl["spp"]
@@ -263,20 +361,30 @@ def main():
         g = synthetic_grad_in(res)
         vals = []
         for i in range(args.warmup + args.steps):
-            r = cpu_port_throughput(sd, wl, g, target_seconds=8.0)
+            r = cpu_port_throughput(sd, wl, g, target_seconds=8.0, prune=not args.full_replay)
             if i >= args.warmup:
                 vals.append(r)
         v = float(np.mean([r["value"] for r in vals])) if vals else 0.0
         r = vals[-1] if vals else {"cores": os.cpu_count(), "kind": "port", "sample": "none"}
+        full = cpu_port_throughput(sd, wl, g, target_seconds=8.0, prune=False) if not args.full_replay else None
+        try:
+            refbin = reference_binary_throughput(sd, wl)
+        except Exception as e:
+            refbin = {"unavailable": f"{type(e).__name__}: {e}"}
         out = {"impl": "reference", "metric": "gradient path samples/sec", "value": v, "unit": "samples/s", "n_gpus": args.gpus,
                "steps": args.steps, "warmup": args.warmup, "ms_per_step": (res * res * spp / v * 1e3) if v else None,
                "ms_per_step_note": "one whole pass of the workload at the sampled rate (each step times a bounded sample, see cpu_baseline.sample)",
                "higher_is_better": True, "scaling": args.scaling,
                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-               "cpu_baseline": {"value": v, "unit": "samples/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+               "cpu_baseline": {"value": v, "unit": "samples/s", "cores": r["cores"], "kind": "port", "sample": r["sample"], "replay": r.get("replay")},
                "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-               "note": "the reference's own path is Python + CUDA-only torch on top of a cmake build (SURVEY F4, §8c) and cannot be compiled from "
-                       "a few source files; this arm times the CPU oracle, a line-by-line port of the same path, on all host cores"}
+               "full_replay": ({"value": full["value"], "unit": "samples/s", "sample": full["sample"],
+                                "note": "the reference's own schedule (no pruning); compare with the GPU line's full_replay key"} if full else None),
+               "reference_binary": refbin,
+               "note": "kind = port: the reference's manifold path is Python + Dr.Jit AD variants + CUDA-only torch (SURVEY F4, §8c); the scalar_rgb build "
+                       "of the reference that exists here (baseline/_ref) has no AD and cannot run it.  `value` times the CPU oracle — a line-by-line "
+                       "port of the same path — on all host cores, on the same pruned schedule the GPU arm runs; `reference_binary` is the unmodified "
+                       "reference binary's primal path tracer (kd-tree and Embree) on the exported scene: BASELINE.md §2's B-trav"}
         print(json.dumps(out)); return
 
     import torch
@@ -356,6 +464,29 @@ def main():
         full_leg = {"value": total_paths / (fms * 1e-3), "unit": "samples/s", "ms_per_step": fms,
                     "note": "epsm_set_full_replay(1): no gradient-liveness pruning, 1 warm-up + 2 timed steps"}
 
+    # ---- weak scaling beside the strong headline (N > 1): every rank traces the workload's spp samples of every pixel
+    weak_leg = None
+    if world > 1 and args.scaling == "strong" and not args.no_weak_leg:
+        spp_w = spp * world
+        w0, w1 = ep.sample_shard(spp_w, rank, world)
+
+        def wstep(k):
+            buf.zero_(); flush.fill_(k & 0xff); torch.cuda.synchronize()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record(cu_stream)
+            scene.set_sample_range(w0, w1)
+            scene.render_backward_raw(wl["variant"], sensor, 100 + k, spp_w, integ.max_depth, integ.rr_depth, g_dev, buf[0], buf[1])
+            ev1.record(cu_stream); scene.synchronize()
+            e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e2.record(); dist.all_reduce(buf); e3.record(); torch.cuda.synchronize()
+            return ev0.elapsed_time(ev1) + e2.elapsed_time(e3)
+        wstep(0); dist.barrier()
+        wm = float(np.mean([wstep(1 + k) for k in range(3)]))
+        t = torch.tensor([wm], device=scene.device); dist.all_reduce(t, op=dist.ReduceOp.MAX); wm = float(t.item())
+        weak_leg = {"value": res * res * spp_w / (wm * 1e-3), "unit": "samples/s", "ms_per_step": wm, "spp": spp_w, "spp_per_gpu": spp,
+                    "note": "weak scaling: per-GPU work fixed (the N-rank job is an N*spp-sample wavefront); 1 warm-up + 3 timed steps, max over ranks"}
+        scene.set_sample_range(s0, s1)
+
     # ---- e2e: the same pass through the C ABI with host buffers (pinned H2D of grad_in, D2H of the gradient buffers)
     e2e = None
     if not args.no_e2e:
@@ -367,16 +498,22 @@ def main():
             if world > 1:
                 dist.barrier()
             t0 = time.perf_counter()
-            scene.render_backward_raw(wl["variant"], sensor, 200 + k, spp_job, integ.max_depth, integ.rr_depth, g_host, gp_h, gn_h)   # returns after D2H
-            if world > 1:
-                b2 = torch.stack([gp_h, gn_h]).cuda(non_blocking=True); dist.all_reduce(b2); gp_h.copy_(b2[0]); torch.cuda.synchronize()
+            if world == 1:
+                scene.render_backward_raw(wl["variant"], sensor, 200 + k, spp_job, integ.max_depth, integ.rr_depth, g_host, gp_h, gn_h)   # host pointers through the C ABI: H2D + pass + D2H
+            else:
+                # N ranks: pinned grad_in H2D, device pass, ONE allreduce of the device buffer, ONE D2H of the reduced gradients
+                g_d = g_host.to(scene.device, non_blocking=True); buf.zero_(); torch.cuda.current_stream().synchronize()
+                scene.render_backward_raw(wl["variant"], sensor, 200 + k, spp_job, integ.max_depth, integ.rr_depth, g_d, buf[0], buf[1])
+                scene.synchronize()
+                dist.all_reduce(buf)
+                gp_h.copy_(buf[0], non_blocking=True); gn_h.copy_(buf[1], non_blocking=True); torch.cuda.synchronize()
             dt = time.perf_counter() - t0
             if k >= 2:
                 ts.append(dt)
         te = float(np.mean(ts))
         if world > 1:
             t = torch.tensor([te], device=scene.device); dist.all_reduce(t, op=dist.ReduceOp.MAX); te = float(t.item())
-        h2d = g_host.numel() * 4 + 2 * gp_h.numel() * 4; d2h = 2 * gp_h.numel() * 4
+        h2d = g_host.numel() * 4 + (2 * gp_h.numel() * 4 if world == 1 else 0); d2h = 2 * gp_h.numel() * 4     # C ABI accumulates: output buffers go up too
         e2e = {"value": total_paths / te, "unit": "samples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": te * 1e3}
     scene.set_sample_range(s0, s1)
@@ -408,8 +545,19 @@ def main():
                 traffic = json.load(open(tp)).get(args.workload)
             except Exception:
                 traffic = None
+        avg_launch_s = trace_ms * 1e-3 / max(trace_launches, 1)
+        scene_bytes = int(stats["n_nodes"]) * int(stats["node_bytes"]) + int(stats["n_triangles"]) * 64
         roof = {"bound": "hbm", "kernel": "k_wf_trace (closest + any-hit launches of one gradient pass)", "achieved": ach, "peak": peak,
                 "peak_source": peak_src, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                "traffic_source": "profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per traversal launch from the committed ncu "
+                                  "--set full capture of this workload (a constant of the capture, NOT re-measured in this run; null for workloads never captured)",
+                "dram_GBps_from_capture": (traffic / avg_launch_s / 1e9) if traffic else None,
+                "dram_frac_of_peak_from_capture": (traffic / avg_launch_s / 1e9 / peak) if traffic else None,
+                "scene_bytes_nodes_plus_triangle_slots": scene_bytes, "l2_bytes": 126 * 1024 * 1024,
+                "reading": "`frac` is the contract's figure: ALGORITHMIC bytes (cache hits not subtracted) over the measured copy bandwidth.  When the BVH "
+                           "and triangle slots fit the 126 MB L2 (scene_bytes <= l2_bytes) the kernel is NOT HBM-bound and frac can exceed 1: DRAM moves "
+                           "only the ray/hit streams (dram_frac_of_peak_from_capture); the binding units are then the L1 data pipe and the ALU (FMNMX) "
+                           "pipe — ncu figures in profiles/.  `--workload room8m` (8 M triangles, ~0.8 GB of nodes + slots) is the case that does not fit L2",
                 "launches_per_step": trace_launches, "kernel_ms_per_step": trace_ms, "share_of_step": trace_ms / k_ms,
                 "algorithmic_bytes_per_step": alg_bytes, "algorithmic_bytes_per_launch": alg_bytes / max(trace_launches, 1),
                 "avg_launch_ms": trace_ms / max(trace_launches, 1),
@@ -426,6 +574,11 @@ def main():
     if rank == 0 and world == 1 and not args.no_iteration_leg:
         iteration = iteration_leg(ep, scene, sd, integ, wl, sensor, spp_job, g_dev, buf)
 
+    # ---- hybrid phase 2 (it >= thres, optim.py:113-119): prb_reparam on sensor 0 with an L2 image loss
+    phase2 = None
+    if rank == 0 and world == 1 and args.phase2_leg:
+        phase2 = phase2_leg(ep, scene, sd, wl, spp_job)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
@@ -437,7 +590,7 @@ def main():
         out = {"metric": "gradient path samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
                "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
-               "roofline": roof, "cpu_baseline": cpu, "full_replay": full_leg, "iteration": iteration,
+               "roofline": roof, "cpu_baseline": cpu, "full_replay": full_leg, "weak": weak_leg, "iteration": iteration, "phase2_iteration": phase2,
                "scene": {"triangles": int(stats["n_triangles"]), "vertices": int(stats["n_vertices"]), "bvh_nodes": int(stats["n_nodes"]),
                          "bvh_build_ms": stats["build_ms"]},
                "wall_s_timed_region": t_wall, "ms_steps": [round(float(x), 3) for x in ms_steps]}

@@ -648,6 +648,7 @@ struct OBVH { std::vector<BNode> nodes; std::vector<uint32_t> prims; bool built 
 struct orc_scene { Scene sc; OBVH bvh; bool use_bvh = false; };
 
 namespace {
+int g_prune_variant = -1;                  // orc_set_prune: −1 full replay (the reference), 0 / 1 = prune like the product for manifold / manifold_caustic
 const orc_scene *g_accel_owner = nullptr;   // set per call (single-threaded entry; OpenMP threads only read)
 
 void bvh_build_rec(const Scene &sc, OBVH &b, uint32_t node, uint32_t first, uint32_t count, std::vector<V3> &cent) {
@@ -1040,6 +1041,7 @@ void orc_path_log(orc_scene *s, uint32_t sensor, uint32_t seed, uint32_t spp, ui
     g_accel_owner = s;
     const Scene &sc = s->sc; const Sensor &se = sc.sensors[sensor];
     const uint32_t max_iter = std::min(max_depth_prop, 6u);                        // epsm.py:549
+    const int prune_variant = g_prune_variant;
     #pragma omp parallel for schedule(dynamic, 64)
     for (int64_t li = 0; li < (int64_t) (lane_end - lane_begin); ++li) {
         uint32_t lane = (uint32_t) (lane_begin + li);
@@ -1055,6 +1057,7 @@ void orc_path_log(orc_scene *s, uint32_t sensor, uint32_t seed, uint32_t spp, ui
         V3 grad_d = (c.d_x - ray.d) * g[3] + (c.d_y - ray.d) * g[4];
         uint32_t depth = 0; V3 L = mk(0, 0, 0), beta = mk(1, 1, 1); float eta = 1.f; bool active = true;
         V3 prev_p = mk(0, 0, 0); float prev_pdf = 1.f; bool prev_delta = true;
+        bool chain = true;
         for (uint32_t it = 0; it < max_iter; ++it) {
             PI pi; SI si;
             if (active) { pi = scene_closest(sc, ray); si = compute_si(sc, ray, pi); }
@@ -1135,6 +1138,13 @@ void orc_path_log(orc_scene *s, uint32_t sensor, uint32_t seed, uint32_t spp, ui
                 }
             }
             L = L + Le + Lr_dir;
+            if (prune_variant >= 0) {
+                // gradient-liveness pruning, the rule of the product's wf_chain_vertex (epsm_device.cuh): calc_grad masks
+                // everything behind the vertex that ends the specular chain, and render_backward consumes nothing else
+                const bool diffuse = (flags & EPSM_BF_DIFFUSE) != 0, vact = active && si.valid;
+                chain = chain && vact && si.ismesh && (prune_variant == 0 ? !diffuse : (it == 0 ? diffuse : !diffuse));
+                if (!chain || it + 1 >= 5) break;                                   // the terminating vertex has been logged
+            }
             if (si.valid) ray = spawn_ray(si, to_world(si, bs.wo));
             eta *= bs.eta; beta = beta * bs.weight;
             prev_p = si.p; prev_pdf = bs.pdf; prev_delta = (bs.type & EPSM_BF_DELTA) != 0;
@@ -1385,6 +1395,10 @@ void orc_prb_log(orc_scene *os, uint32_t sensor, uint32_t seed, uint32_t spp, ui
         R[12] = (float) it;
     }
 }
+
+// CPU-baseline timing only: replay each path up to the vertex that ends its gradient chain (same rule as the product), so
+// that the CPU arm and the GPU arm of bench.py do equal work.  P.L is then the radiance of the prefix only.
+void orc_set_prune(int variant) { g_prune_variant = variant; }
 
 uint32_t orc_sizeof_path() { return (uint32_t) sizeof(orc_path); }
 uint32_t orc_sizeof_vertex() { return (uint32_t) sizeof(orc_vertex); }

@@ -28,12 +28,14 @@ def grid_positions(res: int, dtype=torch.float64) -> torch.Tensor:
     return torch.cat([p1[..., None], p0[..., None]], dim=2).reshape(-1, 2)
 
 
-def clouds(render_rgb, target_rgb, res, dtype=torch.float64):
-    """matcher.py:52-58: (r, g, b, x, y) with rgb clamped to [0, 1]."""
+def clouds(render_rgb, target_rgb, res, dtype=torch.float64, device="cpu"):
+    """matcher.py:52-58: (r, g, b, x, y) with rgb clamped to [0, 1].  `device`: where the dense N×N restatement is
+    evaluated — the production sizes (128² points = 2 GB per float64 cost matrix) are checked with the oracle on a CUDA
+    device in float64; it stays the same torch code."""
     pos = grid_positions(res, dtype)
     r = torch.as_tensor(np.asarray(render_rgb), dtype=dtype).reshape(-1, 3).clamp(0, 1)
     t = torch.as_tensor(np.asarray(target_rgb), dtype=dtype).reshape(-1, 3).clamp(0, 1)
-    return torch.cat([r, pos], 1), torch.cat([t, pos], 1)
+    return torch.cat([r, pos], 1).to(device), torch.cat([t, pos], 1).to(device)
 
 
 def max_diameter(x, y):
@@ -66,7 +68,7 @@ def sinkhorn_potentials(x, y, blur=0.01, scaling=0.9):
     """sinkhorn_loop with debias, balanced, uniform weights.  Returns the four potentials after the last (attached)
     extrapolation, the final ε and the ε schedule."""
     n, m = x.shape[0], y.shape[0]
-    a_log = torch.full((n,), -np.log(n), dtype=x.dtype); b_log = torch.full((m,), -np.log(m), dtype=x.dtype)
+    a_log = torch.full((n,), -np.log(n), dtype=x.dtype, device=x.device); b_log = torch.full((m,), -np.log(m), dtype=x.dtype, device=x.device)
     diameter = max_diameter(x.detach(), y.detach())
     eps_list = epsilon_schedule(2, diameter, blur, scaling)
     c_xx, c_yy = cost(x, x.detach()), cost(y, y.detach())
@@ -93,13 +95,13 @@ def sinkhorn_loss(x, y, blur=0.01, scaling=0.9):
     return (pot["f_ba"] - pot["f_aa"]).sum() / n + (pot["g_ab"] - pot["g_bb"]).sum() / m       # sinkhorn_cost, debias
 
 
-def match_sinkhorn(render_rgb, target_rgb, res, blur=0.01, scaling=0.9, dtype=torch.float64):
+def match_sinkhorn(render_rgb, target_rgb, res, blur=0.01, scaling=0.9, dtype=torch.float64, device="cpu"):
     """Matcher.match_Sinkhorn: returns (g (N,5) float64 numpy, loss)."""
-    x, y = clouds(render_rgb, target_rgb, res, dtype)
+    x, y = clouds(render_rgb, target_rgb, res, dtype, device)
     x.requires_grad_(True)
     loss = sinkhorn_loss(x, y, blur, scaling)
     (g,) = torch.autograd.grad(loss * res * res, [x])
-    return g.numpy(), float(loss.detach())
+    return g.cpu().numpy(), float(loss.detach())
 
 
 def grad_barycentric(render_rgb, target_rgb, res, blur=0.01, scaling=0.9, dtype=torch.float64):

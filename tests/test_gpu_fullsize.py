@@ -121,3 +121,37 @@ def test_glass_config_chunk_size_does_not_matter():
         finally:
             os.environ.pop("EPSM_WF_CHUNK", None)
     assert close(outs[0], outs[1]) and float(outs[0].abs().sum()) > 0
+
+
+@pytest.mark.parametrize("name,make,variant,res,spp,md", [
+    ("glass", lambda: S.glass_sphere_caustic(512, 64, 512), "manifold_caustic", 512, 64, 6),          # BASELINE configs[1]
+    ("stage", lambda: S.articulated_stage(512, 64, 512), "manifold_caustic", 512, 64, 3),             # BASELINE configs[3]: shadow_term branch
+])
+def test_fullsize_path_records_of_configs_1_and_3(orc, name, make, variant, res, spp, md):
+    """Per-path records of lane windows of the FULL configs[1] / configs[3] wavefronts against the oracle + the reference's
+    torch calc_grad (windows: image start, centre — where the object is — and end), and the accumulated gradient of a centre
+    band of pixels against the oracle's scatter."""
+    import epsm_mitsuba3_b200 as ep
+    sd = make()
+    scene, o = ep.Scene(sd, device=0), orc.OracleScene(sd, accel=True)
+    g = parity.synthetic_grad_in(res)
+    total = res * res * spp
+    centre = ((res // 2) * res + res // 2 - 16) * spp
+    n_grad = 0
+    for lb in (0, centre, total - 4096):
+        le = lb + 4096
+        paths = o.path_log(1, 21, spp, md, 5, g, lb, le)
+        rec = scene.path_records(variant, 1, 21, spp, md, 5, g, lb, le)
+        stats, _ = parity.check_path_records(rec, paths, variant, md)
+        n_grad += stats["nonzero"]
+    assert n_grad > 0
+    # accumulated gradients of a 4-row band through the image centre
+    from oracle.calc_grad_ref import calc_grad, scatter_gradients
+    lb, le = (res // 2 - 2) * res * spp, (res // 2 + 2) * res * spp
+    paths = o.path_log(1, 23, spp, md, 5, g, lb, le)
+    nl = min(min(md, 6), 5)
+    pg, lg, dg = calc_grad(paths, variant, nl)
+    rp, rn = scatter_gradients(paths, variant, nl, pg, lg, dg, sd.n_vertices, md)
+    buf = torch.zeros(2, scene.n_vertices, 3, device="cuda"); torch.cuda.synchronize()
+    scene.render_backward_raw(variant, 1, 23, spp, md, 5, torch.from_numpy(g).cuda(), buf[0], buf[1], lane_begin=lb, lane_end=le); scene.synchronize()
+    parity.check_accumulated(buf[0].cpu().numpy(), buf[1].cpu().numpy(), rp, rn)

@@ -64,6 +64,26 @@ def test_gpu_matcher_against_oracle(res):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("res,oracle_device", [(64, "cpu"), (128, "cuda")])
+def test_gpu_matcher_at_production_sizes(res, oracle_device):
+    """match_res of the reference's experiments (EPSM/exp/*.py: 128; 64 as the step below).  At 128² the cloud spans
+    sixteen 1024-column tiles, so the far-tile skip of k_sink_softmin is on the hot path.  The float64 dense oracle runs on
+    the CPU at 64² and — the same torch code — on the CUDA device at 128² (2 GB per cost matrix)."""
+    import epsm_mitsuba3_b200 as ep
+    a, b = images(res, res)
+    m = ep.Matcher(res, "cuda:0")
+    g = m.match_Sinkhorn(torch.from_numpy(a), torch.from_numpy(b), want_loss=True).cpu().numpy()
+    ref, loss = R.match_sinkhorn(a, b, res, device=oracle_device)
+    scale = np.abs(ref).max()
+    err = np.abs(g - ref).max()
+    assert err <= G_RTOL * scale, (err, scale)
+    assert m.last_loss == pytest.approx(loss, rel=2e-3, abs=1e-7)
+    # per-row relative error where the gradient is not negligible: no tile is skipped that matters to any row
+    big = np.abs(ref).max(1) > 0.05 * scale
+    assert (np.abs(g - ref)[big].max(1) / np.abs(ref)[big].max(1)).max() < 0.05
+
+
+@pytest.mark.gpu
 def test_gpu_matcher_identities_and_host_buffers():
     import ctypes as C
     import epsm_mitsuba3_b200 as ep
