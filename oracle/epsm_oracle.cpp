@@ -8,9 +8,11 @@
 // Parity pinning: TEA and PCG32 are pinned by the reference's own known-answer tests
 // (src/core/tests/test_random.py:8-16, src/samplers/tests/test_independent.py:17-29) and the
 // triangle/surface-interaction/BSDF/emitter/sensor functions by values read from the reference's
-// scalar_rgb module (tests/golden/reference_kats.json).  The manifold solve
-// (calc_grad) is "parity unpinned": the reference has no test or golden vector for it;
-// its oracle is the reference's own torch-autograd formulation restated in oracle/calc_grad_ref.py.
+// scalar_rgb module, built unmodified by baseline/build_ref.sh (tests/golden/reference_kats.json and ≥ 1 k seeded vectors
+// per function in tests/golden/reference_vectors.npz).  The manifold solve (oracle/calc_grad_ref.py) is pinned to the
+// outputs of the reference's own calc_grad source executed on CPU torch (tests/golden/calc_grad_reference.npz).
+// "Parity unpinned" remains for prb_reparam's reverse pass (orc_prb_log + oracle/prb_reparam_ref.py: no AD variant of the
+// reference runs in this image; checked against finite differences like the reference's own tests) and for the matcher.
 //
 // Arithmetic conventions follow Dr.Jit's JIT array code so that the CUDA path can be bit-compared:
 //   dot(a,b)   = fma(a.z,b.z, fma(a.y,b.y, a.x*b.x))          ext/drjit/include/drjit/array_base.h:603-628
