@@ -61,6 +61,7 @@ struct epsm_ctx {
     DevBuf<unsigned char> d_workspace; uint32_t wf_capacity = 0, trace_grid = 0;   // wavefront workspace (one chunk of lanes)
     DScene sc;
     bool trace_profiling = false; EpsmEventList trace_events;
+    bool sink_reorder = true;            // Z-curve order of the matcher's clouds (EPSM_SINK_REORDER=0 at context creation: A/B measurements)
     DevBuf<float> d_sink;                           // Sinkhorn matcher: clouds (host-memory calls), potentials ×2, barycentres
     DevBuf<double> d_sink_loss; DevBuf<int> d_sink_bbox;
 };
@@ -177,6 +178,7 @@ int epsm_create(int device, epsm_ctx **out) {
     if (e != cudaSuccess) { delete c; return fail(nullptr, EPSM_E_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e)); }
     memset(&c->sc, 0, sizeof(c->sc));
     if (const char *e = getenv("EPSM_FULL_REPLAY")) c->full_replay = atoi(e) != 0;
+    if (const char *e = getenv("EPSM_SINK_REORDER")) c->sink_reorder = atoi(e) != 0;
     if (const char *e = getenv("EPSM_PRIMAL_MEGAKERNEL")) c->primal_megakernel = atoi(e) != 0;
     cudaDeviceProp prop; cudaGetDeviceProperties(&prop, device);
     c->trace_grid = (uint32_t) prop.multiProcessorCount * 8u;        // persistent traversal CTAs: 148 SMs × 8 resident CTAs of 128 threads (≤ 64 regs)
@@ -686,7 +688,11 @@ int epsm_sinkhorn_grad(epsm_ctx *ctx, const float *x, uint32_t n, const float *y
     const size_t gout = mem == EPSM_MEM_HOST ? 5 * (size_t) n : 0;
     const size_t packed = 2 * (epsm_sink_packed_floats(n) + epsm_sink_packed_floats(m));       // four jobs: columns y, x, x, y (16-byte aligned: first)
     const size_t tinfo = 2 * (epsm_sink_tile_floats(n) + epsm_sink_tile_floats(m));
-    CK(ctx->d_sink.alloc(packed + tinfo + cloud + pots + bary + gout), "sinkhorn alloc");
+    // Z-curve reordering (epsm_launch_sink_order): sorted copies of both clouds, 4 words per point of sort scratch, cub's temp storage
+    const bool reorder = ctx->sink_reorder;
+    const size_t order_temp = reorder ? epsm_sink_order_temp_bytes(n > m ? n : m) / sizeof(float) : 0;
+    const size_t order = reorder ? 5 * ((size_t) n + m) + 4 * ((size_t) n + m) + order_temp + 64 : 0;
+    CK(ctx->d_sink.alloc(packed + tinfo + cloud + pots + bary + gout + order), "sinkhorn alloc");
     CK(ctx->d_sink_loss.alloc(1), "sinkhorn alloc"); CK(ctx->d_sink_bbox.alloc(10), "sinkhorn alloc");
     float4 *pk_y0 = reinterpret_cast<float4 *>(ctx->d_sink.p), *pk_x0 = pk_y0 + epsm_sink_packed_floats(m) / 4,
            *pk_x1 = pk_x0 + epsm_sink_packed_floats(n) / 4, *pk_y1 = pk_x1 + epsm_sink_packed_floats(n) / 4;
@@ -704,6 +710,10 @@ int epsm_sinkhorn_grad(epsm_ctx *ctx, const float *x, uint32_t n, const float *y
     float *g_ab[2] = {p, p + m}, *g_bb[2] = {p + 2 * (size_t) m, p + 3 * (size_t) m}; p += 4 * (size_t) m;
     float *bary_xy = p, *bary_xx = p + 5 * (size_t) n; p += bary;
     float *d_grad = mem == EPSM_MEM_HOST ? p : grad_x;
+    p += gout;
+    float *sorted_x = p, *sorted_y = p + 5 * (size_t) n;
+    uint32_t *words_x = reinterpret_cast<uint32_t *>(p + 5 * ((size_t) n + m)), *words_y = words_x + 4 * (size_t) n;
+    void *order_tmp = reinterpret_cast<void *>((reinterpret_cast<uintptr_t>(words_y + 4 * (size_t) m) + 255) & ~(uintptr_t) 255);
     // ε-schedule (geomloss epsilon_schedule, p = 2) from the diameter of the joint bounding box (max_diameter)
     CK(epsm_launch_sink_bbox(dx, n, dy, m, ctx->d_sink_bbox.p, s), "k_sink_bbox"); ctx->launches += 2;
     int hb[10];
@@ -713,6 +723,14 @@ int epsm_sinkhorn_grad(epsm_ctx *ctx, const float *x, uint32_t n, const float *y
     for (int d = 0; d < 5; ++d) { const float e = epsm_sink_ord_to_float(hb[5 + d]) - epsm_sink_ord_to_float(hb[d]); d2 += e * e; }
     const double diameter = (double) sqrtf(d2);
     if (!(diameter > 0.0)) return fail(ctx, EPSM_E_INVALID, "sinkhorn: degenerate point clouds (zero diameter)");
+    const uint32_t *perm_x = nullptr;
+    if (reorder) {
+        const float lo3 = epsm_sink_ord_to_float(hb[3]), hi3 = epsm_sink_ord_to_float(hb[8]), lo4 = epsm_sink_ord_to_float(hb[4]), hi4 = epsm_sink_ord_to_float(hb[9]);
+        CK(epsm_launch_sink_order(dx, n, lo3, hi3, lo4, hi4, words_x, order_tmp, order_temp * sizeof(float), sorted_x, s), "k_sink_order");
+        CK(epsm_launch_sink_order(dy, m, lo3, hi3, lo4, hi4, words_y, order_tmp, order_temp * sizeof(float), sorted_y, s), "k_sink_order");
+        ctx->launches += 4;
+        dx = sorted_x; dy = sorted_y; perm_x = words_x + 3 * (size_t) n;
+    }
     std::vector<double> eps_list; eps_list.push_back(diameter * diameter);
     {   // numpy.arange(2 ln d, 2 ln blur, 2 ln scaling): ceil((stop − start)/step) values start + k·step
         const double start = 2.0 * log(diameter), stop = 2.0 * log((double) blur), step = 2.0 * log((double) scaling);
@@ -746,7 +764,7 @@ int epsm_sinkhorn_grad(epsm_ctx *ctx, const float *x, uint32_t n, const float *y
         CK(epsm_launch_sink_step(st, 4, true, s), "k_sink_softmin"); ctx->launches += 1;
         cur ^= 1;
     }
-    CK(epsm_launch_sink_finish(bary_xx, bary_xy, scale / (float) n, n, grad_x ? d_grad : nullptr, f_ba[cur], f_aa[cur], g_ab[cur], g_bb[cur], m,
+    CK(epsm_launch_sink_finish(bary_xx, bary_xy, scale / (float) n, n, grad_x ? d_grad : nullptr, perm_x, f_ba[cur], f_aa[cur], g_ab[cur], g_bb[cur], m,
                                ctx->d_sink_loss.p, s), "k_sink_finish");
     ctx->launches += 1;
     if (n_steps) *n_steps = (uint32_t) eps_list.size();

@@ -1169,7 +1169,10 @@ struct AtomicSink {
     __device__ __forceinline__ void pos(uint32_t v, f3 g) { atomicAdd(gp + 3 * v, g.x); atomicAdd(gp + 3 * v + 1, g.y); atomicAdd(gp + 3 * v + 2, g.z); }
     __device__ __forceinline__ void nrm(uint32_t v, f3 g) { atomicAdd(gn + 3 * v, g.x); atomicAdd(gn + 3 * v + 1, g.y); atomicAdd(gn + 3 * v + 2, g.z); }
 };
-__global__ void __launch_bounds__(CTA) k_prb_backward(const __grid_constant__ DScene sc, const __grid_constant__ DLaunch ln, const __grid_constant__ PrbConfig cfg,
+#ifndef EPSM_PRB_MINBLOCKS
+#define EPSM_PRB_MINBLOCKS 2
+#endif
+__global__ void __launch_bounds__(CTA, EPSM_PRB_MINBLOCKS) k_prb_backward(const __grid_constant__ DScene sc, const __grid_constant__ DLaunch ln, const __grid_constant__ PrbConfig cfg,
                                                       const float *__restrict__ film, const float *__restrict__ grad_in, float *grad_pos, float *grad_nrm) {
     __shared__ SharedStack ss;
     TStack st; bind_stack(st, ss);

@@ -17,6 +17,7 @@
 // far too thin for tensor cores, and C/ε at ε = 1e-4 needs the full fp32 mantissa, so distances are formed from
 // coordinate differences (no |x|² + |y|² − 2x·y cancellation).
 #include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
 #include <math.h>
 #include <stdint.h>
 #include "epsm_sinkhorn.h"
@@ -267,13 +268,33 @@ __global__ void k_sink_bbox(const float *x, uint32_t n, const float *y, uint32_t
 }
 __global__ void k_sink_bbox_init(int *out) { if (threadIdx.x < 5) { out[threadIdx.x] = 0x7fffffff; out[5 + threadIdx.x] = (int) 0x80000000; } }
 
+// Z-curve order of a cloud along its last two coordinates (the pixel grid of the matcher's clouds, matcher.py:14-18): consecutive
+// points are then spatially compact, so that the 1024-column tiles and the 64-row blocks of k_sink_softmin have small boxes and the
+// far-tile test skips most tiles once ε is small.  Any permutation leaves the result unchanged up to the order of the fp32 sums.
+__device__ __forceinline__ uint32_t spread16(uint32_t v) { v &= 0xffffu; v = (v | (v << 8)) & 0x00ff00ffu; v = (v | (v << 4)) & 0x0f0f0f0fu; v = (v | (v << 2)) & 0x33333333u; return (v | (v << 1)) & 0x55555555u; }
+__global__ void k_sink_keys(const float *pts, uint32_t n, float lo3, float sc3, float lo4, float sc4, uint32_t *keys, uint32_t *idx) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float a = (pts[5 * (size_t) i + 3] - lo3) * sc3, b = (pts[5 * (size_t) i + 4] - lo4) * sc4;
+    const uint32_t qa = (uint32_t) fminf(fmaxf(a, 0.f), 65535.f), qb = (uint32_t) fminf(fmaxf(b, 0.f), 65535.f);
+    keys[i] = spread16(qa) | (spread16(qb) << 1); idx[i] = i;
+}
+__global__ void k_sink_gather(const float *src, const uint32_t *perm, uint32_t n, float *dst) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *p = src + 5 * (size_t) perm[i];
+#pragma unroll
+    for (int d = 0; d < 5; ++d) dst[5 * (size_t) i + d] = p[d];
+}
+
 // g_i = factor·(bary_xx_i − bary_xy_i);  loss = Σ_i (f_ba − f_aa)_i / n + Σ_j (g_ab − g_bb)_j / m
-__global__ void k_sink_finish(const float *bary_xx, const float *bary_xy, float factor, uint32_t n, float *grad,
+__global__ void k_sink_finish(const float *bary_xx, const float *bary_xy, float factor, uint32_t n, float *grad, const uint32_t *perm,
                               const float *f_ba, const float *f_aa, const float *g_ab, const float *g_bb, uint32_t m, double *loss) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n && grad) {
+        const size_t o = perm ? perm[i] : i;                  // back to the caller's point order
 #pragma unroll
-        for (int d = 0; d < 5; ++d) grad[5 * (size_t) i + d] = factor * (bary_xx[5 * (size_t) i + d] - bary_xy[5 * (size_t) i + d]);
+        for (int d = 0; d < 5; ++d) grad[5 * o + d] = factor * (bary_xx[5 * (size_t) i + d] - bary_xy[5 * (size_t) i + d]);
     }
     double l = 0.0;
     if (i < n) l += ((double) f_ba[i] - (double) f_aa[i]) / (double) n;
@@ -306,12 +327,27 @@ cudaError_t epsm_launch_sink_step(const SinkStep &st, int n_jobs, bool grad, cud
     return cudaGetLastError();
 }
 
-cudaError_t epsm_launch_sink_finish(const float *bary_xx, const float *bary_xy, float factor, uint32_t n, float *grad,
+cudaError_t epsm_launch_sink_finish(const float *bary_xx, const float *bary_xy, float factor, uint32_t n, float *grad, const uint32_t *perm,
                                     const float *f_ba, const float *f_aa, const float *g_ab, const float *g_bb, uint32_t m, double *loss,
                                     cudaStream_t s) {
     cudaError_t e = cudaMemsetAsync(loss, 0, sizeof(double), s);
     if (e != cudaSuccess) return e;
     const uint32_t k = n > m ? n : m;
-    k_sink_finish<<<(k + 255) / 256, 256, 0, s>>>(bary_xx, bary_xy, factor, n, grad, f_ba, f_aa, g_ab, g_bb, m, loss);
+    k_sink_finish<<<(k + 255) / 256, 256, 0, s>>>(bary_xx, bary_xy, factor, n, grad, perm, f_ba, f_aa, g_ab, g_bb, m, loss);
+    return cudaGetLastError();
+}
+size_t epsm_sink_order_temp_bytes(uint32_t n) {
+    size_t t = 0; cub::DeviceRadixSort::SortPairs(nullptr, t, (const uint32_t *) nullptr, (uint32_t *) nullptr, (const uint32_t *) nullptr, (uint32_t *) nullptr, (int) n);
+    return (t + 255) & ~(size_t) 255;
+}
+// words: 4·n uint32 scratch (keys, keys sorted, idx, perm) — perm = words + 3n is the result; sorted = the reordered cloud.
+cudaError_t epsm_launch_sink_order(const float *pts, uint32_t n, float lo3, float hi3, float lo4, float hi4, uint32_t *words, void *temp, size_t temp_bytes,
+                                   float *sorted, cudaStream_t s) {
+    const float sc3 = hi3 > lo3 ? 65535.f / (hi3 - lo3) : 0.f, sc4 = hi4 > lo4 ? 65535.f / (hi4 - lo4) : 0.f;
+    uint32_t *keys = words, *keys2 = words + n, *idx = words + 2 * (size_t) n, *perm = words + 3 * (size_t) n;
+    k_sink_keys<<<(n + 255) / 256, 256, 0, s>>>(pts, n, lo3, sc3, lo4, sc4, keys, idx);
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys, keys2, idx, perm, (int) n, 0, 32, s);
+    if (e != cudaSuccess) return e;
+    k_sink_gather<<<(n + 255) / 256, 256, 0, s>>>(pts, perm, n, sorted);
     return cudaGetLastError();
 }

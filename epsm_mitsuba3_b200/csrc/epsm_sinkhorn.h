@@ -24,6 +24,9 @@ struct SinkStep { SinkJob job[4]; float eps; int average; };
 cudaError_t epsm_launch_sink_bbox(const float *x, uint32_t n, const float *y, uint32_t m, int *out10, cudaStream_t s);
 float epsm_sink_ord_to_float(int ordered);
 cudaError_t epsm_launch_sink_step(const SinkStep &st, int n_jobs, bool grad, cudaStream_t s);
-cudaError_t epsm_launch_sink_finish(const float *bary_xx, const float *bary_xy, float factor, uint32_t n, float *grad,
+size_t epsm_sink_order_temp_bytes(uint32_t n);
+cudaError_t epsm_launch_sink_order(const float *pts, uint32_t n, float lo3, float hi3, float lo4, float hi4, uint32_t *words, void *temp, size_t temp_bytes,
+                                   float *sorted, cudaStream_t s);
+cudaError_t epsm_launch_sink_finish(const float *bary_xx, const float *bary_xy, float factor, uint32_t n, float *grad, const uint32_t *perm,
                                     const float *f_ba, const float *f_aa, const float *g_ab, const float *g_bb, uint32_t m, double *loss,
                                     cudaStream_t s);

@@ -69,7 +69,7 @@ def record_stats(kind, case, stats):
         f.write(json.dumps({"check": kind, "case": case, **{k: v for k, v in stats.items()}}) + "\n")
 
 
-def check_path_records(rec, paths, variant, max_depth, min_same=0.999, reference_lists=None):
+def check_path_records(rec, paths, variant, max_depth, min_same=0.999, reference_lists=None, max_ill_frac=0.01):
     """Per-path records of the backend vs the oracle's path log + torch calc_grad (or, with `reference_lists` =
     ((pg, lg, dg) float32, (pg, lg, dg) float64), vs the committed outputs of the reference's own calc_grad code).
     Returns statistics; asserts the north_star tolerances on the paths whose prim sequences agree."""
@@ -149,7 +149,7 @@ def check_path_records(rec, paths, variant, max_depth, min_same=0.999, reference
         cmp(lg[k], g[:, k, 15:18], f"light_grad[{k}]")
         cmp(dg[k], g[:, k, 18:21], f"diffuse_grad[{k}]")
     assert stats["flipped"] <= max(2, n // 5000)
-    assert stats["ill_conditioned"] <= max(4, n // 100), stats                                # ≤ 1 % of the paths
+    assert stats["ill_conditioned"] <= max(4, int(n * max_ill_frac)), stats                   # ≤ 1 % of the paths by default
     return stats, (pg, lg, dg)
 
 

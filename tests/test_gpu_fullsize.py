@@ -142,7 +142,10 @@ def test_fullsize_path_records_of_configs_1_and_3(orc, name, make, variant, res,
         le = lb + 4096
         paths = o.path_log(1, 21, spp, md, 5, g, lb, le)
         rec = scene.path_records(variant, 1, 21, spp, md, 5, g, lb, le)
-        stats, _ = parity.check_path_records(rec, paths, variant, md)
+        # the centre window lies entirely on the object: every path carries a gradient and the share of ill-conditioned ones
+        # (held to the float64 evaluation within the reference's own float32 error, parity.cmp_ill) is above the scene average
+        # of ≤ 1 % — measured 1.7 % on `stage` (profiles/r02_e_summary.md)
+        stats, _ = parity.check_path_records(rec, paths, variant, md, max_ill_frac=0.03)
         n_grad += stats["nonzero"]
     assert n_grad > 0
     # accumulated gradients of a 4-row band through the image centre
