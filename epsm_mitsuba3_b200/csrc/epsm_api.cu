@@ -61,6 +61,9 @@ struct epsm_ctx {
     DevBuf<unsigned char> d_workspace; uint32_t wf_capacity = 0, trace_grid = 0;   // wavefront workspace (one chunk of lanes)
     DScene sc;
     bool trace_profiling = false; EpsmEventList trace_events;
+    DevBuf<float> d_lane_L, d_scratch_film;          // prb_reparam: per-lane radiance of the primal pass; film of the re-render when the caller owns the film
+    DevBuf<unsigned char> d_prb_workspace; uint32_t prb_capacity = 0, prb_ws_depth = 0, prb_ws_rays = 0;
+    bool prb_megakernel = false;                     // EPSM_PRB_MEGAKERNEL=1: the per-lane megakernel (k_prb_backward) instead of the replay wavefront
     bool sink_reorder = true;            // Z-curve order of the matcher's clouds (EPSM_SINK_REORDER=0 at context creation: A/B measurements)
     DevBuf<float> d_sink;                           // Sinkhorn matcher: clouds (host-memory calls), potentials ×2, barycentres
     DevBuf<double> d_sink_loss; DevBuf<int> d_sink_bbox;
@@ -179,6 +182,7 @@ int epsm_create(int device, epsm_ctx **out) {
     memset(&c->sc, 0, sizeof(c->sc));
     if (const char *e = getenv("EPSM_FULL_REPLAY")) c->full_replay = atoi(e) != 0;
     if (const char *e = getenv("EPSM_SINK_REORDER")) c->sink_reorder = atoi(e) != 0;
+    if (const char *e = getenv("EPSM_PRB_MEGAKERNEL")) c->prb_megakernel = atoi(e) != 0;
     if (const char *e = getenv("EPSM_PRIMAL_MEGAKERNEL")) c->primal_megakernel = atoi(e) != 0;
     cudaDeviceProp prop; cudaGetDeviceProperties(&prop, device);
     c->trace_grid = (uint32_t) prop.multiProcessorCount * 8u;        // persistent traversal CTAs: 148 SMs × 8 resident CTAs of 128 threads (≤ 64 regs)
@@ -192,7 +196,7 @@ int epsm_destroy(epsm_ctx *ctx) {
     ctx->d_nodes.release(); ctx->d_tris.release(); ctx->d_pos.release(); ctx->d_nrm.release(); ctx->d_cdf.release(); ctx->d_pmf.release();
     ctx->d_faces.release(); ctx->d_face_mesh.release(); ctx->d_meshes.release(); ctx->d_bsdfs.release(); ctx->d_emitters.release();
     for (auto &f : ctx->d_films) f.release();
-    ctx->stage_a.release(); ctx->stage_b.release(); ctx->stage_c.release(); ctx->d_counters.release(); ctx->d_workspace.release(); ctx->d_sink.release(); ctx->d_sink_loss.release(); ctx->d_sink_bbox.release();
+    ctx->stage_a.release(); ctx->stage_b.release(); ctx->stage_c.release(); ctx->d_counters.release(); ctx->d_workspace.release(); ctx->d_lane_L.release(); ctx->d_scratch_film.release(); ctx->d_prb_workspace.release(); ctx->d_sink.release(); ctx->d_sink_loss.release(); ctx->d_sink_bbox.release();
     cudaStreamDestroy(ctx->stream);
     delete ctx; return EPSM_OK;
 }
@@ -441,15 +445,17 @@ int epsm_film_raw(epsm_ctx *ctx, uint32_t sensor, float **device_ptr, uint64_t *
     return EPSM_OK;
 }
 
-int epsm_render_accumulate(epsm_ctx *ctx, uint32_t sensor, uint32_t seed, uint32_t spp, uint32_t max_depth, uint32_t rr_depth,
-                           uint64_t lane_begin, uint64_t lane_end, uint64_t *counters) {
+// film == nullptr: the context's film of `sensor`.  lane_L (device, 3 floats per global lane id; wavefront render only): each lane's radiance.
+static int render_accumulate_impl(epsm_ctx *ctx, uint32_t sensor, uint32_t seed, uint32_t spp, uint32_t max_depth, uint32_t rr_depth,
+                                  uint64_t lane_begin, uint64_t lane_end, uint64_t *counters, float *film, float *lane_L) {
     if (!ctx) return EPSM_E_INVALID;
     DLaunch ln; int rc = make_launch(ctx, sensor, seed, spp, max_depth, rr_depth, lane_begin, lane_end, 0, ln);
     if (rc) return rc;
     CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    if (!film) film = ctx->d_films[sensor].p;
     if (counters) { rc = zero_counters(ctx); if (rc) return rc; }
-    if (ctx->primal_megakernel) {
-        CK(epsm_launch_render(ctx->sc, ln, ctx->d_films[sensor].p, counters ? ctx->d_counters.p : nullptr, ctx->stream), "k_render");
+    if (ctx->primal_megakernel && !lane_L) {
+        CK(epsm_launch_render(ctx->sc, ln, film, counters ? ctx->d_counters.p : nullptr, ctx->stream), "k_render");
         ctx->launches += 1;
     } else {
         const uint64_t S = (uint64_t) (ln.s_end - ln.s_begin);
@@ -458,11 +464,15 @@ int epsm_render_accumulate(epsm_ctx *ctx, uint32_t sensor, uint32_t seed, uint32
         const uint64_t y0 = ln.lane_begin / row_lanes, y1 = std::min<uint64_t>((ln.lane_end + row_lanes - 1) / row_lanes, ln.sensor.h);
         const uint64_t tile_rows = y1 > y0 ? (y1 + 3) / 4 - y0 / 4 : 0;
         rc = ensure_workspace(ctx, (uint64_t) ((ln.sensor.w + 7) / 8) * tile_rows * 32ull * S); if (rc) return rc;
-        CK(epsm_launch_render_wf(ctx->sc, ln, ctx->d_films[sensor].p, counters ? ctx->d_counters.p : nullptr, ctx->d_workspace.p, ctx->wf_capacity,
-                                 ctx->trace_grid, &ctx->launches, ctx->stream), "wavefront render");
+        CK(epsm_launch_render_wf(ctx->sc, ln, film, counters ? ctx->d_counters.p : nullptr, ctx->d_workspace.p, ctx->wf_capacity,
+                                 ctx->trace_grid, &ctx->launches, ctx->stream, lane_L), "wavefront render");
     }
     if (counters) return fetch_counters(ctx, counters);
     return EPSM_OK;
+}
+int epsm_render_accumulate(epsm_ctx *ctx, uint32_t sensor, uint32_t seed, uint32_t spp, uint32_t max_depth, uint32_t rr_depth,
+                           uint64_t lane_begin, uint64_t lane_end, uint64_t *counters) {
+    return render_accumulate_impl(ctx, sensor, seed, spp, max_depth, rr_depth, lane_begin, lane_end, counters, nullptr, nullptr);
 }
 
 int epsm_film_develop(epsm_ctx *ctx, uint32_t sensor, float *out_hw5, int mem) {
@@ -531,13 +541,22 @@ int epsm_prb_reparam_backward(epsm_ctx *ctx, uint32_t sensor, uint32_t seed, uin
     if (!(cfg->reparam_kappa > 0.f)) return fail(ctx, EPSM_E_INVALID, "reparam_kappa must be positive");
     if (cfg->rr_depth == 0) return fail(ctx, EPSM_E_INVALID, "\"rr_depth\" must be set to a value greater than zero!");
     int rc;
-    if (!film_ready) {                                   // primal pass of render_backward (common.py:905-935): the film of ALL lanes
-        rc = epsm_film_clear(ctx, sensor); if (rc) return rc;
-        rc = epsm_render_accumulate(ctx, sensor, seed, spp, cfg->max_depth, cfg->rr_depth, 0, 0, nullptr); if (rc) return rc;
-    }
     DLaunch ln; rc = make_launch(ctx, sensor, seed, spp, cfg->max_depth, cfg->rr_depth, lane_begin, lane_end, 0, ln);
     if (rc) return rc;
     CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    // replay wavefront (k_prb_pass over the persistent traversal kernel) unless the path is unbounded or the per-lane megakernel is asked for
+    const bool wavefront = cfg->max_depth <= EPSM_PRB_WF_MAX_DEPTH && !ctx->prb_megakernel;
+    const uint64_t n_lanes_total = (uint64_t) ln.sensor.w * ln.sensor.h * spp;
+    float *lane_L = nullptr;
+    if (wavefront) { CK(ctx->d_lane_L.alloc(3 * n_lanes_total), "lane radiance alloc"); lane_L = ctx->d_lane_L.p; }
+    if (!film_ready) {                                   // primal pass of render_backward (common.py:905-935): the film of ALL lanes
+        rc = epsm_film_clear(ctx, sensor); if (rc) return rc;
+        rc = render_accumulate_impl(ctx, sensor, seed, spp, cfg->max_depth, cfg->rr_depth, 0, 0, nullptr, nullptr, lane_L); if (rc) return rc;
+    } else if (wavefront) {                              // the caller rendered (and reduced) the film: only the lanes' radiance is needed
+        CK(ctx->d_scratch_film.alloc((size_t) ln.sensor.fw * ln.sensor.fh * 4), "scratch film alloc");
+        CK(cudaMemsetAsync(ctx->d_scratch_film.p, 0, (size_t) ln.sensor.fw * ln.sensor.fh * 4 * sizeof(float), ctx->stream), "scratch film clear");
+        rc = render_accumulate_impl(ctx, sensor, seed, spp, cfg->max_depth, cfg->rr_depth, lane_begin, lane_end, nullptr, ctx->d_scratch_film.p, lane_L); if (rc) return rc;
+    }
     const size_t n_img = (size_t) ln.sensor.fw * ln.sensor.fh * 3, n_v = ctx->hs.pos.size();
     const float *d_gin; rc = to_device(ctx, grad_in_hw3, n_img, mem, ctx->stage_a, &d_gin); if (rc) return rc;
     float *d_gp = grad_pos, *d_gn = grad_nrm;
@@ -548,8 +567,28 @@ int epsm_prb_reparam_backward(epsm_ctx *ctx, uint32_t sensor, uint32_t seed, uin
         CK(cudaMemcpyAsync(d_gn, grad_nrm, n_v * sizeof(float), cudaMemcpyHostToDevice, ctx->stream), "H2D grad_nrm");
     }
     PrbConfig pc{cfg->max_depth, cfg->rr_depth, cfg->reparam_max_depth, cfg->reparam_rays, cfg->reparam_kappa, cfg->reparam_exp};
-    CK(epsm_launch_prb_backward(ctx->sc, ln, pc, ctx->d_films[sensor].p, d_gin, d_gp, d_gn, ctx->stream), "k_prb_backward");
-    ctx->launches += 1;
+    if (wavefront) {
+        const uint64_t lanes = (uint64_t) ln.sensor.w * ln.sensor.h * (ln.s_end - ln.s_begin);
+        uint64_t cap = 1ull << 23;
+        if (const char *e = getenv("EPSM_PRB_CHUNK")) { uint64_t v = strtoull(e, nullptr, 10); if (v >= 1024) cap = v; }
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+            free_b += ctx->d_prb_workspace.n;
+            while (cap > (1ull << 16) && epsm_prb_workspace_bytes((uint32_t) cap, pc.max_depth, pc.n_rays) > free_b / 2) cap >>= 1;
+        }
+        if (lanes < cap) cap = (lanes + 1023) & ~1023ull;
+        if (cap < 1024) cap = 1024;
+        if (ctx->prb_capacity < cap || ctx->prb_ws_depth < pc.max_depth || ctx->prb_ws_rays < pc.n_rays) {
+            CK(cudaStreamSynchronize(ctx->stream), "prb workspace sync");
+            CK(ctx->d_prb_workspace.alloc(epsm_prb_workspace_bytes((uint32_t) cap, pc.max_depth, pc.n_rays)), "prb workspace alloc");
+            ctx->prb_capacity = (uint32_t) cap; ctx->prb_ws_depth = pc.max_depth; ctx->prb_ws_rays = pc.n_rays;
+        }
+        CK(epsm_launch_prb_backward_wf(ctx->sc, ln, pc, ctx->d_films[sensor].p, lane_L, d_gin, d_gp, d_gn, ctx->d_prb_workspace.p, ctx->prb_capacity,
+                                       ctx->trace_grid, &ctx->launches, ctx->stream), "k_prb_pass");
+    } else {
+        CK(epsm_launch_prb_backward(ctx->sc, ln, pc, ctx->d_films[sensor].p, d_gin, d_gp, d_gn, ctx->stream), "k_prb_backward");
+        ctx->launches += 1;
+    }
     if (mem == EPSM_MEM_HOST) {
         CK(cudaMemcpyAsync(grad_pos, d_gp, n_v * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream), "D2H grad_pos");
         CK(cudaMemcpyAsync(grad_nrm, d_gn, n_v * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream), "D2H grad_nrm");

@@ -763,7 +763,8 @@ __global__ void __launch_bounds__(128, EPSM_PR_MINBLOCKS) k_pr_stage(const __gri
 
 // ImageBlock::put, coalesced branch (imageblock.cpp:414-494) into a tile-local RGBW block with a 2-pixel apron, then
 // HDRFilm::put_block (hdrfilm.cpp:286-320): pixels outside the film are the cropped border.
-__global__ void __launch_bounds__(128) k_pr_film(const __grid_constant__ DScene sc, const __grid_constant__ DLaunch ln, uint64_t work_base, uint32_t n, WfBuffers wb, float *__restrict__ film) {
+__global__ void __launch_bounds__(128) k_pr_film(const __grid_constant__ DScene sc, const __grid_constant__ DLaunch ln, uint64_t work_base, uint32_t n, WfBuffers wb, float *__restrict__ film,
+                                                 float *__restrict__ lane_L) {
     __shared__ float ftile[FT_H][FT_W][4];
     for (int k = threadIdx.x; k < FT_H * FT_W * 4; k += 128) (&ftile[0][0][0])[k] = 0.f;
     __syncthreads();
@@ -783,6 +784,7 @@ __global__ void __launch_bounds__(128) k_pr_film(const __grid_constant__ DScene 
         PrState St; soa_load(St, wb.states, wb.capacity, i);
         pr_resolve_pending(St, wb.occl[i] != 0u);
         const f3 L = St.L;
+        if (lane_L) { float *o = lane_L + 3 * (size_t) wi.lane; o[0] = L.x; o[1] = L.y; o[2] = L.z; }    // per-lane radiance for prb_reparam's reverse pass
         Pcg rng = pcg_for_lane(ln.seed, (uint32_t) wi.lane);
         const float jx = pcg_f32(rng), jy = pcg_f32(rng);
         const float pos_x = (float) ((int) wi.px - B) + jx, pos_y = (float) ((int) wi.py - B) + jy;     // camera_ray's film position
@@ -997,7 +999,7 @@ cudaError_t epsm_launch_render(const DScene &sc, DLaunch ln, float *film, unsign
 // Wavefront primal render.  `host_count` is a pinned (or pageable) word used to poll the queue size once the path
 // length exceeds 8 bounces (max_depth = −1 means "until every path has died", common.py:33-37).
 cudaError_t epsm_launch_render_wf(const DScene &sc, DLaunch ln, float *film, unsigned long long *counters, void *workspace, uint32_t capacity,
-                                  uint32_t trace_grid, uint64_t *n_launches, cudaStream_t s) {
+                                  uint32_t trace_grid, uint64_t *n_launches, cudaStream_t s, float *lane_L) {
     tile_rows(ln);
     const uint32_t tiles = tile_grid(ln);
     if (tiles == 0 || ln.s_end <= ln.s_begin) return cudaSuccess;
@@ -1041,7 +1043,7 @@ cudaError_t epsm_launch_render_wf(const DScene &sc, DLaunch ln, float *film, uns
         }
         if (shadow_left && ln.max_depth > 0) trace(true, last_slot);      // shadow rays pushed by the last stage
         const uint32_t n_tiles = (uint32_t) ((base + n - 1) / per_tile - base / per_tile + 1);
-        k_pr_film<<<n_tiles, 128, 0, s>>>(sc, ln, base, n, wb, film); ++launches;
+        k_pr_film<<<n_tiles, 128, 0, s>>>(sc, ln, base, n, wb, film, lane_L); ++launches;
         if (counters) { k_count_lanes<<<grid, 128, 0, s>>>(n, wb, counters); ++launches; }
     }
     if (n_launches) *n_launches += launches;
@@ -1185,12 +1187,108 @@ __global__ void __launch_bounds__(CTA, EPSM_PRB_MINBLOCKS) k_prb_backward(const 
     if (lane < ln.lane_begin || lane >= ln.lane_end) return;
     const uint32_t py = (uint32_t) (pixel / ln.sensor.w), px = (uint32_t) (pixel - (uint64_t) py * ln.sensor.w);
     AtomicSink sink{grad_pos, grad_nrm};
-    prb_backward_lane<false>(sc, tr, ln.sensor, cfg, px, py, ln.seed, (uint32_t) lane, film, grad_in, sink);
+    MegaIo<false> io(tr);
+    prb_backward_lane(sc, io, ln.sensor, cfg, px, py, ln.seed, (uint32_t) lane, film, grad_in, sink);
 }
 cudaError_t epsm_launch_prb_backward(const DScene &sc, DLaunch ln, const PrbConfig &cfg, const float *film, const float *grad_in,
                                      float *grad_pos, float *grad_nrm, cudaStream_t s) {
     const uint64_t total = (uint64_t) ln.sensor.w * ln.sensor.h * (ln.s_end - ln.s_begin);
     if (total == 0) return cudaSuccess;
     k_prb_backward<<<(unsigned) ((total + CTA - 1) / CTA), CTA, 0, s>>>(sc, ln, cfg, film, grad_in, grad_pos, grad_nrm);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+//  prb_reparam reverse pass as a replay wavefront.  A lane's rays come in rounds (epsm_prb.cuh, MegaIo comment): pass p of
+//  k_prb_pass replays the lane from its seed — the detached walk is cheap next to its rays — reads the results of rounds
+//  < p from per-lane slots, queues the rays of round p for the persistent traversal kernel (k_wf_trace) and stops; the
+//  adjoint of iteration `it` runs in the one pass (2·it + 3) in which its auxiliary hits are fresh.  No path state is
+//  stored between passes: only hits.  2·K + 2 passes for K iterations, each followed by one closest-hit and one any-hit
+//  drain of the queues; lanes that have finished drop out through their status word.
+// ------------------------------------------------------------------------------------------------
+struct WfPrb {
+    uint32_t *status;       // [C] 0 live, 1 finished / not a lane
+    Hit *hits;              // [(K + 1 + 2n)·C] slot-major: path hits 0 … K, then the auxiliary hits
+    uint32_t *occl;         // [2K·C]
+    QRay *q_closest, *q_any;
+    uint32_t *counters;     // [0] closest count, [1] closest head, [2] any count, [3] any head
+    const float *lane_L;    // per-lane radiance of the primal pass, indexed by global lane id
+    uint32_t C, K, n_aux;
+};
+struct WfIo {
+    static constexpr bool wavefront = true;
+    const WfPrb &wb; int pass; uint32_t i; uint64_t lane;
+    __device__ __forceinline__ void push(QRay *q, uint32_t *count, const Ray &r, uint32_t out) {
+        const uint32_t k = queue_push(count, true); queue_write(q, k, r, out);
+    }
+    __device__ __forceinline__ Hit closest(int round, uint32_t slot, const Ray &r) {
+        if (round == pass) { push(wb.q_closest, wb.counters + 0, r, slot * wb.C + i); return Hit{0.f, 0.f, 0.f, 0xffffffffu}; }
+        return wb.hits[(size_t) slot * wb.C + i];
+    }
+    __device__ __forceinline__ bool occluded(int round, uint32_t slot, const Ray &r) {
+        if (round == pass) { push(wb.q_any, wb.counters + 2, r, slot * wb.C + i); return false; }
+        return wb.occl[(size_t) slot * wb.C + i] != 0u;
+    }
+    __device__ __forceinline__ bool stop_after(int round) const { return pass == round; }
+    __device__ __forceinline__ bool adjoint_now(int round) const { return pass == round + 1; }
+    __device__ __forceinline__ bool aux_push_only(int round) const { return pass == round; }
+    __device__ __forceinline__ bool aux_skip(int round) const { return pass > round + 1; }
+    __device__ __forceinline__ void aux_push(uint32_t j, const Ray &r) { push(wb.q_closest, wb.counters + 0, r, (wb.K + 1 + j) * wb.C + i); }
+    __device__ __forceinline__ Hit aux_hit(uint32_t j, const Ray &) { return wb.hits[(size_t) (wb.K + 1 + j) * wb.C + i]; }
+    __device__ __forceinline__ bool lane_radiance(f3 &L) const { const float *p = wb.lane_L + 3 * lane; L = mk3(p[0], p[1], p[2]); return true; }
+    __device__ __forceinline__ void finished() { wb.status[i] = 1u; }
+};
+EPSM_HD f3 path_primal_io(const DScene &, WfIo &, LocalTrace &, Ray, Pcg &, uint32_t, uint32_t, bool &) { return mk3(0, 0, 0); }   // never reached: lane_radiance() is always available
+
+__global__ void __launch_bounds__(128, 2) k_prb_pass(const __grid_constant__ DScene sc, const __grid_constant__ DLaunch ln, const __grid_constant__ PrbConfig cfg, int pass,
+                                                    uint64_t work_base, uint32_t n, const __grid_constant__ WfPrb wb, const float *__restrict__ film,
+                                                    const float *__restrict__ grad_in, float *grad_pos, float *grad_nrm) {
+    const uint32_t i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= n) return;
+    if (pass > 0 && wb.status[i]) return;
+    const uint32_t S = ln.s_end - ln.s_begin;
+    const uint64_t g = work_base + i, pixel = g / S; const uint32_t smp = ln.s_begin + (uint32_t) (g - pixel * S);
+    const uint64_t lane = pixel * ln.spp + smp;
+    if (pass == 0) {
+        const bool ok = lane >= ln.lane_begin && lane < ln.lane_end;
+        wb.status[i] = ok ? 0u : 1u;
+        if (!ok) return;
+    }
+    const uint32_t py = (uint32_t) (pixel / ln.sensor.w), px = (uint32_t) (pixel - (uint64_t) py * ln.sensor.w);
+    WfIo io{wb, pass, i, lane};
+    AtomicSink sink{grad_pos, grad_nrm};
+    prb_backward_lane(sc, io, ln.sensor, cfg, px, py, ln.seed, (uint32_t) lane, film, grad_in, sink);
+}
+
+size_t epsm_prb_workspace_bytes(uint32_t capacity, uint32_t K, uint32_t n_aux) {
+    const size_t c = capacity;
+    return 1024 + c * 4 + c * sizeof(Hit) * (K + 1 + 2 * (size_t) n_aux) + c * 4 * 2 * (size_t) K + c * sizeof(QRay) * (2 * (size_t) n_aux + 1) + c * sizeof(QRay) + 16 * 256;
+}
+cudaError_t epsm_launch_prb_backward_wf(const DScene &sc, DLaunch ln, const PrbConfig &cfg, const float *film, const float *lane_L, const float *grad_in,
+                                        float *grad_pos, float *grad_nrm, void *workspace, uint32_t capacity, uint32_t trace_grid, uint64_t *n_launches, cudaStream_t s) {
+    const uint64_t total = (uint64_t) ln.sensor.w * ln.sensor.h * (ln.s_end - ln.s_begin);
+    if (total == 0) return cudaSuccess;
+    const uint32_t K = cfg.max_depth, n_aux = cfg.n_rays;
+    WfPrb wb; char *p = (char *) workspace; const size_t c = capacity;
+    auto take = [&](size_t bytes) { char *r = p; p += (bytes + 255) & ~(size_t) 255; return r; };
+    wb.counters = (uint32_t *) take(1024);
+    wb.status = (uint32_t *) take(c * 4);
+    wb.hits = (Hit *) take(c * sizeof(Hit) * (K + 1 + 2 * (size_t) n_aux));
+    wb.occl = (uint32_t *) take(c * 4 * 2 * (size_t) K);
+    wb.q_closest = (QRay *) take(c * sizeof(QRay) * (2 * (size_t) n_aux + 1));
+    wb.q_any = (QRay *) take(c * sizeof(QRay));
+    wb.lane_L = lane_L; wb.C = capacity; wb.K = K; wb.n_aux = n_aux;
+    uint64_t launches = 0;
+    for (uint64_t base = 0; base < total; base += capacity) {
+        const uint32_t n = (uint32_t) ((total - base) < capacity ? (total - base) : capacity);
+        for (int pass = 0; pass <= 2 * (int) K + 1; ++pass) {
+            cudaMemsetAsync(wb.counters, 0, 4 * sizeof(uint32_t), s);
+            k_prb_pass<<<(n + 127) / 128, 128, 0, s>>>(sc, ln, cfg, pass, base, n, wb, film, grad_in, grad_pos, grad_nrm); ++launches;
+            if (pass == 2 * (int) K + 1) break;                                     // the last pass only runs the last adjoint
+            k_wf_trace<false, false><<<trace_grid, CTA, 0, s>>>(sc, wb.q_closest, wb.counters + 0, wb.counters + 1, wb.hits, nullptr, nullptr); ++launches;
+            k_wf_trace<true, false><<<trace_grid, CTA, 0, s>>>(sc, wb.q_any, wb.counters + 2, wb.counters + 3, nullptr, wb.occl, nullptr); ++launches;
+        }
+    }
+    if (n_launches) *n_launches += launches;
     return cudaGetLastError();
 }

@@ -17,7 +17,7 @@ cudaError_t epsm_launch_backward(const DScene &sc, DLaunch ln, const float *grad
                                  EpsmEventList *trace_events, cudaStream_t s);
 // Wavefront primal render (same workspace); k_render (epsm_launch_render) is the single-kernel variant kept for comparison.
 cudaError_t epsm_launch_render_wf(const DScene &sc, DLaunch ln, float *film, unsigned long long *counters, void *workspace, uint32_t capacity,
-                                  uint32_t trace_grid, uint64_t *n_launches, cudaStream_t s);
+                                  uint32_t trace_grid, uint64_t *n_launches, cudaStream_t s, float *lane_L = nullptr);
 cudaError_t epsm_launch_sampler_stream(uint32_t seed, uint64_t lane_begin, uint64_t n_lanes, uint32_t n_floats, float *out, cudaStream_t s);
 cudaError_t epsm_launch_sample_rays(const DSensor &se, uint32_t seed, uint32_t spp, uint64_t lane_begin, uint64_t n_lanes, float *out, cudaStream_t s);
 cudaError_t epsm_launch_vertex_normals(const float *pos, const uint32_t *faces, uint32_t f_off, uint32_t f_cnt, uint32_t v_off, uint32_t v_cnt,
@@ -34,3 +34,9 @@ cudaError_t epsm_launch_refit(f4 *nodes, uint32_t n_nodes, f4 *tris, uint32_t n_
 // prb_reparam reverse pass (k_prb_backward): `film` = RGBW film of the primal pass over all lanes, grad_in (H,W,3).
 cudaError_t epsm_launch_prb_backward(const DScene &sc, DLaunch ln, const PrbConfig &cfg, const float *film, const float *grad_in,
                                      float *grad_pos, float *grad_nrm, cudaStream_t s);
+// The same pass as a replay wavefront over the persistent traversal kernel (max_depth ≤ EPSM_PRB_WF_MAX_DEPTH).  lane_L: per-lane radiance of
+// the primal pass (epsm_launch_render_wf's lane_L output), indexed by global lane id.
+#define EPSM_PRB_WF_MAX_DEPTH 16
+size_t epsm_prb_workspace_bytes(uint32_t capacity, uint32_t K, uint32_t n_aux);
+cudaError_t epsm_launch_prb_backward_wf(const DScene &sc, DLaunch ln, const PrbConfig &cfg, const float *film, const float *lane_L, const float *grad_in,
+                                        float *grad_pos, float *grad_nrm, void *workspace, uint32_t capacity, uint32_t trace_grid, uint64_t *n_launches, cudaStream_t s);

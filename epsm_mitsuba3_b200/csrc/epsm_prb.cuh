@@ -174,24 +174,50 @@ EPSM_HDN float boundary_test(const DScene &sc, const Hit &h, f3 ray_d) {
     return dp * dp;
 }
 struct AuxRec { uint32_t prim; float u, v, w; f3 dw; };
-// One auxiliary ray of _sample_warp_field (reparam.py:83-118): the detached quantities Z_i = w and dZ_i = d_w_omega.
-template <bool COUNT>
-EPSM_HDN void warp_field_sample(const DScene &sc, Tracer &tr, f3 o, f3 d, float sx, float sy, float kappa, float exponent, AuxRec &r) {
+// One auxiliary ray of _sample_warp_field (reparam.py:83-118): its direction, and — from its closest hit — the detached
+// quantities Z_i = w and dZ_i = d_w_omega.
+EPSM_HD f3 warp_field_direction(f3 d, float sx, float sy, float kappa, f3 &tang) {
     const f3 om = square_to_von_mises_fisher(sx, sy, kappa);
     f3 fs, ft; coordinate_system(d, fs, ft);                                       // Frame3f(ray.d)
-    const f3 ad = fma3(d, om.z, fma3(ft, om.y, fs * om.x));
-    const Hit h = trace_closest<COUNT>(tr, Ray{o, ad, FLT_MAX});
+    tang = fma3(d, 0.f, fma3(ft, om.y, fs * om.x));                                // to_world((ω.x, ω.y, 0))
+    return fma3(d, om.z, fma3(ft, om.y, fs * om.x));
+}
+EPSM_HDN void warp_field_weights(const DScene &sc, const Hit &h, f3 aux_d, f3 tang, float sy, float kappa, float exponent, AuxRec &r) {
     const bool hit = h.prim != 0xffffffffu;
-    const float B = hit ? boundary_test(sc, h, ad) : 1.0f;
+    const float B = hit ? boundary_test(sc, h, aux_d) : 1.0f;
     const float inv_vmf = rcp_e(fmaf(sy, expf(-2.f * kappa), 1.f - sy));
     const float w_denom = inv_vmf - 1.f + B;
     const float w_denom_rcp = w_denom > 1e-4f ? rcp_e(w_denom) : 0.f;
     const float w = powf(w_denom_rcp, exponent) * inv_vmf;
     float tmp1 = inv_vmf * w * w_denom_rcp * kappa * exponent;
     tmp1 = fminf(fmaxf(tmp1, -1e10f), 1e10f);
-    const f3 tmp2 = fma3(d, 0.f, fma3(ft, om.y, fs * om.x));
-    r.prim = h.prim; r.u = h.u; r.v = h.v; r.w = w; r.dw = tmp2 * tmp1;
+    r.prim = h.prim; r.u = h.u; r.v = h.v; r.w = w; r.dw = tang * tmp1;
 }
+
+// ------------------------------------------------------------------------------------------------
+//  Where the rays of a lane are traced.  MegaIo: inline, one thread walks the whole lane (k_prb_backward, host harness).
+//  The replay-wavefront policy of epsm_kernels.cu (WfIo) has the same interface: in pass p it pushes the rays of round p
+//  into the queues of the persistent traversal kernel and reads the results of earlier rounds from per-lane slots.
+//  Rounds of a lane: 0 = primary ray + the camera ray's auxiliary rays; 1 + 2·it = NEE shadow ray and next path ray of
+//  iteration it; 2 + 2·it = the run-ahead NEE shadow ray and the auxiliary rays of the emitter ray and of the main ray.
+// ------------------------------------------------------------------------------------------------
+template <bool COUNT>
+struct MegaIo {
+    static constexpr bool wavefront = false;
+    Tracer &tr;
+    EPSM_HD explicit MegaIo(Tracer &t) : tr(t) {}
+    EPSM_HD Hit closest(int, uint32_t, const Ray &r) { return trace_closest<COUNT>(tr, r); }
+    EPSM_HD bool occluded(int, uint32_t, const Ray &r) { return trace_any<COUNT>(tr, r); }
+    EPSM_HD bool stop_after(int) const { return false; }           // pass == round: the round's rays were just pushed
+    EPSM_HD bool adjoint_now(int) const { return true; }           // the adjoint that consumes round r runs in pass r + 1
+    EPSM_HD bool aux_push_only(int) const { return false; }
+    EPSM_HD bool aux_skip(int) const { return false; }
+    EPSM_HD void aux_push(uint32_t, const Ray &) {}
+    EPSM_HD Hit aux_hit(uint32_t, const Ray &r) { return trace_closest<COUNT>(tr, r); }
+    EPSM_HD bool lane_radiance(f3 &) const { return false; }       // false: replay the primal path inline
+    EPSM_HD void finished() {}
+};
+
 // Where a ray origin is glued to (FollowShape: p = Σ bw_k·p_k with detached barycentrics); prim = 0xffffffff: detached origin.
 struct Anchor { uint32_t prim; float bw[3]; };
 template <typename Sink>
@@ -205,18 +231,29 @@ EPSM_HD void scatter_tri(const DScene &sc, Sink &sink, uint32_t prim, float b0, 
 //   g_V = ((I − d̂d̂ᵀ)g_dir/|d| − g_det·dZ/Z)/Z,  g_div = g_det/Z       [direction = normalize(d + V/Z), divergence = (div − V/Z·dZ)/Z at V = 0]
 // and pushes w_i·g_V + g_div·dZ_i through V_direct_i = normalize(p_i − o) (hit; p_i follows its triangle) or = d (miss).
 // The origin's gradient goes to `anchor`; with `d_from`: d = normalize(d_from − o) is attached too (the emitter ray).
-template <bool COUNT, typename Sink>
-EPSM_HDN void reparam_backward(const DScene &sc, Tracer &tr, Sink &sink, Pcg &aux_rng, const PrbConfig &cfg, bool active,
+template <typename Io, typename Sink>
+EPSM_HDN void reparam_backward(const DScene &sc, Io &io, Sink &sink, Pcg &aux_rng, const PrbConfig &cfg, int round, uint32_t aux_base, bool active,
                                f3 o, f3 d, f3 g_dir, float g_det, const Anchor &anchor, bool d_attached, f3 d_from) {
     if (!active) return;                                                           // masked lanes do not advance the generator
     const uint32_t n = cfg.n_rays;
+    if (io.aux_skip(round)) { for (uint32_t i = 0; i < 2 * n; ++i) pcg_next(aux_rng); return; }        // replay of a round long consumed
+    if (io.aux_push_only(round)) {                                                 // wavefront, pass == round: queue the auxiliary rays
+        for (uint32_t i = 0; i < n; ++i) {
+            const float sx = pcg_f32(aux_rng), sy = pcg_f32(aux_rng);
+            f3 tang; const f3 ad = warp_field_direction(d, sx, sy, cfg.kappa, tang);
+            (void) sy; io.aux_push(aux_base + i, Ray{o, ad, FLT_MAX});
+        }
+        return;
+    }
     const bool live = g_det != 0.f || g_dir.x != 0.f || g_dir.y != 0.f || g_dir.z != 0.f;
     if (!live) { for (uint32_t i = 0; i < 2 * n; ++i) pcg_next(aux_rng); return; }
     AuxRec rec[EPSM_PRB_MAX_RAYS];
     float Z = 0.f; f3 dZ = mk3(0, 0, 0);
     for (uint32_t i = 0; i < n; ++i) {
         const float sx = pcg_f32(aux_rng), sy = pcg_f32(aux_rng);
-        warp_field_sample<COUNT>(sc, tr, o, d, sx, sy, cfg.kappa, cfg.exponent, rec[i]);
+        f3 tang; const f3 ad = warp_field_direction(d, sx, sy, cfg.kappa, tang);
+        const Hit h = io.aux_hit(aux_base + i, Ray{o, ad, FLT_MAX});
+        warp_field_weights(sc, h, ad, tang, sy, cfg.kappa, cfg.exponent, rec[i]);
         Z += rec[i].w; dZ = dZ + rec[i].dw;
     }
     Z = fmaxf(Z, 1e-8f);
@@ -290,6 +327,13 @@ EPSM_HDN void frame_backward_si(const DScene &sc, Sink &sink, const SI &si, f3 r
     if (grad) { sink.pos(si.fi[0], g_p0); sink.pos(si.fi[1], g_p1); sink.pos(si.fi[2], g_p2); }
 }
 
+// Inline primal replay for the policies that have no per-lane radiance buffer (MegaIo): EPSMIntegrator.sample's loop is path_primal.
+struct LocalTrace {};
+template <bool COUNT>
+EPSM_HD f3 path_primal_io(const DScene &sc, MegaIo<COUNT> &io, LocalTrace &, Ray ray, Pcg &rng, uint32_t max_depth, uint32_t rr_depth, bool &valid) {
+    return path_primal<COUNT>(sc, io.tr, ray, rng, max_depth, rr_depth, valid);
+}
+
 // GaussianFilter::eval and its derivative (gaussian.cpp:94-96): f = max(0, P(x²)), f' = 2x·P'(x²) where P > 0
 EPSM_HD void filter_eval_d(const float *c, float x, float &f, float &df) {
     const float t = x * x;
@@ -305,58 +349,69 @@ EPSM_HD void filter_eval_d(const float *c, float x, float &f, float &df) {
 // ------------------------------------------------------------------------------------------------
 struct PrevVertex { bool valid; f3 p, sh_s, sh_t, sh_n, wi; int32_t bsdf; Anchor anchor; };
 
-template <bool COUNT, typename Sink>
-EPSM_HDN void prb_backward_lane(const DScene &sc, Tracer &tr, const DSensor &sensor, const PrbConfig &cfg, uint32_t px, uint32_t py,
+template <typename Io, typename Sink>
+EPSM_HDN void prb_backward_lane(const DScene &sc, Io &io, const DSensor &sensor, const PrbConfig &cfg, uint32_t px, uint32_t py,
                                 uint32_t seed, uint32_t lane, const float *film, const float *grad_in, Sink &sink) {
     Pcg rng = pcg_for_lane(seed, lane);
     Pcg aux = pcg_for_lane(0xffffffffu ^ seed, lane);                               // _ReparamWrapper, common.py:1200-1203
     CamRay cr; camera_ray(sensor, px, py, rng, cr);
-    bool valid_path; Pcg rng_p = rng;
-    const f3 Ltot = path_primal<COUNT>(sc, tr, cr.ray, rng_p, cfg.max_depth, cfg.rr_depth, valid_path);   // primal pass, cloned sampler (common.py:905-915)
+    const uint32_t n_aux = cfg.n_rays;
+    const Anchor none{0xffffffffu, {0.f, 0.f, 0.f}};
+    const bool cam_active = 0 < cfg.reparam_max_depth;
 
-    // ---- adjoint of block.put(pos, L·det, weight = det) → develop (common.py:919-945): δL, ∂/∂pos, ∂/∂det
-    f3 dL = mk3(0, 0, 0); float g_px = 0.f, g_py = 0.f, g_det_cam = 0.f;
-    {
-        const int FW = (int) sensor.fw, FH = (int) sensor.fh;
-        const int pix = (int) floorf(cr.pos_x) - 2, piy = (int) floorf(cr.pos_y) - 2;
-        float rel_x = (float) pix + .5f - cr.pos_x, rel_y = (float) piy + .5f - cr.pos_y;
-        float wx[5], wy[5], dwx[5], dwy[5];
-        for (int k = 0; k < 5; ++k) { filter_eval_d(sc.filter, rel_x, wx[k], dwx[k]); filter_eval_d(sc.filter, rel_y, wy[k], dwy[k]); rel_x += 1; rel_y += 1; }
-        for (int ys = 0; ys < 5; ++ys) for (int xs = 0; xs < 5; ++xs) {
-            const int x = pix + xs, y = piy + ys;
-            if (x < 0 || y < 0 || x >= FW || y >= FH) continue;                    // cropped border (hdrfilm.cpp:286-320)
-            const float *fp = film + ((size_t) y * FW + x) * 4, *gp = grad_in + ((size_t) y * FW + x) * 3;
-            const float W = fp[3], iw = W == 0.f ? 1.0f : 1.0f / W, nz = W == 0.f ? 0.f : 1.f;    // develop: rgb / (w == 0 ? 1 : w)
-            const float w = wy[ys] * wx[xs];
-            dL = dL + mk3(gp[0], gp[1], gp[2]) * (w * iw);
-            const float A = (gp[0] * (Ltot.x - nz * fp[0] * iw) + gp[1] * (Ltot.y - nz * fp[1] * iw) + gp[2] * (Ltot.z - nz * fp[2] * iw)) * iw;
-            g_det_cam += w * A; g_px -= wy[ys] * dwx[xs] * A; g_py -= dwy[ys] * wx[xs] * A;
+    // ---- round 0: the primary ray and the auxiliary rays of the camera ray's reparameterisation (common.py:372-397)
+    Hit h = io.closest(0, 0, cr.ray);
+    f3 Ltot = mk3(0, 0, 0);
+    f3 dL = mk3(0, 0, 0); f3 g_d_cam = mk3(0, 0, 0); float g_det_cam = 0.f;
+    if (!io.aux_push_only(0)) {
+        // primal radiance of the lane: the primal pass with the cloned sampler (common.py:905-915)
+        if (!io.lane_radiance(Ltot)) {
+            LocalTrace lt; bool valid_path; Pcg rng_p = rng;
+            Ltot = path_primal_io(sc, io, lt, cr.ray, rng_p, cfg.max_depth, cfg.rr_depth, valid_path);
+        }
+        // ---- adjoint of block.put(pos, L·det, weight = det) → develop (common.py:919-945): δL, ∂/∂pos, ∂/∂det
+        float g_px = 0.f, g_py = 0.f;
+        {
+            const int FW = (int) sensor.fw, FH = (int) sensor.fh;
+            const int pix = (int) floorf(cr.pos_x) - 2, piy = (int) floorf(cr.pos_y) - 2;
+            float rel_x = (float) pix + .5f - cr.pos_x, rel_y = (float) piy + .5f - cr.pos_y;
+            float wx[5], wy[5], dwx[5], dwy[5];
+            for (int k = 0; k < 5; ++k) { filter_eval_d(sc.filter, rel_x, wx[k], dwx[k]); filter_eval_d(sc.filter, rel_y, wy[k], dwy[k]); rel_x += 1; rel_y += 1; }
+            for (int ys = 0; ys < 5; ++ys) for (int xs = 0; xs < 5; ++xs) {
+                const int x = pix + xs, y = piy + ys;
+                if (x < 0 || y < 0 || x >= FW || y >= FH) continue;                // cropped border (hdrfilm.cpp:286-320)
+                const float *fp = film + ((size_t) y * FW + x) * 4, *gp = grad_in + ((size_t) y * FW + x) * 3;
+                const float W = fp[3], iw = W == 0.f ? 1.0f : 1.0f / W, nz = W == 0.f ? 0.f : 1.f;    // develop: rgb / (w == 0 ? 1 : w)
+                const float w = wy[ys] * wx[xs];
+                dL = dL + mk3(gp[0], gp[1], gp[2]) * (w * iw);
+                const float A = (gp[0] * (Ltot.x - nz * fp[0] * iw) + gp[1] * (Ltot.y - nz * fp[1] * iw) + gp[2] * (Ltot.z - nz * fp[2] * iw)) * iw;
+                g_det_cam += w * A; g_px -= wy[ys] * dwx[xs] * A; g_py -= dwy[ys] * wx[xs] * A;
+            }
+        }
+        // pos = resolution · project(camera_to_sample · to_world⁻¹ · (o + d)) (common.py:390-396, perspective.cpp:282-306)
+        {
+            const f3 itp = cr.ray.o + cr.ray.d;
+            const float *m = sensor.w2c, *c2s = sensor.c2s;
+            const f3 q = mk3(m[0] * itp.x + m[1] * itp.y + m[2] * itp.z + m[3], m[4] * itp.x + m[5] * itp.y + m[6] * itp.z + m[7],
+                             m[8] * itp.x + m[9] * itp.y + m[10] * itp.z + m[11]);
+            const float hx = c2s[0] * q.x + c2s[1] * q.y + c2s[2] * q.z + c2s[3], hy = c2s[4] * q.x + c2s[5] * q.y + c2s[6] * q.z + c2s[7],
+                        hw = c2s[12] * q.x + c2s[13] * q.y + c2s[14] * q.z + c2s[15];
+            const float gux = g_px * (float) sensor.fw, guy = g_py * (float) sensor.fh, ihw = 1.0f / hw;
+            const float ghx = gux * ihw, ghy = guy * ihw, ghw = -(gux * hx + guy * hy) * ihw * ihw;
+            const f3 g_q = mk3(c2s[0] * ghx + c2s[4] * ghy + c2s[12] * ghw, c2s[1] * ghx + c2s[5] * ghy + c2s[13] * ghw, c2s[2] * ghx + c2s[6] * ghy + c2s[14] * ghw);
+            g_d_cam = mk3(m[0] * g_q.x + m[4] * g_q.y + m[8] * g_q.z, m[1] * g_q.x + m[5] * g_q.y + m[9] * g_q.z, m[2] * g_q.x + m[6] * g_q.y + m[10] * g_q.z);
         }
     }
-    // pos = resolution · project(camera_to_sample · to_world⁻¹ · (o + d)) (common.py:390-396, perspective.cpp:282-306)
-    f3 g_d_cam = mk3(0, 0, 0);
-    {
-        const f3 itp = cr.ray.o + cr.ray.d;
-        const float *m = sensor.w2c, *c2s = sensor.c2s;
-        const f3 q = mk3(m[0] * itp.x + m[1] * itp.y + m[2] * itp.z + m[3], m[4] * itp.x + m[5] * itp.y + m[6] * itp.z + m[7],
-                         m[8] * itp.x + m[9] * itp.y + m[10] * itp.z + m[11]);
-        const float hx = c2s[0] * q.x + c2s[1] * q.y + c2s[2] * q.z + c2s[3], hy = c2s[4] * q.x + c2s[5] * q.y + c2s[6] * q.z + c2s[7],
-                    hw = c2s[12] * q.x + c2s[13] * q.y + c2s[14] * q.z + c2s[15];
-        const float gux = g_px * (float) sensor.fw, guy = g_py * (float) sensor.fh, ihw = 1.0f / hw;
-        const float ghx = gux * ihw, ghy = guy * ihw, ghw = -(gux * hx + guy * hy) * ihw * ihw;
-        const f3 g_q = mk3(c2s[0] * ghx + c2s[4] * ghy + c2s[12] * ghw, c2s[1] * ghx + c2s[5] * ghy + c2s[13] * ghw, c2s[2] * ghx + c2s[6] * ghy + c2s[14] * ghw);
-        g_d_cam = mk3(m[0] * g_q.x + m[4] * g_q.y + m[8] * g_q.z, m[1] * g_q.x + m[5] * g_q.y + m[9] * g_q.z, m[2] * g_q.x + m[6] * g_q.y + m[10] * g_q.z);
-    }
-    const Anchor none{0xffffffffu, {0.f, 0.f, 0.f}};
-    reparam_backward<COUNT>(sc, tr, sink, aux, cfg, 0 < cfg.reparam_max_depth, cr.ray.o, cr.ray.d, g_d_cam, g_det_cam, none, false, mk3(0, 0, 0));
+    reparam_backward(sc, io, sink, aux, cfg, 0, 0, cam_active, cr.ray.o, cr.ray.d, g_d_cam, g_det_cam, none, false, mk3(0, 0, 0));
+    if (io.stop_after(0)) return;
 
     // ---- sample(mode = Backward) (prb_reparam.py:329-602)
     uint32_t depth = 0; f3 L = Ltot, beta = mk3(1, 1, 1); float eta = 1.f, mis_em = 1.f; bool active = true;
-    Ray ray = cr.ray; Hit h = trace_closest<COUNT>(tr, ray);
+    Ray ray = cr.ray;
     PrevVertex prev; prev.valid = false; prev.anchor = none; prev.bsdf = -1;
     SI si, si_next;
-    auto occl = [&](const Ray &r) { return trace_any<COUNT>(tr, r); };
     for (uint32_t it = 0; it < cfg.max_depth && active; ++it) {
+        const int r1 = 1 + 2 * (int) it, r2 = 2 + 2 * (int) it;                     // this iteration's two rounds of rays
         compute_si(sc, ray, h, si);
         const f3 Le = beta * mis_em * emitter_eval(sc, si);
         bool active_next = (depth + 1 < cfg.max_depth) && si.valid;
@@ -365,7 +420,7 @@ EPSM_HDN void prb_backward_lane(const DScene &sc, Tracer &tr, const DSensor &sen
         bool active_em = active_next && (flags & EPSM_BF_SMOOTH);
         const float e1 = pcg_f32(rng), e2 = pcg_f32(rng);
         DSamp ds; f3 em_weight;
-        sample_emitter_direction(sc, si, e1, e2, active_em, ds, em_weight, occl);
+        sample_emitter_direction(sc, si, e1, e2, active_em, ds, em_weight, [&](const Ray &r) { return io.occluded(r1, 2 * it, r); });
         active_em &= ds.pdf != 0.f;
         Ray em_ray{mk3(0, 0, 0), mk3(0, 0, 1), 0.f};
         f3 Lr_dir = mk3(0, 0, 0); float mis_direct = 0.f;
@@ -392,7 +447,8 @@ EPSM_HDN void prb_backward_lane(const DScene &sc, Tracer &tr, const DSensor &sen
         Ray ray_next = ray;
         if (si.valid) ray_next = spawn_ray(si, to_world(si, bs.wo));
         Hit h_next{0.f, 0.f, 0.f, 0xffffffffu};
-        if (active_next) h_next = trace_closest<COUNT>(tr, ray_next);
+        if (active_next) h_next = io.closest(r1, 1 + it, ray_next);
+        if (io.stop_after(r1)) return;                                             // round r1 queued: NEE visibility and the next hit are pending
         compute_si(sc, ray_next, h_next, si_next);
         const float pdf_em = pdf_emitter_direction(sc, si_next, si.p, !(bs.type & EPSM_BF_DELTA));
         const float mis_next = mis_weight(bs.pdf, pdf_em);
@@ -404,7 +460,7 @@ EPSM_HDN void prb_backward_lane(const DScene &sc, Tracer &tr, const DSensor &sen
         bool active_em_n = active_nn && (nflags & EPSM_BF_SMOOTH);
         const float c1 = pcg_f32(clone), c2 = pcg_f32(clone);
         DSamp dsn; f3 emw_n;
-        sample_emitter_direction(sc, si_next, c1, c2, active_em_n, dsn, emw_n, occl);
+        sample_emitter_direction(sc, si_next, c1, c2, active_em_n, dsn, emw_n, [&](const Ray &r) { return io.occluded(r2, 2 * it + 1, r); });
         active_em_n &= dsn.pdf != 0.f;
         f3 Lr_dir_next = mk3(0, 0, 0);
         if (active_em_n) {
@@ -418,18 +474,18 @@ EPSM_HDN void prb_backward_lane(const DScene &sc, Tracer &tr, const DSensor &sen
         const f3 Le_next = active_next ? beta * mis_next * emitter_eval(sc, si_next) : mk3(0, 0, 0);
         const f3 L_next = L - Le_next - Lr_dir_next;
 
-        // ---- adjoint of Lo = (Le + Lr_dir + Lr_ind)·det + extra, seeded with δL (prb_reparam.py:576-588)
+        // ---- adjoint of Lo = (Le + Lr_dir + Lr_ind)·det + extra, seeded with δL (prb_reparam.py:576-588); in the wavefront it
+        //      runs in the one pass in which the iteration's auxiliary hits are available
         f3 g_d = mk3(0, 0, 0), g_de = mk3(0, 0, 0); float g_det = 0.f, g_det_e = 0.f;
         const bool have_dl = dL.x != 0.f || dL.y != 0.f || dL.z != 0.f;
-        if (si.valid && have_dl) {
+        if (io.adjoint_now(r2) && si.valid && have_dl) {
             // Lr_dir = β·mis·f(wi, to_local(d_e))·em_weight·det_e (:431-435);  Lr_ind = L·f(wi, to_local(ray_next.d))/detach(f) (:553-571)
             const f3 bv = bs.weight * bs.pdf;
             const f3 inv_bv = mk3(bv.x != 0.f ? 1.f / bv.x : 0.f, bv.y != 0.f ? 1.f / bv.y : 0.f, bv.z != 0.f ? 1.f / bv.z : 0.f);
-            f3 g_wi = mk3(0, 0, 0), g_wa = mk3(0, 0, 0), g_wb = mk3(0, 0, 0), tmp, val;
+            f3 g_wi = mk3(0, 0, 0), g_wa = mk3(0, 0, 0), g_wb = mk3(0, 0, 0), val;
             const f3 da = active_em ? ds.d : mk3(0, 0, 0), db = active_next ? ray_next.d : mk3(0, 0, 0);
             if (active_em) { f3 gi; bsdf_grad(b, si.wi, to_local(si, ds.d), dL * beta_in * mis_direct * em_weight, gi, g_wa, val); g_wi = g_wi + gi; }
             if (active_next) { f3 gi; bsdf_grad(b, si.wi, to_local(si, ray_next.d), dL * L * inv_bv, gi, g_wb, val); g_wi = g_wi + gi; }
-            (void) tmp;
             frame_backward_si(sc, sink, si, ray.o, ray.d, da, db, g_wi, g_wa, g_wb, g_d, g_de);
             // adjacent vertices through si_cur.p with the shape detached (:522-551)
             f3 g_pro = mk3(0, 0, 0);
@@ -456,17 +512,19 @@ EPSM_HDN void prb_backward_lane(const DScene &sc, Tracer &tr, const DSensor &sen
             const f3 Lsum = Le + Lr_dir + L;
             g_det = it == 0 ? 0.f : dot3(dL, Lsum);                                // ray_reparam_det[first_vertex] = 1 (:364)
             g_det_e = dot3(dL, Lr_dir);
-        } else if (have_dl && it != 0) {
+        } else if (io.adjoint_now(r2) && have_dl && it != 0) {
             g_det = dot3(dL, Le + L);                                              // escaped ray: Lo = (Le + L)·det with Le = 0 here
         }
         // the emitter ray's custom op is created later in the iteration ⇒ its backward runs first; both draw from one generator
         Anchor cur{si.valid ? si.prim : 0xffffffffu, {si.bw[0], si.bw[1], si.bw[2]}};
-        reparam_backward<COUNT>(sc, tr, sink, aux, cfg, active_em && (depth + 1 < cfg.reparam_max_depth), em_ray.o, em_ray.d, g_de, g_det_e, cur, true, ds.p);
-        reparam_backward<COUNT>(sc, tr, sink, aux, cfg, depth < cfg.reparam_max_depth, ray.o, ray.d, g_d, g_det, prev.anchor, false, mk3(0, 0, 0));
+        reparam_backward(sc, io, sink, aux, cfg, r2, 0, active_em && (depth + 1 < cfg.reparam_max_depth), em_ray.o, em_ray.d, g_de, g_det_e, cur, true, ds.p);
+        reparam_backward(sc, io, sink, aux, cfg, r2, n_aux, depth < cfg.reparam_max_depth, ray.o, ray.d, g_d, g_det, prev.anchor, false, mk3(0, 0, 0));
+        if (io.stop_after(r2)) return;                                             // round r2 queued: the adjoint of this iteration runs next pass
 
         prev.valid = si.valid; prev.p = si.p; prev.sh_s = si.sh_s; prev.sh_t = si.sh_t; prev.sh_n = si.sh_n; prev.wi = si.wi; prev.bsdf = si.bsdf; prev.anchor = cur;
         mis_em = mis_next; h = h_next; ray = ray_next;
         if (si.valid) depth += 1;
         active = active_next;
     }
+    io.finished();
 }

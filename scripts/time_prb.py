@@ -10,7 +10,7 @@ sd = S.indoor_room(1_000_000, res, spp, res)
 scene = ep.Scene(sd)
 integ = ep.load_dict({"type": "prb_reparam", "max_depth": 8})
 g = torch.from_numpy(np.random.default_rng(1).normal(0, 0.1, (res, res, 3)).astype(np.float32)).cuda()
-for k in range(3):
+for k in range(int(sys.argv[3]) if len(sys.argv) > 3 else 3):
     torch.cuda.synchronize(); t = time.perf_counter()
     gp, gn = integ.vertex_gradients(scene, g, 0, k, spp)
     torch.cuda.synchronize(); dt = time.perf_counter() - t

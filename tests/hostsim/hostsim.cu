@@ -284,15 +284,51 @@ void sim_backward(sim_scene *s, int variant, uint32_t sensor, uint32_t seed, uin
 // k_prb_backward on the host: one lane at a time (serial, plain adds).  film = RGBW film of the primal pass over all lanes.
 struct HostSink { float *gp, *gn; EPSM_HD void pos(uint32_t v, f3 g) { gp[3 * v] += g.x; gp[3 * v + 1] += g.y; gp[3 * v + 2] += g.z; }
                   EPSM_HD void nrm(uint32_t v, f3 g) { gn[3 * v] += g.x; gn[3 * v + 1] += g.y; gn[3 * v + 2] += g.z; } };
+// The replay-wavefront policy of k_prb_pass (WfIo, epsm_kernels.cu) emulated per lane on the host: pass p queues the rays of round p,
+// they are traced after the pass, and later passes read them back — the same slots, the same pass arithmetic.
+struct HostWfIo {
+    static constexpr bool wavefront = true;
+    int pass; uint32_t K; std::vector<Hit> &hits; std::vector<uint32_t> &occl;
+    std::vector<std::pair<Ray, uint32_t>> &qc, &qa; f3 L; bool done;
+    Hit closest(int round, uint32_t slot, const Ray &r) { if (round == pass) { qc.push_back({r, slot}); return Hit{0.f, 0.f, 0.f, 0xffffffffu}; } return hits[slot]; }
+    bool occluded(int round, uint32_t slot, const Ray &r) { if (round == pass) { qa.push_back({r, slot}); return false; } return occl[slot] != 0u; }
+    bool stop_after(int round) const { return pass == round; }
+    bool adjoint_now(int round) const { return pass == round + 1; }
+    bool aux_push_only(int round) const { return pass == round; }
+    bool aux_skip(int round) const { return pass > round + 1; }
+    void aux_push(uint32_t j, const Ray &r) { qc.push_back({r, K + 1 + j}); }
+    Hit aux_hit(uint32_t j, const Ray &) { return hits[K + 1 + j]; }
+    bool lane_radiance(f3 &out) const { out = L; return true; }
+    void finished() { done = true; }
+};
+f3 path_primal_io(const DScene &, HostWfIo &, LocalTrace &, Ray, Pcg &, uint32_t, uint32_t, bool &) { return mk3(0, 0, 0); }
+
 void sim_prb_backward(sim_scene *s, uint32_t sensor, uint32_t seed, uint32_t spp, const epsm_reparam_config *cfg, const float *film,
-                      const float *grad_in, uint64_t lane_begin, uint64_t lane_end, float *grad_pos, float *grad_nrm) {
+                      const float *grad_in, uint64_t lane_begin, uint64_t lane_end, float *grad_pos, float *grad_nrm, int wavefront) {
     const DSensor &se = s->hs.sensors[sensor];
     PrbConfig pc{cfg->max_depth, cfg->rr_depth, cfg->reparam_max_depth, cfg->reparam_rays, cfg->reparam_kappa, cfg->reparam_exp};
     HostSink sink{grad_pos, grad_nrm};
     for (uint64_t lane = lane_begin; lane < lane_end; ++lane) {
         LocalStack ls; TStack st; bind(st, ls); Tracer tr(s->sc, st);
         const uint32_t pixel = (uint32_t) (lane / spp);
-        prb_backward_lane<false>(s->sc, tr, se, pc, pixel % se.w, pixel / se.w, seed, (uint32_t) lane, film, grad_in, sink);
+        if (!wavefront) {
+            MegaIo<false> io(tr);
+            prb_backward_lane(s->sc, io, se, pc, pixel % se.w, pixel / se.w, seed, (uint32_t) lane, film, grad_in, sink);
+            continue;
+        }
+        const uint32_t K = pc.max_depth;
+        std::vector<Hit> hits(K + 1 + 2 * pc.n_rays, Hit{0.f, 0.f, 0.f, 0xffffffffu}); std::vector<uint32_t> occl(2 * K, 0u);
+        std::vector<std::pair<Ray, uint32_t>> qc, qa;
+        Pcg rng = pcg_for_lane(seed, (uint32_t) lane); CamRay cr; camera_ray(se, pixel % se.w, pixel / se.w, rng, cr);
+        bool valid; const f3 L = path_primal<false>(s->sc, tr, cr.ray, rng, pc.max_depth, pc.rr_depth, valid);     // what k_pr_film writes to lane_L
+        for (int pass = 0; pass <= 2 * (int) K + 1; ++pass) {
+            HostWfIo io{pass, K, hits, occl, qc, qa, L, false};
+            prb_backward_lane(s->sc, io, se, pc, pixel % se.w, pixel / se.w, seed, (uint32_t) lane, film, grad_in, sink);
+            for (auto &q : qc) hits[q.second] = trace_closest<false>(tr, q.first);
+            for (auto &q : qa) occl[q.second] = trace_any<false>(tr, q.first) ? 1u : 0u;
+            qc.clear(); qa.clear();
+            if (io.done) break;
+        }
     }
 }
 

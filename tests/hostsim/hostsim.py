@@ -36,7 +36,7 @@ def lib():
         L.sim_sampler_stream.argtypes = [u32, u64, u64, u32, vp]
         L.sim_sample_rays.argtypes = [vp, u32, u32, u32, u64, u64, vp]
         L.sim_render_accumulate.argtypes = [vp, u32, u32, u32, u32, u32, u64, u64, vp, i32]
-        L.sim_prb_backward.argtypes = [vp, u32, u32, u32, C.POINTER(capi.ReparamConfig), vp, vp, u64, u64, vp, vp]
+        L.sim_prb_backward.argtypes = [vp, u32, u32, u32, C.POINTER(capi.ReparamConfig), vp, vp, u64, u64, vp, vp, i32]
         L.sim_backward.argtypes = [vp, i32, u32, u32, u32, u32, u32, vp, u64, u64, vp, vp, vp, i32]
         _LIB = L
     return _LIB
@@ -126,12 +126,12 @@ class SimScene:
                            gp.ctypes.data, gn.ctypes.data, None, int(prune))     # 2 = production schedule (fast path + chain prefix)
         return gp, gn
 
-    def prb_backward(self, sensor, seed, spp, cfg: dict, film, grad_in, lb=0, le=None):
+    def prb_backward(self, sensor, seed, spp, cfg: dict, film, grad_in, lb=0, le=None, wavefront=False):
         """k_prb_backward's lane code (epsm_prb.cuh) on the host.  film: (H,W,4) primal film of all lanes; grad_in (H,W,3)."""
         s = self.data.sensors[sensor]; le = s.wavefront(spp) if le is None else le
         c = capi.ReparamConfig(**cfg)
         film = np.ascontiguousarray(film, np.float32); g = np.ascontiguousarray(grad_in, np.float32)
         assert film.shape == (s.height, s.width, 4) and g.shape == (s.height, s.width, 3)
         gp = np.zeros((self.n_vertices, 3), np.float32); gn = np.zeros((self.n_vertices, 3), np.float32)
-        lib().sim_prb_backward(self.h, sensor, seed, spp, C.byref(c), film.ctypes.data, g.ctypes.data, lb, le, gp.ctypes.data, gn.ctypes.data)
+        lib().sim_prb_backward(self.h, sensor, seed, spp, C.byref(c), film.ctypes.data, g.ctypes.data, lb, le, gp.ctypes.data, gn.ctypes.data, 1 if wavefront else 0)
         return gp, gn

@@ -56,6 +56,7 @@ def test_fullsize_path_records_of_sampled_windows(room):
         paths = o.path_log(1, 21, SPP, MD, 5, g, lb, le)
         rec = scene.path_records("manifold", 1, 21, SPP, MD, 5, g, lb, le)
         stats, _ = parity.check_path_records(rec, paths, "manifold", MD)
+        parity.record_stats("gpu_fullsize_window_vs_oracle", f"room/lanes{lb}-{le}", stats)
         assert stats["nonzero"] >= 0
 
 
@@ -146,6 +147,7 @@ def test_fullsize_path_records_of_configs_1_and_3(orc, name, make, variant, res,
         # (held to the float64 evaluation within the reference's own float32 error, parity.cmp_ill) is above the scene average
         # of ≤ 1 % — measured 1.7 % on `stage` (profiles/r02_e_summary.md)
         stats, _ = parity.check_path_records(rec, paths, variant, md, max_ill_frac=0.03)
+        parity.record_stats("gpu_fullsize_window_vs_oracle", f"{name}/lanes{lb}-{le}", stats)
         n_grad += stats["nonzero"]
     assert n_grad > 0
     # accumulated gradients of a 4-row band through the image centre

@@ -131,6 +131,7 @@ def test_per_path_gradients_and_scatter(case):
     paths = o.path_log(2, 11, 8, max_depth, 5, g)
     rec = b.path_records(variant, 2, 11, 8, max_depth, 5, g, 0, n)
     stats, (pg, lg, dg) = parity.check_path_records(rec, paths, variant, max_depth)
+    parity.record_stats("gpu_path_records_vs_oracle", f"{variant}/{sd.name}/{sd.n_triangles}tris", stats)
     assert stats["nonzero"] > 0
     ref_p, ref_n = parity.scatter_gradients(paths, variant, parity.n_logged(max_depth), pg, lg, dg, sd.n_vertices, max_depth)
     gp, gn = b.backward(variant, 2, 11, 8, max_depth, 5, g)

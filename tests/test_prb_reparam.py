@@ -76,6 +76,9 @@ def test_hand_adjoint_equals_autograd_oracle_on_the_host(smooth, rough, md, spp,
     if smooth:
         assert np.abs(gn_o).max() > 1e-4 and _rel(gn[voff[2]:voff[3]], gn_o) < 5e-4
     assert not gp[:voff[2]].any() and not gn[:voff[2]].any()             # only attached meshes receive gradients
+    # the replay wavefront (k_prb_pass's policy, emulated per lane) walks the same lanes pass by pass: identical sums
+    gp_w, gn_w = h.prb_backward(0, 5, spp, _cfg(md, kappa), film, gin, wavefront=True)
+    assert np.array_equal(gp_w, gp) and np.array_equal(gn_w, gn)
 
 
 def test_lane_windows_and_reparam_depth_on_the_host():
