@@ -1240,7 +1240,10 @@ struct WfIo {
 };
 EPSM_HD f3 path_primal_io(const DScene &, WfIo &, LocalTrace &, Ray, Pcg &, uint32_t, uint32_t, bool &) { return mk3(0, 0, 0); }   // never reached: lane_radiance() is always available
 
-__global__ void __launch_bounds__(128, 2) k_prb_pass(const __grid_constant__ DScene sc, const __grid_constant__ DLaunch ln, const __grid_constant__ PrbConfig cfg, int pass,
+#ifndef EPSM_PRBPASS_MINBLOCKS
+#define EPSM_PRBPASS_MINBLOCKS 2
+#endif
+__global__ void __launch_bounds__(128, EPSM_PRBPASS_MINBLOCKS) k_prb_pass(const __grid_constant__ DScene sc, const __grid_constant__ DLaunch ln, const __grid_constant__ PrbConfig cfg, int pass,
                                                     uint64_t work_base, uint32_t n, const __grid_constant__ WfPrb wb, const float *__restrict__ film,
                                                     const float *__restrict__ grad_in, float *grad_pos, float *grad_nrm) {
     const uint32_t i = blockIdx.x * 128 + threadIdx.x;
