@@ -297,7 +297,6 @@ template <uint32_t NW, typename T> __device__ __forceinline__ void soa_store_pre
 #ifndef EPSM_STAGEA_MINBLOCKS
 #define EPSM_STAGEA_MINBLOCKS 3
 #endif
-#define WF_HEAD_INIT_WORDS 6   // PathHead::cam, d — all that k_wf_init knows
 #define WF_NONE 0u      // slot without a lane
 #define WF_LIVE 1u      // path still being traced
 #define WF_DONE 2u      // path has terminated (its remaining logged vertices are inactive)
@@ -377,28 +376,6 @@ __device__ __forceinline__ void queue_write(QRay *q, uint32_t idx, const Ray &r,
     d[0] = make_float4(r.o.x, r.o.y, r.o.z, r.maxt); d[1] = make_float4(r.d.x, r.d.y, r.d.z, __uint_as_float(out));
 }
 
-__global__ void __launch_bounds__(128) k_wf_init(const __grid_constant__ DLaunch ln, uint64_t work_base, uint32_t n, const float *__restrict__ grad_in, WfBuffers wb) {
-    const uint32_t i = blockIdx.x * 128 + threadIdx.x;
-    bool push = false; WfState S;
-    if (i < n) {
-        const WorkItem wi = wf_work_item(ln, work_base + i);
-        if (wi.valid) {
-            // grad_in is film-sized; samples of the border (sample_border sensors) carry no pixel-motion gradient
-            const int fx = (int) wi.px - ln.sensor.border, fy = (int) wi.py - ln.sensor.border;
-            const bool in_film = fx >= 0 && fy >= 0 && fx < (int) ln.sensor.fw && fy < (int) ln.sensor.fh;
-            const uint64_t pixel = in_film ? (uint64_t) fy * ln.sensor.fw + fx : 0;
-            PathHead H;
-            wf_begin(ln.sensor, wi.px, wi.py, ln.seed, (uint32_t) wi.lane, in_film ? grad_in[pixel * 5 + 3] : 0.f, in_film ? grad_in[pixel * 5 + 4] : 0.f, S, H);
-            soa_store_prefix<WF_INIT_WORDS>(S, wb.states, wb.capacity, i);
-            soa_store_prefix<WF_HEAD_INIT_WORDS>(H, wb.heads, wb.capacity, i);       // cam, d: the rest is zero until the first hit
-            push = true;
-        }
-        wb.status[i] = wi.valid ? WF_LIVE : WF_NONE;
-    }
-    const uint32_t q = queue_push(wb.counters + 0, push);
-    if (push) queue_write(wb.q_closest, q, S.ray, i);
-}
-
 // Persistent traversal kernel.  Every lane owns one ray at a time; the warp schedules itself between three phases so
 // that each phase runs with many active lanes (the first wavefront version executed "one step of whatever each lane
 // needs" per iteration and ran its leaf code at 3.2/32 and its refill code at 1.9/32 active lanes: profiles/r01_b_*):
@@ -427,12 +404,15 @@ __global__ void __launch_bounds__(128) k_wf_init(const __grid_constant__ DLaunch
 #ifndef WF_SPECULATE
 #define WF_SPECULATE 1
 #endif
-template <bool ANY, bool COUNT>
-__global__ void __launch_bounds__(CTA) k_wf_trace(const __grid_constant__ DScene sc, const QRay *__restrict__ queue, const uint32_t *__restrict__ count, uint32_t *head,
-                                                  Hit *__restrict__ hits, uint32_t *__restrict__ occl, unsigned long long *counters) {
+// GEN: the rays are the camera rays of work items [work_base, work_base + n_gen) of `ln` (iteration 0 of the gradient pass and
+// of the primal render), generated here exactly as wf_begin / the stage kernels regenerate them — no init kernel, no queue.
+template <bool ANY, bool COUNT, bool GEN>
+__device__ __forceinline__ void wf_trace_body(const DScene &sc, const QRay *__restrict__ queue, const uint32_t *__restrict__ count, uint32_t *head,
+                                              Hit *__restrict__ hits, uint32_t *__restrict__ occl, unsigned long long *counters,
+                                              const DLaunch *ln, uint64_t work_base, uint32_t n_gen) {
     __shared__ uint2 sstack[WF_STACK][CTA];
     uint2 lstack[WF_LSTACK];
-    const uint32_t n = *count; const int lane = threadIdx.x & 31;
+    const uint32_t n = GEN ? n_gen : *count; const int lane = threadIdx.x & 31;
     uint32_t c_nodes = 0, c_tris = 0, c_rays = 0;
     bool has_ray = false, exhausted = false;
     Ray ray; float ix = 0, iy = 0, iz = 0, ox = 0, oy = 0, oz = 0;
@@ -450,9 +430,18 @@ __global__ void __launch_bounds__(CTA) k_wf_trace(const __grid_constant__ DScene
                 base = __shfl_sync(0xffffffffu, base, leader);
                 if (!has_ray) {
                     const uint32_t i = base + __popc(idle & ((1u << lane) - 1));
-                    if (i < n) {
+                    bool take = i < n;
+                    if (GEN) {
+                        if (take) {
+                            const WorkItem wi = wf_work_item(*ln, work_base + i);
+                            take = wi.valid;
+                            if (take) { Pcg rng = pcg_for_lane(ln->seed, (uint32_t) wi.lane); CamRay c; camera_ray(ln->sensor, wi.px, wi.py, rng, c); ray = c.ray; out = i; }
+                        }
+                    } else if (take) {
                         const f8 q = ldg8(reinterpret_cast<const f4 *>(queue + i));
                         ray.o = mk3(q.a.x, q.a.y, q.a.z); ray.d = mk3(q.b.x, q.b.y, q.b.z); ray.maxt = q.a.w; out = f2u(q.b.w);
+                    }
+                    if (take) {
                         const float dx = fabsf(ray.d.x) < 1e-20f ? mulsign(1e-20f, ray.d.x) : ray.d.x;
                         const float dy = fabsf(ray.d.y) < 1e-20f ? mulsign(1e-20f, ray.d.y) : ray.d.y;
                         const float dz = fabsf(ray.d.z) < 1e-20f ? mulsign(1e-20f, ray.d.z) : ray.d.z;
@@ -558,13 +547,25 @@ __global__ void __launch_bounds__(CTA) k_wf_trace(const __grid_constant__ DScene
         if (lane == 0) { atomicAdd(counters, a); atomicAdd(counters + 1, b); atomicAdd(counters + 2, c); }
     }
 }
+template <bool ANY, bool COUNT>
+__global__ void __launch_bounds__(CTA) k_wf_trace(const __grid_constant__ DScene sc, const QRay *__restrict__ queue, const uint32_t *__restrict__ count, uint32_t *head,
+                                                  Hit *__restrict__ hits, uint32_t *__restrict__ occl, unsigned long long *counters) {
+    wf_trace_body<ANY, COUNT, false>(sc, queue, count, head, hits, occl, counters, nullptr, 0, 0);
+}
+// Closest hits of the camera rays of one chunk: hits[i] for work item work_base + i (slots that hold no lane are skipped).
+template <bool COUNT>
+__global__ void __launch_bounds__(CTA, 8) k_wf_trace_primary(const __grid_constant__ DScene sc, const __grid_constant__ DLaunch ln, uint64_t work_base, uint32_t n, uint32_t *head,
+                                                             Hit *__restrict__ hits, unsigned long long *counters) {
+    wf_trace_body<false, COUNT, true>(sc, nullptr, nullptr, head, hits, nullptr, counters, &ln, work_base, n);
+}
 
 // `grad_pos` != NULL enables the first-vertex fast path (scatter passes; the record probe keeps every lane).
 // STRIDED (iterations ≥ WF_LIST_FROM): launched with a small fixed grid that strides over the compacted lane list when few
 // lanes are left (the list size lives on the device; its order is scrambled by the concurrent appends, so it pays only when
 // sparse) and over the slots otherwise.  The dense early iterations use the loop-free instantiation (one slot per thread).
 template <bool STRIDED>
-__global__ void __launch_bounds__(128, EPSM_STAGEA_MINBLOCKS) k_wf_stage_a(const __grid_constant__ DScene sc, const __grid_constant__ DLaunch ln, uint32_t it, uint32_t n, WfBuffers wb, float *__restrict__ grad_pos) {
+__global__ void __launch_bounds__(128, EPSM_STAGEA_MINBLOCKS) k_wf_stage_a(const __grid_constant__ DScene sc, const __grid_constant__ DLaunch ln, uint32_t it, uint32_t n, WfBuffers wb, float *__restrict__ grad_pos,
+                                                                            uint64_t work_base, const float *__restrict__ grad_in) {
     const bool listed = STRIDED && wb.counters[64 + it] < n / WF_LIST_SPARSE;
     const uint32_t cnt = listed ? wb.counters[64 + it] : n;
     uint32_t base = blockIdx.x * 128;
@@ -573,28 +574,41 @@ __global__ void __launch_bounds__(128, EPSM_STAGEA_MINBLOCKS) k_wf_stage_a(const
     const uint32_t j = base + threadIdx.x;
     const uint32_t i = listed ? (j < cnt ? wf_lane_list(wb, it)[j] : 0u) : j;
     bool push = false; Ray sr;
-    if (j < cnt && (listed || (wb.status[i] & 0xffu) == WF_LIVE)) {
-        WfState S; const Hit h = wb.hits[i];
-        bool keep = true;
-        if (it == 0) {
-            soa_load_prefix<WF_INIT_WORDS>(S, wb.states, wb.capacity, i); wf_state_defaults(S);
-            PathHead H; soa_load_prefix<WF_HEAD_INIT_WORDS>(H, wb.heads, wb.capacity, i);
-            H.dldp1 = H.L = mk3(0, 0, 0); H.dlduv0 = H.dlduv1 = 0.f;
-            SI si;
-            push = wf_stage_a(sc, S, H, h, it, ln.max_depth, ln.variant, ln.prune != 0, si);
-            if (grad_pos && wf_first_vertex_final(S, it, ln.prune != 0)) {
-                // the path ends here for the gradient: seed (ii) of its first vertex is its only output
-                f3 dg; const bool sel = wf_first_vertex_seed(sc, S, H, si, dg);
+    if (!STRIDED && it == 0) {
+        // Iteration 0 starts the lane: the camera ray, its random stream and the pixel-motion tangent are regenerated from
+        // the work item (the traversal kernel did the same for the ray), so no init kernel and no state hand-over exist.
+        if (j < cnt) {
+            const WorkItem wi = wf_work_item(ln, work_base + i);
+            uint32_t status = WF_NONE;
+            if (wi.valid) {
+                // grad_in is film-sized; samples of the border (sample_border sensors) carry no pixel-motion gradient
+                const int fx = (int) wi.px - ln.sensor.border, fy = (int) wi.py - ln.sensor.border;
+                const bool in_film = fx >= 0 && fy >= 0 && fx < (int) ln.sensor.fw && fy < (int) ln.sensor.fh;
+                const uint64_t pixel = in_film ? (uint64_t) fy * ln.sensor.fw + fx : 0;
+                WfState S; PathHead H;
+                wf_begin(ln.sensor, wi.px, wi.py, ln.seed, (uint32_t) wi.lane, in_film ? grad_in[pixel * 5 + 3] : 0.f, in_film ? grad_in[pixel * 5 + 4] : 0.f, S, H);
+                SI si;
+                push = wf_stage_a(sc, S, H, wb.hits[i], it, ln.max_depth, ln.variant, ln.prune != 0, si);
+                if (grad_pos && wf_first_vertex_final(S, it, ln.prune != 0)) {
+                    // the path ends here for the gradient: seed (ii) of its first vertex is its only output
+                    f3 dg; const bool sel = wf_first_vertex_seed(sc, S, H, si, dg);
 #pragma unroll
-                for (int c = 0; c < 3; ++c) scatter3(grad_pos, si.fi[c], dg * si.bw[c], sel);
-                wb.status[i] = WF_SCATTERED; keep = false; push = false;
-            } else soa_store(H, wb.heads, wb.capacity, i);
-        } else {
-            soa_load(S, wb.states, wb.capacity, i);
-            PathHead H;                                   // only written at the first hit
-            push = wf_stage_a(sc, S, H, h, it, ln.max_depth, ln.variant, ln.prune != 0);
+                    for (int c = 0; c < 3; ++c) scatter3(grad_pos, si.fi[c], dg * si.bw[c], sel);
+                    status = WF_SCATTERED; push = false;
+                } else {
+                    soa_store(H, wb.heads, wb.capacity, i);
+                    sr = S.shadow_ray; soa_store(S, wb.states, wb.capacity, i);
+                    status = WF_LIVE;
+                }
+            }
+            wb.status[i] = status;
         }
-        if (keep) { sr = S.shadow_ray; soa_store(S, wb.states, wb.capacity, i); }
+    } else if (j < cnt && (listed || (wb.status[i] & 0xffu) == WF_LIVE)) {
+        WfState S; const Hit h = wb.hits[i];
+        soa_load(S, wb.states, wb.capacity, i);
+        PathHead H;                                   // only written at the first hit
+        push = wf_stage_a(sc, S, H, h, it, ln.max_depth, ln.variant, ln.prune != 0);
+        sr = S.shadow_ray; soa_store(S, wb.states, wb.capacity, i);
     }
     const uint32_t q = queue_push(wb.counters + 32 + it, push);
     if (push) queue_write(wb.q_any, q, sr, i);
@@ -717,42 +731,35 @@ __global__ void __launch_bounds__(128, NV < EPSM_MAXV ? EPSM_FINISH_SHORT_BLOCKS
 // ------------------------------------------------------------------------------------------------
 //  Primal render — wavefront (EPSMIntegrator.render / sample, epsm.py:13-82, 308-501)
 //
-//  k_pr_init → [closest] → k_pr_stage(0) → [any ∥ closest] → k_pr_stage(1) → … → k_pr_film.  One stage per bounce
+//  [closest: camera rays generated in k_wf_trace_primary] → k_pr_stage(0) → [any ∥ closest] → k_pr_stage(1) → … → k_pr_film.  One stage per bounce
 //  (pr_stage, epsm_device.cuh); both queries of a bounce are drained by the persistent traversal kernel of the gradient
 //  pass.  The film kernel owns one 8×4-pixel tile per CTA — work items are enumerated tile by tile, so a tile's samples
 //  are contiguous — accumulates the 5×5 Gaussian footprints in shared memory and flushes each film pixel once.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_pr_init(const __grid_constant__ DLaunch ln, uint64_t work_base, uint32_t n, WfBuffers wb) {
-    const uint32_t i = blockIdx.x * 128 + threadIdx.x;
-    bool push = false; PrState S;
-    if (i < n) {
-        const WorkItem wi = wf_work_item(ln, work_base + i);
-        if (wi.valid) {
-            S.rng = pcg_for_lane(ln.seed, (uint32_t) wi.lane);
-            CamRay c; camera_ray(ln.sensor, wi.px, wi.py, S.rng, c);
-            S.ray = c.ray;
-            soa_store_prefix<PR_INIT_WORDS>(S, wb.states, wb.capacity, i);
-            push = true;
-        }
-        wb.status[i] = wi.valid ? WF_LIVE : WF_NONE;
-    }
-    const uint32_t q = queue_push(wb.counters + 0, push);
-    if (push) queue_write(wb.q_closest, q, S.ray, i);
-}
-
 #ifndef EPSM_PR_MINBLOCKS
 #define EPSM_PR_MINBLOCKS 5    // measured (room primal, ms): 4 CTAs/SM (113 registers) 188.4, 5 → 186.5, 6 → 186.7, 8 → 186.9
 #endif
-__global__ void __launch_bounds__(128, EPSM_PR_MINBLOCKS) k_pr_stage(const __grid_constant__ DScene sc, const __grid_constant__ DLaunch ln, uint32_t it, uint32_t n, WfBuffers wb) {
+__global__ void __launch_bounds__(128, EPSM_PR_MINBLOCKS) k_pr_stage(const __grid_constant__ DScene sc, const __grid_constant__ DLaunch ln, uint32_t it, uint32_t n, WfBuffers wb, uint64_t work_base) {
     const uint32_t i = blockIdx.x * 128 + threadIdx.x;
-    bool push_shadow = false, push_next = false; Ray shadow; PrState S;
-    if (i < n && wb.status[i] == WF_LIVE) {
-        if (it == 0) { soa_load_prefix<PR_INIT_WORDS>(S, wb.states, wb.capacity, i); pr_state_defaults(S); }
-        else { soa_load(S, wb.states, wb.capacity, i); pr_resolve_pending(S, wb.occl[i] != 0u); }
+    bool push_shadow = false, push_next = false, live = false; Ray shadow; PrState S;
+    if (i < n) {
+        if (it == 0) {
+            // bounce 0 starts the lane from its work item (the traversal kernel generated the same camera ray)
+            const WorkItem wi = wf_work_item(ln, work_base + i);
+            live = wi.valid;
+            if (live) { S.rng = pcg_for_lane(ln.seed, (uint32_t) wi.lane); CamRay c; camera_ray(ln.sensor, wi.px, wi.py, S.rng, c); S.ray = c.ray; pr_state_defaults(S); }
+            else wb.status[i] = WF_NONE;
+        } else {
+            live = wb.status[i] == WF_LIVE;
+            if (live) { soa_load(S, wb.states, wb.capacity, i); pr_resolve_pending(S, wb.occl[i] != 0u); }
+        }
+    }
+    if (live) {
         push_shadow = pr_stage(sc, S, wb.hits[i], ln.max_depth, ln.rr_depth, shadow);
         push_next = (S.bits & PR_ACTIVE) != 0 && it + 1 < ln.max_depth;
         soa_store(S, wb.states, wb.capacity, i);
-        if (!push_next) wb.status[i] = WF_DONE;
+        if (it == 0) wb.status[i] = push_next ? WF_LIVE : WF_DONE;
+        else if (!push_next) wb.status[i] = WF_DONE;
     }
     const uint32_t slot = (it + 1) & 15u;
     const uint32_t qa = queue_push(wb.counters + 32 + slot, push_shadow);
@@ -1011,7 +1018,6 @@ cudaError_t epsm_launch_render_wf(const DScene &sc, DLaunch ln, float *film, uns
         const uint32_t n = (uint32_t) ((total - base) < capacity ? (total - base) : capacity);
         const uint32_t grid = (n + 127) / 128;
         cudaMemsetAsync(wb.counters, 0, 64 * sizeof(uint32_t), s);
-        k_pr_init<<<grid, 128, 0, s>>>(ln, base, n, wb); ++launches;
         auto trace = [&](bool any, uint32_t slot) {
             if (any) {
                 if (counters) k_wf_trace<true, true><<<trace_grid, CTA, 0, s>>>(sc, wb.q_any, wb.counters + 32 + slot, wb.counters + 48 + slot, nullptr, wb.occl, counters);
@@ -1025,13 +1031,17 @@ cudaError_t epsm_launch_render_wf(const DScene &sc, DLaunch ln, float *film, uns
         uint32_t last_slot = 0; bool shadow_left = true;
         for (uint32_t it = 0; it < ln.max_depth; ++it) {
             const uint32_t slot = it & 15u, next = (it + 1) & 15u;
-            trace(false, slot);
+            if (it == 0) {                                // camera rays: generated inside the traversal kernel
+                if (counters) k_wf_trace_primary<true><<<trace_grid, CTA, 0, s>>>(sc, ln, base, n, wb.counters + 16, wb.hits, counters);
+                else k_wf_trace_primary<false><<<trace_grid, CTA, 0, s>>>(sc, ln, base, n, wb.counters + 16, wb.hits, nullptr);
+                ++launches;
+            } else trace(false, slot);
             if (it > 0) trace(true, slot);
             if (it + 1 >= 16) {                           // the counter slots are reused cyclically
                 cudaMemsetAsync(wb.counters + next, 0, 4, s); cudaMemsetAsync(wb.counters + 16 + next, 0, 4, s);
                 cudaMemsetAsync(wb.counters + 32 + next, 0, 4, s); cudaMemsetAsync(wb.counters + 48 + next, 0, 4, s);
             }
-            k_pr_stage<<<grid, 128, 0, s>>>(sc, ln, it, n, wb); ++launches;
+            k_pr_stage<<<grid, 128, 0, s>>>(sc, ln, it, n, wb, base); ++launches;
             last_slot = next;
             if (it + 1 >= 8 && it + 1 < ln.max_depth) {   // long paths: poll the queue sizes, stop when no path ray is left
                 uint32_t left[2] = {0, 0};
@@ -1072,19 +1082,21 @@ cudaError_t epsm_launch_backward(const DScene &sc, DLaunch ln, const float *grad
         const uint32_t n = (uint32_t) ((total - base) < capacity ? (total - base) : capacity);
         const uint32_t grid = (n + 127) / 128;
         cudaMemsetAsync(wb.counters, 0, WF_COUNTER_WORDS * sizeof(uint32_t), s);
-        k_wf_init<<<grid, 128, 0, s>>>(ln, base, n, grad_in, wb); ++launches;
         for (uint32_t it = 0; it <= max_iter; ++it) {
             // closest-hit queue `it`: path rays of iteration `it` and the direct rays of iteration `it − 1`
             ev_begin();
-            if (counters) k_wf_trace<false, true><<<trace_grid, CTA, 0, s>>>(sc, wb.q_closest, wb.counters + it, wb.counters + 16 + it, wb.hits, nullptr, counters);
+            if (it == 0) {                                // camera rays: generated inside the traversal kernel
+                if (counters) k_wf_trace_primary<true><<<trace_grid, CTA, 0, s>>>(sc, ln, base, n, wb.counters + 16, wb.hits, counters);
+                else k_wf_trace_primary<false><<<trace_grid, CTA, 0, s>>>(sc, ln, base, n, wb.counters + 16, wb.hits, nullptr);
+            } else if (counters) k_wf_trace<false, true><<<trace_grid, CTA, 0, s>>>(sc, wb.q_closest, wb.counters + it, wb.counters + 16 + it, wb.hits, nullptr, counters);
             else k_wf_trace<false, false><<<trace_grid, CTA, 0, s>>>(sc, wb.q_closest, wb.counters + it, wb.counters + 16 + it, wb.hits, nullptr, nullptr);
             ev_end();
             ++launches;
             if (it == max_iter) break;
             const bool strided = it >= WF_LIST_FROM && grid > trace_grid * 4;
             const uint32_t sgrid = strided ? trace_grid * 4 : grid;
-            if (strided) k_wf_stage_a<true><<<sgrid, 128, 0, s>>>(sc, ln, it, n, wb, records ? nullptr : grad_pos);
-            else k_wf_stage_a<false><<<sgrid, 128, 0, s>>>(sc, ln, it, n, wb, records ? nullptr : grad_pos);
+            if (strided) k_wf_stage_a<true><<<sgrid, 128, 0, s>>>(sc, ln, it, n, wb, records ? nullptr : grad_pos, base, grad_in);
+            else k_wf_stage_a<false><<<sgrid, 128, 0, s>>>(sc, ln, it, n, wb, records ? nullptr : grad_pos, base, grad_in);
             ++launches;
             ev_begin();
             if (counters) k_wf_trace<true, true><<<trace_grid, CTA, 0, s>>>(sc, wb.q_any, wb.counters + 32 + it, wb.counters + 48 + it, nullptr, wb.occl, counters);
