@@ -15,7 +15,8 @@
 // the random stream (sampler.cpp:122-130) — is (pixel · spp + s) exactly as in the reference
 // wavefront (common.py:326-343).
 #include <cuda_runtime.h>
-#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
+#include <thrust/iterator/counting_iterator.h>
 #include <cooperative_groups.h>
 #include <stdlib.h>
 #include <stdint.h>
@@ -317,6 +318,7 @@ struct WfBuffers {
     uint32_t capacity;
 };
 #define WF_COUNTER_WORDS 96u
+#define WF_LONG_COUNT 80u      // counters[80]: number of lanes selected for the long-chain finish launch
 // From this iteration on the stage kernels run over the compacted lane list instead of over all slots: by then a few
 // percent of the lanes are left and a full-grid launch is a 0.6 ms floor (262 144 CTAs that read one status word each);
 // in the dense early iterations slot order (coalesced records) wins (profiles/r01_f_refit_iteration.md).
@@ -716,9 +718,16 @@ __device__ __forceinline__ void finish_lane(const DScene &sc, const DLaunch &ln,
     if (RECORD) { if (NV == EPSM_MAXV) { const WorkItem wi = wf_work_item(ln, work_base + i); write_record(reinterpret_cast<const PathLog &>(P), reinterpret_cast<const PathGrads &>(G), n_logged, records + (wi.lane - ln.lane_begin) * EPSM_REC_FLOATS); } }
     else scatter_path<NV>(P, G, ln.variant, n_logged, n_avail, ln.max_depth, grad_pos, grad_nrm);
 }
-// LISTED (the long-chain scatter launch when those lanes are few): one thread per entry of `list`, the lanes that entered
-// iteration 2 — exactly the lanes with more than two logged vertices, appended by stage B(1) and sorted back into slot
-// order by the launcher (neighbouring pixels → similar control flow and neighbouring records).
+// LISTED (the long-chain scatter launch when those lanes are few): one thread per entry of `list`, the slots whose lane
+// logged more than two vertices, selected in slot order by a device compaction (neighbouring pixels → similar control
+// flow and neighbouring records).
+struct WfLongLane {
+    const uint32_t *status;
+    __device__ __forceinline__ bool operator()(uint32_t i) const {
+        const uint32_t st = status[i], code = st & 0xffu;
+        return code != WF_NONE && code != WF_SCATTERED && (st >> 8) > (uint32_t) (WF_SHORT_NV - 1);
+    }
+};
 template <bool RECORD, int NV, bool LISTED>
 __global__ void __launch_bounds__(128, NV < EPSM_MAXV ? EPSM_FINISH_SHORT_BLOCKS : EPSM_FINISH_LONG_BLOCKS) k_wf_finish(const __grid_constant__ DScene sc, const __grid_constant__ DLaunch ln, uint64_t work_base, uint32_t n, WfBuffers wb,
                                                    float *__restrict__ grad_pos, float *__restrict__ grad_nrm, float *__restrict__ records, bool skip_short,
@@ -1076,8 +1085,6 @@ cudaError_t epsm_launch_backward(const DScene &sc, DLaunch ln, const float *grad
     const uint32_t max_iter = wf_replay_iterations(ln.max_depth, ln.prune != 0);
     WfBuffers wb = wf_carve(workspace, capacity);
     uint64_t launches = 0;
-    uint32_t finish_sparse = WF_LIST_SPARSE;
-    if (const char *e = getenv("EPSM_FINISH_SPARSE")) finish_sparse = (uint32_t) strtoul(e, nullptr, 10);   // experiments: 0 never lists, 1 always
     for (uint64_t base = 0; base < total; base += capacity) {
         const uint32_t n = (uint32_t) ((total - base) < capacity ? (total - base) : capacity);
         const uint32_t grid = (n + 127) / 128;
@@ -1111,22 +1118,23 @@ cudaError_t epsm_launch_backward(const DScene &sc, DLaunch ln, const float *grad
         else {
             k_wf_finish<false, WF_SHORT_NV, false><<<grid, 128, 0, s>>>(sc, ln, base, n, wb, grad_pos, grad_nrm, nullptr, false, nullptr); ++launches;
             if (max_iter > 2) {                               // lanes with more than two logged vertices exist only then
-                uint32_t n_long = 0;                          // = size of the lane list of iteration 2 (one 4-byte read-back per chunk)
-                cudaMemcpyAsync(&n_long, wb.counters + 64 + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, s);
-                cudaError_t e = cudaStreamSynchronize(s); if (e != cudaSuccess) return e;
-                const uint32_t *list = nullptr;
-                if (n_long != 0 && finish_sparse != 0 && n_long < n / finish_sparse) {
-                    // back into slot order: keys < n, sorted from live2 into live0 with live1 as scratch (all three are free now)
-                    int bits = 1; while (bits < 32 && (1ull << bits) < n) ++bits;
-                    size_t temp = 0;
-                    cub::DeviceRadixSort::SortKeys(nullptr, temp, wb.live2, wb.live0, (int) n_long, 0, bits, s);
-                    if (temp <= (size_t) capacity * sizeof(uint32_t) &&
-                        cub::DeviceRadixSort::SortKeys(wb.live1, temp, wb.live2, wb.live0, (int) n_long, 0, bits, s) == cudaSuccess) list = wb.live0;               // (the library's sort kernels are not counted as ours)
-                    else list = wb.live2;
+                // Ordered compaction on the device (the lane lists are free by now: live0 receives the selection, live1 is the
+                // library's scratch), then one 4-byte read-back per chunk to size the launch.  Measured alternatives
+                // (profiles/r02_summary.md §L): a fixed grid striding over the device-side count needs no synchronisation
+                // but runs this 255-register kernel 65 % slower (6.8 against 4.1 ms); the radix sort of the appended lane
+                // list that this replaces cost five library launches for the same order.
+                size_t temp = 0; uint32_t n_long = 0; bool listed = false;
+                thrust::counting_iterator<uint32_t> slots(0u);
+                cub::DeviceSelect::If(nullptr, temp, slots, wb.live0, wb.counters + WF_LONG_COUNT, (int) n, WfLongLane{wb.status}, s);
+                if (temp <= (size_t) capacity * sizeof(uint32_t) &&
+                    cub::DeviceSelect::If(wb.live1, temp, slots, wb.live0, wb.counters + WF_LONG_COUNT, (int) n, WfLongLane{wb.status}, s) == cudaSuccess) {   // (the library's kernels are not counted as ours)
+                    cudaMemcpyAsync(&n_long, wb.counters + WF_LONG_COUNT, sizeof(uint32_t), cudaMemcpyDeviceToHost, s);
+                    cudaError_t e = cudaStreamSynchronize(s); if (e != cudaSuccess) return e;
+                    listed = true;
                 }
-                if (list) k_wf_finish<false, EPSM_MAXV, true><<<(n_long + 127) / 128, 128, 0, s>>>(sc, ln, base, n_long, wb, grad_pos, grad_nrm, nullptr, true, list);
-                else if (n_long != 0) k_wf_finish<false, EPSM_MAXV, false><<<grid, 128, 0, s>>>(sc, ln, base, n, wb, grad_pos, grad_nrm, nullptr, true, nullptr);
-                if (n_long != 0) ++launches;
+                if (listed && n_long != 0) k_wf_finish<false, EPSM_MAXV, true><<<(n_long + 127) / 128, 128, 0, s>>>(sc, ln, base, n_long, wb, grad_pos, grad_nrm, nullptr, true, wb.live0);
+                else if (!listed) k_wf_finish<false, EPSM_MAXV, false><<<grid, 128, 0, s>>>(sc, ln, base, n, wb, grad_pos, grad_nrm, nullptr, true, nullptr);
+                if (!listed || n_long != 0) ++launches;
             }
         }
         if (counters) { k_count_lanes<<<grid, 128, 0, s>>>(n, wb, counters); ++launches; }
