@@ -492,6 +492,10 @@ def main():
     if not args.no_e2e:
         gp_h = torch.zeros((scene.n_vertices, 3), dtype=torch.float32).pin_memory(); gn_h = torch.zeros_like(gp_h).pin_memory()
         scene.set_sample_range(s0, s1)
+        if world > 1:
+            g_chunk = (g_host.numel() + world - 1) // world
+            g_host_flat = torch.zeros(g_chunk * world, dtype=torch.float32).pin_memory(); g_host_flat[:g_host.numel()] = g_host.reshape(-1)
+            g_slice = torch.empty(g_chunk, dtype=torch.float32, device=scene.device); g_full = torch.empty(g_chunk * world, dtype=torch.float32, device=scene.device)
         ts = []
         for k in range(2 + args.steps):
             gp_h.zero_(); gn_h.zero_(); flush.fill_(k & 0xff); torch.cuda.synchronize()
@@ -501,8 +505,12 @@ def main():
             if world == 1:
                 scene.render_backward_raw(wl["variant"], sensor, 200 + k, spp_job, integ.max_depth, integ.rr_depth, g_host, gp_h, gn_h)   # host pointers through the C ABI: H2D + pass + D2H
             else:
-                # N ranks: pinned grad_in H2D, device pass, ONE allreduce of the device buffer, ONE D2H of the reduced gradients
-                g_d = g_host.to(scene.device, non_blocking=True); buf.zero_(); torch.cuda.current_stream().synchronize()
+                # N ranks: every rank uploads 1/N of the pinned grad_in over its own PCIe link and the slices are all-gathered
+                # over NVLink (the whole image is needed by every rank: shards are by sample index), device pass, ONE
+                # allreduce of the device buffer, ONE D2H of the reduced gradients
+                g_slice.copy_(g_host_flat[rank * g_chunk:(rank + 1) * g_chunk], non_blocking=True)
+                dist.all_gather_into_tensor(g_full, g_slice)
+                g_d = g_full[:g_host.numel()].view(g_host.shape); buf.zero_(); torch.cuda.current_stream().synchronize()
                 scene.render_backward_raw(wl["variant"], sensor, 200 + k, spp_job, integ.max_depth, integ.rr_depth, g_d, buf[0], buf[1])
                 scene.synchronize()
                 dist.all_reduce(buf)
