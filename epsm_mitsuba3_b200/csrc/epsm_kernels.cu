@@ -1233,6 +1233,7 @@ struct WfPrb {
     QRay *q_closest, *q_any;
     uint32_t *counters;     // [0] closest count, [1] closest head, [2] any count, [3] any head
     const float *lane_L;    // per-lane radiance of the primal pass, indexed by global lane id
+    uint32_t *ckpt;         // PrbCheckpoint, word-major: the state at the top of the lane's latest iteration
     uint32_t C, K, n_aux;
 };
 struct WfIo {
@@ -1257,6 +1258,9 @@ struct WfIo {
     __device__ __forceinline__ Hit aux_hit(uint32_t j, const Ray &) { return wb.hits[(size_t) (wb.K + 1 + j) * wb.C + i]; }
     __device__ __forceinline__ bool lane_radiance(f3 &L) const { const float *p = wb.lane_L + 3 * lane; L = mk3(p[0], p[1], p[2]); return true; }
     __device__ __forceinline__ void finished() { wb.status[i] = 1u; }
+    // passes 0 and 1 start at the camera; every later pass starts at the top of the iteration stored by pass 2·it + 1
+    __device__ __forceinline__ bool resume(PrbCheckpoint &c) const { if (pass < 2) return false; soa_load(c, wb.ckpt, wb.C, i); return true; }
+    __device__ __forceinline__ void checkpoint(uint32_t it, const PrbCheckpoint &c) const { if (pass == 2 * (int) it + 1) soa_store(c, wb.ckpt, wb.C, i); }
 };
 EPSM_HD f3 path_primal_io(const DScene &, WfIo &, LocalTrace &, Ray, Pcg &, uint32_t, uint32_t, bool &) { return mk3(0, 0, 0); }   // never reached: lane_radiance() is always available
 
@@ -1285,7 +1289,7 @@ __global__ void __launch_bounds__(128, EPSM_PRBPASS_MINBLOCKS) k_prb_pass(const 
 
 size_t epsm_prb_workspace_bytes(uint32_t capacity, uint32_t K, uint32_t n_aux) {
     const size_t c = capacity;
-    return 1024 + c * 4 + c * sizeof(Hit) * (K + 1 + 2 * (size_t) n_aux) + c * 4 * 2 * (size_t) K + c * sizeof(QRay) * (2 * (size_t) n_aux + 1) + c * sizeof(QRay) + 16 * 256;
+    return 1024 + c * 4 + c * 4 * WORDS_OF(PrbCheckpoint) + 256 + c * sizeof(Hit) * (K + 1 + 2 * (size_t) n_aux) + c * 4 * 2 * (size_t) K + c * sizeof(QRay) * (2 * (size_t) n_aux + 1) + c * sizeof(QRay) + 16 * 256;
 }
 cudaError_t epsm_launch_prb_backward_wf(const DScene &sc, DLaunch ln, const PrbConfig &cfg, const float *film, const float *lane_L, const float *grad_in,
                                         float *grad_pos, float *grad_nrm, void *workspace, uint32_t capacity, uint32_t trace_grid, uint64_t *n_launches, cudaStream_t s) {
@@ -1296,6 +1300,7 @@ cudaError_t epsm_launch_prb_backward_wf(const DScene &sc, DLaunch ln, const PrbC
     auto take = [&](size_t bytes) { char *r = p; p += (bytes + 255) & ~(size_t) 255; return r; };
     wb.counters = (uint32_t *) take(1024);
     wb.status = (uint32_t *) take(c * 4);
+    wb.ckpt = (uint32_t *) take(c * 4 * WORDS_OF(PrbCheckpoint));
     wb.hits = (Hit *) take(c * sizeof(Hit) * (K + 1 + 2 * (size_t) n_aux));
     wb.occl = (uint32_t *) take(c * 4 * 2 * (size_t) K);
     wb.q_closest = (QRay *) take(c * sizeof(QRay) * (2 * (size_t) n_aux + 1));

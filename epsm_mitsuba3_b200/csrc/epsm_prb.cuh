@@ -216,6 +216,8 @@ struct MegaIo {
     EPSM_HD Hit aux_hit(uint32_t, const Ray &r) { return trace_closest<COUNT>(tr, r); }
     EPSM_HD bool lane_radiance(f3 &) const { return false; }       // false: replay the primal path inline
     EPSM_HD void finished() {}
+    template <typename C> EPSM_HD bool resume(C &) const { return false; }             // no checkpoints: one thread walks the whole lane
+    template <typename C> EPSM_HD void checkpoint(uint32_t, const C &) const {}
 };
 
 // Where a ray origin is glued to (FollowShape: p = Σ bw_k·p_k with detached barycentrics); prim = 0xffffffff: detached origin.
@@ -348,21 +350,34 @@ EPSM_HD void filter_eval_d(const float *c, float x, float &f, float &df) {
 //  (common.py:905-935), grad_in the (H,W,3) image gradient.  Gradients are pushed into `sink` (.pos / .nrm of a vertex).
 // ------------------------------------------------------------------------------------------------
 struct PrevVertex { bool valid; f3 p, sh_s, sh_t, sh_n, wi; int32_t bsdf; Anchor anchor; };
+// Everything iteration `it` of the loop below inherits from the iterations before it.  The replay wavefront stores it when a
+// pass first reaches the top of an iteration (pass 2·it + 1) and the two later passes that need that iteration (2·it + 2: its
+// second round of rays, 2·it + 3: its adjoint) start from there instead of replaying the lane from the camera — without it the
+// replay work grows with the square of the path length (profiles/r02_h_*: k_prb_pass 333 of 500 ms at 512² × 8 spp).
+struct PrbCheckpoint { Pcg rng, aux; Ray ray; Hit h; f3 L, beta, dL; float eta, mis_em; uint32_t depth, it; PrevVertex prev; };
 
 template <typename Io, typename Sink>
 EPSM_HDN void prb_backward_lane(const DScene &sc, Io &io, const DSensor &sensor, const PrbConfig &cfg, uint32_t px, uint32_t py,
                                 uint32_t seed, uint32_t lane, const float *film, const float *grad_in, Sink &sink) {
-    Pcg rng = pcg_for_lane(seed, lane);
-    Pcg aux = pcg_for_lane(0xffffffffu ^ seed, lane);                               // _ReparamWrapper, common.py:1200-1203
-    CamRay cr; camera_ray(sensor, px, py, rng, cr);
+    Pcg rng, aux; Hit h; f3 dL = mk3(0, 0, 0);
     const uint32_t n_aux = cfg.n_rays;
     const Anchor none{0xffffffffu, {0.f, 0.f, 0.f}};
+    uint32_t depth = 0, it0 = 0; f3 L, beta = mk3(1, 1, 1); float eta = 1.f, mis_em = 1.f; bool active = true;
+    Ray ray;
+    PrevVertex prev; prev.valid = false; prev.anchor = none; prev.bsdf = -1;
+    PrbCheckpoint ck;
+    if (io.resume(ck)) {
+        rng = ck.rng; aux = ck.aux; ray = ck.ray; h = ck.h; L = ck.L; beta = ck.beta; dL = ck.dL; eta = ck.eta; mis_em = ck.mis_em; depth = ck.depth; it0 = ck.it; prev = ck.prev;
+    } else {
+    rng = pcg_for_lane(seed, lane);
+    aux = pcg_for_lane(0xffffffffu ^ seed, lane);                                   // _ReparamWrapper, common.py:1200-1203
+    CamRay cr; camera_ray(sensor, px, py, rng, cr);
     const bool cam_active = 0 < cfg.reparam_max_depth;
 
     // ---- round 0: the primary ray and the auxiliary rays of the camera ray's reparameterisation (common.py:372-397)
-    Hit h = io.closest(0, 0, cr.ray);
+    h = io.closest(0, 0, cr.ray);
     f3 Ltot = mk3(0, 0, 0);
-    f3 dL = mk3(0, 0, 0); f3 g_d_cam = mk3(0, 0, 0); float g_det_cam = 0.f;
+    f3 g_d_cam = mk3(0, 0, 0); float g_det_cam = 0.f;
     if (!io.aux_push_only(0)) {
         // primal radiance of the lane: the primal pass with the cloned sampler (common.py:905-915)
         if (!io.lane_radiance(Ltot)) {
@@ -404,14 +419,17 @@ EPSM_HDN void prb_backward_lane(const DScene &sc, Io &io, const DSensor &sensor,
     }
     reparam_backward(sc, io, sink, aux, cfg, 0, 0, cam_active, cr.ray.o, cr.ray.d, g_d_cam, g_det_cam, none, false, mk3(0, 0, 0));
     if (io.stop_after(0)) return;
+    L = Ltot; ray = cr.ray;
+    }
 
     // ---- sample(mode = Backward) (prb_reparam.py:329-602)
-    uint32_t depth = 0; f3 L = Ltot, beta = mk3(1, 1, 1); float eta = 1.f, mis_em = 1.f; bool active = true;
-    Ray ray = cr.ray;
-    PrevVertex prev; prev.valid = false; prev.anchor = none; prev.bsdf = -1;
     SI si, si_next;
-    for (uint32_t it = 0; it < cfg.max_depth && active; ++it) {
+    for (uint32_t it = it0; it < cfg.max_depth && active; ++it) {
         const int r1 = 1 + 2 * (int) it, r2 = 2 + 2 * (int) it;                     // this iteration's two rounds of rays
+        if (Io::wavefront) {
+            ck.rng = rng; ck.aux = aux; ck.ray = ray; ck.h = h; ck.L = L; ck.beta = beta; ck.dL = dL; ck.eta = eta; ck.mis_em = mis_em; ck.depth = depth; ck.it = it; ck.prev = prev;
+            io.checkpoint(it, ck);
+        }
         compute_si(sc, ray, h, si);
         const f3 Le = beta * mis_em * emitter_eval(sc, si);
         bool active_next = (depth + 1 < cfg.max_depth) && si.valid;

@@ -289,7 +289,7 @@ struct HostSink { float *gp, *gn; EPSM_HD void pos(uint32_t v, f3 g) { gp[3 * v]
 struct HostWfIo {
     static constexpr bool wavefront = true;
     int pass; uint32_t K; std::vector<Hit> &hits; std::vector<uint32_t> &occl;
-    std::vector<std::pair<Ray, uint32_t>> &qc, &qa; f3 L; bool done;
+    std::vector<std::pair<Ray, uint32_t>> &qc, &qa; f3 L; bool done; PrbCheckpoint *saved;
     Hit closest(int round, uint32_t slot, const Ray &r) { if (round == pass) { qc.push_back({r, slot}); return Hit{0.f, 0.f, 0.f, 0xffffffffu}; } return hits[slot]; }
     bool occluded(int round, uint32_t slot, const Ray &r) { if (round == pass) { qa.push_back({r, slot}); return false; } return occl[slot] != 0u; }
     bool stop_after(int round) const { return pass == round; }
@@ -300,6 +300,8 @@ struct HostWfIo {
     Hit aux_hit(uint32_t j, const Ray &) { return hits[K + 1 + j]; }
     bool lane_radiance(f3 &out) const { out = L; return true; }
     void finished() { done = true; }
+    bool resume(PrbCheckpoint &c) const { if (pass < 2) return false; c = *saved; return true; }
+    void checkpoint(uint32_t it, const PrbCheckpoint &c) const { if (pass == 2 * (int) it + 1) *saved = c; }
 };
 f3 path_primal_io(const DScene &, HostWfIo &, LocalTrace &, Ray, Pcg &, uint32_t, uint32_t, bool &) { return mk3(0, 0, 0); }
 
@@ -321,8 +323,9 @@ void sim_prb_backward(sim_scene *s, uint32_t sensor, uint32_t seed, uint32_t spp
         std::vector<std::pair<Ray, uint32_t>> qc, qa;
         Pcg rng = pcg_for_lane(seed, (uint32_t) lane); CamRay cr; camera_ray(se, pixel % se.w, pixel / se.w, rng, cr);
         bool valid; const f3 L = path_primal<false>(s->sc, tr, cr.ray, rng, pc.max_depth, pc.rr_depth, valid);     // what k_pr_film writes to lane_L
+        PrbCheckpoint saved;
         for (int pass = 0; pass <= 2 * (int) K + 1; ++pass) {
-            HostWfIo io{pass, K, hits, occl, qc, qa, L, false};
+            HostWfIo io{pass, K, hits, occl, qc, qa, L, false, &saved};
             prb_backward_lane(s->sc, io, se, pc, pixel % se.w, pixel / se.w, seed, (uint32_t) lane, film, grad_in, sink);
             for (auto &q : qc) hits[q.second] = trace_closest<false>(tr, q.first);
             for (auto &q : qa) occl[q.second] = trace_any<false>(tr, q.first) ? 1u : 0u;
