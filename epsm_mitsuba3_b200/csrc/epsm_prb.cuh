@@ -227,6 +227,11 @@ EPSM_HD void scatter_tri(const DScene &sc, Sink &sink, uint32_t prim, float b0, 
     if (prim == 0xffffffffu || !(sc.meshes[sc.face_mesh[prim]].flags & EPSM_MESH_GRAD)) return;
     sink.pos(sc.faces[3 * prim], g * b0); sink.pos(sc.faces[3 * prim + 1], g * b1); sink.pos(sc.faces[3 * prim + 2], g * b2);
 }
+template <typename Sink>
+EPSM_HD void scatter_tri3(const DScene &sc, Sink &sink, uint32_t prim, f3 g0, f3 g1, f3 g2) {      // per-vertex gradients of one triangle
+    if (prim == 0xffffffffu || !(sc.meshes[sc.face_mesh[prim]].flags & EPSM_MESH_GRAD)) return;
+    sink.pos(sc.faces[3 * prim], g0); sink.pos(sc.faces[3 * prim + 1], g1); sink.pos(sc.faces[3 * prim + 2], g2);
+}
 // Backward of one reparameterize_ray call (backward_symbolic, reparam.py:236-330).  The op's outputs have the values
 // (ray.d, 1); (g_dir, g_det) are the gradients that arrived at them.  Traces the n auxiliary rays once (the reference
 // walks them twice with the same random numbers: weight normalisation, then back-propagation), forms
@@ -263,6 +268,10 @@ EPSM_HDN void reparam_backward(const DScene &sc, Io &io, Sink &sink, Pcg &aux_rn
     const f3 g_V = (normalize_bwd(d, g_dir) - dZ * (g_det * iz)) * iz;
     const float g_div = g_det * iz;
     f3 g_o = mk3(0, 0, 0), g_d = mk3(0, 0, 0);
+    // The auxiliary rays form a tight cone (κ = 1e5 by default): consecutive ones mostly land on the same triangle, so their
+    // vertex gradients are summed in registers and scattered once per run of equal triangles (9 atomics per run instead of
+    // 9 per ray: the scatter was the bulk of the adjoint passes, profiles/r02_s_*).
+    uint32_t run = 0xffffffffu; f3 a0 = mk3(0, 0, 0), a1 = mk3(0, 0, 0), a2 = mk3(0, 0, 0);
     for (uint32_t i = 0; i < n; ++i) {
         const f3 g_vd = g_V * rec[i].w + rec[i].dw * g_div;
         if (rec[i].prim != 0xffffffffu) {
@@ -270,12 +279,14 @@ EPSM_HDN void reparam_backward(const DScene &sc, Io &io, Sink &sink, Pcg &aux_rn
             const float b1 = rec[i].u, b2 = rec[i].v, b0 = 1.f - b1 - b2;
             const f3 p = fma3(ld3(sc.pos, sc.faces[3 * pr]), b0, fma3(ld3(sc.pos, sc.faces[3 * pr + 1]), b1, ld3(sc.pos, sc.faces[3 * pr + 2]) * b2));
             const f3 g_r = normalize_bwd(p - o, g_vd);
-            scatter_tri(sc, sink, pr, b0, b1, b2, g_r);
+            if (pr != run) { scatter_tri3(sc, sink, run, a0, a1, a2); run = pr; a0 = a1 = a2 = mk3(0, 0, 0); }
+            a0 = a0 + g_r * b0; a1 = a1 + g_r * b1; a2 = a2 + g_r * b2;
             g_o = g_o - g_r;
         } else {
             g_d = g_d + g_vd;
         }
     }
+    scatter_tri3(sc, sink, run, a0, a1, a2);
     if (d_attached) g_o = g_o - normalize_bwd(d_from - o, g_d);                    // d = normalize(d_from − o), spawn_ray_to (interaction.h:141-147)
     scatter_tri(sc, sink, anchor.prim, anchor.bw[0], anchor.bw[1], anchor.bw[2], g_o);
 }
