@@ -25,14 +25,25 @@ class MeshDesc(C.Structure):
     _fields_ = [("vertex_count", C.c_uint32), ("face_count", C.c_uint32),
                 ("positions", C.POINTER(C.c_float)), ("faces", C.POINTER(C.c_uint32)),
                 ("normals", C.POINTER(C.c_float)),
-                ("bsdf_id", C.c_int32), ("emitter_id", C.c_int32), ("flags", C.c_uint32)]
+                ("bsdf_id", C.c_int32), ("emitter_id", C.c_int32), ("flags", C.c_uint32),
+                ("texcoords", C.POINTER(C.c_float))]
+
+
+TEX_NEAREST, TEX_BILINEAR = 0, 1
+TEX_REPEAT, TEX_CLAMP, TEX_MIRROR = 0, 1, 2
+
+
+class TextureDesc(C.Structure):
+    _fields_ = [("texels", C.POINTER(C.c_float)), ("width", C.c_uint32), ("height", C.c_uint32),
+                ("filter", C.c_uint32), ("wrap", C.c_uint32), ("to_uv", C.c_float * 6)]
 
 
 class BsdfDesc(C.Structure):
     _fields_ = [("kind", C.c_uint32), ("flags", C.c_uint32),
                 ("reflectance", C.c_float * 3), ("transmittance", C.c_float * 3),
                 ("eta", C.c_float * 3), ("k", C.c_float * 3),
-                ("alpha_u", C.c_float), ("alpha_v", C.c_float)]
+                ("alpha_u", C.c_float), ("alpha_v", C.c_float),
+                ("reflectance_texture", C.POINTER(TextureDesc))]
 
 
 class EmitterDesc(C.Structure):

@@ -53,7 +53,7 @@ struct epsm_ctx {
     DevBuf<uint32_t> d_refit;                       // refit scratch: max|coordinate|, Σ half-area, per-node arrival counters
     uint64_t refits_since_build = 0; double refit_ms_last = 0;
     // device
-    DevBuf<f4> d_nodes, d_tris; DevBuf<float> d_pos, d_nrm, d_cdf, d_pmf; DevBuf<uint32_t> d_faces, d_face_mesh;
+    DevBuf<f4> d_nodes, d_tris; DevBuf<float> d_pos, d_nrm, d_cdf, d_pmf, d_uv, d_texels; DevBuf<DTexture> d_textures; DevBuf<uint32_t> d_faces, d_face_mesh;
     DevBuf<DMesh> d_meshes; DevBuf<DBsdf> d_bsdfs; DevBuf<DEmitter> d_emitters;
     std::vector<DevBuf<float>> d_films;
     DevBuf<float> stage_a, stage_b, stage_c;        // device staging for host-memory calls
@@ -87,6 +87,7 @@ int upload_accel(epsm_ctx *ctx) {
     sc.nodes = ctx->d_nodes.p; sc.tris = ctx->d_tris.p; sc.pos = ctx->d_pos.p; sc.nrm = ctx->d_nrm.p;
     sc.faces = ctx->d_faces.p; sc.face_mesh = ctx->d_face_mesh.p; sc.meshes = ctx->d_meshes.p; sc.bsdfs = ctx->d_bsdfs.p;
     sc.emitters = ctx->d_emitters.p; sc.cdf = ctx->d_cdf.p; sc.pmf = ctx->d_pmf.p;
+    sc.uv = ctx->d_uv.p; sc.textures = ctx->d_textures.p; sc.texels = ctx->d_texels.p;
     sc.n_emitters = (uint32_t) ctx->hs.emitters.size(); sc.n_meshes = (uint32_t) ctx->hs.meshes.size();
     sc.n_tris = (uint32_t) (ctx->hs.faces.size() / 3); sc.n_nodes = (uint32_t) (ctx->hs.bvh.nodes.size() / EPSM_NODE_F4);
     memcpy(sc.filter, ctx->hs.filter, sizeof(sc.filter));
@@ -193,7 +194,7 @@ int epsm_destroy(epsm_ctx *ctx) {
     if (!ctx) return EPSM_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    ctx->d_nodes.release(); ctx->d_tris.release(); ctx->d_pos.release(); ctx->d_nrm.release(); ctx->d_cdf.release(); ctx->d_pmf.release();
+    ctx->d_nodes.release(); ctx->d_tris.release(); ctx->d_pos.release(); ctx->d_nrm.release(); ctx->d_cdf.release(); ctx->d_pmf.release(); ctx->d_uv.release(); ctx->d_texels.release(); ctx->d_textures.release();
     ctx->d_faces.release(); ctx->d_face_mesh.release(); ctx->d_meshes.release(); ctx->d_bsdfs.release(); ctx->d_emitters.release();
     for (auto &f : ctx->d_films) f.release();
     ctx->stage_a.release(); ctx->stage_b.release(); ctx->stage_c.release(); ctx->d_counters.release(); ctx->d_workspace.release(); ctx->d_lane_L.release(); ctx->d_scratch_film.release(); ctx->d_prb_workspace.release(); ctx->d_sink.release(); ctx->d_sink_loss.release(); ctx->d_sink_bbox.release();
@@ -219,6 +220,9 @@ int epsm_scene_upload(epsm_ctx *ctx, const epsm_mesh_desc *meshes, uint32_t n_me
     }
     CK(ctx->d_pos.upload(ctx->hs.pos, ctx->stream), "upload pos");
     CK(ctx->d_nrm.upload(ctx->hs.nrm, ctx->stream), "upload nrm");
+    CK(ctx->d_uv.upload(ctx->hs.uv, ctx->stream), "upload uv");
+    CK(ctx->d_texels.upload(ctx->hs.texels, ctx->stream), "upload texels");
+    CK(ctx->d_textures.upload(ctx->hs.textures, ctx->stream), "upload textures");
     CK(ctx->d_faces.upload(ctx->hs.faces, ctx->stream), "upload faces");
     CK(ctx->d_face_mesh.upload(ctx->hs.face_mesh, ctx->stream), "upload face_mesh");
     CK(ctx->d_bsdfs.upload(ctx->hs.bsdfs, ctx->stream), "upload bsdfs");

@@ -377,6 +377,7 @@ struct SI {
     uint32_t mesh_flags, has_normals; int32_t bsdf, emitter;
     // EPSM fields (interaction.h:221-224)
     float b0, b1; f3 p0, p1, p2, n0, n1, n2; uint32_t ismesh;
+    float uv[2];                 // mesh.cpp:731-744
 };
 EPSM_HD f3 to_local(const SI &si, f3 v) { return mk3(dot3(v, si.sh_s), dot3(v, si.sh_t), dot3(v, si.sh_n)); }
 EPSM_HD f3 to_world(const SI &si, f3 v) { return fma3(si.sh_n, v.z, fma3(si.sh_t, v.y, si.sh_s * v.x)); }
@@ -387,7 +388,7 @@ EPSM_HDN void compute_si(const DScene &sc, const Ray &ray, const Hit &h, SI &si)
     si.p = si.n = si.sh_n = si.sh_s = si.sh_t = z; si.wi = -ray.d;
     si.fi[0] = si.fi[1] = si.fi[2] = 0; si.bw[0] = si.bw[1] = si.bw[2] = 0.f;
     si.mesh_flags = 0; si.has_normals = 0; si.bsdf = -1; si.emitter = -1;
-    si.b0 = si.b1 = 0.f; si.p0 = si.p1 = si.p2 = si.n0 = si.n1 = si.n2 = z; si.ismesh = 0;
+    si.b0 = si.b1 = 0.f; si.p0 = si.p1 = si.p2 = si.n0 = si.n1 = si.n2 = z; si.ismesh = 0; si.uv[0] = si.uv[1] = 0.f;
     if (!si.valid) return;
     const uint32_t mid = sc.face_mesh[h.prim]; const DMesh m = sc.meshes[mid];
     const uint32_t f0 = sc.faces[3 * h.prim], f1 = sc.faces[3 * h.prim + 1], f2 = sc.faces[3 * h.prim + 2];
@@ -400,6 +401,19 @@ EPSM_HDN void compute_si(const DScene &sc, const Ray &ray, const Hit &h, SI &si)
     si.p = fma3(p0, b0, fma3(p1, b1, p2 * b2));                                    // mesh.cpp:707
     si.n = norm3(cross3(dp0, dp1));                                                // mesh.cpp:729
     f3 dp_du, dp_dv; coordinate_system(si.n, dp_du, dp_dv);                        // mesh.cpp:734
+    si.uv[0] = b1; si.uv[1] = b2;                                                  // mesh.cpp:731
+    if (m.has_uv) {                                                                // mesh.cpp:736-763 (RayFlags::All): interpolated uv, dp/du, dp/dv
+        const float *t0 = sc.uv + 2 * (size_t) f0, *t1 = sc.uv + 2 * (size_t) f1, *t2 = sc.uv + 2 * (size_t) f2;
+        const float u0 = t0[0], v0 = t0[1], u1 = t1[0], v1 = t1[1], u2 = t2[0], v2 = t2[1];
+        si.uv[0] = fmaf(u2, b2, fmaf(u1, b1, u0 * b0)); si.uv[1] = fmaf(v2, b2, fmaf(v1, b1, v0 * b0));
+        const float du0 = u1 - u0, dv0 = v1 - v0, du1 = u2 - u0, dv1 = v2 - v0;
+        const float det = fmaf(du0, dv1, -(dv0 * du1));
+        if (det != 0.f) {
+            const float inv_det = rcp_e(det);
+            dp_du = mk3(fmaf(dv1, dp0.x, -(dv0 * dp1.x)), fmaf(dv1, dp0.y, -(dv0 * dp1.y)), fmaf(dv1, dp0.z, -(dv0 * dp1.z))) * inv_det;
+            dp_dv = mk3(fmaf(-du1, dp0.x, du0 * dp1.x), fmaf(-du1, dp0.y, du0 * dp1.y), fmaf(-du1, dp0.z, du0 * dp1.z)) * inv_det;
+        }
+    }
     f3 n0, n1, n2;
     if (m.has_normals) {                                                           // mesh.cpp:771-800
         n0 = ld3(sc.nrm, f0); n1 = ld3(sc.nrm, f1); n2 = ld3(sc.nrm, f2);
@@ -415,6 +429,36 @@ EPSM_HDN void compute_si(const DScene &sc, const Ray &ray, const Hit &h, SI &si)
     if (m.flags & EPSM_MESH_ISMESH) {                                              // mesh.cpp:712-720
         si.b0 = b0; si.b1 = b1; si.p0 = p0; si.p1 = p1; si.p2 = p2; si.n0 = n0; si.n1 = n1; si.n2 = n2; si.ismesh = 1;
     }
+}
+
+// Bitmap reflectance at si.uv: Dr.Jit Texture<Float, 2> without hardware acceleration (ext/drjit/include/drjit/texture.h: wrap
+// :1143-1168, nearest :346-360, bilinear :362-405) under src/textures/bitmap.cpp:582-625.
+EPSM_HD int tex_wrap(int p, int n, uint32_t mode) {
+    if (mode == EPSM_TEX_CLAMP) return p < 0 ? 0 : (p > n - 1 ? n - 1 : p);
+    int div = p / n; if (p < 0 && div * n != p) --div;                             // floor division
+    int mod = p - div * n;
+    if (mode == EPSM_TEX_MIRROR && (div & 1)) mod = n - 1 - mod;
+    return mod;
+}
+EPSM_HD f3 tex_fetch(const DScene &sc, const DTexture &t, int x, int y) {
+    const float *c = sc.texels + t.off + 3 * ((size_t) tex_wrap(y, (int) t.h, t.wrap) * t.w + (size_t) tex_wrap(x, (int) t.w, t.wrap));
+    return mk3(c[0], c[1], c[2]);
+}
+EPSM_HD f3 tex_eval(const DScene &sc, const DTexture &t, const float *uv_in) {
+    const float u = fmaf(t.to_uv[0], uv_in[0], fmaf(t.to_uv[1], uv_in[1], t.to_uv[2])), v = fmaf(t.to_uv[3], uv_in[0], fmaf(t.to_uv[4], uv_in[1], t.to_uv[5]));
+    if (t.filter == EPSM_TEX_NEAREST) return tex_fetch(sc, t, (int) floorf(u * (float) t.w), (int) floorf(v * (float) t.h));
+    const float fx = fmaf(u, (float) t.w, -.5f), fy = fmaf(v, (float) t.h, -.5f);
+    const int ix = (int) floorf(fx), iy = (int) floorf(fy);
+    const float w1x = fx - (float) ix, w1y = fy - (float) iy, w0x = 1.f - w1x, w0y = 1.f - w1y;
+    const f3 v00 = tex_fetch(sc, t, ix, iy), v10 = tex_fetch(sc, t, ix + 1, iy), v01 = tex_fetch(sc, t, ix, iy + 1), v11 = tex_fetch(sc, t, ix + 1, iy + 1);
+    const f3 r0 = fma3(v00, w0x, v10 * w1x), r1 = fma3(v01, w0x, v11 * w1x);
+    return fma3(r0, w0y, r1 * w1y);
+}
+// The BSDF of a hit with its textured parameter evaluated at the hit's uv (diffuse.cpp:107-140: m_reflectance->eval(si)).
+EPSM_HD DBsdf bsdf_at(const DScene &sc, int32_t bsdf, const float *uv) {
+    DBsdf b = sc.bsdfs[bsdf];
+    if (b.tex >= 0) { const f3 c = tex_eval(sc, sc.textures[b.tex], uv); b.reflectance[0] = c.x; b.reflectance[1] = c.y; b.reflectance[2] = c.z; }
+    return b;
 }
 
 EPSM_HD f3 offset_p(const SI &si, f3 d) {                                          // interaction.h:161-165
@@ -718,7 +762,7 @@ EPSM_HDN f3 path_primal(const DScene &sc, Tracer &tr, Ray ray, Pcg &rng, uint32_
         f3 Le = beta * mis * emitter_eval(sc, si);
         bool active_next = (depth + 1 < max_depth) && si.valid;
         DBsdf b; uint32_t flags = 0;
-        if (si.valid) { b = sc.bsdfs[si.bsdf]; flags = b.bflags; }
+        if (si.valid) { b = bsdf_at(sc, si.bsdf, si.uv); flags = b.bflags; }
         bool active_em = active_next && (flags & EPSM_BF_SMOOTH);
         float e1 = pcg_f32(rng), e2 = pcg_f32(rng);
         DSamp ds; f3 em_weight;
@@ -785,7 +829,7 @@ EPSM_HDN bool pr_stage(const DScene &sc, PrState &S, const Hit &h, uint32_t max_
     f3 Le = S.beta * mis * emitter_eval(sc, si);
     bool active_next = (S.depth + 1 < max_depth) && si.valid;
     DBsdf b; uint32_t flags = 0;
-    if (si.valid) { b = sc.bsdfs[si.bsdf]; flags = b.bflags; }
+    if (si.valid) { b = bsdf_at(sc, si.bsdf, si.uv); flags = b.bflags; }
     bool active_em = active_next && (flags & EPSM_BF_SMOOTH);
     float e1 = pcg_f32(S.rng), e2 = pcg_f32(S.rng);
     DSamp ds; f3 em_weight; bool need_shadow = false;
@@ -976,7 +1020,7 @@ EPSM_HDN void wf_stage_b(const DScene &sc, WfState &S, VLog &v, const Hit &h_in,
     if (!S.active) { h.t = INFINITY; h.u = h.v = 0.f; h.prim = 0xffffffffu; }
     SI si; compute_si(sc, S.ray, h, si);
     DBsdf b; uint32_t flags = 0;
-    if (si.valid) { b = sc.bsdfs[si.bsdf]; flags = b.bflags; }
+    if (si.valid) { b = bsdf_at(sc, si.bsdf, si.uv); flags = b.bflags; }
     if (S.need_shadow && occluded) { S.em_weight = mk3(0, 0, 0); S.ds.pdf = 0.f; }
     bool active_em = S.smooth && S.ds.pdf != 0.f;
     f3 Lr_dir = mk3(0, 0, 0), dir_to_light = mk3(0, 0, 0);

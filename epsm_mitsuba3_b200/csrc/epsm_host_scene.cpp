@@ -113,7 +113,7 @@ std::string host_scene_build(HostScene &hs, const epsm_mesh_desc *meshes, uint32
                              const epsm_emitter_desc *emitters, uint32_t n_emitters, const epsm_sensor_desc *sensors, uint32_t n_sensors) {
     if (!meshes || n_meshes == 0 || !bsdfs || n_bsdfs == 0 || !sensors || n_sensors == 0)
         return "scene needs at least one mesh, bsdf and sensor";
-    hs.pos.clear(); hs.nrm.clear(); hs.faces.clear(); hs.face_mesh.clear();
+    hs.pos.clear(); hs.nrm.clear(); hs.faces.clear(); hs.face_mesh.clear(); hs.uv.clear(); hs.texels.clear(); hs.textures.clear();
     hs.meshes.clear(); hs.bsdfs.clear(); hs.emitters.clear(); hs.sensors.clear();
     for (uint32_t i = 0; i < n_meshes; ++i) {
         const epsm_mesh_desc &d = meshes[i];
@@ -123,7 +123,9 @@ std::string host_scene_build(HostScene &hs, const epsm_mesh_desc *meshes, uint32
         DMesh m; memset(&m, 0, sizeof(m));
         m.v_off = (uint32_t) (hs.pos.size() / 3); m.f_off = (uint32_t) (hs.faces.size() / 3);
         m.v_cnt = d.vertex_count; m.f_cnt = d.face_count; m.bsdf = d.bsdf_id; m.emitter = d.emitter_id; m.flags = d.flags;
-        m.has_normals = d.normals ? 1u : 0u;
+        m.has_normals = d.normals ? 1u : 0u; m.has_uv = d.texcoords ? 1u : 0u;
+        if (d.texcoords) hs.uv.insert(hs.uv.end(), d.texcoords, d.texcoords + 2 * (size_t) d.vertex_count);
+        else hs.uv.insert(hs.uv.end(), 2 * (size_t) d.vertex_count, 0.f);
         hs.pos.insert(hs.pos.end(), d.positions, d.positions + 3 * (size_t) d.vertex_count);
         if (d.normals) hs.nrm.insert(hs.nrm.end(), d.normals, d.normals + 3 * (size_t) d.vertex_count);
         else hs.nrm.insert(hs.nrm.end(), 3 * (size_t) d.vertex_count, 0.f);
@@ -141,6 +143,16 @@ std::string host_scene_build(HostScene &hs, const epsm_mesh_desc *meshes, uint32
         d.kind = b.kind; d.flags = b.flags; d.bflags = bsdf_flags_word(b);
         memcpy(d.reflectance, b.reflectance, 12); memcpy(d.transmittance, b.transmittance, 12); memcpy(d.eta, b.eta, 12); memcpy(d.k, b.k, 12);
         d.alpha_u = b.alpha_u; d.alpha_v = b.alpha_v;
+        d.tex = -1;
+        if (b.reflectance_texture) {
+            const epsm_texture_desc &t = *b.reflectance_texture;
+            if (b.kind != EPSM_BSDF_DIFFUSE) return "reflectance_texture is supported on diffuse BSDFs only";
+            if (!t.texels || t.width == 0 || t.height == 0 || t.filter > EPSM_TEX_BILINEAR || t.wrap > EPSM_TEX_MIRROR) return "bad texture descriptor";
+            DTexture dt; memset(&dt, 0, sizeof(dt));
+            dt.off = (uint32_t) hs.texels.size(); dt.w = t.width; dt.h = t.height; dt.filter = t.filter; dt.wrap = t.wrap; memcpy(dt.to_uv, t.to_uv, sizeof(dt.to_uv));
+            hs.texels.insert(hs.texels.end(), t.texels, t.texels + 3 * (size_t) t.width * t.height);
+            d.tex = (int32_t) hs.textures.size(); hs.textures.push_back(dt);
+        }
         hs.bsdfs.push_back(d);
     }
     for (uint32_t i = 0; i < n_emitters; ++i) {
@@ -176,6 +188,7 @@ void host_scene_view(const HostScene &hs, DScene &sc) {
     sc.nodes = hs.bvh.nodes.data(); sc.tris = hs.bvh.tris.data(); sc.pos = hs.pos.data(); sc.nrm = hs.nrm.data();
     sc.faces = hs.faces.data(); sc.face_mesh = hs.face_mesh.data(); sc.meshes = hs.meshes.data(); sc.bsdfs = hs.bsdfs.data();
     sc.emitters = hs.emitters.data(); sc.cdf = hs.cdf.data(); sc.pmf = hs.pmf.data();
+    sc.uv = hs.uv.data(); sc.textures = hs.textures.data(); sc.texels = hs.texels.data();
     sc.n_emitters = (uint32_t) hs.emitters.size(); sc.n_meshes = (uint32_t) hs.meshes.size();
     sc.n_tris = (uint32_t) (hs.faces.size() / 3); sc.n_nodes = (uint32_t) (hs.bvh.nodes.size() / EPSM_NODE_F4);
     memcpy(sc.filter, hs.filter, sizeof(sc.filter));

@@ -9,7 +9,8 @@
 #include "epsm_bvh.h"
 
 struct HostScene {
-    std::vector<float> pos, nrm, cdf, pmf;
+    std::vector<float> pos, nrm, cdf, pmf, uv, texels;
+    std::vector<DTexture> textures;
     std::vector<uint32_t> faces, face_mesh;
     std::vector<DMesh> meshes; std::vector<DBsdf> bsdfs; std::vector<DEmitter> emitters; std::vector<DSensor> sensors;
     Bvh4 bvh;

@@ -1,13 +1,16 @@
 // epsm_kernels.cu — sm_100a kernels of the EPSM manifold path and their launchers.
 //
 //   k_trace            Scene::ray_intersect_preliminary / ray_test on a ray batch (BVH4, one thread per ray)
-//   k_render           EPSMIntegrator.render: ray gen + primal path loop + tile-local film accumulation
+//   k_render           EPSMIntegrator.render as one kernel: ray gen + primal path loop + tile-local film (EPSM_PRIMAL_MEGAKERNEL=1)
+//   k_pr_stage / k_pr_film   the default primal render: one stage per bounce over the persistent traversal kernel, tile-local film
 //   k_film_develop     HDRFilm::develop + the two zero channels of epsm.py:76-82
-//   k_backward         EPSMIntegrator.render_backward fused per path: ray gen, sample_path replay with the
-//                      path log in thread-local memory, pixel-motion seeds, manifold solve in registers,
-//                      warp-aggregated scatter into the vertex gradient buffers
+//   k_wf_trace / k_wf_trace_primary   persistent BVH4 traversal over a ray queue / over the camera rays of a chunk
+//   k_wf_stage_a / k_wf_stage_b / k_wf_finish   EPSMIntegrator.render_backward as a wavefront: sample_path replay cut at every
+//                      scene query, path log in HBM (word-major), manifold solve in registers, warp-aggregated scatter
+//   k_prb_pass / k_prb_backward   prb_reparam's reverse pass (hybrid phase 2): replay wavefront with checkpoints / per-lane megakernel
 //   k_sampler_stream / k_sample_rays   parity probes for the RNG and ray-generation contracts
-//   k_normals_*        Mesh::recompute_vertex_normals (mesh.cpp:257-330)
+//   k_normals_*        Mesh::recompute_vertex_normals (mesh.cpp:257-330) and its adjoint
+//   k_refit_tris / k_refit_nodes   per-iteration BVH refit
 //
 // Work decomposition: a CTA of 128 threads owns an 8×4 pixel tile; thread i handles pixel (i & 31)
 // of the tile and the samples s = (i >> 5) + 4k of that pixel, so a warp is always 32 neighbouring

@@ -312,13 +312,21 @@ EPSM_HDN void frame_backward_si(const DScene &sc, Sink &sink, const SI &si, f3 r
     const f3 p0 = ld3(sc.pos, si.fi[0]), p1 = ld3(sc.pos, si.fi[1]), p2 = ld3(sc.pos, si.fi[2]);
     const f3 e1 = p1 - p0, e2 = p2 - p0, ng_raw = cross3(e1, e2), ng = norm3(ng_raw);
     f3 dp_du, dp_dv; coordinate_system(ng, dp_du, dp_dv);
+    // meshes with texture coordinates: dp_du = (Δv₁·e1 − Δv₀·e2)/det (mesh.cpp:746-760), linear in the edges
+    float ka = 0.f, kb = 0.f; bool uv_frame = false;
+    if (sc.meshes[si.mesh].has_uv) {
+        const float *t0 = sc.uv + 2 * (size_t) si.fi[0], *t1 = sc.uv + 2 * (size_t) si.fi[1], *t2 = sc.uv + 2 * (size_t) si.fi[2];
+        const float du0 = t1[0] - t0[0], dv0 = t1[1] - t0[1], du1 = t2[0] - t0[0], dv1 = t2[1] - t0[1];
+        const float det = fmaf(du0, dv1, -(dv0 * du1));
+        if (det != 0.f) { const float inv_det = rcp_e(det); ka = dv1 * inv_det; kb = -dv0 * inv_det; dp_du = e1 * ka + e2 * kb; uv_frame = true; }
+    }
     const float c = dot3(n, dp_du);
     const f3 q = fma3(n, -c, dp_du);
     const f3 g_q = normalize_bwd(q, g_s);
     const float ngq = dot3(n, g_q);
     const f3 g_dpdu = g_q - n * ngq;
     g_n = g_n - g_q * c - dp_du * ngq;
-    f3 g_ng = onb_s_bwd(ng, g_dpdu);
+    f3 g_ng = uv_frame ? mk3(0, 0, 0) : onb_s_bwd(ng, g_dpdu);
     f3 g_shn = flip ? -g_n : g_n;                                                  // gradient of the unflipped shading normal
     float g_u = 0.f, g_v = 0.f;
     if (si.has_normals) {
@@ -332,6 +340,7 @@ EPSM_HDN void frame_backward_si(const DScene &sc, Sink &sink, const SI &si, f3 r
     }
     const f3 g_raw = normalize_bwd(ng_raw, g_ng);
     f3 g_p1 = cross3(e2, g_raw), g_p2 = cross3(g_raw, e1);                          // ng_raw = e1 × e2
+    if (uv_frame) { g_p1 = g_p1 + g_dpdu * ka; g_p2 = g_p2 + g_dpdu * kb; }
     f3 g_p0 = -(g_p1 + g_p2);
     if (g_u != 0.f || g_v != 0.f) {                                                // (u, v) re-derived by Möller–Trumbore (mesh.cpp:676-686)
         MtGrad M; mt_uv_bwd(ray_o, ray_d, p0, p1, p2, g_u, g_v, M);
@@ -360,7 +369,7 @@ EPSM_HD void filter_eval_d(const float *c, float x, float &f, float &df) {
 //  One lane of RBIntegrator.render_backward for prb_reparam.  `film` is the RGBW film of the primal pass over ALL lanes
 //  (common.py:905-935), grad_in the (H,W,3) image gradient.  Gradients are pushed into `sink` (.pos / .nrm of a vertex).
 // ------------------------------------------------------------------------------------------------
-struct PrevVertex { bool valid; f3 p, sh_s, sh_t, sh_n, wi; int32_t bsdf; Anchor anchor; };
+struct PrevVertex { bool valid; f3 p, sh_s, sh_t, sh_n, wi; int32_t bsdf; float uv[2]; Anchor anchor; };
 // Everything iteration `it` of the loop below inherits from the iterations before it.  The replay wavefront stores it when a
 // pass first reaches the top of an iteration (pass 2·it + 1) and the two later passes that need that iteration (2·it + 2: its
 // second round of rays, 2·it + 3: its adjoint) start from there instead of replaying the lane from the camera — without it the
@@ -445,7 +454,7 @@ EPSM_HDN void prb_backward_lane(const DScene &sc, Io &io, const DSensor &sensor,
         const f3 Le = beta * mis_em * emitter_eval(sc, si);
         bool active_next = (depth + 1 < cfg.max_depth) && si.valid;
         DBsdf b; uint32_t flags = 0;
-        if (si.valid) { b = sc.bsdfs[si.bsdf]; flags = b.bflags; }
+        if (si.valid) { b = bsdf_at(sc, si.bsdf, si.uv); flags = b.bflags; }
         bool active_em = active_next && (flags & EPSM_BF_SMOOTH);
         const float e1 = pcg_f32(rng), e2 = pcg_f32(rng);
         DSamp ds; f3 em_weight;
@@ -485,7 +494,7 @@ EPSM_HDN void prb_backward_lane(const DScene &sc, Io &io, const DSensor &sensor,
         Pcg clone = rng;
         const bool active_nn = active_next && si_next.valid && (depth + 2 < cfg.max_depth);
         DBsdf bn; uint32_t nflags = 0;
-        if (si_next.valid) { bn = sc.bsdfs[si_next.bsdf]; nflags = bn.bflags; }
+        if (si_next.valid) { bn = bsdf_at(sc, si_next.bsdf, si_next.uv); nflags = bn.bflags; }
         bool active_em_n = active_nn && (nflags & EPSM_BF_SMOOTH);
         const float c1 = pcg_f32(clone), c2 = pcg_f32(clone);
         DSamp dsn; f3 emw_n;
@@ -519,7 +528,7 @@ EPSM_HDN void prb_backward_lane(const DScene &sc, Io &io, const DSensor &sensor,
             // adjacent vertices through si_cur.p with the shape detached (:522-551)
             f3 g_pro = mk3(0, 0, 0);
             if (prev.valid && prev.bsdf >= 0) {
-                const DBsdf bp = sc.bsdfs[prev.bsdf];
+                const DBsdf bp = bsdf_at(sc, prev.bsdf, prev.uv);
                 const f3 r = si.p - prev.p, w = norm3(r), wl = mk3(dot3(w, prev.sh_s), dot3(w, prev.sh_t), dot3(w, prev.sh_n));
                 f3 f0, gi, go; bsdf_grad(bp, prev.wi, wl, mk3(0, 0, 0), gi, go, f0);
                 const f3 aw = dL * L_prev * mk3(1.f / fmaxf(1e-8f, f0.x), 1.f / fmaxf(1e-8f, f0.y), 1.f / fmaxf(1e-8f, f0.z));
@@ -550,7 +559,7 @@ EPSM_HDN void prb_backward_lane(const DScene &sc, Io &io, const DSensor &sensor,
         reparam_backward(sc, io, sink, aux, cfg, r2, n_aux, depth < cfg.reparam_max_depth, ray.o, ray.d, g_d, g_det, prev.anchor, false, mk3(0, 0, 0));
         if (io.stop_after(r2)) return;                                             // round r2 queued: the adjoint of this iteration runs next pass
 
-        prev.valid = si.valid; prev.p = si.p; prev.sh_s = si.sh_s; prev.sh_t = si.sh_t; prev.sh_n = si.sh_n; prev.wi = si.wi; prev.bsdf = si.bsdf; prev.anchor = cur;
+        prev.valid = si.valid; prev.p = si.p; prev.sh_s = si.sh_s; prev.sh_t = si.sh_t; prev.sh_n = si.sh_n; prev.wi = si.wi; prev.bsdf = si.bsdf; prev.uv[0] = si.uv[0]; prev.uv[1] = si.uv[1]; prev.anchor = cur;
         mis_em = mis_next; h = h_next; ray = ray_next;
         if (si.valid) depth += 1;
         active = active_next;

@@ -44,17 +44,21 @@ struct DMesh {
     uint32_t cdf_off;            // into DScene::cdf / pmf (only meaningful for emitter meshes)
     uint32_t valid_lo, valid_hi;
     float    area_sum, area_norm;
-    float    _pad[3];
+    uint32_t has_uv;             // vertex texture coordinates present (DScene::uv)
+    float    _pad[2];
 };
 
 struct DBsdf {
-    uint32_t kind, flags, bflags, _pad;   // bflags = Mitsuba BSDFFlags word
+    uint32_t kind, flags, bflags; int32_t tex;   // bflags = Mitsuba BSDFFlags word; tex: reflectance texture (DScene::textures) or -1
     float reflectance[3], transmittance[3], eta[3], k[3];
     float alpha_u, alpha_v;
     float _pad2[2];
 };
 
 struct DEmitter { float radiance[3]; int32_t mesh; };
+
+// Bitmap reflectance (src/textures/bitmap.cpp over Dr.Jit's Texture): linear RGB texels at texels[off + 3·(y·w + x)].
+struct DTexture { uint32_t off, w, h, filter, wrap; float to_uv[6]; uint32_t _pad; };
 
 struct DSensor {
     float s2c[16], to_world[16];
@@ -72,6 +76,8 @@ struct DScene {
     const uint32_t *faces; const uint32_t *face_mesh;
     const DMesh *meshes; const DBsdf *bsdfs; const DEmitter *emitters;
     const float *cdf; const float *pmf;
+    const float *uv;             // float[2·V] vertex texture coordinates (zeros for meshes without)
+    const DTexture *textures; const float *texels;
     uint32_t n_emitters, n_meshes, n_tris, n_nodes;
     float filter[10];            // scaled Remez coefficients of the Gaussian rfilter (gaussian.cpp:57-89)
 };

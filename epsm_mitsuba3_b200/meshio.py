@@ -216,14 +216,19 @@ def load_ply(path: str, to_world: Optional[Transform4f] = None, face_normals: bo
 def save_ply(path: str, mesh: Mesh, binary: bool = True):
     """Writer used by the tests and for exporting the synthetic scenes (vertex x y z [nx ny nz], triangle faces)."""
     has_n = mesh.normals is not None
+    has_uv = getattr(mesh, "texcoords", None) is not None
     hdr = ["ply", "format binary_little_endian 1.0" if binary else "format ascii 1.0", f"element vertex {mesh.positions.shape[0]}",
            "property float x", "property float y", "property float z"]
     if has_n:
         hdr += ["property float nx", "property float ny", "property float nz"]
+    if has_uv:
+        hdr += ["property float u", "property float v"]
     hdr += [f"element face {mesh.faces.shape[0]}", "property list uchar int vertex_indices", "end_header"]
     with open(path, "wb") as f:
         f.write(("\n".join(hdr) + "\n").encode())
         v = np.concatenate([mesh.positions, mesh.normals], 1) if has_n else mesh.positions
+        if has_uv:
+            v = np.concatenate([v, np.asarray(mesh.texcoords, np.float32).reshape(-1, 2)], 1)
         if binary:
             f.write(np.ascontiguousarray(v, "<f4").tobytes())
             rec = np.zeros(mesh.faces.shape[0], np.dtype([("n", "u1"), ("i", "<i4", 3)]))

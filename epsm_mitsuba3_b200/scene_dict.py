@@ -8,8 +8,8 @@ Supported plugins — everything BASELINE's configs and the programmatic EPSM/ex
   shape       obj | ply | serialized | rectangle | cube | sphere                   src/shapes/*.cpp (analytic shapes are tessellated
               and flagged non-mesh, which is how the EPSM fields see them: si.ismesh = 0, epsm.py:793-796)
   emitter     area                                                                 src/emitters/area.cpp
-  texture     rgb / spectrum / float values; `bitmap` reflectance is averaged to one colour (src/textures/bitmap.cpp is not on
-              the path of any BASELINE config — stated limitation, a warning is issued)
+  texture     rgb / spectrum / float values; `bitmap` as a diffuse reflectance (src/textures/bitmap.cpp: nearest / bilinear,
+              repeat / clamp / mirror, to_uv, raw) — elsewhere a bitmap is reduced to its mean colour
 Anything else raises `Plugin "<type>" not found`, as the reference's plugin manager does (src/core/plugin.cpp:174-211)."""
 from __future__ import annotations
 
@@ -54,7 +54,7 @@ def _rgb(v, default=None):
         if t in ("rgb", "srgb", "spectrum", "uniform", "d65"):
             return _rgb(v.get("value", v.get("color", 1.0)))
         if t == "bitmap":
-            return _bitmap_mean(v)
+            return _bitmap_texture(v).mean()
         raise PluginNotFound(t)
     a = np.asarray(v.numpy() if hasattr(v, "numpy") else v, np.float64).reshape(-1)
     if a.size == 1:
@@ -64,17 +64,36 @@ def _rgb(v, default=None):
     return tuple(float(x) for x in a)
 
 
-def _bitmap_mean(v):
-    import cv2
-    path = v.get("filename")
-    img = cv2.imread(path, cv2.IMREAD_UNCHANGED) if path and os.path.exists(path) else None
-    if img is None:
-        raise FileNotFoundError(f'bitmap texture "{path}" not found')
-    img = img[..., :3][..., ::-1].astype(np.float64) / (65535.0 if img.dtype == np.uint16 else 255.0)
-    if not v.get("raw", False):                     # sRGB → linear (bitmap.cpp applies the inverse gamma unless raw)
-        img = np.where(img <= 0.04045, img / 12.92, ((img + 0.055) / 1.055) ** 2.4)
-    warnings.warn(f'bitmap texture "{path}": spatially varying reflectance is not on the EPSM path; using its mean colour')
-    return tuple(float(x) for x in img.reshape(-1, 3).mean(0))
+def _bitmap_texture(v, base_dir: str = "") -> S.Texture:
+    """`bitmap` texture plugin (src/textures/bitmap.cpp:118-200): 8/16-bit files are converted to linear floats with the
+    inverse sRGB gamma unless raw; `data` may hand over a float array (H,W[,3]) directly, as mi.Bitmap objects do."""
+    if v.get("data") is not None or v.get("bitmap") is not None:
+        img = np.asarray(v.get("data") if v.get("data") is not None else v.get("bitmap"), np.float64)
+    else:
+        fn = v.get("filename")
+        path = fn if fn and (os.path.isabs(fn) or not base_dir) else os.path.join(base_dir, fn or "")
+        if not fn or not os.path.exists(path):
+            raise FileNotFoundError(f'bitmap texture "{fn}" not found')
+        try:
+            import cv2
+            raw_img = cv2.imread(path, cv2.IMREAD_UNCHANGED)
+            if raw_img is not None and raw_img.ndim == 3:
+                raw_img = raw_img[..., :3][..., ::-1]
+        except ImportError:
+            raw_img = None
+        if raw_img is None:
+            from PIL import Image
+            raw_img = np.asarray(Image.open(path).convert("RGB"))
+        if raw_img.dtype in (np.uint8, np.uint16):
+            img = raw_img.astype(np.float64) / (65535.0 if raw_img.dtype == np.uint16 else 255.0)
+            if not v.get("raw", False):                 # Bitmap::convert with srgb_gamma: the inverse sRGB transfer function
+                img = np.where(img <= 0.04045, img / 12.92, ((img + 0.055) / 1.055) ** 2.4)
+        else:
+            img = raw_img.astype(np.float64)            # float formats are linear already
+    m = None
+    if v.get("to_uv") is not None:                      # ScalarTransform4f → the 3×3 of transform_affine(Point2f): rows/cols 0, 1, 3
+        t4 = _matrix(v.get("to_uv")); m = np.array([[t4[0, 0], t4[0, 1], t4[0, 3]], [t4[1, 0], t4[1, 1], t4[1, 3]], [0, 0, 1]])
+    return S.Texture(np.ascontiguousarray(img, np.float32), filter=v.get("filter_type", "bilinear"), wrap=v.get("wrap_mode", "repeat"), to_uv=m)
 
 
 _IOR = {"vacuum": 1.0, "air": 1.000277, "water": 1.3330, "bk7": 1.5046, "diamond": 2.419, "glass": 1.5046, "acrylic glass": 1.49, "pyrex": 1.470,
@@ -92,16 +111,21 @@ def _ior(v, default):
     return float(v)
 
 
-def parse_bsdf(d: dict) -> S.Bsdf:
+def parse_bsdf(d: dict, base_dir: str = "") -> S.Bsdf:
     t = d.get("type")
     if t == "twosided":
         inner = [v for k, v in d.items() if isinstance(v, dict) and v.get("type") in BSDFS]
         if len(inner) != 1:
             raise ValueError("twosided expects exactly one nested BSDF")        # twosided.cpp (a second BSDF for the back side is not on the path)
-        b = parse_bsdf(inner[0]); b.twosided = True
+        b = parse_bsdf(inner[0], base_dir); b.twosided = True
         return b
     if t == "diffuse":
-        return S.Bsdf.diffuse(_rgb(d.get("reflectance"), (0.5, 0.5, 0.5)))
+        r = d.get("reflectance")
+        if isinstance(r, dict) and r.get("type") == "bitmap":
+            tex = _bitmap_texture(r, base_dir)
+            b = S.Bsdf.diffuse(tex.mean()); b.texture = tex       # `reflectance` keeps the mean colour for summaries; the kernels sample the texture
+            return b
+        return S.Bsdf.diffuse(_rgb(r, (0.5, 0.5, 0.5)))
     if t == "dielectric":
         b = S.Bsdf.dielectric(_ior(d.get("int_ior"), 1.5046), _ior(d.get("ext_ior"), 1.000277))
         b.reflectance = _rgb(d.get("specular_reflectance"), (1.0, 1.0, 1.0)); b.transmittance = _rgb(d.get("specular_transmittance"), (1.0, 1.0, 1.0))
@@ -157,12 +181,14 @@ def _shape_mesh(key: str, d: dict, base_dir: str) -> S.Mesh:
         fn = d["filename"]
         path = fn if os.path.isabs(fn) or not base_dir else os.path.join(base_dir, fn)
         kw = dict(to_world=tw, face_normals=bool(d.get("face_normals", False)), name=key)
+        kw["return_texcoords"] = True
         if t == "obj":
-            m = meshio.load_obj(path, **kw)
+            m, uv = meshio.load_obj(path, **kw)
         elif t == "ply":
-            m = meshio.load_ply(path, **kw)
+            m, uv = meshio.load_ply(path, **kw)
         else:
-            m = meshio.load_serialized(path, shape_index=int(d.get("shape_index", 0)), **kw)
+            m, uv = meshio.load_serialized(path, shape_index=int(d.get("shape_index", 0)), **kw)
+        m.texcoords = uv                                 # si.uv and the uv-aligned dp_du / dp_dv of the shading frame (mesh.cpp:737-763)
     elif t == "rectangle":
         m = S.rectangle(tw, name=key)
     elif t == "cube":
@@ -194,7 +220,7 @@ def scene_from_dict(d: dict, base_dir: str = "") -> S.SceneData:
             if rid not in named_bsdfs:
                 raise KeyError(f'reference to unknown object "{rid}"')
             return named_bsdfs[rid]
-        i = sd.add_bsdf(parse_bsdf(spec))
+        i = sd.add_bsdf(parse_bsdf(spec, base_dir))
         for name in (spec.get("id"), own_key):
             if name:
                 named_bsdfs[name] = i

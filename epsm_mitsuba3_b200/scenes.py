@@ -79,6 +79,34 @@ T = Transform4f
 #  Containers
 # --------------------------------------------------------------------------------------------
 @dataclass
+class Texture:
+    """Bitmap reflectance (src/textures/bitmap.cpp): linear-RGB texels (H,W,3), row 0 first, looked up at to_uv·si.uv."""
+    texels: np.ndarray
+    filter: str = "bilinear"              # 'nearest' | 'bilinear' (bitmap.cpp:146-153; its default is bilinear)
+    wrap: str = "repeat"                  # 'repeat' | 'clamp' | 'mirror' (bitmap.cpp:155-166)
+    to_uv: Optional[np.ndarray] = None    # 3×3, identity by default
+
+    def __post_init__(self):
+        self.texels = np.ascontiguousarray(self.texels, dtype=np.float32)
+        if self.texels.ndim == 2:
+            self.texels = np.repeat(self.texels[..., None], 3, axis=2)
+        assert self.texels.ndim == 3 and self.texels.shape[2] == 3, "texels must be (H,W,3)"
+        assert self.filter in ("nearest", "bilinear") and self.wrap in ("repeat", "clamp", "mirror")
+
+    def to_c(self):
+        t = capi.TextureDesc()
+        t.texels = self.texels.ctypes.data_as(C.POINTER(C.c_float)); t.height, t.width = self.texels.shape[:2]
+        t.filter = capi.TEX_NEAREST if self.filter == "nearest" else capi.TEX_BILINEAR
+        t.wrap = {"repeat": capi.TEX_REPEAT, "clamp": capi.TEX_CLAMP, "mirror": capi.TEX_MIRROR}[self.wrap]
+        m = np.eye(3, dtype=np.float32) if self.to_uv is None else np.asarray(self.to_uv, np.float32).reshape(3, 3)
+        t.to_uv[:] = [float(x) for x in m[:2].ravel()]
+        return t
+
+    def mean(self):
+        return tuple(float(x) for x in self.texels.reshape(-1, 3).mean(0))
+
+
+@dataclass
 class Bsdf:
     kind: int
     reflectance: tuple = (1.0, 1.0, 1.0)
@@ -90,6 +118,7 @@ class Bsdf:
     twosided: bool = False
     ggx: bool = False
     sample_visible: bool = True
+    texture: Optional["Texture"] = None   # diffuse: bitmap reflectance (src/textures/bitmap.cpp); `reflectance` is then unused
 
     @staticmethod
     def diffuse(rgb, twosided=False):
@@ -125,6 +154,7 @@ class Mesh:
     grad: bool = False
     flip_normals: bool = False
     is_rectangle: bool = False            # tessellated Mitsuba `rectangle` (emitter sampling parameterisation)
+    texcoords: Optional[np.ndarray] = None   # (V,2) float32 or None: si.uv and the dp_du/dp_dv of the shading frame (mesh.cpp:737-763)
 
     def __post_init__(self):
         self.positions = np.ascontiguousarray(self.positions, dtype=np.float32).reshape(-1, 3)
@@ -219,6 +249,10 @@ class _CScene:
             d.faces = m.faces.ctypes.data_as(uptr)
             d.normals = m.normals.ctypes.data_as(fptr) if m.normals is not None else fptr()
             d.bsdf_id, d.emitter_id, d.flags = m.bsdf, m.emitter, m.flags_word()
+            if m.texcoords is not None:
+                uv = np.ascontiguousarray(m.texcoords, np.float32).reshape(-1, 2)
+                assert uv.shape[0] == m.positions.shape[0], "one texture coordinate per vertex"
+                d.texcoords = uv.ctypes.data_as(fptr); self.keep.append(uv)
             self.keep += [m.positions, m.faces, m.normals]
         self.bsdfs = (capi.BsdfDesc * max(1, len(sd.bsdfs)))()
         for i, b in enumerate(sd.bsdfs):
@@ -229,6 +263,8 @@ class _CScene:
             d.eta[:] = [float(x) for x in b.eta]
             d.k[:] = [float(x) for x in b.k]
             d.alpha_u, d.alpha_v = b.alpha_u, b.alpha_v
+            if b.texture is not None:
+                t = b.texture.to_c(); d.reflectance_texture = C.pointer(t); self.keep += [t, b.texture]
         self.emitters = (capi.EmitterDesc * max(1, len(sd.emitters)))()
         for i, e in enumerate(sd.emitters):
             self.emitters[i].radiance[:] = [float(x) for x in e.radiance]
@@ -480,6 +516,41 @@ def articulated_stage(res: int = 512, spp: int = 64, match_res: int = 256, seed:
 # --------------------------------------------------------------------------------------------
 #  Small extra parity scenes
 # --------------------------------------------------------------------------------------------
+def textured_scene(res: int = 64, spp: int = 8, match_res: int = 32, filter: str = "nearest", wrap: str = "repeat") -> SceneData:
+    """The mirror-plane scene with uv-mapped meshes and bitmap reflectances (EPSM/exp/human.py:101-163: wood textures, nearest,
+    repeat): the wall and a floor carry seeded RGB textures, the wavy conductor carries texture coordinates too, so every
+    textured-mesh branch is exercised — interpolated si.uv, the uv-aligned dp_du / dp_dv of the shading frame (mesh.cpp:737-763)
+    and the texture lookup behind the diffuse BSDF (bitmap.cpp:582-625)."""
+    rng = np.random.default_rng(12)
+    sd = SceneData(name=f"textured_{filter}_{wrap}")
+    mirror = sd.add_bsdf(Bsdf.conductor(twosided=True))
+    wood = Texture(rng.uniform(0.05, 0.9, (6, 9, 3)).astype(np.float32), filter=filter, wrap=wrap)
+    tiles = Texture(rng.uniform(0.1, 0.8, (5, 4, 3)).astype(np.float32), filter=filter, wrap=wrap,
+                    to_uv=np.array([[1.5, 0.2, 0.1], [-0.3, 2.0, 0.25], [0, 0, 1]]))
+    wall = sd.add_bsdf(Bsdf(capi.BSDF_DIFFUSE, reflectance=wood.mean(), twosided=True, texture=wood))
+    floor = sd.add_bsdf(Bsdf(capi.BSDF_DIFFUSE, reflectance=tiles.mean(), texture=tiles))
+    black = sd.add_bsdf(Bsdf.diffuse((0, 0, 0)))
+
+    def with_uv(m, scale=1.0, skew=0.0):
+        n = m.positions.shape[0]
+        side = int(round(math.sqrt(n)))
+        u, v = np.meshgrid(np.linspace(0, 1, side), np.linspace(0, 1, side), indexing="xy")
+        m.texcoords = np.stack([scale * u.ravel() + skew * v.ravel(), scale * v.ravel() - 0.5 * skew * u.ravel()], -1).astype(np.float32)
+        return m
+
+    m = grid(T().translate([0, 0, 0.4]).scale([1.0, 1.0, 1]), 6, 6, name="mirror", bsdf=mirror, grad=True)
+    m.positions[:, 2] += 0.05 * np.sin(2.0 * m.positions[:, 0]) * np.cos(1.5 * m.positions[:, 1])
+    m.normals = vertex_normals(m.positions, m.faces)
+    sd.add_mesh(with_uv(m, 1.0, 0.3))
+    sd.add_mesh(with_uv(grid(T().translate([0, 2.0, 1.5]).rotate([1, 0, 0], 90).scale([2.5, 1.5, 1]), 4, 4, name="wall", bsdf=wall, grad=True), 2.5, 0.4))
+    sd.add_mesh(with_uv(grid(T().scale([3.0, 3.0, 1]), 3, 3, name="floor", bsdf=floor, grad=True), 1.7, -0.2))
+    sd.add_mesh(grid(T().translate([0, 0, 4]).rotate([1, 0, 0], 180).scale([0.6, 0.6, 1]), 1, 1,
+                     name="light", bsdf=black), radiance=(40.0, 40.0, 40.0))
+    base = Sensor(T.look_at([0, -3.0, 2.0], [0, 0.3, 0.3], [0, 0, 1]), 45.0, res, res, 0.01, 1000.0, spp)
+    sd.sensor_trio(base, match_res)
+    return sd
+
+
 def mirror_plane_scene(res: int = 64, spp: int = 8, match_res: int = 32, rough: bool = False) -> SceneData:
     """A (rough) conductor slab reflecting a diffuse wall, lit by an area light: exercises the
     specular-chain rows of calc_grad (cam → specular → diffuse) for `manifold`."""

@@ -70,7 +70,24 @@ typedef struct epsm_mesh_desc {
     int32_t         bsdf_id;     /* index into the bsdf table                                */
     int32_t         emitter_id;  /* index into the emitter table, or -1                      */
     uint32_t        flags;       /* EPSM_MESH_*                                              */
+    const float    *texcoords;   /* 2*vertex_count or NULL, host: Mesh::vertex_texcoord (mesh.cpp:737-763): si.uv and the
+                                    dp_du / dp_dv that orient the shading frame follow them                               */
 } epsm_mesh_desc;
+
+/* src/textures/bitmap.cpp as a diffuse reflectance: RGB texels already converted to linear floats (raw = false applies the
+   inverse sRGB gamma at load time), looked up at to_uv * si.uv with Dr.Jit's Texture (ext/drjit/include/drjit/texture.h). */
+#define EPSM_TEX_NEAREST  0u
+#define EPSM_TEX_BILINEAR 1u
+#define EPSM_TEX_REPEAT   0u
+#define EPSM_TEX_CLAMP    1u
+#define EPSM_TEX_MIRROR   2u
+typedef struct epsm_texture_desc {
+    const float *texels;         /* 3*width*height, row-major, row 0 first (as Bitmap stores them), host */
+    uint32_t     width, height;
+    uint32_t     filter;         /* EPSM_TEX_NEAREST | EPSM_TEX_BILINEAR                                  */
+    uint32_t     wrap;           /* EPSM_TEX_REPEAT | EPSM_TEX_CLAMP | EPSM_TEX_MIRROR                    */
+    float        to_uv[6];       /* rows 0 and 1 of the 3x3 uv transform (identity: 1 0 0 / 0 1 0)         */
+} epsm_texture_desc;
 
 typedef struct epsm_bsdf_desc {
     uint32_t kind;               /* EPSM_BSDF_*                                              */
@@ -80,6 +97,7 @@ typedef struct epsm_bsdf_desc {
     float    eta[3];             /* conductor eta (RGB); dielectric: eta[0] = int_ior/ext_ior */
     float    k[3];               /* conductor k (RGB)                                        */
     float    alpha_u, alpha_v;   /* roughconductor roughness                                 */
+    const epsm_texture_desc *reflectance_texture;   /* diffuse only: replaces `reflectance` where non-NULL (src/bsdfs/diffuse.cpp:107-140) */
 } epsm_bsdf_desc;
 
 typedef struct epsm_emitter_desc {   /* src/emitters/area.cpp, uniform radiance */

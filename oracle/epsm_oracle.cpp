@@ -160,7 +160,7 @@ void coordinate_system(V3 n, V3 *s, V3 *t) {
 // ------------------------------------------------------------------------------------------------
 struct Mesh {
     uint32_t v_off, f_off, v_cnt, f_cnt;
-    int32_t bsdf, emitter; uint32_t flags; bool has_normals;
+    int32_t bsdf, emitter; uint32_t flags; bool has_normals, has_uv;
     std::vector<float> cdf; float area_sum, area_norm; uint32_t valid_lo, valid_hi;   // distr_1d.h:212-239
     std::vector<float> pmf;
 };
@@ -170,8 +170,11 @@ struct Sensor {
     uint32_t fw, fh;        // film / crop size
     int border;             // rfilter.border_size() = 2 for the Gaussian, 0 without sample_border
 };
+struct Texture { epsm_texture_desc d; std::vector<float> texels; };
 struct Scene {
     std::vector<V3> pos, nrm;
+    std::vector<float> uv;              // 2 per vertex (zeros for meshes without texture coordinates)
+    std::vector<Texture> textures;      // owned copies; bsdfs[i].reflectance_texture points into them
     std::vector<uint32_t> faces;        // global vertex ids
     std::vector<uint32_t> face_mesh;
     std::vector<Mesh> meshes;
@@ -306,6 +309,7 @@ struct SI {
     uint32_t prim, mesh, fi[3]; float bw[3];           // bw = (b0,b1,b2) = (1-u-v, u, v)
     // EPSM additions (interaction.h:221-224)
     float b0, b1; V3 p0, p1, p2, n0, n1, n2; uint32_t ismesh;
+    float uv[2];                                       // si.uv (mesh.cpp:731-744)
 };
 inline V3 to_local(const SI &si, V3 v) { return mk(dot(v, si.sh_s), dot(v, si.sh_t), dot(v, si.sh_n)); }
 inline V3 to_world(const SI &si, V3 v) { return fmadd(si.sh_n, v.z, fmadd(si.sh_t, v.y, si.sh_s * v.x)); }   // frame.h:41
@@ -323,7 +327,20 @@ SI compute_si(const Scene &sc, const Ray &ray, const PI &pi) {
     si.fi[0] = f[0]; si.fi[1] = f[1]; si.fi[2] = f[2]; si.bw[0] = b0; si.bw[1] = b1; si.bw[2] = b2;
     si.p = fmadd(p0, b0, fmadd(p1, b1, p2 * b2));                                   // mesh.cpp:707
     si.n = normalize(cross(dp0, dp1));                                              // mesh.cpp:729
-    V3 dp_du, dp_dv; coordinate_system(si.n, &dp_du, &dp_dv);                       // mesh.cpp:734 (no texcoords)
+    V3 dp_du, dp_dv; coordinate_system(si.n, &dp_du, &dp_dv);                       // mesh.cpp:734
+    si.uv[0] = b1; si.uv[1] = b2;                                                   // mesh.cpp:731
+    if (m.has_uv) {                                                                 // mesh.cpp:736-763 (RayFlags::All)
+        const float *t0 = &sc.uv[2 * f[0]], *t1 = &sc.uv[2 * f[1]], *t2 = &sc.uv[2 * f[2]];
+        si.uv[0] = fmaf(t2[0], b2, fmaf(t1[0], b1, t0[0] * b0)); si.uv[1] = fmaf(t2[1], b2, fmaf(t1[1], b1, t0[1] * b0));
+        const float du0 = t1[0] - t0[0], dv0 = t1[1] - t0[1], du1 = t2[0] - t0[0], dv1 = t2[1] - t0[1];
+        const float det = fmaf(du0, dv1, -(dv0 * du1));                             // fmsub(duv0.x, duv1.y, duv0.y·duv1.x)
+        if (det != 0.f) {
+            const float inv_det = rcp_(det);
+            // fmsub(duv1.y, dp0, duv0.y·dp1)·inv_det ; fnmadd(duv1.x, dp0, duv0.x·dp1)·inv_det
+            dp_du = mk(fmaf(dv1, dp0.x, -(dv0 * dp1.x)), fmaf(dv1, dp0.y, -(dv0 * dp1.y)), fmaf(dv1, dp0.z, -(dv0 * dp1.z))) * inv_det;
+            dp_dv = mk(fmaf(-du1, dp0.x, du0 * dp1.x), fmaf(-du1, dp0.y, du0 * dp1.y), fmaf(-du1, dp0.z, du0 * dp1.z)) * inv_det;
+        }
+    }
     V3 n0, n1, n2;
     if (m.has_normals) {
         n0 = sc.nrm[f[0]]; n1 = sc.nrm[f[1]]; n2 = sc.nrm[f[2]];
@@ -342,6 +359,41 @@ SI compute_si(const Scene &sc, const Ray &ray, const PI &pi) {
         si.b0 = b0; si.b1 = b1; si.p0 = p0; si.p1 = p1; si.p2 = p2; si.n0 = n0; si.n1 = n1; si.n2 = n2; si.ismesh = 1;
     }
     return si;
+}
+
+// Dr.Jit Texture<Float, 2> without hardware acceleration (ext/drjit/include/drjit/texture.h: wrap :1143-1168, nearest
+// :346-360, bilinear :362-405) under src/textures/bitmap.cpp:582-625: uv' = to_uv·uv, RGB texels are linear floats.
+inline int tex_wrap(int p, int n, uint32_t mode) {
+    if (mode == EPSM_TEX_CLAMP) return p < 0 ? 0 : (p > n - 1 ? n - 1 : p);
+    // floor division (divisor<int32_t> with the sign fix-up of texture.h:1150-1153)
+    int div = p / n; if (p < 0 && div * n != p) --div;
+    int mod = p - div * n;
+    if (mode == EPSM_TEX_MIRROR && (div & 1)) mod = n - 1 - mod;
+    return mod;
+}
+inline V3 tex_fetch(const epsm_texture_desc &t, int x, int y) {
+    const float *c = t.texels + 3 * ((size_t) tex_wrap(y, (int) t.height, t.wrap) * t.width + (size_t) tex_wrap(x, (int) t.width, t.wrap));
+    return mk(c[0], c[1], c[2]);
+}
+inline V3 tex_eval(const epsm_texture_desc &t, const float *uv_in) {
+    const float u = fmaf(t.to_uv[0], uv_in[0], fmaf(t.to_uv[1], uv_in[1], t.to_uv[2])), v = fmaf(t.to_uv[3], uv_in[0], fmaf(t.to_uv[4], uv_in[1], t.to_uv[5]));
+    if (t.filter == EPSM_TEX_NEAREST) {
+        const float fx = u * (float) t.width, fy = v * (float) t.height;
+        return tex_fetch(t, (int) floorf(fx), (int) floorf(fy));
+    }
+    const float fx = fmaf(u, (float) t.width, -.5f), fy = fmaf(v, (float) t.height, -.5f);
+    const int ix = (int) floorf(fx), iy = (int) floorf(fy);
+    const float w1x = fx - (float) ix, w1y = fy - (float) iy, w0x = 1.f - w1x, w0y = 1.f - w1y;
+    const V3 v00 = tex_fetch(t, ix, iy), v10 = tex_fetch(t, ix + 1, iy), v01 = tex_fetch(t, ix, iy + 1), v11 = tex_fetch(t, ix + 1, iy + 1);
+    // fmadd(w0.y, fmadd(w0.x, v00, w1.x·v10), w1.y·fmadd(w0.x, v01, w1.x·v11))   (texture.h:398-403)
+    const V3 r0 = fmadd(v00, w0x, v10 * w1x), r1 = fmadd(v01, w0x, v11 * w1x);
+    return fmadd(r0, w0y, r1 * w1y);
+}
+// The BSDF of a hit with its textured parameters evaluated at si.uv (diffuse.cpp:107-140: m_reflectance->eval(si)).
+inline epsm_bsdf_desc bsdf_at(const Scene &sc, const SI &si) {
+    epsm_bsdf_desc b = sc.bsdfs[sc.meshes[si.mesh].bsdf];
+    if (b.reflectance_texture) { const V3 c = tex_eval(*b.reflectance_texture, si.uv); b.reflectance[0] = c.x; b.reflectance[1] = c.y; b.reflectance[2] = c.z; }
+    return b;
 }
 
 // interaction.h:136-165
@@ -787,7 +839,7 @@ V3 sample_primal(const Scene &sc, Ray ray, PCG32 &rng, uint32_t max_depth, uint3
         float mis = mis_weight(prev_pdf, em_pdf);
         V3 Le = beta * mis * emitter_eval(sc, si);
         bool active_next = (depth + 1 < max_depth) && si.valid;
-        const epsm_bsdf_desc *b = si.valid ? &sc.bsdfs[sc.meshes[si.mesh].bsdf] : nullptr;
+        epsm_bsdf_desc b_tex; const epsm_bsdf_desc *b = nullptr; if (si.valid) { b_tex = bsdf_at(sc, si); b = &b_tex; }
         uint32_t flags = b ? bsdf_flags(*b) : 0u;
         bool active_em = active_next && (flags & EPSM_BF_SMOOTH);
         float e1 = rng.next_f32(), e2 = rng.next_f32();
@@ -875,10 +927,11 @@ orc_scene *orc_scene_create(const epsm_mesh_desc *meshes, uint32_t n_meshes, con
         const epsm_mesh_desc &d = meshes[i]; Mesh m;
         m.v_off = (uint32_t) sc.pos.size(); m.f_off = (uint32_t) (sc.faces.size() / 3);
         m.v_cnt = d.vertex_count; m.f_cnt = d.face_count; m.bsdf = d.bsdf_id; m.emitter = d.emitter_id; m.flags = d.flags;
-        m.has_normals = d.normals != nullptr;
+        m.has_normals = d.normals != nullptr; m.has_uv = d.texcoords != nullptr;
         for (uint32_t v = 0; v < d.vertex_count; ++v) {
             sc.pos.push_back(mk(d.positions[3 * v], d.positions[3 * v + 1], d.positions[3 * v + 2]));
             sc.nrm.push_back(d.normals ? mk(d.normals[3 * v], d.normals[3 * v + 1], d.normals[3 * v + 2]) : mk(0, 0, 0));
+            sc.uv.push_back(d.texcoords ? d.texcoords[2 * v] : 0.f); sc.uv.push_back(d.texcoords ? d.texcoords[2 * v + 1] : 0.f);
         }
         for (uint32_t f = 0; f < d.face_count; ++f) {
             for (int k = 0; k < 3; ++k) sc.faces.push_back(d.faces[3 * f + k] + m.v_off);
@@ -887,6 +940,12 @@ orc_scene *orc_scene_create(const epsm_mesh_desc *meshes, uint32_t n_meshes, con
         sc.meshes.push_back(m);
     }
     sc.bsdfs.assign(bsdfs, bsdfs + n_bsdfs);
+    sc.textures.reserve(n_bsdfs);                                   // no reallocation: the descriptors point into it
+    for (auto &b : sc.bsdfs) if (b.reflectance_texture) {
+        Texture t; t.d = *b.reflectance_texture; t.texels.assign(t.d.texels, t.d.texels + 3 * (size_t) t.d.width * t.d.height);
+        sc.textures.push_back(std::move(t)); sc.textures.back().d.texels = sc.textures.back().texels.data();
+        b.reflectance_texture = &sc.textures.back().d;
+    }
     sc.emitters.assign(emitters, emitters + n_emitters);
     for (auto &m : sc.meshes) build_pmf(sc, m);
     sc.sensors.resize(n_sensors);
@@ -949,6 +1008,21 @@ void orc_surface_interaction(orc_scene *s, const float *r, float *out) {
     *o++ = si.t; put3(si.p); put3(si.n); put3(si.sh_n); put3(si.wi); *o++ = si.b0; *o++ = si.b1; *o++ = (float) si.ismesh;
     put3(si.p0); put3(si.p1); put3(si.p2); put3(si.n0); put3(si.n1); put3(si.n2);
     *o++ = (float) si.prim; *o++ = si.valid ? (float) bsdf_flags(s->sc.bsdfs[s->sc.meshes[si.mesh].bsdf]) : 0.f; *o++ = pi.u; *o++ = pi.v;
+}
+// Texture-side probe of a hit: out = [uv(2), sh_s(3), sh_t(3), diffuse reflectance at the hit (3)]
+void orc_surface_uv(orc_scene *s, const float *r, float *out) {
+    g_accel_owner = s;
+    Ray ray{mk(r[0], r[1], r[2]), mk(r[4], r[5], r[6]), r[3]};
+    PI pi = scene_closest(s->sc, ray); SI si = compute_si(s->sc, ray, pi);
+    for (int i = 0; i < 11; ++i) out[i] = 0.f;
+    if (!si.valid) return;
+    const epsm_bsdf_desc b = bsdf_at(s->sc, si);
+    out[0] = si.uv[0]; out[1] = si.uv[1]; out[2] = si.sh_s.x; out[3] = si.sh_s.y; out[4] = si.sh_s.z; out[5] = si.sh_t.x; out[6] = si.sh_t.y; out[7] = si.sh_t.z;
+    out[8] = b.reflectance[0]; out[9] = b.reflectance[1]; out[10] = b.reflectance[2];
+}
+// Texture lookup on its own: n uv pairs → n RGB values
+void orc_texture_eval(const epsm_texture_desc *t, const float *uv, uint32_t n, float *out) {
+    for (uint32_t i = 0; i < n; ++i) { const V3 c = tex_eval(*t, uv + 2 * i); out[3 * i] = c.x; out[3 * i + 1] = c.y; out[3 * i + 2] = c.z; }
 }
 // BSDF probe: out = [wo(3), pdf, eta, type, weight(3), hf(3)]
 void orc_bsdf_sample(const epsm_bsdf_desc *b, const float *wi, float s1, float s2x, float s2y, float *out) {
@@ -1091,7 +1165,7 @@ void orc_path_log(orc_scene *s, uint32_t sensor, uint32_t seed, uint32_t spp, ui
             float mis = mis_weight(prev_pdf, em_pdf);
             V3 Le = beta * mis * emitter_eval(sc, si);
             bool active_next = (depth + 1 < max_depth_prop) && si.valid;
-            const epsm_bsdf_desc *b = si.valid ? &sc.bsdfs[sc.meshes[si.mesh].bsdf] : nullptr;
+            epsm_bsdf_desc b_tex; const epsm_bsdf_desc *b = nullptr; if (si.valid) { b_tex = bsdf_at(sc, si); b = &b_tex; }
             uint32_t flags = b ? bsdf_flags(*b) : 0u;
             bool smooth = active_next && (flags & EPSM_BF_SMOOTH);
             bool active_em = smooth;
@@ -1309,7 +1383,7 @@ void orc_prb_log(orc_scene *os, uint32_t sensor, uint32_t seed, uint32_t spp, ui
             SI si = compute_si(sc, ray, pi);
             V3 Le = beta * mis_em * emitter_eval(sc, si);
             bool active_next = (depth + 1 < max_depth) && si.valid;
-            const epsm_bsdf_desc *b = si.valid ? &sc.bsdfs[sc.meshes[si.mesh].bsdf] : nullptr;
+            epsm_bsdf_desc b_tex; const epsm_bsdf_desc *b = nullptr; if (si.valid) { b_tex = bsdf_at(sc, si); b = &b_tex; }
             uint32_t flags = b ? bsdf_flags(*b) : 0u;
             bool active_em = active_next && (flags & EPSM_BF_SMOOTH);
             float e1 = rng.next_f32(), e2 = rng.next_f32();
@@ -1348,7 +1422,7 @@ void orc_prb_log(orc_scene *os, uint32_t sensor, uint32_t seed, uint32_t spp, ui
             // run-ahead with a clone of the sampler, prb_reparam.py:484-520
             PCG32 clone = rng;
             bool active_next_next = active_next && si_next.valid && (depth + 2 < max_depth);
-            const epsm_bsdf_desc *bn = si_next.valid ? &sc.bsdfs[sc.meshes[si_next.mesh].bsdf] : nullptr;
+            epsm_bsdf_desc bn_tex; const epsm_bsdf_desc *bn = nullptr; if (si_next.valid) { bn_tex = bsdf_at(sc, si_next); bn = &bn_tex; }
             bool active_em_next = active_next_next && bn && (bsdf_flags(*bn) & EPSM_BF_SMOOTH);
             float c1 = clone.next_f32(), c2 = clone.next_f32();
             DS dsn; V3 emw_n;

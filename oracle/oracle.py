@@ -68,6 +68,8 @@ def lib() -> C.CDLL:
         L.orc_filter_eval.restype = C.c_float
         L.orc_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int]
         L.orc_surface_interaction.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_surface_uv.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_texture_eval.argtypes = [C.POINTER(capi.TextureDesc), C.c_void_p, C.c_uint32, C.c_void_p]
         L.orc_bsdf_sample.argtypes = [C.POINTER(capi.BsdfDesc), C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_void_p]
         L.orc_bsdf_eval_pdf.argtypes = [C.POINTER(capi.BsdfDesc), C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_sample_emitter.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p]
@@ -124,6 +126,12 @@ def bsdf_eval_pdf(bsdf, wi, wo):
     lib().orc_bsdf_eval_pdf(C.byref(d), _p(wi), _p(wo), _p(out)); return out[:3], out[3]
 
 
+def texture_eval(tex, uv):
+    """Oracle lookup of a scenes.Texture at (n,2) uv coordinates."""
+    t = tex.to_c(); uv = np.ascontiguousarray(uv, np.float32).reshape(-1, 2); out = np.zeros((uv.shape[0], 3), np.float32)
+    lib().orc_texture_eval(C.byref(t), _p(uv), uv.shape[0], _p(out)); return out
+
+
 def bsdf_flags(bsdf):
     d = _bsdf_desc(bsdf); return int(lib().orc_bsdf_flags(C.byref(d)))
 
@@ -175,6 +183,11 @@ class OracleScene:
         return dict(t=out[0], p=out[1:4], n=out[4:7], sh_n=out[7:10], wi=out[10:13], b0=out[13], b1=out[14],
                     ismesh=int(out[15]), p0=out[16:19], p1=out[19:22], p2=out[22:25], n0=out[25:28], n1=out[28:31],
                     n2=out[31:34], prim=int(out[34]) if np.isfinite(out[0]) else -1, bsdf_flags=int(out[35]), uv=out[36:38])
+
+    def surface_uv(self, o, d, maxt=np.float32(3.4e38)):
+        r = np.array([o[0], o[1], o[2], maxt, d[0], d[1], d[2], 0], np.float32); out = np.zeros(11, np.float32)
+        lib().orc_surface_uv(self.h, _p(r), _p(out))
+        return dict(uv=out[0:2], sh_s=out[2:5], sh_t=out[5:8], reflectance=out[8:11])
 
     def sample_emitter(self, o, d, sample):
         r = np.array([o[0], o[1], o[2], 3.4e38, d[0], d[1], d[2], 0], np.float32); out = np.zeros(14, np.float32)

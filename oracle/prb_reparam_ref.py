@@ -95,6 +95,10 @@ class Geometry:
         self.mesh_bsdf = torch.tensor([m.bsdf for m in sd.meshes])
         self.mesh_emitter = torch.tensor([m.emitter for m in sd.meshes])
         self.bsdfs = sd.bsdfs
+        # vertex texture coordinates (constants: Mesh::vertex_texcoord is not a differentiable parameter here)
+        uv = [np.asarray(m.texcoords, np.float64).reshape(-1, 2) if getattr(m, "texcoords", None) is not None else np.zeros((m.positions.shape[0], 2)) for m in sd.meshes]
+        self.UV = torch.tensor(np.concatenate(uv), dtype=F64)
+        self.has_uv = torch.tensor([getattr(m, "texcoords", None) is not None for m in sd.meshes])
 
 
 def surface_interaction(G: Geometry, prim, b1, b2, valid, ray_o, ray_d, mode):
@@ -121,6 +125,15 @@ def surface_interaction(G: Geometry, prim, b1, b2, valid, ray_o, ray_d, mode):
     p = p0 * b0[:, None] + p1 * u[:, None] + p2 * v[:, None]
     n = normalize(torch.linalg.cross(dp0, dp1))
     dp_du, _ = coordinate_system(n)
+    # meshes with texture coordinates: interpolated uv and the uv-aligned dp/du (mesh.cpp:731-763)
+    t0, t1, t2 = G.UV[f[:, 0]], G.UV[f[:, 1]], G.UV[f[:, 2]]
+    huv = G.has_uv[mesh]
+    uv = torch.where(huv[:, None], t0 * b0[:, None] + t1 * u[:, None] + t2 * v[:, None], torch.stack([u, v], -1))
+    duv0, duv1 = t1 - t0, t2 - t0
+    det = duv0[:, 0] * duv1[:, 1] - duv0[:, 1] * duv1[:, 0]
+    use = huv & (det != 0)
+    inv_det = 1.0 / torch.where(use, det, torch.ones_like(det))
+    dp_du = torch.where(use[:, None], (duv1[:, 1:2] * dp0 - duv0[:, 1:2] * dp1) * inv_det[:, None], dp_du)
     hn = G.has_normals[mesh]
     n0, n1, n2 = N[f[:, 0]], N[f[:, 1]], N[f[:, 2]]
     ns = n0 * b0[:, None] + n1 * u[:, None] + n2 * v[:, None]
@@ -132,7 +145,7 @@ def surface_interaction(G: Geometry, prim, b1, b2, valid, ray_o, ray_d, mode):
     sh_t = torch.linalg.cross(sh_n, sh_s)
     wi_w = -ray_d
     wi = torch.stack([dot(wi_w, sh_s), dot(wi_w, sh_t), dot(wi_w, sh_n)], -1)
-    return dict(p=p, n=n, sh_n=sh_n, sh_s=sh_s, sh_t=sh_t, wi=wi, mesh=mesh, valid=valid, f=f, bw=torch.stack([b0, u, v], -1))
+    return dict(p=p, n=n, sh_n=sh_n, sh_s=sh_s, sh_t=sh_t, wi=wi, mesh=mesh, valid=valid, f=f, bw=torch.stack([b0, u, v], -1), uv=uv)
 
 
 def to_local(si, v):
@@ -152,7 +165,7 @@ def _fresnel_conductor(c, eta, k):                                        # incl
     return 0.5 * (rs + rp)
 
 
-def _bsdf_eval_one(b, wi, wo):
+def _bsdf_eval_one(b, wi, wo, uv=None):
     from epsm_mitsuba3_b200 import capi
     zero = torch.zeros(wi.shape[0], 3, dtype=F64)
     if b.twosided:                                                        # twosided.cpp:226-232
@@ -160,9 +173,15 @@ def _bsdf_eval_one(b, wi, wo):
         wo = torch.stack([wo[:, 0], wo[:, 1], torch.where(neg, -wo[:, 2], wo[:, 2])], -1)
         wi = torch.stack([wi[:, 0], wi[:, 1], wi[:, 2].abs()], -1)
     refl = torch.tensor(b.reflectance, dtype=F64)
+    if getattr(b, "texture", None) is not None and uv is not None:
+        # bitmap reflectance at the hit's uv, detached (exact for `nearest`, the filter of EPSM/exp/human.py; a bilinear lookup's
+        # ∂ρ/∂uv term is not carried by the product either — stated in DESIGN §7)
+        refl = torch.tensor(_o.texture_eval(b.texture, uv.detach().numpy().astype(np.float32)).astype(np.float64))
+    else:
+        refl = refl[None, :]
     if b.kind == capi.BSDF_DIFFUSE:                                       # diffuse.cpp:158-175
         act = (wi[:, 2] > 0) & (wo[:, 2] > 0)
-        return torch.where(act[:, None], refl[None, :] * (wo[:, 2:3] / math.pi), zero)
+        return torch.where(act[:, None], refl * (wo[:, 2:3] / math.pi), zero)
     if b.kind == capi.BSDF_ROUGHCONDUCTOR:                                # roughconductor.cpp:417-492, microfacet.h:183-210,365-392
         H = normalize(wo + wi)
         act = (wi[:, 2] > 0) & (wo[:, 2] > 0) & (dot(wi, H) > 0) & (dot(wo, H) > 0)
@@ -188,18 +207,18 @@ def _bsdf_eval_one(b, wi, wo):
         val = D * g1(wi) * g1(wo) / (4.0 * wi[:, 2])
         c = dot(wi, H)
         Fr = torch.stack([_fresnel_conductor(c, float(b.eta[i]), float(b.k[i])) for i in range(3)], -1)
-        return torch.where(act[:, None], Fr * refl[None, :] * val[:, None], zero)
+        return torch.where(act[:, None], Fr * refl * val[:, None], zero)
     return zero                                                           # delta BSDFs evaluate to zero
 
 
-def bsdf_eval(G: Geometry, mesh, wi, wo, mask):
+def bsdf_eval(G: Geometry, mesh, wi, wo, mask, uv=None):
     out = torch.zeros(wi.shape[0], 3, dtype=F64)
     bid = G.mesh_bsdf[mesh]
     for i, b in enumerate(G.bsdfs):
         sel = (bid == i) & mask
         if bool(sel.any()):
             idx = sel.nonzero()[:, 0]
-            out = out.index_put((idx,), _bsdf_eval_one(b, wi[idx], wo[idx]))
+            out = out.index_put((idx,), _bsdf_eval_one(b, wi[idx], wo[idx], None if uv is None else uv[idx]))
     return out
 
 
@@ -331,13 +350,13 @@ def render_backward(o_scene, sd, grad_in, sensor=0, seed=0, spp=4, max_depth=6, 
         d_e_in = replace_grad(em_d0, normalize(d_e_in))
         d_e, det_e = reparam(G, o_e, d_e_in, aux_em, em_act)
         wo_em = to_local(si, d_e)
-        bsdf_em = bsdf_eval(G, si["mesh"], si["wi"], wo_em, active_em)
+        bsdf_em = bsdf_eval(G, si["mesh"], si["wi"], wo_em, active_em, si["uv"])
         Lr_dir = beta * mis_direct[:, None] * bsdf_em * em_weight * det_e[:, None]          # :431-435 (em_weight: constant radiance)
         Lr_dir = torch.where(active_em[:, None], Lr_dir, torch.zeros_like(Lr_dir))
 
         # indirect term: L · bsdf_val / detach(bsdf_val) (:553-571)
         wo_next = to_local(si, ray_next_d)
-        bsdf_val = bsdf_eval(G, si["mesh"], si["wi"], wo_next, active_next)
+        bsdf_val = bsdf_eval(G, si["mesh"], si["wi"], wo_next, active_next, si["uv"])
         bv_det = bs_weight * bs_pdf[:, None]
         inv_bv = torch.where(bv_det != 0, 1.0 / bv_det, torch.zeros_like(bv_det))
         ratio = inv_bv * bsdf_val
@@ -349,12 +368,12 @@ def render_backward(o_scene, sd, grad_in, sensor=0, seed=0, spp=4, max_depth=6, 
         if prev is not None:
             si_p = prev["si"]
             wo_prev = normalize(torch.where(valid[:, None], si_ro["p"] - si_p["p"], torch.ones_like(si_ro["p"])))
-            bv_prev = bsdf_eval(G, si_p["mesh"], si_p["wi"], to_local(si_p, wo_prev), prev["valid"] & valid)
+            bv_prev = bsdf_eval(G, si_p["mesh"], si_p["wi"], to_local(si_p, wo_prev), prev["valid"] & valid, si_p["uv"])
             extra = extra + torch.where((prev["valid"] & valid)[:, None], L_prev * bv_prev / bv_prev.detach().clamp(min=1e-8), torch.zeros_like(extra))
         si_n = surface_interaction(G, nprim, nb1, nb2, nvalid, ray_o, ray_next_d, "follow")
         si_n = {k: (v.detach() if torch.is_tensor(v) and v.dtype == F64 else v) for k, v in si_n.items()}
         wi_next = normalize(torch.where((valid & nvalid)[:, None], si_ro["p"] - si_n["p"], torch.ones_like(si_ro["p"])))
-        bv_next = bsdf_eval(G, si_n["mesh"], to_local(si_n, wi_next), bsn_wo, valid & nvalid)
+        bv_next = bsdf_eval(G, si_n["mesh"], to_local(si_n, wi_next), bsn_wo, valid & nvalid, si_n["uv"])
         extra = extra + torch.where((valid & nvalid)[:, None], L_next * bv_next / bv_next.detach().clamp(min=1e-8), torch.zeros_like(extra))
 
         Lo = (Le + Lr_dir + Lr_ind) * det_rp[:, None] + extra               # :576

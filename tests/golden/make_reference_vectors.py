@@ -55,11 +55,13 @@ def _import_reference():
 # ---------------------------------------------------------------------------------------------------------------------
 #  SceneData → reference scene
 # ---------------------------------------------------------------------------------------------------------------------
-def bsdf_dict(b):
+def bsdf_dict(b, mi=None):
     from epsm_mitsuba3_b200 import capi
     rgb = lambda v: {"type": "rgb", "value": [float(x) for x in v]}
     unb = lambda v: {"type": "srgb", "color": [float(x) for x in v], "unbounded": True}       # conductor eta / k exceed 1
-    if b.kind == capi.BSDF_DIFFUSE:
+    if b.kind == capi.BSDF_DIFFUSE and getattr(b, "texture", None) is not None:
+        d = {"type": "diffuse", "reflectance": texture_dict(mi, b.texture)}
+    elif b.kind == capi.BSDF_DIFFUSE:
         d = {"type": "diffuse", "reflectance": rgb(b.reflectance)}
     elif b.kind == capi.BSDF_DIELECTRIC:
         d = {"type": "dielectric", "int_ior": float(b.eta[0]), "ext_ior": 1.0}
@@ -69,6 +71,16 @@ def bsdf_dict(b):
         d = {"type": "roughconductor", "eta": unb(b.eta), "k": unb(b.k), "alpha": float(b.alpha_u),
              "distribution": "ggx" if b.ggx else "beckmann", "sample_visible": bool(b.sample_visible)}
     return {"type": "twosided", "nested": d} if b.twosided else d
+
+
+def texture_dict(mi, tex):
+    """scenes.Texture → the reference's `bitmap` plugin on the same linear float texels (raw: no colour conversion)."""
+    d = {"type": "bitmap", "bitmap": mi.Bitmap(np.ascontiguousarray(tex.texels, np.float32)), "raw": True,
+         "filter_type": tex.filter, "wrap_mode": tex.wrap}
+    if tex.to_uv is not None:
+        m = np.asarray(tex.to_uv, np.float32)
+        d["to_uv"] = mi.ScalarTransform4f([[m[0, 0], m[0, 1], 0, m[0, 2]], [m[1, 0], m[1, 1], 0, m[1, 2]], [0, 0, 1, 0], [0, 0, 0, 1]])
+    return d
 
 
 def sensor_dict(mi, s):
@@ -92,7 +104,7 @@ def to_reference_scene(mi, sd, tmpdir, integrator=None):
         path = os.path.join(tmpdir, f"{sd.name}_{i}.ply")
         meshio.save_ply(path, m)
         e = {"type": "ply", "filename": path, "face_normals": m.normals is None, "flip_normals": bool(m.flip_normals),
-             "bsdf": bsdf_dict(sd.bsdfs[m.bsdf])}
+             "bsdf": bsdf_dict(sd.bsdfs[m.bsdf], mi)}
         if m.emitter >= 0:
             e["emitter"] = {"type": "area", "radiance": {"type": "rgb", "value": [float(x) for x in sd.emitters[m.emitter].radiance]}}
         d[f"mesh{i:04d}"] = e

@@ -66,6 +66,18 @@ void sim_scene_copy_accel(sim_scene *s, float *nodes, float *tris) {
     if (nodes) memcpy(nodes, s->hs.bvh.nodes.data(), s->hs.bvh.nodes.size() * sizeof(f4));
     if (tris) memcpy(tris, s->hs.bvh.tris.data(), s->hs.bvh.tris.size() * sizeof(f4));
 }
+// Texture-side probe of a hit with the product's compute_si / bsdf_at: out = [uv(2), sh_s(3), sh_t(3), reflectance(3)]
+void sim_surface_uv(sim_scene *s, const float *r, float *out) {
+    LocalStack ls; TStack st; bind(st, ls); Tracer tr(s->sc, st);
+    Ray ray{mk3(r[0], r[1], r[2]), mk3(r[4], r[5], r[6]), r[3]};
+    const Hit h = trace_closest<false>(tr, ray);
+    SI si; compute_si(s->sc, ray, h, si);
+    for (int i = 0; i < 11; ++i) out[i] = 0.f;
+    if (!si.valid) return;
+    const DBsdf b = bsdf_at(s->sc, si.bsdf, si.uv);
+    out[0] = si.uv[0]; out[1] = si.uv[1]; out[2] = si.sh_s.x; out[3] = si.sh_s.y; out[4] = si.sh_s.z; out[5] = si.sh_t.x; out[6] = si.sh_t.y; out[7] = si.sh_t.z;
+    out[8] = b.reflectance[0]; out[9] = b.reflectance[1]; out[10] = b.reflectance[2];
+}
 // The product's BSDF code on its own (for the known answers of the reference's BSDF tests).
 void sim_bsdf_sample(sim_scene *s, uint32_t bsdf_id, const float *wi, float s1, float s2x, float s2y, float *out12) {
     BSample bs; bsdf_sample(s->hs.bsdfs[bsdf_id], mk3(wi[0], wi[1], wi[2]), s1, s2x, s2y, true, bs);

@@ -29,6 +29,7 @@ def lib():
         L.sim_scene_refit.argtypes = [vp, u32, vp]; L.sim_scene_refit.restype = C.c_double
         L.sim_scene_cost.argtypes = [vp]; L.sim_scene_cost.restype = C.c_double
         L.sim_scene_copy_accel.argtypes = [vp, vp, vp]
+        L.sim_surface_uv.argtypes = [vp, vp, vp]
         L.sim_bsdf_sample.argtypes = [vp, u32, vp, C.c_float, C.c_float, C.c_float, vp]
         L.sim_bsdf_eval_pdf.argtypes = [vp, u32, vp, vp, vp]
         L.sim_bsdf_grad.argtypes = [vp, u32, vp, vp, vp, vp]
@@ -78,6 +79,11 @@ class SimScene:
         nodes = np.zeros((st["n_nodes"], 32), np.float32); tris = np.zeros((st["n_triangles"], 16), np.float32)
         lib().sim_scene_copy_accel(self.h, nodes.ctypes.data, tris.ctypes.data)
         return nodes, tris
+
+    def surface_uv(self, o, d, maxt=np.float32(3.4e38)):
+        r = np.array([o[0], o[1], o[2], maxt, d[0], d[1], d[2], 0], np.float32); out = np.zeros(11, np.float32)
+        lib().sim_surface_uv(self.h, r.ctypes.data, out.ctypes.data)
+        return dict(uv=out[0:2], sh_s=out[2:5], sh_t=out[5:8], reflectance=out[8:11])
 
     def bsdf_sample(self, bsdf_id, wi, s1, s2):
         wi = np.asarray(wi, np.float32); out = np.zeros(12, np.float32)

@@ -16,6 +16,9 @@ CASES = {
     "cbox_glass": (lambda: S.cornell_box(16, 4, 12, box_bsdf=S.Bsdf.dielectric(1.5)), "manifold_caustic", 5),
     "room": (lambda: S.indoor_room(6000, 16, 4, 16), "manifold", 6),
     "stage": (lambda: S.articulated_stage(16, 4, 16), "manifold_caustic", 3),      # BASELINE configs[3] at test size
+    # uv-mapped meshes + bitmap reflectances (EPSM/exp/human.py:101-163): si.uv, uv-aligned shading frame, texture lookup
+    "textured": (lambda: S.textured_scene(16, 4, 12, "nearest", "repeat"), "manifold", 6),
+    "textured_bilinear": (lambda: S.textured_scene(16, 4, 12, "bilinear", "mirror"), "manifold", 4),
 }
 
 

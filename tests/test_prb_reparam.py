@@ -15,7 +15,7 @@ from epsm_mitsuba3_b200 import scenes as S
 RES = 16
 
 
-def occluder_scene(smooth: bool, rough_floor: bool, res: int = RES, offset=(0.0, 0.0, 0.0)) -> S.SceneData:
+def occluder_scene(smooth: bool, rough_floor: bool, res: int = RES, offset=(0.0, 0.0, 0.0), textured: bool = False) -> S.SceneData:
     """Floor + small area light + an icosphere between them (the differentiable mesh), seen from above at an angle."""
     sd = S.SceneData(); T = S.Transform4f
     dif = sd.add_bsdf(S.Bsdf.diffuse((0.7, 0.6, 0.5))); dif2 = sd.add_bsdf(S.Bsdf.diffuse((0.3, 0.5, 0.8)))
@@ -26,6 +26,13 @@ def occluder_scene(smooth: bool, rough_floor: bool, res: int = RES, offset=(0.0,
     v, f = S.icosphere(1)
     p = v * 0.5 + np.array([0.1, 0.0, 1.2]) + np.asarray(offset)
     occ = S.Mesh("occ", p, f, normals=(v.astype(np.float32) if smooth else None), grad=True); occ.bsdf = dif2
+    if textured:
+        # uv-mapped occluder with a nearest-filtered bitmap reflectance (EPSM/exp/human.py:101-163) and a uv-mapped floor: the
+        # shading frames follow dp/du (mesh.cpp:746-763), the texture is piecewise constant
+        rng = np.random.default_rng(4)
+        occ.texcoords = np.stack([np.arctan2(v[:, 1], v[:, 0]) / (2 * np.pi) + 0.5 + 0.1 * v[:, 2], 0.5 * v[:, 2] + 0.5 + 0.05 * v[:, 0]], -1).astype(np.float32)
+        sd.bsdfs[dif2].texture = S.Texture(rng.uniform(0.2, 0.9, (4, 5, 3)).astype(np.float32), filter="nearest", wrap="repeat")
+        floor.texcoords = np.array([[0, 0], [2, 0.3], [2.2, 1.5], [-0.1, 1.2]], np.float32)
     sd.add_mesh(occ)
     sd.sensors = [S.Sensor(T.look_at([0.5, -4.0, 3.0], [0, 0, 0.8], [0, 0, 1]), 45.0, res, res, 0.1, 100.0, 4, True)]
     return sd
@@ -58,6 +65,29 @@ def _oracle(sd, gin, seed, spp, md, kappa, rays=16, **kw):
     gp, gn = R.render_backward(o, sd, gin, sensor=0, seed=seed, spp=spp, max_depth=md, kappa=kappa, n_rays=rays, **kw)
     voff = sd.vertex_offsets()
     return gp[voff[2]:voff[3]], gn[voff[2]:voff[3]], o
+
+
+@pytest.mark.parametrize("smooth", (False, True))
+def test_hand_adjoint_with_uv_aligned_frames_and_a_bitmap_reflectance(smooth):
+    """Meshes with texture coordinates: sh_frame.s follows dp/du = (Δv₁·e1 − Δv₀·e2)/det, which is linear in the edges — its
+    adjoint replaces that of coordinate_system(n_g); the nearest-filtered texture is piecewise constant in uv."""
+    from tests.hostsim import hostsim as HS
+    md, spp, kappa = 3, 4, 1e3
+    sd = occluder_scene(smooth, True, textured=True)
+    gin = image_weights(RES)
+    gp_o, gn_o, o = _oracle(sd, gin, 5, spp, md, kappa)
+    h = HS.SimScene(sd)
+    film = h.render_raw(0, 5, spp, md, 5)
+    assert np.array_equal(film, o.render_raw(0, 5, spp, md, 5))
+    gp, gn = h.prb_backward(0, 5, spp, _cfg(md, kappa), film, gin)
+    voff = sd.vertex_offsets()
+    assert np.abs(gp_o).max() > 1e-3 and _rel(gp[voff[2]:voff[3]], gp_o) < 5e-4
+    if smooth:
+        assert _rel(gn[voff[2]:voff[3]], gn_o) < 5e-4
+    # and the frames do differ from the untextured scene's (the case is not vacuous)
+    plain = occluder_scene(smooth, True)
+    gp_p, _ = HS.SimScene(plain).prb_backward(0, 5, spp, _cfg(md, kappa), HS.SimScene(plain).render_raw(0, 5, spp, md, 5), gin)
+    assert _rel(gp_p[voff[2]:voff[3]], gp_o) > 1e-2
 
 
 @pytest.mark.parametrize("smooth,rough,md,spp,kappa", CONFIGS)
