@@ -18,6 +18,7 @@
 //   film           src/render/imageblock.cpp:414-494, src/rfilters/gaussian.cpp:48-96
 #pragma once
 #include <math.h>
+#include <stddef.h>
 #include <float.h>
 #include <string.h>
 #include "epsm_types.h"
@@ -880,11 +881,19 @@ EPSM_HD f3 outlier3(f3 v) { return mk3(outlier(v.x), outlier(v.y), outlier(v.z))
 struct VLog {
     bool active, active_em, direct_valid, direct_any, direct_grad, direct_traced;
     uint32_t flags, ismesh, mesh_flags, has_normals, prim;
-    uint32_t fi[3], dfi[3];
-    float bw[3], dbw[3];
-    float eta, b0, b1, lr_sum, dis;
-    f3 light, p0, p1, p2, n0, n1, n2, hf, p;
+    uint32_t fi[3];
+    float bw[3];
+    float eta, b0, b1, lr_sum;
+    f3 light, p0, p1, p2, n0, n1, n2, p;
+    // ---- the first VLOG_STAGE_WORDS words are what stage B knows and the wavefront keeps in HBM; the rest is filled by
+    //      wf_direct_hit in the finish kernel (dfi, dbw, dis) or is never read (hf: its seed is identically zero)
+    uint32_t dfi[3];
+    float dbw[3];
+    float dis;
+    f3 hf;
 };
+#define VLOG_STAGE_WORDS 41       // 2 (flags) + 5 + 3 + 3 + 4 + 8 × 3
+static_assert(offsetof(VLog, dfi) == 4 * VLOG_STAGE_WORDS, "VLog prefix");
 struct PathHead { f3 cam, d, dldp1, L; float dlduv0, dlduv1; };
 // NV = vertex slots held: EPSM_MAXV in general; the short-chain instantiation of the gradient pass (k_wf_finish) holds 3
 // (two logged vertices + the inactive terminator), which lets the compiler keep the whole solve in registers.

@@ -637,7 +637,7 @@ __global__ void __launch_bounds__(128, EPSM_STAGEB_MINBLOCKS) k_wf_stage_b(const
         const bool occluded = S.need_shadow && wb.occl[i] != 0u;
         VLog v;
         wf_stage_b(sc, S, v, h, occluded, it, ln.rr_depth, ln.prune != 0, direct, push_direct);
-        if (it < EPSM_MAXV) soa_store(v, wb.vlogs + (size_t) it * WORDS_OF(VLog) * wb.capacity, wb.capacity, i);
+        if (it < EPSM_MAXV) soa_store_prefix<VLOG_STAGE_WORDS>(v, wb.vlogs + (size_t) it * WORDS_OF(VLog) * wb.capacity, wb.capacity, i);   // the tail is the finish kernel's
         push_next = S.active && it + 1 < max_iter; next = S.ray;
         if (S.active || keep_state) soa_store(S, wb.states, wb.capacity, i);       // a finished lane's state is read by the record probe only (P.L)
         const uint32_t n_written = it + 1 < EPSM_MAXV ? it + 1 : EPSM_MAXV;
@@ -698,8 +698,9 @@ __device__ __forceinline__ void finish_lane(const DScene &sc, const DLaunch &ln,
     EPSM_UNROLL_NV
     for (int k = 0; k < NV; ++k) {
         if (k < n_logged && k < n_written && (chain || RECORD)) {
-            soa_load(P.v[k], wb.vlogs + (size_t) k * WORDS_OF(VLog) * wb.capacity, wb.capacity, i);
+            soa_load_prefix<VLOG_STAGE_WORDS>(P.v[k], wb.vlogs + (size_t) k * WORDS_OF(VLog) * wb.capacity, wb.capacity, i);
             VLog &v = P.v[k];
+            v.dfi[0] = v.dfi[1] = v.dfi[2] = 0u; v.dbw[0] = v.dbw[1] = v.dbw[2] = 0.f; v.dis = 0.f; v.hf = mk3(0, 0, 0);
             if (v.active && v.direct_traced) wf_direct_hit(sc, v, wb.hits[wb.capacity + (size_t) k * wb.capacity + i]);
             const bool diffuse = (v.flags & EPSM_BF_DIFFUSE) != 0;
             n_diffuse += diffuse ? 1 : 0;
