@@ -397,7 +397,9 @@ __device__ __forceinline__ void queue_write(QRay *q, uint32_t idx, const Ray &r,
 // a thread-local array beyond WF_STACK.  The arithmetic is that of bvh_trace (epsm_device.cuh) and the result does
 // not depend on the visiting order (closest t, ties → larger primitive index; every subtree whose padded box reaches
 // t ≤ best is visited), so hits stay bit-identical to the oracle.
-#define WF_STACK 16
+#ifndef WF_STACK
+#define WF_STACK 16          // shared-memory stack entries per thread (16 KB per CTA: 8 CTAs/SM leave ≈ 100 KB of L1); A/B in profiles/r02_summary.md §O
+#endif
 #define WF_LSTACK 80
 #define WF_REF_NONE 0x7fffffffu
 #ifndef WF_REFILL_MIN

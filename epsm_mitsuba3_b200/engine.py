@@ -222,6 +222,7 @@ class Scene:
         """Device views of the BVH4 nodes (n,32) and triangle slots (n,16), for tests."""
         pn, nn, pt, nt = C.c_void_p(), C.c_uint64(), C.c_void_p(), C.c_uint64()
         self._check(self.lib.epsm_scene_accel_raw(self.ctx, C.byref(pn), C.byref(nn), C.byref(pt), C.byref(nt)))
+        self.synchronize()        # the views are read on torch's stream: a refit still running on the library's stream must be done
         return _wrap_device(pn.value, (nn.value // 32, 32), self.device), _wrap_device(pt.value, (nt.value // 16, 16), self.device)
 
     def apply_updates(self):
