@@ -38,6 +38,29 @@ def test_record_layout_constants_match_header():
     assert capi.REC_FLOATS == capi.REC_MAXV * (capi.REC_VSTRIDE + capi.REC_GSTRIDE) + 14
 
 
+def test_descriptor_layouts_match_header(tmp_path):
+    """sizeof / offsetof of every descriptor struct as the C compiler sees include/epsm_b200.h against the ctypes mirrors: a
+    mismatch would make epsm_scene_upload read garbage past the first array element without any error."""
+    import subprocess
+    structs = {"epsm_mesh_desc": capi.MeshDesc, "epsm_bsdf_desc": capi.BsdfDesc, "epsm_texture_desc": capi.TextureDesc,
+               "epsm_emitter_desc": capi.EmitterDesc, "epsm_sensor_desc": capi.SensorDesc, "epsm_reparam_config": capi.ReparamConfig,
+               "epsm_scene_stats": capi.SceneStats}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "epsm_b200.h")}"', "int main(void) {"]
+    for cname, cls in structs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"; src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-o", str(exe), str(src)])
+    got = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).splitlines())
+    for cname, cls in structs.items():
+        assert int(got[cname]) == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, f"{cname}.{fname}"
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
 def test_no_cpu_fallback():
     import epsm_mitsuba3_b200 as ep
