@@ -1260,7 +1260,14 @@ struct WfIo {
     __device__ __forceinline__ bool adjoint_now(int round) const { return pass == round + 1; }
     __device__ __forceinline__ bool aux_push_only(int round) const { return pass == round; }
     __device__ __forceinline__ bool aux_skip(int round) const { return pass > round + 1; }
-    __device__ __forceinline__ void aux_push(uint32_t j, const Ray &r) { push(wb.q_closest, wb.counters + 0, r, (wb.K + 1 + j) * wb.C + i); }
+    // n consecutive entries of the closest-hit queue for this lane (one atomic per warp for all the lanes that reserve together)
+    __device__ __forceinline__ uint32_t aux_reserve(uint32_t n) {
+        const cooperative_groups::coalesced_group g = cooperative_groups::coalesced_threads();
+        uint32_t base = 0;
+        if (g.thread_rank() == 0) base = atomicAdd(wb.counters + 0, n * g.size());
+        return g.shfl(base, 0) + n * g.thread_rank();
+    }
+    __device__ __forceinline__ void aux_push(uint32_t j, uint32_t q, const Ray &r) { queue_write(wb.q_closest, q, r, (wb.K + 1 + j) * wb.C + i); }
     __device__ __forceinline__ Hit aux_hit(uint32_t j, const Ray &) { return wb.hits[(size_t) (wb.K + 1 + j) * wb.C + i]; }
     __device__ __forceinline__ bool lane_radiance(f3 &L) const { const float *p = wb.lane_L + 3 * lane; L = mk3(p[0], p[1], p[2]); return true; }
     __device__ __forceinline__ void finished() { wb.status[i] = 1u; }

@@ -212,7 +212,8 @@ struct MegaIo {
     EPSM_HD bool adjoint_now(int) const { return true; }           // the adjoint that consumes round r runs in pass r + 1
     EPSM_HD bool aux_push_only(int) const { return false; }
     EPSM_HD bool aux_skip(int) const { return false; }
-    EPSM_HD void aux_push(uint32_t, const Ray &) {}
+    EPSM_HD uint32_t aux_reserve(uint32_t) { return 0u; }
+    EPSM_HD void aux_push(uint32_t, uint32_t, const Ray &) {}
     EPSM_HD Hit aux_hit(uint32_t, const Ray &r) { return trace_closest<COUNT>(tr, r); }
     EPSM_HD bool lane_radiance(f3 &) const { return false; }       // false: replay the primal path inline
     EPSM_HD void finished() {}
@@ -245,10 +246,14 @@ EPSM_HDN void reparam_backward(const DScene &sc, Io &io, Sink &sink, Pcg &aux_rn
     const uint32_t n = cfg.n_rays;
     if (io.aux_skip(round)) { for (uint32_t i = 0; i < 2 * n; ++i) pcg_next(aux_rng); return; }        // replay of a round long consumed
     if (io.aux_push_only(round)) {                                                 // wavefront, pass == round: queue the auxiliary rays
+        // the n rays of one reparameterised ray go into n CONSECUTIVE queue entries: they share an origin and lie in a cone of
+        // κ = 1e5 around d, so a warp of the traversal kernel that picks them up together walks one path through the BVH
+        // (one L1 wavefront per node instead of one per thread, no divergence)
+        const uint32_t q0 = io.aux_reserve(n);
         for (uint32_t i = 0; i < n; ++i) {
             const float sx = pcg_f32(aux_rng), sy = pcg_f32(aux_rng);
             f3 tang; const f3 ad = warp_field_direction(d, sx, sy, cfg.kappa, tang);
-            (void) sy; io.aux_push(aux_base + i, Ray{o, ad, FLT_MAX});
+            (void) sy; io.aux_push(aux_base + i, q0 + i, Ray{o, ad, FLT_MAX});
         }
         return;
     }

@@ -308,7 +308,8 @@ struct HostWfIo {
     bool adjoint_now(int round) const { return pass == round + 1; }
     bool aux_push_only(int round) const { return pass == round; }
     bool aux_skip(int round) const { return pass > round + 1; }
-    void aux_push(uint32_t j, const Ray &r) { qc.push_back({r, K + 1 + j}); }
+    uint32_t aux_reserve(uint32_t) { return 0u; }
+    void aux_push(uint32_t j, uint32_t, const Ray &r) { qc.push_back({r, K + 1 + j}); }
     Hit aux_hit(uint32_t j, const Ray &) { return hits[K + 1 + j]; }
     bool lane_radiance(f3 &out) const { out = L; return true; }
     void finished() { done = true; }
