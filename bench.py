@@ -178,11 +178,15 @@ def phase2_leg(ep, scene, sd, wl, spp, n=2):
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
 
-    def __init__(self, gpu=0):
-        super().__init__(daemon=True); self.gpu = gpu; self.rows = []; self.stop_evt = threading.Event(); self.proc = None
-        self.t_begin = None
+    def __init__(self, gpus=(0,), enabled=True):
+        """One nvidia-smi process for all the job's GPUs, started by rank 0 only (`enabled`): eight of them polling the driver
+        every 200 ms from eight ranks showed up as multi-millisecond outliers in the 8-GPU strong-scaling steps."""
+        super().__init__(daemon=True); self.gpus = list(gpus); self.rows = []; self.stop_evt = threading.Event(); self.proc = None
+        self.t_begin = None; self.enabled = enabled
 
     def wait_first(self, timeout):
+        if not self.enabled:
+            return
         t0 = time.time()
         while not self.rows and time.time() - t0 < timeout:
             time.sleep(0.02)
@@ -193,8 +197,10 @@ class ClockSampler(threading.Thread):
     def run(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        if not self.enabled:
+            return
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200"],
+            self.proc = subprocess.Popen(["nvidia-smi", "--id=" + ",".join(str(g) for g in self.gpus), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 self.rows.append([c.strip() for c in line.split(",")] + [time.time()])
@@ -226,7 +232,7 @@ class ClockSampler(threading.Thread):
             except Exception:
                 continue
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(np.max(mx)) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "gpus": self.gpus}
 
 
 def cpu_port_throughput(sd, wl, grad_in, target_seconds=12.0, prune=True):
@@ -426,7 +432,11 @@ def main():
             ms += e2.elapsed_time(e3)
         return ms
 
-    clk = ClockSampler(local); clk.start()                  # nvidia-smi takes a while to start on an 8-GPU box: launch it before the warm-up
+    clk = ClockSampler(list(range(world)) if world > 1 else [local], enabled=(rank == 0)); clk.start()                  # nvidia-smi takes a while to start on an 8-GPU box: launch it before the warm-up
+    if world > 1:                                            # communicator set-up (NCCL channels, NVLS buffers) is not a step
+        for _ in range(3):
+            dist.all_reduce(buf)
+        torch.cuda.synchronize()
     for k in range(args.warmup):
         step(k, False)
     clk.wait_first(2.0)
