@@ -310,6 +310,7 @@ struct SI {
     // EPSM additions (interaction.h:221-224)
     float b0, b1; V3 p0, p1, p2, n0, n1, n2; uint32_t ismesh;
     float uv[2];                                       // si.uv (mesh.cpp:731-744)
+    V3 dp_du, dp_dv;                                   // mesh.cpp:734,746-763
 };
 inline V3 to_local(const SI &si, V3 v) { return mk(dot(v, si.sh_s), dot(v, si.sh_t), dot(v, si.sh_n)); }
 inline V3 to_world(const SI &si, V3 v) { return fmadd(si.sh_n, v.z, fmadd(si.sh_t, v.y, si.sh_s * v.x)); }   // frame.h:41
@@ -350,6 +351,7 @@ SI compute_si(const Scene &sc, const Ray &ray, const PI &pi) {
     } else {
         si.sh_n = si.n; n0 = n1 = n2 = si.n;                                        // mesh.cpp:810-815
     }
+    si.dp_du = dp_du; si.dp_dv = dp_dv;
     if (m.flags & EPSM_MESH_FLIP_NORMALS) { si.n = -si.n; si.sh_n = -si.sh_n; n0 = -n0; n1 = -n1; n2 = -n2; }
     // initialize_sh_frame, interaction.h:262-275
     si.sh_s = normalize(fmadd(si.sh_n, -dot(si.sh_n, dp_du), dp_du));
@@ -1009,14 +1011,15 @@ void orc_surface_interaction(orc_scene *s, const float *r, float *out) {
     put3(si.p0); put3(si.p1); put3(si.p2); put3(si.n0); put3(si.n1); put3(si.n2);
     *o++ = (float) si.prim; *o++ = si.valid ? (float) bsdf_flags(s->sc.bsdfs[s->sc.meshes[si.mesh].bsdf]) : 0.f; *o++ = pi.u; *o++ = pi.v;
 }
-// Texture-side probe of a hit: out = [uv(2), sh_s(3), sh_t(3), diffuse reflectance at the hit (3)]
+// Texture-side probe of a hit: out = [uv(2), sh_s(3), sh_t(3), diffuse reflectance at the hit (3), dp_du(3), dp_dv(3)]
 void orc_surface_uv(orc_scene *s, const float *r, float *out) {
     g_accel_owner = s;
     Ray ray{mk(r[0], r[1], r[2]), mk(r[4], r[5], r[6]), r[3]};
     PI pi = scene_closest(s->sc, ray); SI si = compute_si(s->sc, ray, pi);
-    for (int i = 0; i < 11; ++i) out[i] = 0.f;
+    for (int i = 0; i < 17; ++i) out[i] = 0.f;
     if (!si.valid) return;
     const epsm_bsdf_desc b = bsdf_at(s->sc, si);
+    out[11] = si.dp_du.x; out[12] = si.dp_du.y; out[13] = si.dp_du.z; out[14] = si.dp_dv.x; out[15] = si.dp_dv.y; out[16] = si.dp_dv.z;
     out[0] = si.uv[0]; out[1] = si.uv[1]; out[2] = si.sh_s.x; out[3] = si.sh_s.y; out[4] = si.sh_s.z; out[5] = si.sh_t.x; out[6] = si.sh_t.y; out[7] = si.sh_t.z;
     out[8] = b.reflectance[0]; out[9] = b.reflectance[1]; out[10] = b.reflectance[2];
 }

@@ -185,9 +185,9 @@ class OracleScene:
                     n2=out[31:34], prim=int(out[34]) if np.isfinite(out[0]) else -1, bsdf_flags=int(out[35]), uv=out[36:38])
 
     def surface_uv(self, o, d, maxt=np.float32(3.4e38)):
-        r = np.array([o[0], o[1], o[2], maxt, d[0], d[1], d[2], 0], np.float32); out = np.zeros(11, np.float32)
+        r = np.array([o[0], o[1], o[2], maxt, d[0], d[1], d[2], 0], np.float32); out = np.zeros(17, np.float32)
         lib().orc_surface_uv(self.h, _p(r), _p(out))
-        return dict(uv=out[0:2], sh_s=out[2:5], sh_t=out[5:8], reflectance=out[8:11])
+        return dict(uv=out[0:2], sh_s=out[2:5], sh_t=out[5:8], reflectance=out[8:11], dp_du=out[11:14], dp_dv=out[14:17])
 
     def sample_emitter(self, o, d, sample):
         r = np.array([o[0], o[1], o[2], 3.4e38, d[0], d[1], d[2], 0], np.float32); out = np.zeros(14, np.float32)

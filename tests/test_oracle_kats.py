@@ -60,6 +60,23 @@ def test_rectangle_mesh_hit_record(orc, kats):
         assert np.allclose(si["p"], r["p"], atol=1e-6)
 
 
+def test_rectangle_mesh_texture_coordinates(orc, kats):
+    """The rest of src/render/tests/test_mesh.py:257-291: rectangle.obj carries uv = (xy + 1)/2, and the reference asserts
+    si.uv = (0.35, 0.35) / (0.65, 0.65), si.dp_du = (2, 0, 0), si.dp_dv = (0, 2, 0) at the two hits."""
+    from tests.hostsim.hostsim import SimScene
+    k = kats["rectangle_mesh"]
+    sd = _rect_scene(k)
+    sd.meshes[0].texcoords = ((np.array(k["vertices"], np.float32)[:, :2] + 1) / 2).astype(np.float32)
+    o, sim = orc.OracleScene(sd), SimScene(sd)
+    for r, uv in zip(k["rays"], ([0.35, 0.35], [0.65, 0.65])):
+        s = o.surface_uv(r["o"], r["d"])
+        assert np.allclose(s["uv"], uv, atol=1e-6)
+        assert np.allclose(s["dp_du"], [2, 0, 0], atol=1e-5) and np.allclose(s["dp_dv"], [0, 2, 0], atol=1e-5)
+        assert np.allclose(s["sh_s"], [1, 0, 0], atol=1e-6)                       # initialize_sh_frame: s follows dp_du
+        p = sim.surface_uv(r["o"], r["d"])                                        # the product's device code on the host
+        assert np.allclose(p["uv"], uv, atol=1e-6) and np.allclose(p["sh_s"], [1, 0, 0], atol=1e-6)
+
+
 def test_cornell_box_surface_interaction(orc, kats):
     k = kats["cornell_box"]
     sd = S.cornell_box(k["film"], 4, 64)
