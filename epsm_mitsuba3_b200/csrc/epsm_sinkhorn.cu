@@ -14,8 +14,9 @@
 // with softmin(ε, C, h)_i = −ε ln Σ_j exp(h_j − C_ij/ε), C_ij = |x_i − y_j|²/2.  The reference materialises N×N matrices
 // (tensorized backend) or streams them through KeOps; here one kernel evaluates all four softmins of a step as an online
 // log-sum-exp over column tiles staged in shared memory — nothing of size N² ever exists.  FP32 FMA + SFU ex2: K = 5 is
-// far too thin for tensor cores, and C/ε at ε = 1e-4 needs the full fp32 mantissa, so distances are formed from
-// coordinate differences (no |x|² + |y|² − 2x·y cancellation).
+// far too thin for tensor cores, and C/ε at ε = 1e-4 needs the full fp32 mantissa: the inner loop uses the dot-product form
+// only after recentring both clouds on the CTA's rows (term2), which keeps the cancelling terms small; the gradient launch
+// forms distances from coordinate differences.
 #include <cuda_runtime.h>
 #include <cub/device/device_radix_sort.cuh>
 #include <math.h>
@@ -45,10 +46,15 @@ struct RowAcc { float m, s, a[5]; };
 
 // Packed columns: `x` holds (x_d, x_d), the tile holds (y_d[j], y_d[j+1]); log2 of the two terms comes back packed.
 struct RowAcc2 { float m; u64 s; };
-__device__ __forceinline__ u64 term2(const u64 *x, const ulonglong2 t0, const ulonglong2 t1, const ulonglong2 t2, u64 neg_halfk) {
-    const u64 d0 = sub2(x[0], t0.x), d1 = sub2(x[1], t0.y), d2 = sub2(x[2], t1.x), d3 = sub2(x[3], t1.y), d4 = sub2(x[4], t2.x);
-    const u64 q = fma2(d4, d4, fma2(d3, d3, fma2(d2, d2, fma2(d1, d1, mul2(d0, d0)))));
-    return fma2(neg_halfk, q, t2.y);
+// log2 of two terms in the recentred dot-product form: with c the centre of the CTA's rows, x̂ = (x − c)·log2e/ε (per row),
+// ỹ = y − c and h' = h·log2e − ½·log2e/ε·|ỹ|² (per column, formed while the tile is staged),
+//     (h − |x − y|²/2ε)·log2e = h' + x̂·ỹ − ½·log2e/ε·|x − c|²,
+// and the last term is a per-row constant that leaves the sum and is applied once at the end.  Five packed FMAs per pair of
+// columns instead of eleven operations.  Precision: the products are of size |x − c|·|y − c|/ε — for the pairs that matter
+// (|x − y|² ≲ 60 ε) and rows of one 8×8-pixel block that is ≤ a few units, i.e. an error of ≤ 1e-3 in the exponent at ε = blur²,
+// the same as the rounding of h' itself (|h| ~ 1/ε); the un-centred |x|² + |y|² − 2x·y would lose three more digits.
+__device__ __forceinline__ u64 term2(const u64 *xh, const ulonglong2 t0, const ulonglong2 t1, const ulonglong2 t2) {
+    return fma2(xh[4], t2.x, fma2(xh[3], t1.y, fma2(xh[2], t1.x, fma2(xh[1], t0.y, fma2(xh[0], t0.x, t2.y)))));
 }
 // Four columns (two packed pairs) into one row's running log-sum-exp: one maximum test per four terms.
 __device__ __forceinline__ void fold4(RowAcc2 &r, u64 ta, u64 tb) {
@@ -119,13 +125,6 @@ __global__ void __launch_bounds__(SK_THREADS, GRAD ? 2 : 3) k_sink_softmin(SinkS
         }
     } else {
         u64 xp[2][5]; RowAcc2 a2[2];
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-#pragma unroll
-            for (int d = 0; d < 5; ++d) xp[r][d] = pk(x[r][d], x[r][d]);
-            a2[r].m = -INFINITY; a2[r].s = pk(0.f, 0.f);
-        }
-        const u64 neg_halfk = pk(-halfk, -halfk);
         const ulonglong2 *tp = reinterpret_cast<const ulonglong2 *>(tile);
         // Far-tile test.  Every term of a tile is at most hmax − halfk·d², d = distance between the boxes of this CTA's rows and
         // of the tile's points; once that is 40 binary orders below the running maximum of every row, the tile cannot change an
@@ -136,6 +135,18 @@ __global__ void __launch_bounds__(SK_THREADS, GRAD ? 2 : 3) k_sink_softmin(SinkS
         for (int d = 0; d < 5; ++d) {
             rlo[d] = fminf(x[0][d], x[1][d]); rhi[d] = fmaxf(x[0][d], x[1][d]);
             for (int of = 16; of > 0; of >>= 1) { rlo[d] = fminf(rlo[d], __shfl_xor_sync(0xffffffffu, rlo[d], of)); rhi[d] = fmaxf(rhi[d], __shfl_xor_sync(0xffffffffu, rhi[d], of)); }
+        }
+        // frame of this CTA: the centre of its rows' box; x̂ = (x − c)·2·halfk, r = halfk·|x − c|² (removed from the maximum at the end)
+        float ctr[5], rsh[2];
+#pragma unroll
+        for (int d = 0; d < 5; ++d) ctr[d] = 0.5f * (rlo[d] + rhi[d]);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            float q = 0.f;
+#pragma unroll
+            for (int d = 0; d < 5; ++d) { const float xc = x[r][d] - ctr[d]; q = fmaf(xc, xc, q); const float xh = xc * (2.f * halfk); xp[r][d] = pk(xh, xh); }
+            rsh[r] = halfk * q;
+            a2[r].m = -INFINITY; a2[r].s = pk(0.f, 0.f);
         }
         const uint32_t n_tiles = (job.n_cols + SK_TILE - 1) / SK_TILE;
         auto tile_bound = [&](uint32_t t) {
@@ -158,7 +169,7 @@ __global__ void __launch_bounds__(SK_THREADS, GRAD ? 2 : 3) k_sink_softmin(SinkS
             else { if (off > t_near) continue; t = t_near - off; }
             const uint32_t slot = visited++ & 1u;                               // double-buffered: a skip has no second barrier
             if (warp == 0) {
-                float mm = fminf(a2[0].m, a2[1].m);
+                float mm = fminf(a2[0].m - rsh[0], a2[1].m - rsh[1]);                // running maxima in absolute terms
                 for (int of = 16; of > 0; of >>= 1) mm = fminf(mm, __shfl_xor_sync(0xffffffffu, mm, of));
                 if (lane == 0) s_mmin[slot] = mm;
             }
@@ -169,21 +180,30 @@ __global__ void __launch_bounds__(SK_THREADS, GRAD ? 2 : 3) k_sink_softmin(SinkS
             // the columns arrive packed by k_sink_pack: group of four columns = 6 float4
             // (y0a y0b y1a y1b | y2a y2b y3a y3b | y4a y4b ha hb) × 2 pairs, h = (ln w + pot/ε)·log2 e, tail padded with h = −∞
             {
+                // one pair of columns (3 float4: y0a y0b y1a y1b | y2a y2b y3a y3b | y4a y4b ha hb) per thread and turn:
+                // ỹ = y − c, h' = h − halfk·|ỹ|²
                 const float4 *src = job.packed + (size_t) (j0 / 4) * 6;
-                for (uint32_t k = threadIdx.x; k < 6 * nq; k += SK_THREADS) tile[k] = src[k];
+                for (uint32_t k = threadIdx.x; k < 2 * nq; k += SK_THREADS) {
+                    float4 a = src[3 * k], b = src[3 * k + 1], c = src[3 * k + 2];
+                    a.x -= ctr[0]; a.y -= ctr[0]; a.z -= ctr[1]; a.w -= ctr[1]; b.x -= ctr[2]; b.y -= ctr[2]; b.z -= ctr[3]; b.w -= ctr[3]; c.x -= ctr[4]; c.y -= ctr[4];
+                    const float qa = fmaf(c.x, c.x, fmaf(b.z, b.z, fmaf(b.x, b.x, fmaf(a.z, a.z, a.x * a.x))));
+                    const float qb = fmaf(c.y, c.y, fmaf(b.w, b.w, fmaf(b.y, b.y, fmaf(a.w, a.w, a.y * a.y))));
+                    c.z = fmaf(-halfk, qa, c.z); c.w = fmaf(-halfk, qb, c.w);
+                    tile[3 * k] = a; tile[3 * k + 1] = b; tile[3 * k + 2] = c;
+                }
             }
             __syncthreads();
             // warp w walks groups w, w + 8, … of four columns: every lane reads the same 96 bytes (broadcast)
             for (uint32_t k = warp; k < nq; k += SK_THREADS / 32) {
                 const ulonglong2 t0 = tp[6 * k], t1 = tp[6 * k + 1], t2 = tp[6 * k + 2], u0 = tp[6 * k + 3], u1 = tp[6 * k + 4], u2 = tp[6 * k + 5];
-                const u64 a0 = term2(xp[0], t0, t1, t2, neg_halfk), b0 = term2(xp[0], u0, u1, u2, neg_halfk);
-                const u64 a1 = term2(xp[1], t0, t1, t2, neg_halfk), b1 = term2(xp[1], u0, u1, u2, neg_halfk);
+                const u64 a0 = term2(xp[0], t0, t1, t2), b0 = term2(xp[0], u0, u1, u2);
+                const u64 a1 = term2(xp[1], t0, t1, t2), b1 = term2(xp[1], u0, u1, u2);
                 fold4(a2[0], a0, b0);
                 fold4(a2[1], a1, b1);
             }
         }
 #pragma unroll
-        for (int r = 0; r < 2; ++r) { float sa, sb; upk(a2[r].s, sa, sb); acc[r].m = a2[r].m; acc[r].s = sa + sb; }
+        for (int r = 0; r < 2; ++r) { float sa, sb; upk(a2[r].s, sa, sb); acc[r].m = a2[r].m - rsh[r]; acc[r].s = sa + sb; }
     }
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
