@@ -90,7 +90,10 @@ EPSM_HDN void bsdf_eval_d6(const DBsdf &b, D6v3 wi, D6v3 wo, D6 out[3]) {
     }
 }
 // Σ_c a_c·f_c(wi, wo): value and gradient w.r.t. the two local directions.
-EPSM_HDN void bsdf_grad(const DBsdf &b, f3 wi, f3 wo, f3 a, f3 &g_wi, f3 &g_wo, f3 &value) {
+#ifndef EPSM_PRB_BSDFGRAD_INLINE
+#define EPSM_PRB_BSDFGRAD_INLINE EPSM_HDN
+#endif
+EPSM_PRB_BSDFGRAD_INLINE void bsdf_grad(const DBsdf &b, f3 wi, f3 wo, f3 a, f3 &g_wi, f3 &g_wo, f3 &value) {
     D6v3 dwi{d6v(wi.x, 0), d6v(wi.y, 1), d6v(wi.z, 2)}, dwo{d6v(wo.x, 3), d6v(wo.y, 4), d6v(wo.z, 5)};
     D6 f[3]; bsdf_eval_d6(b, dwi, dwo, f);
     value = mk3(f[0].v, f[1].v, f[2].v);
@@ -239,8 +242,17 @@ EPSM_HD void scatter_tri3(const DScene &sc, Sink &sink, uint32_t prim, f3 g0, f3
 //   g_V = ((I − d̂d̂ᵀ)g_dir/|d| − g_det·dZ/Z)/Z,  g_div = g_det/Z       [direction = normalize(d + V/Z), divergence = (div − V/Z·dZ)/Z at V = 0]
 // and pushes w_i·g_V + g_div·dZ_i through V_direct_i = normalize(p_i − o) (hit; p_i follows its triangle) or = d (miss).
 // The origin's gradient goes to `anchor`; with `d_from`: d = normalize(d_from − o) is attached too (the emitter ray).
+// reparam_backward has three call sites in the lane function; kept out of line the reverse-pass kernels are smaller (218 instead of
+// 230 registers) and 10 % faster (293.7 → 265.5 ms at 512² × 8 spp, profiles/r02_summary.md §N)
+#ifndef EPSM_PRB_REPARAM_INLINE
+#if defined(__CUDACC__)
+#define EPSM_PRB_REPARAM_INLINE __host__ __device__ __noinline__
+#else
+#define EPSM_PRB_REPARAM_INLINE
+#endif
+#endif
 template <typename Io, typename Sink>
-EPSM_HDN void reparam_backward(const DScene &sc, Io &io, Sink &sink, Pcg &aux_rng, const PrbConfig &cfg, int round, uint32_t aux_base, bool active,
+EPSM_PRB_REPARAM_INLINE void reparam_backward(const DScene &sc, Io &io, Sink &sink, Pcg &aux_rng, const PrbConfig &cfg, int round, uint32_t aux_base, bool active,
                                f3 o, f3 d, f3 g_dir, float g_det, const Anchor &anchor, bool d_attached, f3 d_from) {
     if (!active) return;                                                           // masked lanes do not advance the generator
     const uint32_t n = cfg.n_rays;
