@@ -133,9 +133,10 @@ EPSM_HD void mt_uv_bwd(f3 o, f3 d, f3 p0, f3 p1, f3 p2, float g_u, float g_v, Mt
 // ------------------------------------------------------------------------------------------------
 //  Reparameterisation (reparam.py)
 // ------------------------------------------------------------------------------------------------
-EPSM_HD f3 square_to_von_mises_fisher(float sx, float sy_, float kappa) {                 // warp.h:546-583, approach 1.2
+// e2k = expf(−2κ): the same for every auxiliary ray of a call, so the callers evaluate it once
+EPSM_HD f3 square_to_von_mises_fisher(float sx, float sy_, float kappa, float e2k) {      // warp.h:546-583, approach 1.2
     const float sy = fmaxf(1.f - sy_, 1e-6f);
-    const float cos_theta = 1.f + logf(fmaf(1.f - sy, expf(-2.f * kappa), sy)) / kappa;
+    const float cos_theta = 1.f + logf(fmaf(1.f - sy, e2k, sy)) / kappa;
     float s, c; sincos_dr(6.283185307179586f * sx, s, c);
     const float sin_theta = safe_sqrt(1.f - cos_theta * cos_theta);
     return mk3(c * sin_theta, s * sin_theta, cos_theta);
@@ -179,19 +180,23 @@ EPSM_HDN float boundary_test(const DScene &sc, const Hit &h, f3 ray_d) {
 struct AuxRec { uint32_t prim; float u, v, w; f3 dw; };
 // One auxiliary ray of _sample_warp_field (reparam.py:83-118): its direction, and — from its closest hit — the detached
 // quantities Z_i = w and dZ_i = d_w_omega.
-EPSM_HD f3 warp_field_direction(f3 d, float sx, float sy, float kappa, f3 &tang) {
-    const f3 om = square_to_von_mises_fisher(sx, sy, kappa);
-    f3 fs, ft; coordinate_system(d, fs, ft);                                       // Frame3f(ray.d)
+// (fs, ft) = coordinate_system(d), the frame of the reparameterised ray: also the same for all its auxiliary rays
+struct AuxFrame { f3 fs, ft; float e2k; };
+EPSM_HD AuxFrame aux_frame(f3 d, float kappa) { AuxFrame a; coordinate_system(d, a.fs, a.ft); a.e2k = expf(-2.f * kappa); return a; }   // Frame3f(ray.d)
+EPSM_HD f3 warp_field_direction(f3 d, const AuxFrame &fr, float sx, float sy, float kappa, f3 &tang) {
+    const f3 om = square_to_von_mises_fisher(sx, sy, kappa, fr.e2k);
+    const f3 fs = fr.fs, ft = fr.ft;
     tang = fma3(d, 0.f, fma3(ft, om.y, fs * om.x));                                // to_world((ω.x, ω.y, 0))
     return fma3(d, om.z, fma3(ft, om.y, fs * om.x));
 }
-EPSM_HDN void warp_field_weights(const DScene &sc, const Hit &h, f3 aux_d, f3 tang, float sy, float kappa, float exponent, AuxRec &r) {
+EPSM_HDN void warp_field_weights(const DScene &sc, const Hit &h, f3 aux_d, f3 tang, float sy, float kappa, float e2k, float exponent, AuxRec &r) {
     const bool hit = h.prim != 0xffffffffu;
     const float B = hit ? boundary_test(sc, h, aux_d) : 1.0f;
-    const float inv_vmf = rcp_e(fmaf(sy, expf(-2.f * kappa), 1.f - sy));
+    const float inv_vmf = rcp_e(fmaf(sy, e2k, 1.f - sy));
     const float w_denom = inv_vmf - 1.f + B;
     const float w_denom_rcp = w_denom > 1e-4f ? rcp_e(w_denom) : 0.f;
-    const float w = powf(w_denom_rcp, exponent) * inv_vmf;
+    // dr.power(x, exponent): the reference's default exponent 3 as two multiplications, anything else through powf
+    const float w = (exponent == 3.f ? w_denom_rcp * w_denom_rcp * w_denom_rcp : powf(w_denom_rcp, exponent)) * inv_vmf;
     float tmp1 = inv_vmf * w * w_denom_rcp * kappa * exponent;
     tmp1 = fminf(fmaxf(tmp1, -1e10f), 1e10f);
     r.prim = h.prim; r.u = h.u; r.v = h.v; r.w = w; r.dw = tang * tmp1;
@@ -262,9 +267,10 @@ EPSM_PRB_REPARAM_INLINE void reparam_backward(const DScene &sc, Io &io, Sink &si
         // κ = 1e5 around d, so a warp of the traversal kernel that picks them up together walks one path through the BVH
         // (one L1 wavefront per node instead of one per thread, no divergence)
         const uint32_t q0 = io.aux_reserve(n);
+        const AuxFrame fr = aux_frame(d, cfg.kappa);
         for (uint32_t i = 0; i < n; ++i) {
             const float sx = pcg_f32(aux_rng), sy = pcg_f32(aux_rng);
-            f3 tang; const f3 ad = warp_field_direction(d, sx, sy, cfg.kappa, tang);
+            f3 tang; const f3 ad = warp_field_direction(d, fr, sx, sy, cfg.kappa, tang);
             (void) sy; io.aux_push(aux_base + i, q0 + i, Ray{o, ad, FLT_MAX});
         }
         return;
@@ -273,11 +279,12 @@ EPSM_PRB_REPARAM_INLINE void reparam_backward(const DScene &sc, Io &io, Sink &si
     if (!live) { for (uint32_t i = 0; i < 2 * n; ++i) pcg_next(aux_rng); return; }
     AuxRec rec[EPSM_PRB_MAX_RAYS];
     float Z = 0.f; f3 dZ = mk3(0, 0, 0);
+    const AuxFrame fr = aux_frame(d, cfg.kappa);
     for (uint32_t i = 0; i < n; ++i) {
         const float sx = pcg_f32(aux_rng), sy = pcg_f32(aux_rng);
-        f3 tang; const f3 ad = warp_field_direction(d, sx, sy, cfg.kappa, tang);
+        f3 tang; const f3 ad = warp_field_direction(d, fr, sx, sy, cfg.kappa, tang);
         const Hit h = io.aux_hit(aux_base + i, Ray{o, ad, FLT_MAX});
-        warp_field_weights(sc, h, ad, tang, sy, cfg.kappa, cfg.exponent, rec[i]);
+        warp_field_weights(sc, h, ad, tang, sy, cfg.kappa, fr.e2k, cfg.exponent, rec[i]);
         Z += rec[i].w; dZ = dZ + rec[i].dw;
     }
     Z = fmaxf(Z, 1e-8f);
