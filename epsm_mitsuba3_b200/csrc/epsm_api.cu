@@ -156,7 +156,7 @@ int make_launch(epsm_ctx *ctx, uint32_t sensor, uint32_t seed, uint32_t spp, uin
     if (lane_begin > lane_end) return fail(ctx, EPSM_E_INVALID, "lane_begin > lane_end");
     ln.seed = seed; ln.spp = spp; ln.max_depth = max_depth; ln.rr_depth = rr_depth;
     ln.lane_begin = lane_begin; ln.lane_end = lane_end; ln.variant = variant; ln.tile_y0 = ln.tile_y1 = 0;
-    ln.s_begin = 0; ln.s_end = spp; ln.prune = ctx->full_replay ? 0u : 1u;
+    ln.s_begin = 0; ln.s_end = spp; ln.prune = ctx->full_replay ? 0u : 1u; ln.pixel_major = 0u;
     if (ctx->s_end != 0) {
         if (ctx->s_begin > ctx->s_end || ctx->s_end > spp) return fail(ctx, EPSM_E_INVALID, "sample range exceeds spp");
         ln.s_begin = ctx->s_begin; ln.s_end = ctx->s_end;

@@ -361,7 +361,14 @@ __device__ __forceinline__ WorkItem wf_work_item(const DLaunch &ln, uint64_t w) 
     if (w < 0x100000000ull) { const uint32_t w32 = (uint32_t) w; tile = w32 / per_tile; r = w32 - tile * per_tile; }   // 32-bit divisions: the common case
     else { tile = (uint32_t) (w / per_tile); r = (uint32_t) (w % per_tile); }
     const uint32_t ty_rel = tile / tiles_x, tx = tile - ty_rel * tiles_x, ty = ln.tile_y0 + ty_rel;
-    WorkItem wi; wi.s = ln.s_begin + r / 32; const uint32_t pin = r & 31;
+    // Inside a tile, either the tile's 32 pixels at one sample index (a warp = neighbouring pixels: the primal render, whose film
+    // kernel splats a warp's samples into 32 different pixels of the shared tile), or consecutive samples of one pixel (the
+    // gradient pass: a warp's camera rays are all but identical — one path through the BVH, one hit triangle for the first-hit
+    // gathers, one vertex triple for the aggregated scatter; room pass 41.97 → 39.7 ms, profiles/r02_summary.md §R).  Lane ids, and
+    // with them every random stream, do not depend on the order.
+    WorkItem wi; uint32_t pin;
+    if (ln.pixel_major) { pin = r / S; wi.s = ln.s_begin + (r - pin * S); }
+    else { wi.s = ln.s_begin + r / 32; pin = r & 31; }
     wi.px = tx * TILE_W + (pin & (TILE_W - 1)); wi.py = ty * TILE_H + pin / TILE_W;
     wi.lane = ((uint64_t) wi.py * W + wi.px) * ln.spp + wi.s;
     wi.valid = wi.px < W && wi.py < H && ty < ln.tile_y1 && wi.lane >= ln.lane_begin && wi.lane < ln.lane_end;
@@ -1016,7 +1023,7 @@ cudaError_t epsm_launch_trace(const DScene &sc, const float *rays, uint64_t n, v
     return cudaGetLastError();
 }
 cudaError_t epsm_launch_render(const DScene &sc, DLaunch ln, float *film, unsigned long long *counters, cudaStream_t s) {
-    tile_rows(ln); const uint32_t grid = tile_grid(ln);
+    ln.pixel_major = 0u; tile_rows(ln); const uint32_t grid = tile_grid(ln);
     if (grid == 0) return cudaSuccess;
     if (counters) k_render<true><<<grid, CTA, 0, s>>>(sc, ln, film, counters); else k_render<false><<<grid, CTA, 0, s>>>(sc, ln, film, nullptr);
     return cudaGetLastError();
@@ -1025,6 +1032,7 @@ cudaError_t epsm_launch_render(const DScene &sc, DLaunch ln, float *film, unsign
 // length exceeds 8 bounces (max_depth = −1 means "until every path has died", common.py:33-37).
 cudaError_t epsm_launch_render_wf(const DScene &sc, DLaunch ln, float *film, unsigned long long *counters, void *workspace, uint32_t capacity,
                                   uint32_t trace_grid, uint64_t *n_launches, cudaStream_t s, float *lane_L) {
+    ln.pixel_major = 0u;
     tile_rows(ln);
     const uint32_t tiles = tile_grid(ln);
     if (tiles == 0 || ln.s_end <= ln.s_begin) return cudaSuccess;
@@ -1087,6 +1095,7 @@ cudaError_t epsm_launch_backward(const DScene &sc, DLaunch ln, const float *grad
                                  EpsmEventList *trace_events, cudaStream_t s) {
     auto ev_begin = [&]() { if (trace_events) { cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, s); trace_events->push_back({a, b}); } };
     auto ev_end = [&]() { if (trace_events) cudaEventRecord(trace_events->back().second, s); };
+    ln.pixel_major = 1u;
     tile_rows(ln);
     const uint32_t tiles = tile_grid(ln);
     if (tiles == 0 || ln.s_end <= ln.s_begin) return cudaSuccess;

@@ -91,6 +91,7 @@ struct DLaunch {
     uint32_t s_begin, s_end;     // sample slots of each pixel handled by this launch (multi-GPU sharding)
     int variant;
     uint32_t prune;              // gradient pass: stop each path where its gradient chain ends (epsm_device.cuh: wf_chain_vertex)
+    uint32_t pixel_major;        // work-item order inside a tile: 1 = consecutive samples of one pixel (gradient pass), 0 = the tile's 32 pixels at one sample index (primal render)
 };
 
 // prb_reparam properties (prb_reparam.py:225-247) as the kernels take them.
