@@ -349,9 +349,9 @@ static WfBuffers wf_carve(void *base, uint32_t capacity) {
     w.capacity = capacity; return w;
 }
 
-// Work index → lane.  Work items are enumerated tile by tile (8×4 pixels), then by sample, then by pixel in the
-// tile, so 32 consecutive items are neighbouring pixels at the same sample index (coherent primary rays), and the
-// lane id — which alone fixes the random stream — is pixel·spp + s as in the reference wavefront.
+// Work index → lane.  Work items are enumerated tile by tile (8×4 pixels); inside a tile either by sample, then by pixel
+// (32 consecutive items = neighbouring pixels at the same sample index) or by pixel, then by sample (DLaunch::pixel_major, below).
+// The lane id — which alone fixes the random stream — is pixel·spp + s as in the reference wavefront.
 struct WorkItem { uint32_t px, py, s; uint64_t lane; bool valid; };
 __device__ __forceinline__ WorkItem wf_work_item(const DLaunch &ln, uint64_t w) {
     const uint32_t W = ln.sensor.w, H = ln.sensor.h, S = ln.s_end - ln.s_begin;
