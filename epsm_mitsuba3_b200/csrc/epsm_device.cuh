@@ -1137,10 +1137,7 @@ EPSM_HD f3 frame_backward(f3 t, f3 nh, float inv_ln, float inv_lv, f3 gt, f3 gb,
     return (gnh - nh * dot3(nh, gnh)) * inv_ln;
 }
 // half-vector constraint rows.  `attached`: differentiate through the frame (false in caustic section A, epsm.py:1022)
-#ifndef EPSM_HVJ_INLINE
-#define EPSM_HVJ_INLINE EPSM_HD
-#endif
-EPSM_HVJ_INLINE void halfvector_jac(f3 xp, f3 xc, f3 xn, f3 n, float eta, bool attached, RowJac &J) {
+EPSM_HD void halfvector_jac(f3 xp, f3 xc, f3 xn, f3 n, float eta, bool attached, RowJac &J) {
     f3 t, b, nh; float inv_ln, inv_lv; frame_from_normal(n, t, b, nh, inv_ln, inv_lv);
     f3 di = xp - xc, dO = xn - xc;
     float ili = 1.0f / len3(di), ilo = 1.0f / len3(dO);

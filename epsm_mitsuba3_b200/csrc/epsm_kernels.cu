@@ -151,10 +151,7 @@ __global__ void k_film_develop(const float *__restrict__ film, uint64_t n_pixels
 //  Warp-aggregated gradient scatter (the adjoint of the vertex gathers; cf. the reference's scatter_reduce
 //  codegen, ext/drjit/ext/drjit-core/src/cuda_eval.cpp:808-905)
 // ------------------------------------------------------------------------------------------------
-#ifndef EPSM_SCATTER3_INLINE
-#define EPSM_SCATTER3_INLINE __device__ __forceinline__
-#endif
-EPSM_SCATTER3_INLINE void scatter3(float *__restrict__ buf, uint32_t idx, f3 v, bool pred) {
+__device__ __forceinline__ void scatter3(float *__restrict__ buf, uint32_t idx, f3 v, bool pred) {
     pred = pred && (v.x != 0.f || v.y != 0.f || v.z != 0.f);
     if (!pred) return;
     // Opportunistic aggregation over the lanes that arrived together, partitioned by target vertex (match.any); each

@@ -90,10 +90,7 @@ EPSM_HDN void bsdf_eval_d6(const DBsdf &b, D6v3 wi, D6v3 wo, D6 out[3]) {
     }
 }
 // Σ_c a_c·f_c(wi, wo): value and gradient w.r.t. the two local directions.
-#ifndef EPSM_PRB_BSDFGRAD_INLINE
-#define EPSM_PRB_BSDFGRAD_INLINE EPSM_HDN
-#endif
-EPSM_PRB_BSDFGRAD_INLINE void bsdf_grad(const DBsdf &b, f3 wi, f3 wo, f3 a, f3 &g_wi, f3 &g_wo, f3 &value) {
+EPSM_HDN void bsdf_grad(const DBsdf &b, f3 wi, f3 wo, f3 a, f3 &g_wi, f3 &g_wo, f3 &value) {
     D6v3 dwi{d6v(wi.x, 0), d6v(wi.y, 1), d6v(wi.z, 2)}, dwo{d6v(wo.x, 3), d6v(wo.y, 4), d6v(wo.z, 5)};
     D6 f[3]; bsdf_eval_d6(b, dwi, dwo, f);
     value = mk3(f[0].v, f[1].v, f[2].v);
