@@ -151,6 +151,9 @@ __global__ void k_film_develop(const float *__restrict__ film, uint64_t n_pixels
 //  Warp-aggregated gradient scatter (the adjoint of the vertex gathers; cf. the reference's scatter_reduce
 //  codegen, ext/drjit/ext/drjit-core/src/cuda_eval.cpp:808-905)
 // ------------------------------------------------------------------------------------------------
+// BFLY: also test for the whole warp adding to one vertex (worth it where that is common — the first-vertex fast path and the
+// short-chain finish kernel; the 255-register long-chain finish kernel only pays registers for it)
+template <bool BFLY = true>
 __device__ __forceinline__ void scatter3(float *__restrict__ buf, uint32_t idx, f3 v, bool pred) {
     pred = pred && (v.x != 0.f || v.y != 0.f || v.z != 0.f);
     if (!pred) return;
@@ -163,7 +166,7 @@ __device__ __forceinline__ void scatter3(float *__restrict__ buf, uint32_t idx, 
     // all of them), and nothing between the mask query and the match can split the lanes.
     const unsigned peers = __match_any_sync(__activemask(), idx);
     const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
-    if (peers == 0xffffffffu) {
+    if (BFLY && peers == 0xffffffffu) {
         // the whole warp adds to one vertex (pixel-major gradient pass: a warp's samples of one pixel hit one triangle): butterfly
         // sum, 15 shuffles instead of the 96 of the general loop below
 #pragma unroll
@@ -197,7 +200,7 @@ __device__ void scatter_path(const PathLogT<NV> &P, const PathGradsT<NV> &G, int
         const bool sel = v.active && (v.mesh_flags & EPSM_MESH_GRAD);
         if (5 * k + 4 < n_pg) {
 #pragma unroll
-            for (int c = 0; c < 3; ++c) scatter3(grad_pos, v.fi[c], G.pg[k][c], sel);                   // (i)
+            for (int c = 0; c < 3; ++c) scatter3<(NV < EPSM_MAXV)>(grad_pos, v.fi[c], G.pg[k][c], sel);                   // (i)
             const f3 g3 = G.pg[k][3];                                                                     // (iv)
             const bool any_g3 = sel && (g3.x != 0.f || g3.y != 0.f || g3.z != 0.f);
             const float flip = (v.mesh_flags & EPSM_MESH_FLIP_NORMALS) ? -1.f : 1.f;
@@ -207,26 +210,26 @@ __device__ void scatter_path(const PathLogT<NV> &P, const PathGradsT<NV> &G, int
                 const float il = 1.0f / len3(nt); const f3 nh = nt * il;
                 const f3 gt = (g3 - nh * dot3(nh, g3)) * (il * flip);
 #pragma unroll
-                for (int c = 0; c < 3; ++c) scatter3(grad_nrm, v.fi[c], gt * v.bw[c], true);
+                for (int c = 0; c < 3; ++c) scatter3<(NV < EPSM_MAXV)>(grad_nrm, v.fi[c], gt * v.bw[c], true);
             } else if (any_g3 && v.ismesh) {
                 // flat-shaded mesh: sh_frame.n = normalize(cross(p1−p0, p2−p0)) → vertex positions (mesh.cpp:729,811)
                 const f3 e1 = v.p1 - v.p0, e2 = v.p2 - v.p0, cr = cross3(e1, e2);
                 const float il = 1.0f / len3(cr); const f3 nh = cr * il;
                 const f3 gc = (g3 - nh * dot3(nh, g3)) * (il * flip);
                 const f3 ge1 = cross3(e2, gc), ge2 = cross3(gc, e1);
-                scatter3(grad_pos, v.fi[1], ge1, true); scatter3(grad_pos, v.fi[2], ge2, true); scatter3(grad_pos, v.fi[0], -(ge1 + ge2), true);
+                scatter3<(NV < EPSM_MAXV)>(grad_pos, v.fi[1], ge1, true); scatter3<(NV < EPSM_MAXV)>(grad_pos, v.fi[2], ge2, true); scatter3<(NV < EPSM_MAXV)>(grad_pos, v.fi[0], -(ge1 + ge2), true);
             }
         }
 #pragma unroll
-        for (int c = 0; c < 3; ++c) scatter3(grad_pos, v.fi[c], G.dg[k] * v.bw[c], sel);                 // (ii)
+        for (int c = 0; c < 3; ++c) scatter3<(NV < EPSM_MAXV)>(grad_pos, v.fi[c], G.dg[k] * v.bw[c], sel);                 // (ii)
         if (k == 0 && shadow_term) {                                                                      // epsm.py:609-620
             const f3 g = G.dg[0] * v.dis;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) scatter3(grad_pos, v.dfi[c], g * v.dbw[c], v.direct_any && v.direct_grad);
+            for (int c = 0; c < 3; ++c) scatter3<(NV < EPSM_MAXV)>(grad_pos, v.dfi[c], g * v.dbw[c], v.direct_any && v.direct_grad);
         }
         const f3 gl = G.lg[k] * v.lr_sum;                                                                 // (iii) epsm.py:622-627
 #pragma unroll
-        for (int c = 0; c < 3; ++c) scatter3(grad_pos, v.dfi[c], gl * v.dbw[c], v.direct_valid && v.direct_grad);
+        for (int c = 0; c < 3; ++c) scatter3<(NV < EPSM_MAXV)>(grad_pos, v.dfi[c], gl * v.dbw[c], v.direct_valid && v.direct_grad);
     }
 }
 
