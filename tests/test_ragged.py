@@ -77,3 +77,29 @@ def test_ragged_gradient_sensor_gpu(orc, match):
         a = scene.render_backward_raw("manifold", 2, 11, 8, 6, 5, g, lane_begin=0, lane_end=37)
         b = scene.render_backward_raw("manifold", 2, 11, 8, 6, 5, g, lane_begin=37, lane_end=n)
         assert np.allclose(a[0] + b[0], gp, rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_gradient_pass_odd_sample_counts_and_sample_shards_gpu(orc):
+    """The gradient pass enumerates a tile pixel-major (a warp = consecutive samples of one pixel): sample counts that are not a
+    multiple of the warp size, on a ragged sensor, against the host harness; and sample-index shards (the multi-GPU partition,
+    epsm_set_sample_range) of unequal, odd sizes must add up to the whole."""
+    import epsm_mitsuba3_b200 as ep
+    sd = ragged_scene(16, 16, match=13)
+    scene, sim = ep.Scene(sd, device=0), SimScene(sd)
+    g = parity.synthetic_grad_in(13)
+    for spp in (5, 100):
+        gp, gn = scene.render_backward_raw("manifold", 2, 7, spp, 6, 5, g)
+        hp, hn = sim.backward("manifold", 2, 7, spp, 6, 5, g)
+        gp, gn = np.asarray(gp), np.asarray(gn)                 # numpy grad_in → numpy buffers back
+        scale = max(1e-6, float(np.abs(hp).max()))
+        assert np.abs(gp - hp).max() < 2e-4 * scale and np.abs(gn - hn).max() < 2e-4 * max(1e-6, float(np.abs(hn).max())), spp
+    parts = []
+    for s0, s1 in ((0, 37), (37, 100)):
+        scene.set_sample_range(s0, s1)
+        try:
+            a, _ = scene.render_backward_raw("manifold", 2, 7, 100, 6, 5, g)
+        finally:
+            scene.set_sample_range(0, 0)
+        parts.append(np.asarray(a))
+    assert np.allclose(parts[0] + parts[1], gp, rtol=2e-4, atol=2e-4 * scale)
