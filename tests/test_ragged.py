@@ -103,3 +103,19 @@ def test_gradient_pass_odd_sample_counts_and_sample_shards_gpu(orc):
             scene.set_sample_range(0, 0)
         parts.append(np.asarray(a))
     assert np.allclose(parts[0] + parts[1], gp, rtol=2e-4, atol=2e-4 * scale)
+
+
+@pytest.mark.gpu
+def test_gradient_pass_on_the_border_sensor_gpu(orc):
+    """The C ABI takes any sensor: the gradient pass on sensor 0 (hdrfilm sample_border: (W+4)·(H+4)·spp lanes, the border's samples
+    carry no pixel-motion gradient) against the host harness, at an odd sample count."""
+    import epsm_mitsuba3_b200 as ep
+    sd = ragged_scene(14, 11, match=12)
+    assert sd.sensors[0].sample_border
+    scene, sim = ep.Scene(sd, device=0), SimScene(sd)
+    g = parity.synthetic_grad_in(14)[:11]                       # (H, W, 5) of sensor 0's film
+    for spp in (3, 40):
+        gp, gn = scene.render_backward_raw("manifold", 0, 9, spp, 6, 5, np.ascontiguousarray(g))
+        hp, hn = sim.backward("manifold", 0, 9, spp, 6, 5, g)
+        scale = max(1e-6, float(np.abs(hp).max()))
+        assert np.abs(hp).max() > 0 and np.abs(np.asarray(gp) - hp).max() < 2e-4 * scale, spp
